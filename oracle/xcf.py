@@ -1,0 +1,155 @@
+"""Oracle double of the reference module ``picca.xcf`` (hot-path subset).
+TEST INFRASTRUCTURE ONLY -- the referee for picca_b200.xcf, never the product.
+
+Restates: fill_neighs (xcf.py:71-123), compute_xi (xcf.py:126-220), compute_dmat (xcf.py:325-424).
+"""
+import sys
+
+import numpy as np
+
+from . import _host, _kernels
+
+# ---- module globals, names and defaults as reference xcf.py:27-62
+num_bins_r_par = None
+num_bins_r_trans = None
+num_model_bins_r_par = None
+num_model_bins_r_trans = None
+r_par_max = None
+r_par_min = None
+r_trans_max = None
+z_min_pairs = None
+z_max_pairs = None
+ang_max = None
+nside = None
+zerr_cut_deg = None
+zerr_cut_kms = None
+counter = None
+num_data = None
+z_ref = None
+alpha = None
+alpha_obj = None
+lambda_abs = None
+alpha_abs = None
+data = None
+objs = None
+reject = None
+lock = None
+cosmo = None
+rmu_binning = False
+ang_correlation = False
+redshift_evolution_in_distortion_matrix = True
+
+_THIS = sys.modules[__name__]
+
+
+class _ObjCatalogue:
+    def __init__(self, cat):
+        self.z_qso = np.array([o.z_qso for o in cat.objs], dtype=np.float64)
+        self.has_dist = all(o.r_comov is not None for o in cat.objs)
+        if self.has_dist:
+            self.r_comov = np.array([o.r_comov for o in cat.objs], dtype=np.float64)
+            self.dist_m = np.array([o.dist_m for o in cat.objs], dtype=np.float64)
+        self.weights = np.array([o.weights for o in cat.objs], dtype=np.float64)
+
+
+def _obj_arrays():
+    cat = _host.catalogue(objs)
+    if not hasattr(cat, "_obj"):
+        cat._obj = _ObjCatalogue(cat)
+    return cat, cat._obj
+
+
+def fill_neighs(healpixs):
+    """xcf.py:71-123; neighbours stored as an index array into the ascending-healpix object
+    catalogue plus the object list itself (``delta.neighbours`` is a NumPy object array)."""
+    cat, arr = _obj_arrays()
+    for healpix in healpixs:
+        for delta in data[healpix]:
+            ang = _host.angle_between_many(delta, cat)
+            w = (cat.thingid != delta.thingid) & (ang < ang_max)
+            if zerr_cut_deg is not None:  # xcf.py:102-115
+                ang_deg = 180.0 / np.pi * ang
+                z_qq = 0.5 * (delta.z_qso + arr.z_qso)
+                dv_kms = np.abs(delta.z_qso - arr.z_qso) / (1 + z_qq)
+                dv_kms *= _host.SPEED_LIGHT
+                zerr_cut_mask = ang_deg < zerr_cut_deg
+                zerr_cut_mask &= dv_kms < zerr_cut_kms
+                w &= ~zerr_cut_mask
+            if not ang_correlation:  # xcf.py:117-121
+                f = r_trans_max if rmu_binning else 1
+                w &= (delta.r_comov[0] - arr.r_comov) * np.cos(ang / 2.) < r_par_max * f
+                w &= (delta.r_comov[-1] - arr.r_comov) * np.cos(ang / 2.) > r_par_min * f
+            idx = np.nonzero(w)[0]
+            neighbours = np.empty(idx.size, dtype=object)
+            for k, q in enumerate(idx):
+                neighbours[k] = cat.objs[q]
+            delta.neighbours = neighbours
+            delta._neighbour_index = idx
+
+
+def compute_xi(healpixs):
+    """xcf.py:126-220."""
+    p = _kernels.params_from_module(_THIS, cross=True)
+    cat, arr = _obj_arrays()
+    nb = num_bins_r_par * num_bins_r_trans
+    out = [np.zeros(nb) for _ in range(5)] + [np.zeros(nb, dtype=np.int64)]
+    for healpix in healpixs:
+        for delta in data[healpix]:
+            _host.progress(_THIS)
+            if delta.neighbours.size != 0:
+                idx = delta._neighbour_index
+                ang = _host.angle_between_many(delta, cat, idx)
+                z_qso = arr.z_qso[idx]
+                weights_qso = arr.weights[idx]
+                if ang_correlation:
+                    lambda_qso = np.array([10.0**obj.log_lambda for obj in delta.neighbours])
+                    _kernels.xi_cross_forest(p, delta, z_qso, lambda_qso, lambda_qso, weights_qso,
+                                             ang, out, ang_correlation=True)
+                else:
+                    _kernels.xi_cross_forest(p, delta, z_qso, arr.r_comov[idx], arr.dist_m[idx],
+                                             weights_qso, ang, out)
+            setattr(delta, "neighbours", None)
+    weights, xi, r_par, r_trans, z, num_pairs = out
+    w = weights > 0
+    xi[w] /= weights[w]
+    r_par[w] /= weights[w]
+    r_trans[w] /= weights[w]
+    z[w] /= weights[w]
+    return weights, xi, r_par, r_trans, z, num_pairs
+
+
+def compute_dmat(healpixs):
+    """xcf.py:325-424."""
+    p = _kernels.params_from_module(_THIS, cross=True)
+    cat, arr = _obj_arrays()
+    nb = num_bins_r_par * num_bins_r_trans
+    nbm = num_model_bins_r_par * num_model_bins_r_trans
+    dmat = np.zeros(nb * nbm)
+    weights_dmat = np.zeros(nb)
+    r_par_eff = np.zeros(nbm)
+    r_trans_eff = np.zeros(nbm)
+    z_eff = np.zeros(nbm)
+    weight_eff = np.zeros(nbm)
+    num_pairs = 0
+    num_pairs_used = 0
+    for healpix in healpixs:
+        for delta1 in data[healpix]:
+            _host.progress(_THIS)
+            if delta1.order is None:
+                raise RuntimeError("Trying to compute the distortion matrix but "
+                                   "order is not defined for the deltas. "
+                                   "Check previous warning to solve this issue")
+            w = np.random.rand(len(delta1.neighbours)) > reject  # xcf.py:379
+            if w.sum() == 0:
+                continue  # xcf.py:380-381 (Q7: forest not counted, neighbours not cleared)
+            num_pairs += len(delta1.neighbours)
+            num_pairs_used += w.sum()
+            idx = delta1._neighbour_index[w]
+            ang = _host.angle_between_many(delta1, cat, idx)
+            _kernels.dmat_cross_forest(p, delta1, arr.r_comov[idx], arr.dist_m[idx],
+                                       arr.z_qso[idx], arr.weights[idx], ang, weights_dmat, dmat,
+                                       r_par_eff, r_trans_eff, z_eff, weight_eff)
+            setattr(delta1, "neighbours", None)
+    dmat = dmat.reshape(nb, nbm)
+    return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
+            num_pairs_used)
