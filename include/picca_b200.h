@@ -1,0 +1,181 @@
+/*
+ * picca_b200.h -- C ABI of libpicca_b200.so: the B200 (sm_100a) implementation of picca's forest
+ * pair-counting hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference has no native layer: its "plugin API" for this path is the Python module surface
+ * of picca.cf / picca.xcf (module globals + fill_neighs / compute_xi / compute_dmat, reference
+ * py/picca/cf.py:28-79,82,138,390 and py/picca/xcf.py:27-68,71,126,325).  picca_b200/cf.py and
+ * picca_b200/xcf.py mirror that surface and bind the entry points below with ctypes; each entry
+ * point names the reference code it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer inside pb2_catalog / pb2_pairs / passed as `d_*` is a DEVICE pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions return 0 on success, a positive cudaError_t value or a negative PB2_E* code on
+ *     failure; pb2_last_error() returns the message for the calling thread;
+ *   - all launches are asynchronous on `stream` unless stated otherwise.
+ */
+#ifndef PICCA_B200_H
+#define PICCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_ABI_VERSION 3
+
+#define PB2_EINVAL (-1)   /* bad argument */
+#define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
+
+/* Module globals of picca.cf / picca.xcf, snapshotted at call time (cf.py:28-79, xcf.py:27-68). */
+typedef struct pb2_params {
+    int32_t num_bins_r_par;         /* np  */
+    int32_t num_bins_r_trans;       /* nt  */
+    int32_t num_model_bins_r_par;   /* npm */
+    int32_t num_model_bins_r_trans; /* ntm */
+    double r_par_min;
+    double r_par_max;
+    double r_trans_max;
+    int32_t has_z_min_pairs;
+    int32_t has_z_max_pairs;
+    double z_min_pairs;
+    double z_max_pairs;
+    int32_t has_zerr_cut;
+    int32_t x_correlation;
+    double zerr_cut_deg;
+    double zerr_cut_kms;
+    int32_t rmu_binning;
+    int32_t ang_correlation;
+    int32_t remove_same_half_plate_close_pairs;
+    int32_t redshift_evolution_in_distortion_matrix;
+    double z_ref;
+    double alpha;
+    double alpha2; /* cf: alpha2 ; xcf: alpha_obj */
+    double ang_max;
+} pb2_params;
+
+/*
+ * A catalogue of lines of sight packed as SoA + CSR in HBM (replaces the dict[healpix] ->
+ * list[Delta|QSO] object graph the reference walks, py/picca/data.py:14-162,238-373).
+ * Lines of sight are stored in ascending-HEALPix, list order -- the iteration order of
+ * fill_neighs (cf.py:91-122).  A quasar catalogue (xcf `objs`) is the same structure with one
+ * pixel per object: r_comov/dist_m/weights scalars, z = z_qso.
+ */
+typedef struct pb2_catalog {
+    int64_t n_los;            /* number of forests / objects */
+    int64_t n_pix;            /* total pixels = offset[n_los] */
+    const int64_t *offset;    /* [n_los+1] first pixel of each line of sight */
+    /* per pixel, fp64 */
+    const double *r_comov;    /* Delta.r_comov (or 10**log_lambda when ang_correlation) */
+    const double *dist_m;     /* Delta.dist_m  (same remark) */
+    const double *z;          /* Delta.z */
+    const double *weights;    /* Delta.weights */
+    const double *delta_w;    /* Delta.delta * Delta.weights, 0 where weights == 0 */
+    const double *log_lambda; /* Delta.log_lambda (distortion matrix only; may be NULL) */
+    /* per line of sight */
+    const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;
+    const int64_t *thingid, *plate, *fiberid;
+    const int32_t *order;     /* Delta.order, -1 when None */
+    const int32_t *row;       /* index of the line of sight's HEALPix pixel in sorted(data) */
+    /* per HEALPix pixel: member range and a bounding cap (centre, angular radius) of members */
+    int32_t n_hp;
+    int32_t sorted;           /* 1 if r_comov and dist_m are non-decreasing inside every forest */
+    const int32_t *hp_first;  /* [n_hp+1] */
+    const double *cap_x, *cap_y, *cap_z, *cap_rad;
+    int32_t max_pix;          /* longest line of sight */
+    int32_t reserved;
+} pb2_catalog;
+
+/*
+ * Neighbour (forest-pair) list in CSR form over the `n_f1` lines of sight selected by f1_index.
+ * Order inside a segment = ascending index in the second catalogue = the reference's neighbour
+ * order (ascending HEALPix id, then list order), which the --rej RNG contract depends on.
+ */
+typedef struct pb2_pairs {
+    int64_t n_f1;
+    int64_t n_pairs;
+    const int32_t *f1_index;   /* [n_f1] line-of-sight index in catalogue 1 */
+    const int64_t *nb_offset;  /* [n_f1+1] */
+    const int32_t *nb_f1;      /* [n_pairs] position k in f1_index of the owning line of sight */
+    const int32_t *nb_f2;      /* [n_pairs] line-of-sight index in catalogue 2 */
+    const double *nb_ang;      /* [n_pairs] angular separation (get_angle_between) */
+    const double *nb_cos;      /* [n_pairs] cos(ang/2) */
+    const double *nb_sin;      /* [n_pairs] sin(ang/2) */
+    const uint8_t *nb_keep;    /* [n_pairs] or NULL: 0 = pair dropped by the --rej draw (dmat) */
+} pb2_pairs;
+
+int32_t pb2_abi_version(void);
+const char *pb2_last_error(void);
+int32_t pb2_sizeof_params(void);
+int32_t pb2_sizeof_catalog(void);
+int32_t pb2_sizeof_pairs(void);
+
+/* ---- neighbour search: replaces cf.fill_neighs (cf.py:82-135) and xcf.fill_neighs
+ * (xcf.py:71-123), including QSO.get_angle_between (data.py:106-162).
+ * mode 0: auto  (same catalogue, thingid != and ra1 > ra2, cf.py:109,129-135)
+ * mode 1: cross (two delta catalogues, thingid != only, cf.py:99-110)
+ * mode 2: xcf   (forest x object: thingid !=, optional zerr cut xcf.py:102-115 and the r_par
+ *                pre-filter xcf.py:117-121)
+ * Pass 1 writes the neighbour count of every selected line of sight; the caller turns counts into
+ * nb_offset (exclusive scan) and pass 2 fills nb_f1/nb_f2/nb_ang/nb_cos/nb_sin in reference order. */
+int32_t pb2_neigh_count(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                        int32_t mode, int64_t n_f1, const int32_t *d_f1_index,
+                        int32_t *d_count, void *stream);
+int32_t pb2_neigh_fill(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                       int32_t mode, int64_t n_f1, const int32_t *d_f1_index,
+                       const int64_t *d_nb_offset, int32_t *d_nb_f1, int32_t *d_nb_f2,
+                       double *d_nb_ang, double *d_nb_cos, double *d_nb_sin, void *stream);
+
+/* ---- auto / delta-delta cross correlation: replaces cf.compute_xi's pair loop and
+ * cf.compute_xi_forest_pairs_fast (cf.py:161-240, 250-387).
+ * d_out is [n_rows][6][np*nt]: un-normalised sums of weight, xi, r_par, r_trans, z (fp64) and
+ * num_pairs (int64 stored in the same 8-byte slots); it is accumulated into (caller zeroes it).
+ * d_out_row[k] is the output row of f1_index[k].  The per-call normalisation of cf.py:242-246
+ * is pb2_xi_normalise.  `variant`: 0 = tiled diagonal-sweep kernel (product), 1 = brute-force
+ * validation kernel (same results, used by tests to cross-check). */
+int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                    const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
+                    double *d_out, int32_t variant, void *stream);
+
+/* ---- forest x object correlation: replaces xcf.compute_xi's loop and
+ * xcf.compute_xi_forest_pairs_fast (xcf.py:149-213, 223-322).  Same output layout. */
+int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                     const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
+                     double *d_out, int32_t variant, void *stream);
+
+/* xi, r_par, r_trans, z /= weights where weights > 0, per row (cf.py:242-246, xcf.py:215-219). */
+int32_t pb2_xi_normalise(int64_t n_rows, int32_t nb, double *d_out, void *stream);
+
+/* ---- distortion matrix: replaces cf.compute_dmat's pair loop + cf.compute_dmat_forest_pairs_fast
+ * (cf.py:424-502, 520-887) and the xcf equivalents (xcf.py:360-409, 427-674).  pairs->nb_keep
+ * carries the host-drawn --rej mask (cf.py:444 / xcf.py:379).  Outputs are accumulated into:
+ * d_dmat [nb][nbm], d_weights_dmat [nb], d_r_par_eff/d_r_trans_eff/d_z_eff/d_weight_eff [nbm].
+ * d_scratch/scratch_bytes: workspace (query the size with pb2_dmat_scratch_bytes). */
+int64_t pb2_dmat_scratch_bytes(const pb2_catalog *cat1, const pb2_catalog *cat2,
+                               const pb2_params *par, int32_t cross);
+int32_t pb2_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                      const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
+                      double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                      double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream);
+int32_t pb2_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                       const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
+                       double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                       double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* ---- measurement helpers
+ * pb2_fp64_peak: dependent-free DFMA microbenchmark; returns achieved FP64 op/s (1 DFMA = 1 op,
+ * i.e. warp-instruction lanes per second) -- the measured denominator of the FP64 roofline.
+ * Synchronous.  pb2_launch_count: number of kernels this library has launched in the process. */
+int32_t pb2_fp64_peak(int32_t iters, double *ops_per_second, double *elapsed_ms);
+int64_t pb2_launch_count(void);
+/* time (ms) spent in the most recent pair-kernel launch sequence, measured with CUDA events on the
+ * launching stream when timing is enabled with pb2_set_timing(1) (adds a stream sync). */
+int32_t pb2_set_timing(int32_t enable);
+double pb2_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICCA_B200_H */

@@ -1,0 +1,139 @@
+"""Host logic shared by picca_b200.cf and picca_b200.xcf: neighbour batches, lazy neighbour
+views, progress accounting.  No arithmetic of the hot path happens here."""
+import os
+
+import numpy as np
+
+from . import catalog as _catalog
+from .engine import get_engine
+
+HOST_ANGLES = os.environ.get("PICCA_B200_HOST_ANGLES", "0") == "1"
+
+# reference py/picca/constants.py:16
+SMALL_ANGLE_CUT_OFF = 2. / 3600. * np.pi / 180.
+
+
+class LazyNeighbours:
+    """What ``delta.neighbours`` holds between fill_neighs and compute_*: a sequence view of the
+    device neighbour list of one line of sight (reference stores a list/array of objects,
+    cf.py:125-135, xcf.py:123).  Materialised only if somebody iterates it."""
+
+    def __init__(self, pairs, k, objs2):
+        self._pairs, self._k, self._objs2 = pairs, k, objs2
+
+    def _index(self):
+        off = self._pairs.host_offset()
+        return self._pairs.host_f2()[off[self._k]:off[self._k + 1]]
+
+    def __len__(self):
+        off = self._pairs.host_offset()
+        return int(off[self._k + 1] - off[self._k])
+
+    @property
+    def size(self):
+        return len(self)
+
+    def __iter__(self):
+        return (self._objs2[q] for q in self._index())
+
+    def __getitem__(self, item):
+        idx = self._index()[item]
+        if np.ndim(idx) == 0:
+            return self._objs2[int(idx)]
+        return [self._objs2[q] for q in idx]
+
+
+class NeighbourStore:
+    """Neighbour lists produced by fill_neighs, kept on the device until compute_* uses them."""
+
+    def __init__(self):
+        self.by_healpix = {}
+
+    def put(self, healpixs, pairs, ranges):
+        for hp in healpixs:
+            self.by_healpix[hp] = (pairs, ranges[hp])
+
+    def take(self, healpixs):
+        """Return (pairs, None) when ``healpixs`` is exactly one stored batch, else a merged
+        PairList built from the stored per-healpix pieces."""
+        missing = [hp for hp in healpixs if hp not in self.by_healpix]
+        if missing:
+            raise RuntimeError("picca_b200: compute called before fill_neighs for healpix %r"
+                               % (missing[:5],))
+        first = self.by_healpix[healpixs[0]][0]
+        same = all(self.by_healpix[hp][0] is first for hp in healpixs)
+        covered = sum(r[1] - r[0] for _, r in (self.by_healpix[hp] for hp in healpixs))
+        in_order = same and all(
+            self.by_healpix[a][1][1] == self.by_healpix[b][1][0]
+            for a, b in zip(healpixs[:-1], healpixs[1:]))
+        if same and in_order and covered == first.n_f1:
+            return first
+        return None
+
+    def drop(self, healpixs):
+        for hp in healpixs:
+            self.by_healpix.pop(hp, None)
+
+
+def forest_index_of(host_cat, healpixs):
+    """Catalogue indices of the lines of sight of ``healpixs`` (in call order) + per-healpix
+    [k0, k1) ranges inside that list."""
+    parts, ranges, k = [], {}, 0
+    for hp in healpixs:
+        a, b = host_cat.first_of(hp)
+        parts.append(np.arange(a, b, dtype=np.int32))
+        ranges[hp] = (k, k + (b - a))
+        k += b - a
+    index = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int32)
+    return index, ranges
+
+
+def host_angles(cat1, cat2, f1_of_pair, f2_of_pair):
+    """QSO.get_angle_between for every listed pair, evaluated on the host with NumPy exactly as
+    the reference does (data.py:126-141); used by the parity mode only."""
+    A, B = cat1.arrays, cat2.arrays
+    cos = (B["x_cart"][f2_of_pair] * A["x_cart"][f1_of_pair] +
+           B["y_cart"][f2_of_pair] * A["y_cart"][f1_of_pair] +
+           B["z_cart"][f2_of_pair] * A["z_cart"][f1_of_pair])
+    cos = np.where(cos >= 1., 1., cos)
+    cos = np.where(cos <= -1., -1., cos)
+    ang = np.arccos(cos)
+    dra = B["ra"][f2_of_pair] - A["ra"][f1_of_pair]
+    ddec = B["dec"][f2_of_pair] - A["dec"][f1_of_pair]
+    w = (np.absolute(dra) < SMALL_ANGLE_CUT_OFF) & (np.absolute(ddec) < SMALL_ANGLE_CUT_OFF)
+    if w.sum() != 0:
+        ang[w] = np.sqrt(ddec[w]**2 + (A["cos_dec"][f1_of_pair][w] * dra[w])**2)
+    return ang
+
+
+def apply_host_angles(pairs, cat1, cat2):
+    f1 = pairs.f1_index.cpu().numpy()[pairs.nb_f1.cpu().numpy()]
+    pairs.set_host_angles(host_angles(cat1, cat2, f1, pairs.host_f2()))
+
+
+class _NoLock:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def bump_progress(mod, n_forests, userprint):
+    """The shared progress counter of cf.py:163-167 / xcf.py:151-155, advanced in bulk."""
+    counter = getattr(mod, "counter", None)
+    if counter is None or n_forests == 0:
+        return
+    lock = getattr(mod, "lock", None) or _NoLock()
+    num_data = getattr(mod, "num_data", None) or 1
+    with lock:
+        before = counter.value
+        counter.value += n_forests
+        if before // 1000 != counter.value // 1000 or before == 0:
+            userprint("computing xi: {}%".format(round(before * 100.0 / num_data, 2)))
+
+
+def engine_and_catalog(data, is_object=False, ang_correlation=False):
+    eng = get_engine()
+    host = _catalog.cached_pack(data, is_object=is_object, ang_correlation=ang_correlation)
+    return eng, host, eng.device_catalog(host)

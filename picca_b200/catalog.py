@@ -1,0 +1,212 @@
+"""Delta / object loader: packs ``dict[healpix] -> list[Delta|QSO]`` (what ``picca.io.read_deltas``
+and ``read_objects`` return, reference py/picca/io.py:383-512, :515-614) into SoA + CSR buffers and
+places them in HBM.
+
+Layout: lines of sight in ascending-HEALPix, list order -- the iteration order of
+the reference's fill_neighs (cf.py:91-122).  Per pixel: r_comov, dist_m, z, weights, delta*weights,
+log_lambda (fp64, one contiguous array each, 8-byte elements, forests back to back).  Per line of
+sight: CSR offset, unit vector, ra, dec, cos_dec, z_qso, thingid, plate, fiberid, order, HEALPix
+row.  Per HEALPix pixel: member range and the bounding cap of its members (used by the device
+neighbour search instead of healpy.query_disc).
+"""
+import numpy as np
+
+from . import _lib
+
+_PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "log_lambda")
+_LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
+_LOS_I64 = ("thingid", "plate", "fiberid")
+
+
+class HostCatalog:
+    """Packed catalogue in host memory (NumPy)."""
+
+    def __init__(self):
+        self.healpixs = None      # sorted list of HEALPix ids
+        self.objs = None          # flat list of the original objects, catalogue order
+        self.n_los = 0
+        self.n_pix = 0
+        self.arrays = {}          # name -> ndarray
+        self.sorted = 1
+        self.max_pix = 0
+        self.ids_are_int = True
+        self.is_object = False
+
+    def first_of(self, healpix):
+        k = self.hp_index[healpix]
+        return int(self.arrays["hp_first"][k]), int(self.arrays["hp_first"][k + 1])
+
+    def nbytes(self):
+        return int(sum(a.nbytes for a in self.arrays.values()))
+
+
+def _as_int64(values):
+    """plate / fiberid / thingid columns; string ids (combined re-observations) are flagged."""
+    try:
+        arr = np.array(values)
+        if arr.dtype.kind in "iu":
+            return arr.astype(np.int64), True
+        if arr.dtype.kind == "f" and np.all(arr == np.floor(arr)):
+            return arr.astype(np.int64), True
+    except (TypeError, ValueError):
+        pass
+    return np.zeros(len(values), dtype=np.int64), False
+
+
+def pack(data, is_object=False, ang_correlation=False):
+    """Pack a ``dict[healpix] -> list`` into a HostCatalog.
+
+    ``ang_correlation``: the reference then feeds ``10**log_lambda`` in place of both distances
+    (cf.py:186-208, xcf.py:161-182); the packed r_comov/dist_m hold that instead.
+    """
+    cat = HostCatalog()
+    cat.is_object = is_object
+    cat.healpixs = sorted(data)
+    cat.hp_index = {hp: k for k, hp in enumerate(cat.healpixs)}
+    objs = [obj for hp in cat.healpixs for obj in data[hp]]
+    cat.objs = objs
+    n = len(objs)
+    cat.n_los = n
+    A = cat.arrays
+    counts = np.array([len(data[hp]) for hp in cat.healpixs], dtype=np.int64)
+    hp_first = np.zeros(len(cat.healpixs) + 1, dtype=np.int32)
+    hp_first[1:] = np.cumsum(counts)
+    A["hp_first"] = hp_first
+    A["row"] = np.repeat(np.arange(len(cat.healpixs), dtype=np.int32), counts)
+
+    A["x_cart"] = np.array([o.x_cart for o in objs], dtype=np.float64).reshape(n)
+    A["y_cart"] = np.array([o.y_cart for o in objs], dtype=np.float64).reshape(n)
+    A["z_cart"] = np.array([o.z_cart for o in objs], dtype=np.float64).reshape(n)
+    A["ra"] = np.array([o.ra for o in objs], dtype=np.float64).reshape(n)
+    A["dec"] = np.array([o.dec for o in objs], dtype=np.float64).reshape(n)
+    A["cos_dec"] = np.array([o.cos_dec for o in objs], dtype=np.float64).reshape(n)
+    A["z_qso"] = np.array([o.z_qso for o in objs], dtype=np.float64).reshape(n)
+    A["thingid"], ok_t = _as_int64([o.thingid for o in objs])
+    if not ok_t:
+        # non-integer ids: map equal ids to equal integers (only equality is ever used)
+        table = {}
+        A["thingid"] = np.array([table.setdefault(o.thingid, len(table)) for o in objs],
+                                dtype=np.int64)
+    A["plate"], ok_p = _as_int64([o.plate for o in objs])
+    A["fiberid"], ok_f = _as_int64([o.fiberid for o in objs])
+    cat.ids_are_int = bool(ok_p and ok_f)
+
+    if is_object:
+        offset = np.arange(n + 1, dtype=np.int64)
+        zq = A["z_qso"]
+        if ang_correlation:
+            lam = np.array([10.0**o.log_lambda for o in objs], dtype=np.float64).reshape(n)
+            A["r_comov"] = lam
+            A["dist_m"] = lam.copy()
+        else:
+            A["r_comov"] = np.array([o.r_comov for o in objs], dtype=np.float64).reshape(n)
+            A["dist_m"] = np.array([o.dist_m for o in objs], dtype=np.float64).reshape(n)
+        A["z"] = zq.copy()
+        A["weights"] = np.array([o.weights for o in objs], dtype=np.float64).reshape(n)
+        A["delta_w"] = np.zeros(n, dtype=np.float64)
+        A["log_lambda"] = np.zeros(n, dtype=np.float64)
+        A["order"] = np.zeros(n, dtype=np.int32)
+    else:
+        npix = np.array([len(o.weights) for o in objs], dtype=np.int64)
+        offset = np.zeros(n + 1, dtype=np.int64)
+        offset[1:] = np.cumsum(npix)
+
+        def cat_field(getter):
+            if n == 0:
+                return np.zeros(0, dtype=np.float64)
+            return np.ascontiguousarray(
+                np.concatenate([np.asarray(getter(o), dtype=np.float64) for o in objs]))
+
+        weights = cat_field(lambda o: o.weights)
+        delta = cat_field(lambda o: o.delta)
+        log_lambda = cat_field(lambda o: o.log_lambda)
+        A["z"] = cat_field(lambda o: o.z)
+        if ang_correlation:
+            lam = 10.0**log_lambda
+            A["r_comov"] = lam
+            A["dist_m"] = lam.copy()
+        else:
+            A["r_comov"] = cat_field(lambda o: o.r_comov)
+            A["dist_m"] = cat_field(lambda o: o.dist_m)
+        A["weights"] = weights
+        # delta*weights is the product the reference forms first (cf.py:367-368); zero-weight
+        # pixels never contribute (cf.py:318, :331) so a NaN delta there must not leak
+        A["delta_w"] = np.where(weights != 0, delta * weights, 0.0)
+        A["log_lambda"] = log_lambda
+        A["order"] = np.array([-1 if getattr(o, "order", None) is None else int(o.order)
+                               for o in objs], dtype=np.int32)
+    A["offset"] = offset
+    cat.n_pix = int(offset[-1])
+    lengths = np.diff(offset)
+    cat.max_pix = int(lengths.max()) if n else 0
+
+    # sortedness inside each forest (enables the column windows of the pair kernel)
+    cat.sorted = 1
+    if not is_object and cat.n_pix > 1:
+        inner = np.ones(cat.n_pix - 1, dtype=bool)
+        inner[offset[1:-1][(offset[1:-1] > 0) & (offset[1:-1] < cat.n_pix)] - 1] = False
+        for name in ("r_comov", "dist_m"):
+            d = np.diff(A[name])
+            if np.any((d < 0) & inner) or not np.all(np.isfinite(A[name])):
+                cat.sorted = 0
+
+    # bounding caps per HEALPix pixel
+    nhp = len(cat.healpixs)
+    cap = np.zeros((4, nhp), dtype=np.float64)
+    xyz = np.stack([A["x_cart"], A["y_cart"], A["z_cart"]], axis=1) if n else np.zeros((0, 3))
+    for k in range(nhp):
+        a, b = hp_first[k], hp_first[k + 1]
+        v = xyz[a:b]
+        c = v.sum(axis=0)
+        norm = np.sqrt((c * c).sum())
+        c = c / norm if norm > 0 else v[0]
+        dots = np.clip(v @ c, -1.0, 1.0)
+        cap[:3, k] = c
+        cap[3, k] = float(np.arccos(dots.min())) + 1e-7
+    A["cap_x"], A["cap_y"], A["cap_z"], A["cap_rad"] = (np.ascontiguousarray(cap[0]),
+                                                        np.ascontiguousarray(cap[1]),
+                                                        np.ascontiguousarray(cap[2]),
+                                                        np.ascontiguousarray(cap[3]))
+    return cat
+
+
+class DeviceCatalog:
+    """A HostCatalog resident in HBM (torch tensors own the memory) + its ``pb2_catalog``."""
+
+    def __init__(self, host, device, pin=False):
+        import torch
+        self.host = host
+        self.device = device
+        self.tensors = {}
+        self.h2d_bytes = 0
+        for name, arr in host.arrays.items():
+            t = torch.from_numpy(arr)
+            if pin:
+                t = t.pin_memory()
+            self.tensors[name] = t.to(device, non_blocking=pin)
+            self.h2d_bytes += arr.nbytes
+        c = _lib.Catalog()
+        c.n_los = host.n_los
+        c.n_pix = host.n_pix
+        for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
+                "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
+            setattr(c, name, self.tensors[name].data_ptr())
+        c.n_hp = len(host.healpixs)
+        c.sorted = host.sorted
+        c.max_pix = host.max_pix
+        self.struct = c
+
+
+_HOST_CACHE = {}
+
+
+def cached_pack(data, is_object=False, ang_correlation=False):
+    """Pack once per (dict object, flavour); the scripts keep the same dict for a whole run."""
+    key = (id(data), is_object, bool(ang_correlation))
+    n_now = sum(len(v) for v in data.values())
+    hit = _HOST_CACHE.get(key)
+    if hit is not None and hit[0] is data and hit[1].n_los == n_now:
+        return hit[1]
+    cat = pack(data, is_object=is_object, ang_correlation=ang_correlation)
+    _HOST_CACHE[key] = (data, cat)
+    return cat

@@ -1,0 +1,249 @@
+"""B200 implementation of the hot path of ``picca.cf`` behind the reference's module API.
+
+Same module globals (reference py/picca/cf.py:28-79), same functions, same return tuples:
+
+    fill_neighs(healpixs)                         cf.py:82-135
+    compute_xi(healpixs) -> 6-tuple               cf.py:138-247
+    compute_dmat(healpixs) -> 8-tuple             cf.py:390-517
+    compute_xi_forest_pairs_fast(...)             cf.py:250-387  (in-place accumulate)
+    compute_dmat_forest_pairs_fast(...)           cf.py:520-887  (in-place accumulate)
+
+so that picca_cf.py / picca_dmat.py run unchanged once this module is importable as ``picca.cf``
+(see ``picca_b200.overlay`` and INTEGRATION.md).  All arithmetic runs in the CUDA kernels of
+libpicca_b200.so; there is no Numba and no CPU fallback.  Globals are read at call time.
+"""
+import sys
+
+import numpy as np
+
+from . import _corr, catalog as _catalog
+from .engine import MODE_AUTO, MODE_CROSS, get_engine
+from .forest import Delta as _Delta
+from .params import params_from_module
+
+
+def userprint(*args, **kwds):
+    """reference py/picca/utils.py:20-28"""
+    print(*args, **kwds)
+    sys.stdout.flush()
+
+
+# ---- module globals: names and defaults of reference cf.py:28-79
+num_bins_r_par = None
+num_bins_r_trans = None
+num_model_bins_r_trans = None
+num_model_bins_r_par = None
+r_par_max = None
+r_par_min = None
+z_min_pairs = None
+z_max_pairs = None
+r_trans_max = None
+ang_max = None
+nside = None
+
+zerr_cut_deg = None
+zerr_cut_kms = None
+
+counter = None
+num_data = None
+num_data2 = None
+
+z_ref = None
+alpha = None
+alpha2 = None
+alpha_abs = None
+lambda_abs = None
+lambda_abs2 = None
+
+data = None
+data2 = None
+
+cosmo = None
+
+reject = None
+lock = None
+x_correlation = False
+rmu_binning = False
+ang_correlation = False
+remove_same_half_plate_close_pairs = False
+
+# variables for distortion matrix
+redshift_evolution_in_distortion_matrix = True
+
+# variables used in the 1D correlation function analysis (kept for attribute parity)
+num_pixels = None
+log_lambda_min = None
+log_lambda_max = None
+delta_log_lambda = None
+
+# variables used in the wick covariance matrix computation (kept for attribute parity)
+get_variance_1d = {}
+xi_1d = {}
+max_diagram = None
+xi_wick = {}
+
+_THIS = sys.modules[__name__]
+_STORE = _corr.NeighbourStore()
+# xi kernel variant: 0 = product (diagonal sweep), 1 = brute-force validation kernel
+_XI_VARIANT = 0
+
+
+def _catalogs():
+    eng, host1, dev1 = _corr.engine_and_catalog(data, ang_correlation=ang_correlation)
+    if data2 is not None:
+        _, host2, dev2 = _corr.engine_and_catalog(data2, ang_correlation=ang_correlation)
+    else:
+        host2, dev2 = host1, dev1
+    return eng, host1, dev1, host2, dev2
+
+
+def _check_half_plate(host1, host2):
+    if remove_same_half_plate_close_pairs and not (host1.ids_are_int and host2.ids_are_int):
+        raise RuntimeError("Trying to figure out if two spectra "
+                           "come from the same half plate but "
+                           "combined reobservations were given")  # cf.py:172-179
+
+
+def fill_neighs(healpixs):
+    """Create the neighbour list of every forest of ``healpixs`` (cf.py:82-135) on the device."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS)
+    index, ranges = _corr.forest_index_of(host1, healpixs)
+    mode = MODE_CROSS if data2 is not None else MODE_AUTO
+    pairs = eng.neighbours(dev1, dev2, params, mode, index)
+    if _corr.HOST_ANGLES:
+        _corr.apply_host_angles(pairs, host1, host2)
+    _STORE.put(healpixs, pairs, ranges)
+    for k, f1 in enumerate(index):
+        host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
+
+
+def _pairs_for(healpixs):
+    pairs = _STORE.take(healpixs)
+    if pairs is None:  # stored in different batches: rebuild for exactly this list
+        fill_neighs(healpixs)
+        pairs = _STORE.take(healpixs)
+    return pairs
+
+
+def compute_xi(healpixs):
+    """Correlation function of the forests of ``healpixs`` with their neighbours (cf.py:138-247).
+
+    Returns (weights, xi, r_par, r_trans, z, num_pairs), normalised per call like the reference.
+    """
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    _check_half_plate(host1, host2)
+    params = params_from_module(_THIS)
+    pairs = _pairs_for(healpixs)
+    out_row = eng.torch.zeros(pairs.n_f1, dtype=eng.torch.int32, device=eng.device)
+    out = eng.xi(dev1, dev2, params, pairs, out_row, 1, variant=_XI_VARIANT, normalise=True)
+    host = out.cpu().numpy()[0]
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in pairs.f1_index.cpu().numpy():
+        setattr(host1.objs[f1], "neighbours", None)  # cf.py:240
+    _STORE.drop(healpixs)
+    weights, xi, r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in range(5))
+    num_pairs = np.ascontiguousarray(host[5]).view(np.int64)
+    return weights, xi, r_par, r_trans, z, num_pairs
+
+
+def compute_xi_batch(healpixs, normalise=True):
+    """One launch for many HEALPix pixels: row k of the result is ``compute_xi([healpixs[k]])``.
+    Returns an array [len(healpixs), 6, nb] (row 5 = int64 counts viewed as float64 slots) --
+    what picca_cf.py stacks from its Pool.map (picca_cf.py:466-473)."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    _check_half_plate(host1, host2)
+    params = params_from_module(_THIS)
+    pairs = _pairs_for(healpixs)
+    rows = np.concatenate([np.full(host1.first_of(hp)[1] - host1.first_of(hp)[0], k, np.int32)
+                           for k, hp in enumerate(healpixs)]) if healpixs else np.zeros(0, np.int32)
+    out = eng.xi(dev1, dev2, params, pairs, rows, len(healpixs), variant=_XI_VARIANT,
+                 normalise=normalise)
+    host = out.cpu().numpy()
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in pairs.f1_index.cpu().numpy():
+        setattr(host1.objs[f1], "neighbours", None)
+    _STORE.drop(healpixs)
+    return host
+
+
+def compute_xi_forest_pairs_fast(z1, r_comov1, dist_m1, weights1, delta1, z_qso_1, z2, r_comov2,
+                                 dist_m2, weights2, delta2, z_qso_2, ang, same_half_plate,
+                                 rebin_weight, rebin_xi, rebin_r_par, rebin_r_trans, rebin_z,
+                                 rebin_num_pairs):
+    """One forest pair, accumulated in place into the caller's rebin arrays (cf.py:250-387).
+    Kept for signature parity; compute_xi does not go through it."""
+    from .engine import PairList
+    eng = get_engine()
+    torch = eng.torch
+
+    def one(z, rc, dm, w, de, zq, plate):
+        d = _Delta(1, 0., 0., zq, plate, 0, 1 if same_half_plate else plate, np.zeros(len(z)),
+                   np.asarray(w, dtype=np.float64), np.asarray(de, dtype=np.float64), 0)
+        d.z, d.r_comov, d.dist_m = (np.asarray(z, dtype=np.float64),
+                                    np.asarray(rc, dtype=np.float64),
+                                    np.asarray(dm, dtype=np.float64))
+        return d
+
+    # plate/fiberid chosen so that pb2_same_half_plate() reproduces the caller's flag
+    d1 = one(z1, r_comov1, dist_m1, weights1, delta1, z_qso_1, 1)
+    d2 = one(z2, r_comov2, dist_m2, weights2, delta2, z_qso_2, 1 if same_half_plate else 2)
+    dev1 = eng.device_catalog(_catalog.pack({0: [d1]}), cache=False)
+    dev2 = eng.device_catalog(_catalog.pack({0: [d2]}), cache=False)
+    params = params_from_module(_THIS)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=eng.device)
+    f64 = lambda v: torch.tensor(v, dtype=torch.float64, device=eng.device)
+    ang = float(ang)
+    pairs = PairList(eng, i32([0]), torch.tensor([0, 1], dtype=torch.int64, device=eng.device),
+                     i32([0]), i32([0]), f64([ang]), f64([np.cos(ang / 2)]),
+                     f64([np.sin(ang / 2)]))
+    out = eng.xi(dev1, dev2, params, pairs, i32([0]), 1, variant=_XI_VARIANT).cpu().numpy()[0]
+    rebin_weight += out[0]
+    rebin_xi += out[1]
+    rebin_r_par += out[2]
+    rebin_r_trans += out[3]
+    rebin_z += out[4]
+    rebin_num_pairs += out[5].view(np.int64)
+
+
+# older picca spelling (module docstring of the reference, cf.py:5-9)
+compute_xi_forest_pairs = compute_xi_forest_pairs_fast
+
+
+def compute_dmat(healpixs):
+    """Distortion matrix of the forests of ``healpixs`` (cf.py:390-517).  The --rej draw uses the
+    global legacy NumPy RNG in the reference's order (cf.py:444), so results match the reference
+    for the same seed and chunking.  Returns the reference's 8-tuple of un-normalised sums."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    _check_half_plate(host1, host2)
+    params = params_from_module(_THIS)
+    pairs = _pairs_for(healpixs)
+    f1_index = pairs.f1_index.cpu().numpy()
+    order1 = host1.arrays["order"]
+    if np.any(order1[f1_index] < 0):
+        raise RuntimeError("Trying to compute the distortion matrix but "
+                           "order is not defined for the deltas. "
+                           "Check previous warning to solve this issue")  # cf.py:433-438
+    offset = pairs.host_offset()
+    # one draw per forest, in catalogue order, len(neighbours) numbers each (cf.py:444);
+    # consecutive rand(n) calls consume the MT19937 stream exactly like one rand(sum n)
+    keep = np.random.rand(int(offset[-1])) > reject
+    num_pairs = int(offset[-1])
+    num_pairs_used = int(keep.sum())
+    if np.any(host2.arrays["order"][pairs.host_f2()[keep]] < 0):
+        raise RuntimeError("Trying to compute the distortion matrix but "
+                           "order is not defined for the deltas. "
+                           "Check previous warning to solve this issue")  # cf.py:464-469
+    pairs.nb_keep = eng.torch.from_numpy(keep.astype(np.uint8)).to(eng.device)
+    res = eng.dmat(dev1, dev2, params, pairs)
+    weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = (t.cpu().numpy() for t in res)
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in f1_index:
+        setattr(host1.objs[f1], "neighbours", None)  # cf.py:502
+    _STORE.drop(healpixs)
+    return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
+            num_pairs_used)

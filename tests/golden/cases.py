@@ -1,0 +1,74 @@
+"""Definition of the golden cases: seeded synthetic inputs (regenerated identically wherever the
+tests run) + the module configuration.  ``make_golden.py`` runs the LIVE reference on them and
+stores its outputs in ``golden_*.npz``; the tests replay the same cases on the oracle (CPU) and on
+the CUDA path (GPU)."""
+from picca_b200 import synth
+from tests import helpers
+
+R60 = dict(r_par_max=60., r_trans_max=60., num_bins_r_par=15, num_bins_r_trans=15,
+           num_model_bins_r_par=15, num_model_bins_r_trans=15)
+
+CF_CASES = {
+    "default": dict(R60),
+    "half_plate": dict(R60, remove_same_half_plate_close_pairs=True),
+    "zcuts": dict(R60, z_min_pairs=2.0, z_max_pairs=2.6),
+    "zerr": dict(R60, zerr_cut_deg=0.5, zerr_cut_kms=40000.),
+    "rmu": dict(R60, rmu_binning=True, r_par_min=0., r_par_max=1.),
+    "prod": dict(r_par_max=200., r_trans_max=200., num_bins_r_par=50, num_bins_r_trans=50),
+    "cross": dict(R60, x_correlation=True, r_par_min=-60., num_bins_r_par=30, second=True),
+}
+
+DMAT_CASES = {
+    "default": dict(R60, reject=0.9),
+    "noevol_halfplate": dict(R60, reject=0.9, redshift_evolution_in_distortion_matrix=False,
+                             remove_same_half_plate_close_pairs=True),
+    "zcuts": dict(R60, reject=0.9, z_min_pairs=2.0, z_max_pairs=2.6),
+    "coef2": dict(R60, reject=0.95, num_model_bins_r_par=30, num_model_bins_r_trans=30),
+    "cross": dict(R60, reject=0.9, x_correlation=True, r_par_min=-60., num_bins_r_par=30,
+                  num_model_bins_r_par=30, second=True),
+}
+
+XCF_BASE = dict(r_par_max=60., r_par_min=-60., r_trans_max=60., num_bins_r_par=30,
+                num_bins_r_trans=15, num_model_bins_r_par=30, num_model_bins_r_trans=15,
+                alpha_obj=1.44)
+XCF_CASES = {
+    "default": dict(XCF_BASE),
+    "zcuts": dict(XCF_BASE, z_min_pairs=2.0, z_max_pairs=2.6),
+    "zerr": dict(XCF_BASE, zerr_cut_deg=0.5, zerr_cut_kms=40000.),
+    "rmu": dict(XCF_BASE, rmu_binning=True, r_par_min=-1., r_par_max=1.),
+}
+XDMAT_CASES = {
+    "default": dict(XCF_BASE, reject=0.8),
+    "noevol": dict(XCF_BASE, reject=0.8, redshift_evolution_in_distortion_matrix=False),
+    "zcuts": dict(XCF_BASE, reject=0.8, z_min_pairs=2.0, z_max_pairs=2.6),
+}
+
+
+def forests(second=False):
+    """(data, num_data, z_min, cosmo); ``second`` gives the independent second sample used by the
+    delta x delta cross-correlation cases."""
+    if second:
+        data, num, z_min, _, cosmo = helpers.small_sample(n=200, seed=23, max_pix=100,
+                                                          id_offset=5000)
+    else:
+        data, num, z_min, _, cosmo = helpers.small_sample(n=300, seed=11, max_pix=120)
+    return data, num, z_min, cosmo
+
+
+def dmat_forests(second=False):
+    """smaller forests: the as-written reference dmat is O(N_pairs * U) per forest pair."""
+    if second:
+        data, num, z_min, _, cosmo = helpers.small_sample(n=80, seed=29, max_pix=60, side_deg=3.,
+                                                          id_offset=5000)
+    else:
+        data, num, z_min, _, cosmo = helpers.small_sample(n=120, seed=17, max_pix=70, side_deg=3.)
+    return data, num, z_min, cosmo
+
+
+def quasars(cosmo):
+    return synth.make_quasars(400, seed=31, nside=16, ra_deg=(10., 16.), dec_deg=(5., 11.),
+                              z_range=(1.9, 3.2), cosmo=cosmo)
+
+
+def ang_max_for(cosmo, cfg, z_min, z_min2=None):
+    return synth.compute_ang_max(cosmo, cfg["r_trans_max"], z_min, z_min2)

@@ -1,0 +1,158 @@
+"""Generate the golden vectors by running the LIVE reference (its Numba path, imported unmodified
+from /root/reference through tests/refharness) on the seeded cases of ``cases.py``.
+
+    python -m tests.golden.make_golden          # writes tests/golden/golden_*.npz
+
+Only works where /root/reference exists; the resulting small .npz files are committed and travel
+to the GPU box.  Host of record: see ``host`` inside each file (NumPy's arccos differs in the last
+ulp between SIMD back-ends).
+"""
+import os
+import platform
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from tests import helpers  # noqa: E402
+from tests.golden import cases  # noqa: E402
+from tests.refharness import load  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def checksum(data):
+    tot = 0.
+    for hp in sorted(data):
+        for d in data[hp]:
+            for name in ("weights", "delta", "z", "r_comov", "dist_m", "log_lambda"):
+                v = getattr(d, name, None)
+                if v is not None:
+                    tot += float(np.sum(np.asarray(v, dtype=np.float64)))
+    return tot
+
+
+def neighbour_ids(data, hps):
+    counts, ids = [], []
+    for hp in hps:
+        for d in data[hp]:
+            counts.append(len(d.neighbours))
+            ids.extend(int(o.thingid) for o in d.neighbours)
+    return np.array(counts, dtype=np.int64), np.array(ids, dtype=np.int64)
+
+
+def run_cf(out):
+    for name, cfg in cases.CF_CASES.items():
+        cf, _, _, _, _ = load.reference_modules()
+        cf.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        second = cfg.pop("second", False)
+        data, num, z_min, cosmo = cases.forests()
+        rdata = load.to_reference_deltas(data)
+        over = dict(cfg)
+        z_min2 = None
+        if second:
+            data2, num2, z_min2, _ = cases.forests(second=True)
+            over["data2"] = load.to_reference_deltas(data2)
+            over["num_data2"] = num2
+        helpers.configure(cf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+        hps = sorted(rdata)
+        rows, counts, ids = [], [], []
+        for hp in hps:
+            cf.fill_neighs([hp])
+            c, i = neighbour_ids(rdata, [hp])
+            counts.append(c)
+            ids.append(i)
+            res = cf.compute_xi([hp])
+            rows.append(np.stack([np.asarray(r, dtype=np.float64) for r in res[:5]] +
+                                 [np.asarray(res[5], dtype=np.int64).view(np.float64)]))
+        out["cf_%s" % name] = np.stack(rows)
+        out["cf_%s_nbcount" % name] = np.concatenate(counts)
+        out["cf_%s_nbid" % name] = np.concatenate(ids)
+        out["cf_%s_checksum" % name] = np.array([checksum(data)])
+        print("cf", name, "pairs", int(np.stack(rows)[:, 5].view(np.int64).sum()))
+
+
+def pack8(res):
+    return dict(weights_dmat=res[0], dmat=res[1], r_par_eff=res[2], r_trans_eff=res[3],
+                z_eff=res[4], weight_eff=res[5], counts=np.array([res[6], res[7]], dtype=np.int64))
+
+
+def run_dmat(out):
+    for name, cfg in cases.DMAT_CASES.items():
+        cf, _, _, _, _ = load.reference_modules()
+        cf.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        second = cfg.pop("second", False)
+        data, num, z_min, cosmo = cases.dmat_forests()
+        rdata = load.to_reference_deltas(data)
+        over = dict(cfg)
+        z_min2 = None
+        if second:
+            data2, num2, z_min2, _ = cases.dmat_forests(second=True)
+            over["data2"] = load.to_reference_deltas(data2)
+            over["num_data2"] = num2
+        helpers.configure(cf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+        hps = sorted(rdata)
+        cf.fill_neighs(hps)
+        np.random.seed(hps[0])  # picca_dmat.py:36
+        res = cf.compute_dmat(hps)
+        for key, val in pack8(res).items():
+            out["dmat_%s_%s" % (name, key)] = np.asarray(val)
+        print("dmat", name, "pairs", res[6], "used", res[7])
+
+
+def run_xcf(out):
+    for name, cfg in cases.XCF_CASES.items():
+        _, xcf, _, _, _ = load.reference_modules()
+        xcf.userprint = lambda *a, **k: None
+        data, num, z_min, cosmo = cases.forests()
+        objs, z_min2 = cases.quasars(cosmo)
+        rdata, robjs = load.to_reference_deltas(data), load.to_reference_qsos(objs)
+        helpers.configure(xcf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2),
+                          objs=robjs, **cfg)
+        hps = sorted(rdata)
+        rows, counts, ids = [], [], []
+        for hp in hps:
+            xcf.fill_neighs([hp])
+            c, i = neighbour_ids(rdata, [hp])
+            counts.append(c)
+            ids.append(i)
+            res = xcf.compute_xi([hp])
+            rows.append(np.stack([np.asarray(r, dtype=np.float64) for r in res[:5]] +
+                                 [np.asarray(res[5], dtype=np.int64).view(np.float64)]))
+        out["xcf_%s" % name] = np.stack(rows)
+        out["xcf_%s_nbcount" % name] = np.concatenate(counts)
+        out["xcf_%s_nbid" % name] = np.concatenate(ids)
+        print("xcf", name, "pairs", int(np.stack(rows)[:, 5].view(np.int64).sum()))
+
+
+def run_xdmat(out):
+    for name, cfg in cases.XDMAT_CASES.items():
+        _, xcf, _, _, _ = load.reference_modules()
+        xcf.userprint = lambda *a, **k: None
+        data, num, z_min, cosmo = cases.dmat_forests()
+        objs, z_min2 = cases.quasars(cosmo)
+        rdata, robjs = load.to_reference_deltas(data), load.to_reference_qsos(objs)
+        helpers.configure(xcf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2),
+                          objs=robjs, **cfg)
+        hps = sorted(rdata)
+        xcf.fill_neighs(hps)
+        np.random.seed(hps[0])  # picca_xdmat.py:37
+        res = xcf.compute_dmat(hps)
+        for key, val in pack8(res).items():
+            out["xdmat_%s_%s" % (name, key)] = np.asarray(val)
+        print("xdmat", name, "pairs", res[6], "used", res[7])
+
+
+def main():
+    for tag, fn in (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat)):
+        out = {"host": np.array([platform.processor() + " numpy " + np.__version__])}
+        fn(out)
+        np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)
+
+
+if __name__ == "__main__":
+    main()

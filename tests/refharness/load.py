@@ -58,3 +58,33 @@ def load_objects(cosmo, nside=16, z_min_obj=0., z_max_obj=10., z_evol_obj=1., z_
     objs, z_min2 = io.read_objects(DATA + "/test_delta/cat.fits", nside, z_min_obj, z_max_obj,
                                    z_evol_obj, z_ref, cosmo, mode="sdss")
     return objs, z_min2
+
+
+def to_reference_deltas(data):
+    """Rebuild a dict of picca_b200.forest.Delta stand-ins as the reference's own
+    ``picca.data.Delta`` objects (so that its get_angle_between etc. are the code under test)."""
+    assert shims.install()
+    from picca.data import Delta
+    out = {}
+    for hp, forests in data.items():
+        out[hp] = []
+        for d in forests:
+            r = Delta(d.thingid, d.ra, d.dec, d.z_qso, d.plate, d.mjd, d.fiberid,
+                      d.log_lambda.copy(), d.weights.copy(), None, d.delta.copy(), d.order,
+                      None, None, None, None, None)
+            r.z, r.r_comov, r.dist_m = d.z.copy(), d.r_comov.copy(), d.dist_m.copy()
+            out[hp].append(r)
+    return out
+
+
+def to_reference_qsos(objs):
+    assert shims.install()
+    from picca.data import QSO
+    out = {}
+    for hp, qsos in objs.items():
+        out[hp] = []
+        for q in qsos:
+            r = QSO(q.thingid, q.ra, q.dec, q.z_qso, q.plate, q.mjd, q.fiberid)
+            r.weights, r.r_comov, r.dist_m = q.weights, q.r_comov, q.dist_m
+            out[hp].append(r)
+    return out
