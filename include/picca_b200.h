@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 3
+#define PB2_ABI_VERSION 4
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
@@ -73,6 +73,7 @@ typedef struct pb2_catalog {
     const double *z;          /* Delta.z */
     const double *weights;    /* Delta.weights */
     const double *delta_w;    /* Delta.delta * Delta.weights, 0 where weights == 0 */
+    const double *z_w;        /* Delta.z * Delta.weights */
     const double *log_lambda; /* Delta.log_lambda (distortion matrix only; may be NULL) */
     /* per line of sight */
     const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;

@@ -54,6 +54,7 @@ class Catalog(ctypes.Structure):
         ("z", c_void_p),
         ("weights", c_void_p),
         ("delta_w", c_void_p),
+        ("z_w", c_void_p),
         ("log_lambda", c_void_p),
         ("x_cart", c_void_p),
         ("y_cart", c_void_p),
@@ -103,7 +104,7 @@ EXPORTS = [
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def lib():

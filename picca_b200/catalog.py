@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 
-_PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "log_lambda")
+_PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
 _LOS_I64 = ("thingid", "plate", "fiberid")
 
@@ -104,6 +104,7 @@ def pack(data, is_object=False, ang_correlation=False):
         A["z"] = zq.copy()
         A["weights"] = np.array([o.weights for o in objs], dtype=np.float64).reshape(n)
         A["delta_w"] = np.zeros(n, dtype=np.float64)
+        A["z_w"] = A["z"] * A["weights"]
         A["log_lambda"] = np.zeros(n, dtype=np.float64)
         A["order"] = np.zeros(n, dtype=np.int32)
     else:
@@ -132,6 +133,7 @@ def pack(data, is_object=False, ang_correlation=False):
         # delta*weights is the product the reference forms first (cf.py:367-368); zero-weight
         # pixels never contribute (cf.py:318, :331) so a NaN delta there must not leak
         A["delta_w"] = np.where(weights != 0, delta * weights, 0.0)
+        A["z_w"] = A["z"] * weights
         A["log_lambda"] = log_lambda
         A["order"] = np.array([-1 if getattr(o, "order", None) is None else int(o.order)
                                for o in objs], dtype=np.int32)

@@ -30,6 +30,7 @@
 
 struct XiFast {
     double kp_lo, kp_hi, kt_lo, kt_hi;  // bin scale factors bracketing np/(max-min), nt/rt_max
+    double magic;                       // 2^52 + 2^51 (kept out of the immediate field)
     int fast;                           // 1: windows + sandwiched bins are valid for this call
     int tmax;                           // tiles per forest pair (longest forest 1)
 };
@@ -95,154 +96,143 @@ __device__ __forceinline__ double transpose_reduce5(double a0, double a1, double
     return w;
 }
 
-struct Run {
-    double we, xi, rp, rt, z;
-    int cnt;
-    int key;  // flat bin, -1 = empty
-};
-
-__device__ __forceinline__ void run_clear(Run &r)
-{
-    r.we = r.xi = r.rp = r.rt = r.z = 0.;
-    r.cnt = 0;
-    r.key = -1;
-}
-
-// Flush the runs held by the lanes of a warp into the output row (one red.f64 per distinct key).
-// out_row_ptr points at [6][nb].  Clears the runs.
-__device__ __forceinline__ void flush_runs(Run &r, double *__restrict__ out_row_ptr, int nb,
-                                           int lane)
-{
-    unsigned pending = __ballot_sync(0xffffffffu, r.key >= 0);
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int key = __shfl_sync(0xffffffffu, r.key, leader);
-        const bool mine = (r.key == key);
-        // r.z accumulates (z1 + z2) * w12; the reference's z = (z1 + z2) / 2 (cf.py:334)
-        const double tot = transpose_reduce5(mine ? r.we : 0., mine ? r.xi : 0., mine ? r.rp : 0.,
-                                             mine ? r.rt : 0., mine ? 0.5 * r.z : 0., lane);
-        const int cnt = __reduce_add_sync(0xffffffffu, mine ? r.cnt : 0);
-        if (lane < 20 && (lane & 3) == 0) {
-            atomic_add_f64(out_row_ptr + (size_t)(lane >> 2) * nb + key, tot);
-        } else if (lane == 20) {
-            atomic_add_i64(out_row_ptr + (size_t)5 * nb + key, (long long)cnt);
-        }
-        if (mine) run_clear(r);
-        pending = __ballot_sync(0xffffffffu, r.key >= 0);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // product kernel
 // ------------------------------------------------------------------------------------------
-#define XI_THREADS 512
-#define XI_CHUNK 16
+// A "slot" is a warp-level run: every lane holds private partial sums for ONE warp-uniform bin
+// (the key).  Two slots per row set cover the common situations (a bin boundary crossing the
+// warp, or the warp straddling two r_trans bins); a third simultaneous bin falls back to direct
+// atomics.  Partial sums are kept in factored form (row constants applied at flush time):
+//   sw  = sum w2            -> weight  = w1 * sw
+//   sdw = sum delta2*w2     -> xi      = (delta1*w1) * sdw
+//   srp = sum r_par * w2    -> r_par   = w1 * srp
+//   srt = sum r_trans * w2  -> r_trans = w1 * srt
+//   szw = sum z2*w2         -> z       = (z1 * weight + w1 * szw) / 2      (cf.py:334, :386)
+struct Slot {
+    double sw, sdw, srp, srt, szw;
+    int cnt;
+};
+
+__device__ __forceinline__ void slot_clear(Slot &s)
+{
+    s.sw = s.sdw = s.srp = s.srt = s.szw = 0.;
+    s.cnt = 0;
+}
+
+// Reduce one slot over the warp and add it to bin `key` of the output row ([6][nb]).
+__device__ __forceinline__ void slot_flush(Slot &s, int key, double w1, double dw1, double z1,
+                                           double *__restrict__ orow, int nb, int lane)
+{
+    const double we = w1 * s.sw;
+    const double tot = transpose_reduce5(we, dw1 * s.sdw, w1 * s.srp, w1 * s.srt,
+                                         0.5 * (z1 * we + w1 * s.szw), lane);
+    const int cnt = __reduce_add_sync(0xffffffffu, s.cnt);
+    if (lane < 20 && (lane & 3) == 0) {
+        atomic_add_f64(orow + (size_t)(lane >> 2) * nb + key, tot);
+    } else if (lane == 20) {
+        atomic_add_i64(orow + (size_t)5 * nb + key, (long long)cnt);
+    }
+    slot_clear(s);
+}
+
+#define XI_THREADS 384
+#define XI_CHUNK 8
 
 template <int R, bool FAST>
 __global__ void __launch_bounds__(XI_THREADS, 1)
 pb2_xi_auto_tiled(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, XiFast F,
-                  const int32_t *__restrict__ out_row, double *__restrict__ out,
-                  unsigned long long *__restrict__ g_counter)
+                  const int32_t *__restrict__ out_row, double *__restrict__ out)
 {
-    __shared__ long long s_e0;
-    __shared__ int s_ctr;
+    // CTA b owns chunks b, b + G, b + 2G, ... of XI_CHUNK forest pairs; its warps take
+    // (pair, row tile) units from a CTA-local counter, so warps of one SM work on the same few
+    // forest pairs at a time (L1 reuse of forest 2) without any block-wide barrier.
+    __shared__ unsigned s_ctr;
+    if (threadIdx.x == 0) s_ctr = 0;
+    __syncthreads();
+
     const int lane = threadIdx.x & 31;
     const int nb = P.num_bins_r_par * P.num_bins_r_trans;
     const unsigned np_u = (unsigned)P.num_bins_r_par, nt_u = (unsigned)P.num_bins_r_trans;
-    const int tmax = F.tmax;
+    const unsigned tmax = (unsigned)F.tmax;
+    const unsigned units_per_chunk = XI_CHUNK * tmax;
     const double zerr_ang = mul_rn(P.zerr_cut_deg, PB2_PI) / 180.0;  // cf.py:321
     const double close_rp = div_rn(sub_rn(P.r_par_max, P.r_par_min), (double)P.num_bins_r_par);
+    const bool zcut = P.has_z_min_pairs || P.has_z_max_pairs;
+    const double magic = F.magic;
 
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_e0 = (long long)atomicAdd(g_counter, (unsigned long long)XI_CHUNK);
-            s_ctr = 0;
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(&s_ctr, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        const long long chunk = (long long)blockIdx.x + (long long)(u / units_per_chunk) * gridDim.x;
+        const unsigned local = u % units_per_chunk;
+        const long long e = chunk * XI_CHUNK + local / tmax;
+        if (chunk * XI_CHUNK >= pr.n_pairs) break;
+        if (e >= pr.n_pairs) continue;
+        const int tile = (int)(local % tmax);
+
+        const int k = pr.nb_f1[e];
+        const int f1 = pr.f1_index[k];
+        const int f2 = pr.nb_f2[e];
+        const long long a = c1.offset[f1];
+        const int n1 = (int)(c1.offset[f1 + 1] - a);
+        const int i0 = tile * 32 * R;
+        if (i0 >= n1) continue;
+        const long long b = c2.offset[f2];
+        const int n2 = (int)(c2.offset[f2 + 1] - b);
+        if (n2 == 0) continue;
+        const double ang = pr.nb_ang[e];
+        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
+
+        const bool zerr_on = P.has_zerr_cut && (ang < zerr_ang);
+        const bool shp = P.remove_same_half_plate_close_pairs && pb2_same_half_plate(c1, c2, f1, f2);
+        const bool extras = zcut || zerr_on || shp;
+        const double zq1 = c1.z_qso[f1], zq2 = c2.z_qso[f2];
+
+        // ---- rows of this tile -> registers
+        double rc1[R], dm1[R], z1[R], w1[R], dw1[R];
+        bool v1[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = i0 + 32 * r + lane;
+            const bool ok = i < n1;
+            const long long p = a + (ok ? i : 0);
+            rc1[r] = __ldg(c1.r_comov + p);
+            dm1[r] = __ldg(c1.dist_m + p);
+            z1[r] = __ldg(c1.z + p);
+            w1[r] = __ldg(c1.weights + p);
+            dw1[r] = __ldg(c1.delta_w + p);
+            v1[r] = ok && (w1[r] != 0.);                                           // cf.py:318
+            if (zerr_on && v1[r] && pb2_zerr_close(P, z1[r], zq2)) v1[r] = false;  // cf.py:321-328
         }
-        __syncthreads();
-        const long long e0 = s_e0;
-        if (e0 >= pr.n_pairs) break;
-        const long long left = pr.n_pairs - e0;
-        const int nunits = (int)(left < XI_CHUNK ? left : XI_CHUNK) * tmax;
 
-        for (;;) {
-            int u = 0;
-            if (lane == 0) u = atomicAdd(&s_ctr, 1);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            if (u >= nunits) break;
-            const long long e = e0 + u / tmax;
-            const int tile = u % tmax;
-
-            const int k = pr.nb_f1[e];
-            const int f1 = pr.f1_index[k];
-            const int f2 = pr.nb_f2[e];
-            const long long a = c1.offset[f1];
-            const int n1 = (int)(c1.offset[f1 + 1] - a);
-            const int i0 = tile * 32 * R;
-            if (i0 >= n1) continue;
-            const long long b = c2.offset[f2];
-            const int n2 = (int)(c2.offset[f2 + 1] - b);
-            if (n2 == 0) continue;
-            const double ang = pr.nb_ang[e];
-            const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
-            double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
-
-            const bool zerr_on = P.has_zerr_cut && (ang < zerr_ang);
-            const bool shp = P.remove_same_half_plate_close_pairs &&
-                             pb2_same_half_plate(c1, c2, f1, f2);
-            const bool zcut = P.has_z_min_pairs || P.has_z_max_pairs;
-            const double zq1 = c1.z_qso[f1], zq2 = c2.z_qso[f2];
-
-            // ---- rows of this tile -> registers
-            double rc1[R], dm1[R], z1[R], w1[R], dw1[R];
-            bool v1[R];
+        // ---- column window per row set (conservative superset; the exact test still runs)
+        int jl[R], jh[R];
+        int JL = 0, JH = n2;
+        if (FAST) {
+            const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
+            const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
+            const double dmin = P.r_par_min * inv_c;
+            const double dlow = P.x_correlation ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
+            const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
+            JL = n2;
+            JH = 0;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int i = i0 + 32 * r + lane;
-                const bool ok = i < n1;
-                const long long p = a + (ok ? i : 0);
-                rc1[r] = __ldg(c1.r_comov + p);
-                dm1[r] = __ldg(c1.dist_m + p);
-                z1[r] = __ldg(c1.z + p);
-                w1[r] = __ldg(c1.weights + p);
-                dw1[r] = __ldg(c1.delta_w + p);
-                v1[r] = ok && (w1[r] != 0.);                                 // cf.py:318
-                if (zerr_on && v1[r] && pb2_zerr_close(P, z1[r], zq2)) v1[r] = false;  // :321-328
-            }
-
-            // ---- column window per row set
-            int jl[R], jh[R];
-            int JL = 0, JH = n2;
-            if (FAST) {
-                // |r_par| < r_par_max  (or r_par_min <= r_par < r_par_max when signed) and
-                // r_trans < r_trans_max, widened by 1e-9 relative: a superset, never a cut.
-                const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
-                const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
-                const double dmin = P.x_correlation ? (P.r_par_min * inv_c) : -dmax;
-                const double dlow = P.x_correlation ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : dmin;
-                const double tmax_sum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
-                JL = n2;
-                JH = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int ifirst = i0 + 32 * r;
-                    if (ifirst >= n1) {
-                        jl[r] = n2;
-                        jh[r] = 0;
-                        continue;
-                    }
+                const int ifirst = i0 + 32 * r;
+                jl[r] = n2;
+                jh[r] = 0;
+                if (ifirst < n1) {
                     const int ilast = min(ifirst + 31, n1 - 1);
                     const double rc_first = __ldg(c1.r_comov + a + ifirst);
                     const double rc_last = __ldg(c1.r_comov + a + ilast);
                     const double dm_first = __ldg(c1.dist_m + a + ifirst);
-                    // need rc2 > rc1 - dmax  and  rc2 < rc1 - dlow  and dm2 < tmax_sum - dm1
+                    // rc2 > rc1 - dmax, rc2 < rc1 - dlow, dm2 < tsum - dm1
                     const int lo = warp_lower_bound(c2.r_comov + b, n2, rc_first - dmax, false, lane);
                     int hi = warp_lower_bound(c2.r_comov + b, n2, rc_last - dlow, true, lane);
-                    if (isfinite(tmax_sum)) {
-                        const int hi2 = warp_lower_bound(c2.dist_m + b, n2, tmax_sum - dm_first,
-                                                         true, lane);
-                        hi = min(hi, hi2);
-                    }
+                    if (isfinite(tsum))
+                        hi = min(hi, warp_lower_bound(c2.dist_m + b, n2, tsum - dm_first, true, lane));
                     jl[r] = lo;
                     jh[r] = hi;
                     if (hi > lo) {
@@ -250,130 +240,160 @@ pb2_xi_auto_tiled(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Xi
                         JH = max(JH, hi);
                     }
                 }
-                if (JH <= JL) continue;
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    jl[r] = 0;
-                    jh[r] = n2;
-                }
             }
-
-            Run live[R], parked[R];
+            if (JH <= JL) continue;
+        } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                run_clear(live[r]);
-                run_clear(parked[r]);
+                jl[r] = 0;
+                jh[r] = n2;
             }
+        }
 
-            const int nsteps = JH - JL + 31;
-            const double *__restrict__ p_rc2 = c2.r_comov + b;
-            const double *__restrict__ p_dm2 = c2.dist_m + b;
-            const double *__restrict__ p_z2 = c2.z + b;
-            const double *__restrict__ p_w2 = c2.weights + b;
-            const double *__restrict__ p_dw2 = c2.delta_w + b;
+        Slot sa[R], sb[R];
+        int ka[R], kb[R];  // warp-uniform keys, -1 = empty
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            slot_clear(sa[r]);
+            slot_clear(sb[r]);
+            ka[r] = kb[r] = -1;
+        }
 
-            // software pipeline: columns of step s+1 are loaded while step s is computed
-            double n_rc2 = 0., n_dm2 = 0., n_z2 = 0., n_w2 = 0., n_dw2 = 0.;
-            {
-                const int j = JL - 31 + lane;
-                if (j >= 0 && j < n2) {
-                    n_rc2 = __ldg(p_rc2 + j);
-                    n_dm2 = __ldg(p_dm2 + j);
-                    n_z2 = __ldg(p_z2 + j);
-                    n_w2 = __ldg(p_w2 + j);
-                    n_dw2 = __ldg(p_dw2 + j);
-                }
+        const int nsteps = JH - JL + 31;
+        const double *__restrict__ p_rc2 = c2.r_comov + b;
+        const double *__restrict__ p_dm2 = c2.dist_m + b;
+        const double *__restrict__ p_z2 = c2.z + b;
+        const double *__restrict__ p_w2 = c2.weights + b;
+        const double *__restrict__ p_dw2 = c2.delta_w + b;
+        const double *__restrict__ p_zw2 = c2.z_w + b;
+
+        for (int s = 0; s < nsteps; s++) {
+            const int j0 = JL - 31 + s;  // column of lane 0
+            const int j = j0 + lane;
+            double rc2 = 0., dm2 = 0., w2 = 0., dw2 = 0., zw2 = 0., z2 = 0.;
+            const bool jok = (j >= 0) && (j < n2);
+            if (jok) {
+                rc2 = __ldg(p_rc2 + j);
+                dm2 = __ldg(p_dm2 + j);
+                w2 = __ldg(p_w2 + j);
+                dw2 = __ldg(p_dw2 + j);
+                zw2 = __ldg(p_zw2 + j);
+                if (extras) z2 = __ldg(p_z2 + j);
             }
-            for (int s = 0; s < nsteps; s++) {
-                const int j0 = JL - 31 + s;  // column of lane 0
-                const int j = j0 + lane;
-                const double rc2 = n_rc2, dm2 = n_dm2, z2 = n_z2, w2 = n_w2, dw2 = n_dw2;
-                {
-                    const int jn = j + 1;
-                    n_w2 = 0.;
-                    if (jn >= 0 && jn < n2 && s + 1 < nsteps) {
-                        n_rc2 = __ldg(p_rc2 + jn);
-                        n_dm2 = __ldg(p_dm2 + jn);
-                        n_z2 = __ldg(p_z2 + jn);
-                        n_w2 = __ldg(p_w2 + jn);
-                        n_dw2 = __ldg(p_dw2 + jn);
-                    }
-                }
-                bool v2 = (j >= 0) && (j < n2) && (w2 != 0.);                  // cf.py:331
-                if (zerr_on && v2 && pb2_zerr_close(P, z2, zq1)) v2 = false;    // cf.py:341-348
+            bool v2 = jok && (w2 != 0.);                                  // cf.py:331
+            if (zerr_on && v2 && pb2_zerr_close(P, z2, zq1)) v2 = false;  // cf.py:341-348
 
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    // warp-uniform: does any lane of this row set see a column of its window?
-                    if (j0 + 31 < jl[r] || j0 >= jh[r]) continue;
+            for (int r = 0; r < R; r++) {
+                // warp-uniform: does any lane of this row set see a column of its window?
+                if (j0 + 31 < jl[r] || j0 >= jh[r]) continue;
 
-                    bool in;
-                    int bin;
-                    double rp, rt;
-                    if (FAST) {
-                        rp = mul_rn(sub_rn(rc1[r], rc2), ch);
-                        if (!P.x_correlation) rp = fabs(rp);
-                        rt = mul_rn(add_rn(dm1[r], dm2), sh);
-                        const double x = sub_rn(rp, P.r_par_min);
-                        const int bpl = __double2loint(__fma_rd(x, F.kp_lo, PB2_MAGIC));
-                        const int bph = __double2loint(__fma_rd(x, F.kp_hi, PB2_MAGIC));
-                        const int btl = __double2loint(__fma_rd(rt, F.kt_lo, PB2_MAGIC));
-                        const int bth = __double2loint(__fma_rd(rt, F.kt_hi, PB2_MAGIC));
-                        const bool both = v1[r] && v2;
-                        const bool sure = (bpl == bph) && (btl == bth);
-                        in = both && sure && ((unsigned)bpl < np_u) && ((unsigned)btl < nt_u);
-                        bin = btl + (int)nt_u * bpl;
-                        if (__any_sync(0xffffffffu, both && !sure)) {
-                            if (both && !sure) {  // reference expression, true divisions
-                                PairGeom g = pb2_pair_exact(P, rc1[r], dm1[r], rc2, dm2, ang, ch,
-                                                            sh, false, false);
-                                in = g.bin >= 0;
-                                bin = g.bin;
-                            }
-                        }
-                    } else {
+                bool in, unsure = false;
+                int bin;
+                double rp, rt;
+                if (FAST) {
+                    rp = mul_rn(sub_rn(rc1[r], rc2), ch);
+                    if (!P.x_correlation) rp = fabs(rp);
+                    rt = mul_rn(add_rn(dm1[r], dm2), sh);
+                    const double x = sub_rn(rp, P.r_par_min);
+                    const int bpl = __double2loint(__fma_rd(x, F.kp_lo, magic));
+                    const int bph = __double2loint(__fma_rd(x, F.kp_hi, magic));
+                    const int btl = __double2loint(__fma_rd(rt, F.kt_lo, magic));
+                    const int bth = __double2loint(__fma_rd(rt, F.kt_hi, magic));
+                    const bool both = v1[r] && v2;
+                    const bool sure = (bpl == bph) && (btl == bth);
+                    in = both && sure && ((unsigned)bpl < np_u) && ((unsigned)btl < nt_u);
+                    bin = btl + (int)nt_u * bpl;
+                    unsure = both && !sure;
+                } else {
+                    PairGeom g = pb2_pair_exact(P, rc1[r], dm1[r], rc2, dm2, ang, ch, sh, false,
+                                                false);
+                    in = v1[r] && v2 && (g.bin >= 0);
+                    bin = g.bin;
+                    rp = g.r_par;
+                    rt = g.r_trans;
+                }
+                if (extras && in) {
+                    const double zm = div_rn(add_rn(z1[r], z2), 2.);              // cf.py:334
+                    if (P.has_z_min_pairs && zm < P.z_min_pairs) in = false;      // cf.py:336
+                    if (P.has_z_max_pairs && zm > P.z_max_pairs) in = false;
+                    if (shp && fabs(rp) < close_rp) in = false;                   // cf.py:378-380
+                }
+
+                bool is_a = in && (bin == ka[r]);
+                bool is_b = in && (bin == kb[r]);
+                if (__any_sync(0xffffffffu, unsure || (in && !is_a && !is_b))) {
+                    // ---- rare path: resolve borderline bins exactly, then open / recycle slots
+                    if (unsure) {
                         PairGeom g = pb2_pair_exact(P, rc1[r], dm1[r], rc2, dm2, ang, ch, sh,
                                                     false, false);
-                        in = v1[r] && v2 && (g.bin >= 0);
+                        in = g.bin >= 0;
                         bin = g.bin;
-                        rp = g.r_par;
-                        rt = g.r_trans;
-                    }
-                    const double zz = add_rn(z1[r], z2);
-                    if (zcut || shp) {
-                        const double zm = div_rn(zz, 2.);
-                        if (P.has_z_min_pairs && zm < P.z_min_pairs) in = false;  // cf.py:336
-                        if (P.has_z_max_pairs && zm > P.z_max_pairs) in = false;
-                        if (shp && fabs(rp) < close_rp) in = false;               // cf.py:378-380
-                    }
-
-                    const bool brk = in && (bin != live[r].key);
-                    if (__any_sync(0xffffffffu, brk)) {
-                        const bool need = brk && live[r].key >= 0 && parked[r].key >= 0;
-                        if (__any_sync(0xffffffffu, need)) flush_runs(parked[r], orow, nb, lane);
-                        if (brk) {
-                            if (live[r].key >= 0) parked[r] = live[r];
-                            run_clear(live[r]);
-                            live[r].key = bin;
+                        if (extras && in) {
+                            const double zm = div_rn(add_rn(z1[r], z2), 2.);
+                            if (P.has_z_min_pairs && zm < P.z_min_pairs) in = false;
+                            if (P.has_z_max_pairs && zm > P.z_max_pairs) in = false;
+                            if (shp && fabs(rp) < close_rp) in = false;
                         }
                     }
-                    if (in) {
-                        const double w12 = mul_rn(w1[r], w2);
-                        live[r].we += w12;
-                        live[r].xi = fma(dw1[r], dw2, live[r].xi);
-                        live[r].rp = fma(rp, w12, live[r].rp);
-                        live[r].rt = fma(rt, w12, live[r].rt);
-                        live[r].z = fma(zz, w12, live[r].z);  // halved at flush time
-                        live[r].cnt += 1;
+                    for (;;) {
+                        is_a = in && (bin == ka[r]);
+                        is_b = in && (bin == kb[r]);
+                        const unsigned other = __ballot_sync(0xffffffffu, in && !is_a && !is_b);
+                        if (!other) break;
+                        const int key = __shfl_sync(0xffffffffu, bin, __ffs(other) - 1);
+                        const unsigned ma = __ballot_sync(0xffffffffu, is_a);
+                        const unsigned mb = __ballot_sync(0xffffffffu, is_b);
+                        if (ka[r] < 0) {
+                            ka[r] = key;
+                        } else if (kb[r] < 0) {
+                            kb[r] = key;
+                        } else if (!ma) {
+                            slot_flush(sa[r], ka[r], w1[r], dw1[r], z1[r], orow, nb, lane);
+                            ka[r] = key;
+                        } else if (!mb) {
+                            slot_flush(sb[r], kb[r], w1[r], dw1[r], z1[r], orow, nb, lane);
+                            kb[r] = key;
+                        } else {
+                            // three bins live at once: these lanes add their pair directly
+                            if (in && bin == key) {
+                                const double w12 = mul_rn(w1[r], w2);
+                                atomic_add_f64(orow + 0 * (size_t)nb + bin, w12);
+                                atomic_add_f64(orow + 1 * (size_t)nb + bin, mul_rn(dw1[r], dw2));
+                                atomic_add_f64(orow + 2 * (size_t)nb + bin, mul_rn(rp, w12));
+                                atomic_add_f64(orow + 3 * (size_t)nb + bin, mul_rn(rt, w12));
+                                atomic_add_f64(orow + 4 * (size_t)nb + bin,
+                                               0.5 * (z1[r] * w12 + w1[r] * zw2));
+                                atomic_add_i64(orow + 5 * (size_t)nb + bin, 1);
+                                in = false;
+                            }
+                        }
                     }
                 }
+                if (__any_sync(0xffffffffu, is_b)) {
+                    if (is_b) {
+                        sb[r].sw += w2;
+                        sb[r].sdw += dw2;
+                        sb[r].szw += zw2;
+                        sb[r].srp = fma(rp, w2, sb[r].srp);
+                        sb[r].srt = fma(rt, w2, sb[r].srt);
+                        sb[r].cnt += 1;
+                    }
+                }
+                if (is_a) {
+                    sa[r].sw += w2;
+                    sa[r].sdw += dw2;
+                    sa[r].szw += zw2;
+                    sa[r].srp = fma(rp, w2, sa[r].srp);
+                    sa[r].srt = fma(rt, w2, sa[r].srt);
+                    sa[r].cnt += 1;
+                }
             }
+        }
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                flush_runs(parked[r], orow, nb, lane);
-                flush_runs(live[r], orow, nb, lane);
-            }
+        for (int r = 0; r < R; r++) {
+            if (ka[r] >= 0) slot_flush(sa[r], ka[r], w1[r], dw1[r], z1[r], orow, nb, lane);
+            if (kb[r] >= 0) slot_flush(sb[r], kb[r], w1[r], dw1[r], z1[r], orow, nb, lane);
         }
     }
 }
@@ -443,16 +463,6 @@ __global__ void pb2_xi_normalise_kernel(long long n_rows, int nb, double *out)
 }
 
 // ------------------------------------------------------------------------------------------
-static unsigned long long *g_counter_dev = nullptr;
-
-static int32_t get_counter(unsigned long long **ptr, cudaStream_t s)
-{
-    if (!g_counter_dev) PB2_CUDA(cudaMalloc(&g_counter_dev, 64));
-    PB2_CUDA(cudaMemsetAsync(g_counter_dev, 0, 64, s));
-    *ptr = g_counter_dev;
-    return 0;
-}
-
 template <int R>
 static int32_t launch_tiled(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                             const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
@@ -471,8 +481,7 @@ static int32_t launch_tiled(const pb2_catalog *c1, const pb2_catalog *c2, const 
               par->r_par_max > par->r_par_min && par->r_trans_max > 0.) ? 1 : 0;
     F.tmax = (c1->max_pix + 32 * R - 1) / (32 * R);
     if (F.tmax < 1) F.tmax = 1;
-    unsigned long long *ctr = nullptr;
-    if (int32_t e = get_counter(&ctr, s)) return e;
+    F.magic = PB2_MAGIC;
     int dev = 0, sms = 0;
     PB2_CUDA(cudaGetDevice(&dev));
     PB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -481,10 +490,10 @@ static int32_t launch_tiled(const pb2_catalog *c1, const pb2_catalog *c2, const 
     if (blocks < 1) blocks = 1;
     if (F.fast)
         pb2_xi_auto_tiled<R, true><<<blocks, XI_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, F,
-                                                                  d_out_row, d_out, ctr);
+                                                                  d_out_row, d_out);
     else
         pb2_xi_auto_tiled<R, false><<<blocks, XI_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, F,
-                                                                   d_out_row, d_out, ctr);
+                                                                   d_out_row, d_out);
     pb2_count_launch(1);
     return pb2_check_launch("pb2_xi_auto_tiled");
 }

@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the product that needs no GPU -- the delta loader (SoA/CSR packing,
+bounding caps, sortedness), the parameter snapshot, the RNG stream contract, the generator."""
+import numpy as np
+import pytest
+
+from picca_b200 import catalog, synth
+from picca_b200.params import params_from_module
+from tests import helpers
+
+
+@pytest.fixture(scope="module")
+def sample():
+    return helpers.small_sample(n=200, seed=3, max_pix=60)
+
+
+def test_pack_order_and_csr(sample):
+    data = sample[0]
+    cat = catalog.pack(data)
+    flat = [d for hp in sorted(data) for d in data[hp]]
+    assert cat.n_los == len(flat) == 200
+    off = cat.arrays["offset"]
+    assert off[0] == 0 and off[-1] == cat.n_pix == sum(len(d.weights) for d in flat)
+    for k in (0, 17, 199):
+        a, b = off[k], off[k + 1]
+        assert np.array_equal(cat.arrays["r_comov"][a:b], flat[k].r_comov)
+        assert np.array_equal(cat.arrays["delta_w"][a:b],
+                              np.where(flat[k].weights != 0, flat[k].delta * flat[k].weights, 0.))
+        assert cat.arrays["thingid"][k] == flat[k].thingid
+    hp_first = cat.arrays["hp_first"]
+    assert list(np.diff(hp_first)) == [len(data[hp]) for hp in sorted(data)]
+    assert cat.sorted == 1 and cat.max_pix == 60
+
+
+def test_caps_contain_members(sample):
+    cat = catalog.pack(sample[0])
+    A = cat.arrays
+    for k in range(len(cat.healpixs)):
+        a, b = A["hp_first"][k], A["hp_first"][k + 1]
+        dots = (A["x_cart"][a:b] * A["cap_x"][k] + A["y_cart"][a:b] * A["cap_y"][k] +
+                A["z_cart"][a:b] * A["cap_z"][k])
+        assert np.all(np.arccos(np.clip(dots, -1, 1)) <= A["cap_rad"][k])
+
+
+def test_unsorted_forest_is_flagged(sample):
+    data = {hp: list(v) for hp, v in sample[0].items()}
+    hp = sorted(data)[0]
+    d = data[hp][0]
+    import copy
+    d2 = copy.copy(d)
+    d2.r_comov = d.r_comov[::-1].copy()
+    data[hp][0] = d2
+    assert catalog.pack(data).sorted == 0
+
+
+def test_zero_weight_nan_delta_does_not_leak(sample):
+    import copy
+    data = {hp: list(v) for hp, v in sample[0].items()}
+    hp = sorted(data)[0]
+    d = copy.copy(data[hp][0])
+    d.weights, d.delta = d.weights.copy(), d.delta.copy()
+    d.weights[3], d.delta[3] = 0., np.nan
+    data[hp][0] = d
+    assert np.all(np.isfinite(catalog.pack(data).arrays["delta_w"]))
+
+
+def test_params_snapshot_reads_globals_at_call_time():
+    class M:
+        pass
+    m = M()
+    helpers.configure(m, {}, 0, 0.01)
+    p = params_from_module(m)
+    assert (p.num_bins_r_par, p.has_z_min_pairs, p.has_zerr_cut) == (15, 0, 0)
+    m.z_min_pairs, m.zerr_cut_deg, m.zerr_cut_kms, m.num_bins_r_par = 2.1, 0.5, 400., 50
+    p = params_from_module(m)
+    assert (p.num_bins_r_par, p.has_z_min_pairs, p.z_min_pairs, p.has_zerr_cut) == (50, 1, 2.1, 1)
+    m.r_par_max = None
+    with pytest.raises(RuntimeError):
+        params_from_module(m)
+
+
+def test_rej_draw_stream_equals_per_forest_draws():
+    """cf.py:444 draws rand(len(neighbours)) per forest; one rand(total) is the same stream."""
+    lens = [3, 0, 11, 1, 0, 40]
+    np.random.seed(1234)
+    a = np.concatenate([np.random.rand(n) for n in lens])
+    np.random.seed(1234)
+    b = np.random.rand(sum(lens))
+    assert np.array_equal(a, b)
+
+
+def test_generator_is_deterministic():
+    a = helpers.small_sample(n=50, seed=9, max_pix=40)[0]
+    b = helpers.small_sample(n=50, seed=9, max_pix=40)[0]
+    assert sorted(a) == sorted(b)
+    for hp in a:
+        for x, y in zip(a[hp], b[hp]):
+            assert np.array_equal(x.delta, y.delta) and np.array_equal(x.weights, y.weights)
+
+
+def test_ang2pix_ring_known_values():
+    # pixel centres map back to their own index (nside 4, all 192 pixels), via the test shim
+    from tests.refharness import shims
+    nside = 8
+    vec = shims.pix2vec(nside, np.arange(12 * nside * nside))
+    theta = np.arccos(vec[:, 2])
+    phi = np.arctan2(vec[:, 1], vec[:, 0])
+    assert np.array_equal(synth.ang2pix_ring(nside, theta, phi), np.arange(12 * nside * nside))

@@ -1,0 +1,161 @@
+"""CPU, this container only: pin the oracle against (1) the LIVE reference on the reference's own
+bundled fixtures, bit for bit, and (2) the reference's golden FITS files, by running the
+reference's UNMODIFIED CLI scripts on top of the oracle's module doubles with the exact command
+lines of reference py/picca/tests/test_3_cor.py (:229-257, :318-349, :636-698).
+Skipped where /root/reference does not exist (the GPU box)."""
+import numpy as np
+import pytest
+
+from tests.refharness import shims
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not shims.reference_available(), reason="needs /root/reference")]
+
+DATA = "/root/reference/py/picca/tests/data"
+
+
+@pytest.fixture(scope="module")
+def fixture_data():
+    from tests.refharness import load
+    data, num_data, z_min, z_max, cosmo = load.load_deltas()
+    objs, z_min2 = load.load_objects(cosmo)
+    return data, num_data, z_min, cosmo, objs, z_min2
+
+
+def _setup(mod, fx, utils, load, cross_obj=False, **over):
+    data, num_data, z_min, cosmo, objs, z_min2 = fx
+    cfg = dict(r_par_max=60., r_trans_max=60., r_par_min=0., num_bins_r_par=15,
+               num_bins_r_trans=15, num_model_bins_r_par=15, num_model_bins_r_trans=15, nside=16,
+               z_ref=2.25, alpha=2.9, alpha2=2.9, reject=0.99)
+    cfg.update(over)
+    for k, v in cfg.items():
+        setattr(mod, k, v)
+    mod.data, mod.num_data = data, num_data
+    if cross_obj:
+        mod.objs = objs
+        mod.ang_max = utils.compute_ang_max(cosmo, mod.r_trans_max, z_min, z_min2)
+    else:
+        mod.ang_max = utils.compute_ang_max(cosmo, mod.r_trans_max, z_min)
+    mod.lock, mod.counter = load.DummyLock(), load.DummyCounter()
+
+
+def test_cf_bit_exact_on_bundled_fixtures(fixture_data):
+    from tests.refharness import load
+    from oracle import cf as ocf
+    cf, _, _, _, utils = load.reference_modules()
+    cf.userprint = lambda *a, **k: None
+    data = fixture_data[0]
+    over = dict(remove_same_half_plate_close_pairs=True)
+    _setup(cf, fixture_data, utils, load, **over)
+    _setup(ocf, fixture_data, utils, load, **over)
+    total = 0
+    for hp in sorted(data)[:8]:
+        cf.fill_neighs([hp])
+        want_n = [[d2.thingid for d2 in d.neighbours] for d in data[hp]]
+        want = cf.compute_xi([hp])
+        ocf.fill_neighs([hp])
+        assert [[d2.thingid for d2 in d.neighbours] for d in data[hp]] == want_n
+        got = ocf.compute_xi([hp])
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+        total += int(got[5].sum())
+    assert total > 10**6
+
+
+@pytest.mark.parametrize("evol", [False, True])
+def test_dmat_bit_exact_on_bundled_fixtures(fixture_data, evol):
+    from tests.refharness import load
+    from oracle import cf as ocf
+    cf, _, _, _, utils = load.reference_modules()
+    cf.userprint = lambda *a, **k: None
+    hps = sorted(fixture_data[0])
+    over = dict(remove_same_half_plate_close_pairs=True,
+                redshift_evolution_in_distortion_matrix=evol)
+    _setup(cf, fixture_data, utils, load, **over)
+    _setup(ocf, fixture_data, utils, load, **over)
+    cf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    want = cf.compute_dmat(hps)
+    ocf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    got = ocf.compute_dmat(hps)
+    assert (want[6], want[7]) == (11845, 121) == (got[6], got[7])  # golden NPALL / NPUSED
+    for a, b in zip(want[:6], got[:6]):
+        assert np.array_equal(a, b)
+
+
+def test_xcf_and_xdmat_bit_exact_on_bundled_fixtures(fixture_data):
+    from tests.refharness import load
+    from oracle import xcf as oxcf
+    _, xcf, _, _, utils = load.reference_modules()
+    xcf.userprint = lambda *a, **k: None
+    data = fixture_data[0]
+    hps = sorted(data)
+    over = dict(r_par_min=-60., num_bins_r_par=30, num_model_bins_r_par=30, alpha_obj=1.,
+                redshift_evolution_in_distortion_matrix=False)
+    _setup(xcf, fixture_data, utils, load, cross_obj=True, **over)
+    _setup(oxcf, fixture_data, utils, load, cross_obj=True, **over)
+    total = 0
+    for hp in hps:
+        xcf.fill_neighs([hp])
+        want = xcf.compute_xi([hp])
+        oxcf.fill_neighs([hp])
+        got = oxcf.compute_xi([hp])
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+        total += int(got[5].sum())
+    assert total == 353334  # NB total of the reference's golden xcf.fits.gz
+    xcf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    want = xcf.compute_dmat(hps)
+    oxcf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    got = oxcf.compute_dmat(hps)
+    assert (want[6], want[7]) == (1202, 102) == (got[6], got[7])
+    for a, b in zip(want[:6], got[:6]):
+        assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# unmodified scripts on top of the oracle doubles vs the reference's golden FITS
+# ---------------------------------------------------------------------------------------------
+def _compare_fits(path_got, path_want):
+    """reference tests/test_helpers.py:45-112: same columns, array_equal else allclose(1e-5,1e-8)"""
+    from tests.refharness import minifits
+    got, want = minifits.FITS(path_got), minifits.FITS(path_want)
+    assert len(got) == len(want)
+    for h in range(1, len(want)):
+        tg, tw = got[h].read(), want[h].read()
+        assert tg.dtype.names == tw.dtype.names
+        for name in tw.dtype.names:
+            if not np.array_equal(tg[name], tw[name]):
+                assert np.allclose(tg[name], tw[name], rtol=1e-5, atol=1e-8), (h, name)
+
+
+COMMON = (" --rp-max +60.0 --rt-max +60.0 --nt 15 --nproc 1 --in-attributes " + DATA +
+          "/test_delta/delta_attributes.fits.gz --in-dir " + DATA + "/test_delta/Delta_LYA/")
+
+
+@pytest.mark.parametrize("script,double,flags,golden", [
+    ("picca_cf", "cf", " --rp-min +0.0 --np 15 --remove-same-half-plate-close-pairs", "cf"),
+    ("picca_dmat", "cf", " --rp-min +0.0 --np 15 --rej 0.99 --remove-same-half-plate-close-pairs"
+     " --no-redshift-evolution", "dmat"),
+    ("picca_xcf", "xcf", " --rp-min -60.0 --np 30 --z-evol-obj 1. --drq " + DATA +
+     "/test_delta/cat.fits", "xcf"),
+    ("picca_xdmat", "xcf", " --rp-min -60.0 --np 30 --rej 0.99 --z-evol-obj 1."
+     " --no-redshift-evolution --drq " + DATA + "/test_delta/cat.fits", "xdmat"),
+])
+def test_unmodified_script_on_oracle_matches_golden_fits(tmp_path, script, double, flags, golden):
+    import importlib
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin." + script)
+    oracle_mod = importlib.reload(importlib.import_module("oracle." + double))
+    saved = getattr(mod, double)
+    setattr(mod, double, oracle_mod)  # the script now drives the oracle double of picca.cf/xcf
+    out = str(tmp_path / (golden + ".fits.gz"))
+    try:
+        mod.main((COMMON + flags + " --out " + out).split())
+    finally:
+        setattr(mod, double, saved)
+    _compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz")
