@@ -64,6 +64,9 @@ void orc_xi_auto_pair(const orc_params *P, int64_t n1, const double *z1, const d
 {
     const double r_par_max = P->r_par_max, r_par_min = P->r_par_min, r_trans_max = P->r_trans_max;
     const int num_bins_r_par = P->num_bins_r_par, num_bins_r_trans = P->num_bins_r_trans;
+    /* loop-invariant libm calls, hoisted exactly as LLVM hoists them in the Numba build: the
+     * values are identical to evaluating np.cos(ang / 2) inside the loop (cf.py:356-357) */
+    const double cos_half = cos(ang / 2), sin_half = sin(ang / 2);
     for (int64_t i = 0; i < n1; i++) {
         if (weights1[i] == 0) continue; /* cf.py:318 */
 
@@ -96,8 +99,8 @@ void orc_xi_auto_pair(const orc_params *P, int64_t n1, const double *z1, const d
                 if (!P->x_correlation && r_par < 1.0) r_par = 1.0 / r_par;
                 r_trans = ang;
             } else { /* cf.py:356-362 */
-                r_par = (r_comov1[i] - r_comov2[j]) * cos(ang / 2);
-                r_trans = (dist_m1[i] + dist_m2[j]) * sin(ang / 2);
+                r_par = (r_comov1[i] - r_comov2[j]) * cos_half;
+                r_trans = (dist_m1[i] + dist_m2[j]) * sin_half;
                 if (P->rmu_binning) {
                     r_trans = sqrt(r_trans * r_trans + r_par * r_par);
                     r_par /= r_trans;
@@ -229,6 +232,7 @@ int orc_dmat_auto_pair(const orc_params *P, int64_t n1, const double *log_lambda
     const int num_model_bins_r_trans = P->num_model_bins_r_trans;
     const int64_t nbm = (int64_t)num_model_bins_r_par * num_model_bins_r_trans;
     const double z_ref = P->z_ref, alpha = P->alpha, alpha2 = P->alpha2;
+    const double cos_half = cos(ang / 2), sin_half = sin(ang / 2); /* hoisted, same values */
 
     /* pass 0: count relevant pixel pairs, cf.py:547-571 */
     int64_t num_pairs = 0;
@@ -236,8 +240,8 @@ int orc_dmat_auto_pair(const orc_params *P, int64_t n1, const double *log_lambda
         if (weights1[i] == 0) continue;
         for (int64_t j = 0; j < n2; j++) {
             if (weights2[j] == 0) continue;
-            double r_par = (r_comov1[i] - r_comov2[j]) * cos(ang / 2);
-            double r_trans = (dist_m1[i] + dist_m2[j]) * sin(ang / 2);
+            double r_par = (r_comov1[i] - r_comov2[j]) * cos_half;
+            double r_trans = (dist_m1[i] + dist_m2[j]) * sin_half;
             if (P->rmu_binning) {
                 r_trans = sqrt(r_trans * r_trans + r_par * r_par);
                 r_par /= r_trans;
@@ -309,8 +313,8 @@ int orc_dmat_auto_pair(const orc_params *P, int64_t n1, const double *log_lambda
                 dv_kms *= ORC_SPEED_LIGHT;
                 if (dv_kms < P->zerr_cut_kms) j_selected = 0;
             }
-            double r_par = (r_comov1[i] - r_comov2[j]) * cos(ang / 2);
-            double r_trans = (dist_m1[i] + dist_m2[j]) * sin(ang / 2);
+            double r_par = (r_comov1[i] - r_comov2[j]) * cos_half;
+            double r_trans = (dist_m1[i] + dist_m2[j]) * sin_half;
             if (P->rmu_binning) {
                 r_trans = sqrt(r_trans * r_trans + r_par * r_par);
                 r_par /= r_trans;
@@ -578,8 +582,9 @@ int orc_dmat_cross_forest(const orc_params *P, int64_t n1, const double *log_lam
  *   nb_index[nb_offset[k] .. nb_offset[k+1]) with angles nb_ang[...] (and flags).
  * Its output row is out_row[k] (its HEALPix row; listed forests are grouped by ascending row);
  * rows are un-normalised sums laid out [n_rows][6][nb]: weight, xi, r_par, r_trans, z (double)
- * and num_pairs (int64 bits).  Threads (pthreads) take whole rows from a shared counter -- the
- * analogue of the reference's Pool.map over HEALPix pixels (picca_cf.py:454-457).
+ * and num_pairs (int64 bits).  num_threads = 1 reproduces the reference's summation order; more
+ * threads (pthreads) split the forests dynamically (timing baseline, cf. the reference's Pool.map
+ * over HEALPix pixels, picca_cf.py:454-457).
  * ---------------------------------------------------------------------------------------- */
 #include <pthread.h>
 
@@ -589,73 +594,104 @@ typedef struct {
     const int64_t *offset2; const double *z2, *rc2, *dm2, *w2, *d2, *zq2;
     const int64_t *f1_index, *nb_offset, *nb_index; const double *nb_ang;
     const int32_t *nb_same_half_plate;
-    const int64_t *row_start; int64_t n_rows; double *out;
+    const int64_t *out_row; int64_t n_f1; int64_t n_rows; double *out;
     int64_t next_row; int cross;
 } orc_batch;
 
-static void orc_batch_row(orc_batch *B, int64_t r)
+static void orc_batch_forest(orc_batch *B, int64_t k, double *base)
 {
     const orc_params *P = B->P;
     const int64_t nb = (int64_t)P->num_bins_r_par * P->num_bins_r_trans;
-    double *base = B->out + r * 6 * nb;
-    for (int64_t k = B->row_start[r]; k < B->row_start[r + 1]; k++) {
-        int64_t f1 = B->f1_index[k];
-        int64_t a = B->offset1[f1], n1 = B->offset1[f1 + 1] - a;
-        if (!B->cross) {
-            for (int64_t e = B->nb_offset[k]; e < B->nb_offset[k + 1]; e++) {
-                int64_t f2 = B->nb_index[e];
-                int64_t b = B->offset2[f2], n2 = B->offset2[f2 + 1] - b;
-                orc_xi_auto_pair(P, n1, B->z1 + a, B->rc1 + a, B->dm1 + a, B->w1 + a, B->d1 + a,
-                                 B->zq1[f1], n2, B->z2 + b, B->rc2 + b, B->dm2 + b, B->w2 + b,
-                                 B->d2 + b, B->zq2[f2], B->nb_ang[e],
-                                 B->nb_same_half_plate ? B->nb_same_half_plate[e] : 0,
-                                 base + 0 * nb, base + 1 * nb, base + 2 * nb, base + 3 * nb,
-                                 base + 4 * nb, (int64_t *)(base + 5 * nb));
-            }
-        } else {
-            int64_t m = B->nb_offset[k + 1] - B->nb_offset[k];
-            if (m == 0) continue; /* xcf.py:157 */
-            double *gz = (double *)malloc(sizeof(double) * (size_t)m * 4);
-            double *grc = gz + m, *gdm = gz + 2 * m, *gw = gz + 3 * m;
-            for (int64_t e = 0; e < m; e++) { /* the gathers of xcf.py:159-185 */
-                int64_t q = B->nb_index[B->nb_offset[k] + e];
-                gz[e] = B->z2[q]; grc[e] = B->rc2[q]; gdm[e] = B->dm2[q]; gw[e] = B->w2[q];
-            }
-            orc_xi_cross_forest(P, n1, B->z1 + a, B->rc1 + a, B->dm1 + a, B->w1 + a, B->d1 + a, m,
-                                gz, grc, gdm, gw, B->nb_ang + B->nb_offset[k], base + 0 * nb,
-                                base + 1 * nb, base + 2 * nb, base + 3 * nb, base + 4 * nb,
-                                (int64_t *)(base + 5 * nb));
-            free(gz);
+    int64_t f1 = B->f1_index[k];
+    int64_t a = B->offset1[f1], n1 = B->offset1[f1 + 1] - a;
+    if (!B->cross) {
+        for (int64_t e = B->nb_offset[k]; e < B->nb_offset[k + 1]; e++) {
+            int64_t f2 = B->nb_index[e];
+            int64_t b = B->offset2[f2], n2 = B->offset2[f2 + 1] - b;
+            orc_xi_auto_pair(P, n1, B->z1 + a, B->rc1 + a, B->dm1 + a, B->w1 + a, B->d1 + a,
+                             B->zq1[f1], n2, B->z2 + b, B->rc2 + b, B->dm2 + b, B->w2 + b,
+                             B->d2 + b, B->zq2[f2], B->nb_ang[e],
+                             B->nb_same_half_plate ? B->nb_same_half_plate[e] : 0,
+                             base + 0 * nb, base + 1 * nb, base + 2 * nb, base + 3 * nb,
+                             base + 4 * nb, (int64_t *)(base + 5 * nb));
         }
+    } else {
+        int64_t m = B->nb_offset[k + 1] - B->nb_offset[k];
+        if (m == 0) return; /* xcf.py:157 */
+        double *gz = (double *)malloc(sizeof(double) * (size_t)m * 4);
+        double *grc = gz + m, *gdm = gz + 2 * m, *gw = gz + 3 * m;
+        for (int64_t e = 0; e < m; e++) { /* the gathers of xcf.py:159-185 */
+            int64_t q = B->nb_index[B->nb_offset[k] + e];
+            gz[e] = B->z2[q]; grc[e] = B->rc2[q]; gdm[e] = B->dm2[q]; gw[e] = B->w2[q];
+        }
+        orc_xi_cross_forest(P, n1, B->z1 + a, B->rc1 + a, B->dm1 + a, B->w1 + a, B->d1 + a, m,
+                            gz, grc, gdm, gw, B->nb_ang + B->nb_offset[k], base + 0 * nb,
+                            base + 1 * nb, base + 2 * nb, base + 3 * nb, base + 4 * nb,
+                            (int64_t *)(base + 5 * nb));
+        free(gz);
     }
+}
+
+/* One thread: rows in order, forests in order, accumulating straight into the output -- the
+ * reference's sequential summation order (used by the parity tests). */
+static void orc_batch_serial(orc_batch *B, int64_t n_f1)
+{
+    const int64_t nb = (int64_t)B->P->num_bins_r_par * B->P->num_bins_r_trans;
+    for (int64_t k = 0; k < n_f1; k++) orc_batch_forest(B, k, B->out + B->out_row[k] * 6 * nb);
+}
+
+/* Several threads: forests are handed out dynamically (the reference forks workers over HEALPix
+ * pixels; finer units keep every core busy on a bounded sample); each thread accumulates into a
+ * private block and merges it under a lock when its row changes.  Counts are exact; the order of
+ * fp64 additions differs from the serial run at the 1e-16 level.  Timing baseline only. */
+static pthread_mutex_t orc_merge_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void orc_merge(orc_batch *B, int64_t row, double *priv)
+{
+    const int64_t nb = (int64_t)B->P->num_bins_r_par * B->P->num_bins_r_trans;
+    double *dst = B->out + row * 6 * nb;
+    pthread_mutex_lock(&orc_merge_lock);
+    for (int64_t x = 0; x < 5 * nb; x++) dst[x] += priv[x];
+    int64_t *dc = (int64_t *)(dst + 5 * nb), *pc = (int64_t *)(priv + 5 * nb);
+    for (int64_t x = 0; x < nb; x++) dc[x] += pc[x];
+    pthread_mutex_unlock(&orc_merge_lock);
+    memset(priv, 0, sizeof(double) * (size_t)(6 * nb));
 }
 
 static void *orc_batch_worker(void *arg)
 {
     orc_batch *B = (orc_batch *)arg;
+    const int64_t nb = (int64_t)B->P->num_bins_r_par * B->P->num_bins_r_trans;
+    double *priv = (double *)calloc((size_t)(6 * nb), sizeof(double));
+    int64_t cur = -1;
     for (;;) {
-        int64_t r = __atomic_fetch_add(&B->next_row, 1, __ATOMIC_RELAXED);
-        if (r >= B->n_rows) break;
-        orc_batch_row(B, r);
+        int64_t k = __atomic_fetch_add(&B->next_row, 1, __ATOMIC_RELAXED);
+        if (k >= B->n_f1) break;
+        if (B->out_row[k] != cur) {
+            if (cur >= 0) orc_merge(B, cur, priv);
+            cur = B->out_row[k];
+        }
+        orc_batch_forest(B, k, priv);
     }
+    if (cur >= 0) orc_merge(B, cur, priv);
+    free(priv);
     return NULL;
 }
 
 static void orc_batch_run(orc_batch *B, int64_t n_f1, const int64_t *out_row, int32_t num_threads)
 {
-    int64_t *row_start = (int64_t *)calloc((size_t)(B->n_rows + 1), sizeof(int64_t));
-    for (int64_t k = 0; k < n_f1; k++) row_start[out_row[k] + 1] = k + 1;
-    for (int64_t r = 0; r < B->n_rows; r++)
-        if (row_start[r + 1] < row_start[r]) row_start[r + 1] = row_start[r];
-    B->row_start = row_start;
+    B->out_row = out_row;
+    B->n_f1 = n_f1;
     B->next_row = 0;
-    if (num_threads < 1) num_threads = 1;
+    if (num_threads <= 1) {
+        orc_batch_serial(B, n_f1);
+        return;
+    }
     if (num_threads > 256) num_threads = 256;
     pthread_t th[256];
     for (int t = 1; t < num_threads; t++) pthread_create(&th[t], NULL, orc_batch_worker, B);
     orc_batch_worker(B);
     for (int t = 1; t < num_threads; t++) pthread_join(th[t], NULL);
-    free(row_start);
 }
 
 void orc_xi_auto_batch(const orc_params *P, const int64_t *offset1, const double *z1,

@@ -187,16 +187,21 @@ class DeviceCatalog:
                 t = t.pin_memory()
             self.tensors[name] = t.to(device, non_blocking=pin)
             self.h2d_bytes += arr.nbytes
-        c = _lib.Catalog()
-        c.n_los = host.n_los
-        c.n_pix = host.n_pix
-        for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
-                "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
-            setattr(c, name, self.tensors[name].data_ptr())
-        c.n_hp = len(host.healpixs)
-        c.sorted = host.sorted
-        c.max_pix = host.max_pix
-        self.struct = c
+        self.struct = build_struct(host, self.tensors)
+
+
+def build_struct(host, tensors):
+    """``pb2_catalog`` pointing at the device tensors of a packed catalogue."""
+    c = _lib.Catalog()
+    c.n_los = host.n_los
+    c.n_pix = host.n_pix
+    for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
+            "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
+        setattr(c, name, tensors[name].data_ptr())
+    c.n_hp = len(host.healpixs)
+    c.sorted = host.sorted
+    c.max_pix = host.max_pix
+    return c
 
 
 _HOST_CACHE = {}

@@ -90,7 +90,7 @@ def project(delta, weights, log_lambda, order):
 
 
 def make_forests(n_forest, seed=20260102, nside=32, ra_deg=(0., 120.), dec_deg=(0., 40.2),
-                 rest_range=(1060., 1175.), lambda_min=3600., dlambda=0.8, z_ref=2.25, alpha=2.9,
+                 rest_range=(1045., 1192.), lambda_min=3600., dlambda=0.8, z_ref=2.25, alpha=2.9,
                  order=1, zero_weight_frac=0.02, cosmo=None, id_offset=0, max_pix=None):
     """DR16-like synthetic Lyman-alpha forests.
 

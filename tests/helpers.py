@@ -41,7 +41,7 @@ def configure(mod, data, num_data, ang_max, **over):
 def small_sample(n=300, seed=11, side_deg=6., max_pix=120, nside=16, **kw):
     data, num, z_min, z_max, cosmo = synth.make_forests(
         n, seed=seed, nside=nside, ra_deg=(10., 10. + side_deg), dec_deg=(5., 5. + side_deg),
-        max_pix=max_pix, **kw)
+        max_pix=max_pix, rest_range=kw.pop("rest_range", (1045., 1192.)), **kw)
     return data, num, z_min, z_max, cosmo
 
 

@@ -28,7 +28,8 @@ def _setup(mod, fx, utils, load, cross_obj=False, **over):
                num_bins_r_trans=15, num_model_bins_r_par=15, num_model_bins_r_trans=15, nside=16,
                z_ref=2.25, alpha=2.9, alpha2=2.9, reject=0.99)
     cfg.update(over)
-    for k, v in cfg.items():
+    from tests import helpers
+    for k, v in dict(helpers.CF_DEFAULTS, **cfg).items():  # no state leaks from earlier tests
         setattr(mod, k, v)
     mod.data, mod.num_data = data, num_data
     if cross_obj:
