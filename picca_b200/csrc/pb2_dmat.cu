@@ -1,23 +1,743 @@
-// Distortion matrix -- placeholder until the kernels land.
+// Distortion matrix: replaces cf.compute_dmat's pair loop + cf.compute_dmat_forest_pairs_fast
+// (reference py/picca/cf.py:424-502, 520-887) and the xcf equivalents (py/picca/xcf.py:360-409,
+// 427-674).
+//
+// The reference updates, for every selected pixel pair (i,j) in data bin A and every model bin k
+// the forest pair touches,
+//     dmat[A,k] += w12 * ( [k == B(i,j)] zf + eta5[k] + eta6[k] dll2_j + eta7[k] dll1_i
+//                          + eta8[k] dll1_i dll2_j - eta1[i,k] - eta2[j,k]
+//                          - eta3[i,k] dll2_j - eta4[j,k] dll1_i )                 (cf.py:851-887)
+// i.e. N_selected x U read-modify-writes into a 50 MB matrix per forest pair.  Summing over the
+// pairs of a data bin first turns this into one small dense contraction per forest pair
+// (SURVEY.md Appendix B):
+//     dmat[A,k] += sum_r X[r,A] * Y[r,k]       r over {pixels of forest 1 (x2), pixels of forest 2
+//                                                (x2), four rank-1 terms}
+//     X = (-Q1, -Q1d, -Q2, -Q2d, P0, P2, P1, P12),   Y = (eta1, eta3, eta2, eta4, eta5..eta8)
+// with Q1[A,i] = w1_i sum_{j in S,A} w2_j etc.  One CTA per kept forest pair:
+//   pass 0  exact bins of every in-range pixel pair -> sets of touched model / data bins, compact
+//           indices (U, UA), early exit when nothing is in range (cf.py:547-571);
+//   sweep 1 one thread per pixel of forest 1 walks its row: run-length sums per (A,B) segment give
+//           eta1/eta3 and Q1/Q1d rows (no atomics: the thread owns the row) and, per segment,
+//           native fp64 reductions for the diagonal term, weights_dmat, the effective r_par /
+//           r_trans / z / weight and the rank-1 factors;
+//   sweep 2 one thread per pixel of forest 2 walks its column: eta2/eta4 and Q2/Q2d rows;
+//   GEMM    64x64 register-tiled fp64 contraction over r, epilogue = red.global.add.f64 into dmat.
+// All bins use the reference expression with true IEEE divisions (no fast path here: the sweeps
+// are <5 % of the work).  The sums are re-associated with respect to the reference, which stays
+// within 1e-9 (measured 2e-11 in the survey) but is not bit-exact; counts of pairs are exact.
 #include "pb2_common.cuh"
 
+#define DM_THREADS 256
+#define DM_TILE 64
+#define DM_KCH 16
+#define DM_CAP 512  // compact bins handled per chunk (padded to DM_TILE)
+
+struct DmatGeom {
+    bool in;       // inside the model range (cf.py:667)
+    bool close;    // same-half-plate close pair (cf.py:669-671)
+    int A, B;      // data bin, model bin
+    double rp, rt;
+};
+
+// exact evaluation of one pixel pair for the distortion matrix (cf.py:660-700 / xcf.py:528-564)
+__device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, double rc1, double dm1,
+                                              double rc2, double dm2, double ch, double sh,
+                                              bool cross_obj, bool shp)
+{
+    DmatGeom g;
+    g.in = false;
+    g.close = false;
+    g.A = g.B = -1;
+    double r_par = mul_rn(sub_rn(rc1, rc2), ch);
+    double r_trans = mul_rn(add_rn(dm1, dm2), sh);
+    if (P.rmu_binning) {
+        r_trans = sqrt(add_rn(mul_rn(r_trans, r_trans), mul_rn(r_par, r_par)));
+        r_par = div_rn(r_par, r_trans);
+    }
+    if (!cross_obj && !P.x_correlation) r_par = fabs(r_par);
+    g.rp = r_par;
+    g.rt = r_trans;
+    if (r_par >= P.r_par_max || r_trans >= P.r_trans_max || r_par < P.r_par_min) return g;
+    const double span = sub_rn(P.r_par_max, P.r_par_min);
+    if (shp && fabs(r_par) < div_rn(span, (double)P.num_bins_r_par)) g.close = true;
+    const double fp = div_rn(sub_rn(r_par, P.r_par_min), span);
+    const double ft = div_rn(r_trans, P.r_trans_max);
+    const double bp = floor(mul_rn(fp, (double)P.num_bins_r_par));
+    const double bt = floor(mul_rn(ft, (double)P.num_bins_r_trans));
+    const double mp = floor(mul_rn(fp, (double)P.num_model_bins_r_par));
+    const double mt = floor(mul_rn(ft, (double)P.num_model_bins_r_trans));
+    const long long A = (long long)add_rn(bt, mul_rn((double)P.num_bins_r_trans, bp));
+    const long long B = (long long)add_rn(mt, mul_rn((double)P.num_model_bins_r_trans, mp));
+    const long long nb = (long long)P.num_bins_r_par * P.num_bins_r_trans;
+    const long long nbm = (long long)P.num_model_bins_r_par * P.num_model_bins_r_trans;
+    if (A < 0 || A >= nb || B < 0 || B >= nbm) return g;  // the reference would index out of bounds
+    g.in = true;
+    g.A = (int)A;
+    g.B = (int)B;
+    return g;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    __syncthreads();
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < DM_THREADS / 32; w++) t += red[w];
+    return t;
+}
+
+// conservative column window of a row (sorted forests, standard binning); full range otherwise
+__device__ __forceinline__ void row_window(const pb2_params &P, bool windows, double rc_i,
+                                           double dm_i, const double *rc2, const double *dm2,
+                                           int n2, double ch, double sh, bool signed_rp, int &lo,
+                                           int &hi)
+{
+    lo = 0;
+    hi = n2;
+    if (!windows) return;
+    const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
+    const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
+    const double dmin = P.r_par_min * inv_c;
+    const double dlow = signed_rp ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
+    // rc2 > rc_i - dmax, rc2 < rc_i - dlow, dm2 < r_trans_max/sh - dm_i
+    int a = 0, b = n2;
+    const double v0 = rc_i - dmax;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (rc2[m] <= v0) a = m + 1; else b = m;
+    }
+    lo = a;
+    a = lo;
+    b = n2;
+    const double v1 = rc_i - dlow;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (rc2[m] < v1) a = m + 1; else b = m;
+    }
+    hi = a;
+    const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
+    if (isfinite(tsum)) {
+        a = lo;
+        b = hi;
+        const double v2 = tsum - dm_i;
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (dm2[m] < v2) a = m + 1; else b = m;
+        }
+        hi = a;
+    }
+}
+
+struct DmatWork {
+    long long *kept;            // kept pair indices
+    unsigned long long *count;  // [0] number of kept pairs, [1] claim counter
+    char *cta_base;             // per-CTA scratch
+    long long cta_stride;
+    int rows_max;               // 2*max_pix1 + 2*max_pix2 + 4
+    int cap;                    // DM_CAP
+};
+
+__global__ void dmat_compact_kernel(pb2_pairs pr, DmatWork W)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pr.n_pairs) return;
+    if (pr.nb_keep == nullptr || pr.nb_keep[e]) {
+        const unsigned long long slot = atomicAdd(W.count, 1ull);
+        W.kept[slot] = e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// auto / delta x delta
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DM_THREADS, 2)
+pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DmatWork W,
+                     double *__restrict__ weights_dmat, double *__restrict__ dmat,
+                     double *__restrict__ r_par_eff, double *__restrict__ r_trans_eff,
+                     double *__restrict__ z_eff, double *__restrict__ weight_eff)
+{
+    __shared__ double red[DM_THREADS / 32];
+    __shared__ long long s_e;
+    __shared__ int s_cnt[2];   // in-range pairs that are not close, in-range pairs
+    __shared__ int s_U, s_UA;
+    __shared__ __align__(16) double Xs[DM_KCH][DM_TILE];
+    __shared__ __align__(16) double Ys[DM_KCH][DM_TILE];
+
+    const int tid = threadIdx.x;
+    const int nb = P.num_bins_r_par * P.num_bins_r_trans;
+    const int nbm = P.num_model_bins_r_par * P.num_model_bins_r_trans;
+    const double zerr_ang = mul_rn(P.zerr_cut_deg, PB2_PI) / 180.0;
+    const bool windows = !P.rmu_binning && c1.sorted && c2.sorted;
+
+    // per-CTA scratch carve-up
+    char *base = W.cta_base + (long long)blockIdx.x * W.cta_stride;
+    int *kidx = (int *)base;                     // [nbm] compact model index, -1 = untouched
+    int *aidx = kidx + nbm;                      // [nb]
+    int *klist = aidx + nb;                      // [nbm]
+    int *alist = klist + nbm;                    // [nb]
+    double *f1z = (double *)(((uintptr_t)(alist + nb) + 15) & ~(uintptr_t)15);  // [max_pix1]
+    double *f2z = f1z + c1.max_pix;              // [max_pix2]
+    double *dl1 = f2z + c2.max_pix;              // [max_pix1] log_lambda - mean
+    double *dl2 = dl1 + c1.max_pix;              // [max_pix2]
+    double *X = dl2 + c2.max_pix;                // [rows_max][cap]
+    double *Y = X + (long long)W.rows_max * W.cap;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long t = atomicAdd(W.count + 1, 1ull);
+            s_e = (t < W.count[0]) ? W.kept[t] : -1;
+        }
+        __syncthreads();
+        const long long e = s_e;
+        if (e < 0) break;
+
+        const int k1 = pr.nb_f1[e];
+        const int f1 = pr.f1_index[k1], f2 = pr.nb_f2[e];
+        const long long a = c1.offset[f1], b = c2.offset[f2];
+        const int n1 = (int)(c1.offset[f1 + 1] - a), n2 = (int)(c2.offset[f2 + 1] - b);
+        const double ang = pr.nb_ang[e], ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        const bool zerr_on = P.has_zerr_cut && (ang < zerr_ang);
+        const bool shp = P.remove_same_half_plate_close_pairs && pb2_same_half_plate(c1, c2, f1, f2);
+        const double zq1 = c1.z_qso[f1], zq2 = c2.z_qso[f2];
+        const int order1 = c1.order[f1], order2 = c2.order[f2];
+        const double *rc1 = c1.r_comov + a, *dm1 = c1.dist_m + a, *z1 = c1.z + a;
+        const double *w1 = c1.weights + a, *ll1 = c1.log_lambda + a;
+        const double *rc2 = c2.r_comov + b, *dm2 = c2.dist_m + b, *z2 = c2.z + b;
+        const double *w2 = c2.weights + b, *ll2 = c2.log_lambda + b;
+
+        // ---------------- pass 0: touched bins (cf.py:547-571 and the bins of pass 1)
+        for (int x = tid; x < nbm; x += DM_THREADS) kidx[x] = -1;
+        for (int x = tid; x < nb; x += DM_THREADS) aidx[x] = -1;
+        if (tid == 0) s_cnt[0] = s_cnt[1] = 0;
+        __syncthreads();
+        {
+            int cnt_nc = 0, cnt_in = 0;
+            for (int i = tid; i < n1; i += DM_THREADS) {
+                if (w1[i] == 0.) continue;
+                bool i_sel = true;
+                if (zerr_on && pb2_zerr_close(P, z1[i], zq2)) i_sel = false;
+                int lo, hi;
+                row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation, lo, hi);
+                for (int j = lo; j < hi; j++) {
+                    if (w2[j] == 0.) continue;
+                    DmatGeom g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                    if (!g.in) continue;
+                    cnt_in++;
+                    if (!g.close) cnt_nc++;
+                    kidx[g.B] = 0;
+                    bool sel = i_sel && !g.close;
+                    if (sel) {
+                        const double z = div_rn(add_rn(z1[i], z2[j]), 2.);
+                        if ((P.has_z_min_pairs && z < P.z_min_pairs) ||
+                            (P.has_z_max_pairs && z > P.z_max_pairs)) sel = false;
+                        if (sel && zerr_on && pb2_zerr_close(P, z2[j], zq1)) sel = false;
+                    }
+                    if (sel) aidx[g.A] = 0;
+                }
+            }
+            if (cnt_nc) atomicAdd(&s_cnt[0], cnt_nc);
+            if (cnt_in) atomicAdd(&s_cnt[1], cnt_in);
+        }
+        __syncthreads();
+        if (s_cnt[0] == 0) continue;  // cf.py:570-571
+
+        // compact indices in ascending bin order (np.unique order, cf.py:846-848)
+        if (tid == 0) {
+            int u = 0;
+            for (int x = 0; x < nbm; x++)
+                if (kidx[x] == 0) { kidx[x] = u; klist[u++] = x; }
+            s_U = u;
+            u = 0;
+            for (int x = 0; x < nb; x++)
+                if (aidx[x] == 0) { aidx[x] = u; alist[u++] = x; }
+            s_UA = u;
+        }
+        __syncthreads();
+        const int U = s_U, UA = s_UA;
+
+        // ---------------- per-forest constants (cf.py:577-594)
+        double t1 = 0., t2 = 0.;
+        for (int i = tid; i < n1; i += DM_THREADS) t1 += w1[i];
+        const double sw1 = block_sum(t1, red);
+        for (int j = tid; j < n2; j += DM_THREADS) t2 += w2[j];
+        const double sw2 = block_sum(t2, red);
+        t1 = t2 = 0.;
+        for (int i = tid; i < n1; i += DM_THREADS) t1 += ll1[i] * w1[i];
+        const double mll1 = block_sum(t1, red) / sw1;
+        for (int j = tid; j < n2; j += DM_THREADS) t2 += ll2[j] * w2[j];
+        const double mll2 = block_sum(t2, red) / sw2;
+        t1 = t2 = 0.;
+        for (int i = tid; i < n1; i += DM_THREADS) {
+            const double d = ll1[i] - mll1;
+            dl1[i] = d;
+            t1 += w1[i] * (d * d);
+            f1z[i] = P.redshift_evolution_in_distortion_matrix
+                         ? pow((1. + z1[i]) / (1. + P.z_ref), P.alpha - 1.) : 1.;  // cf.py:680-685
+        }
+        const double swsll1 = block_sum(t1, red);
+        for (int j = tid; j < n2; j += DM_THREADS) {
+            const double d = ll2[j] - mll2;
+            dl2[j] = d;
+            t2 += w2[j] * (d * d);
+            f2z[j] = P.redshift_evolution_in_distortion_matrix
+                         ? pow((1. + z2[j]) / (1. + P.z_ref), P.alpha2 - 1.) : 1.;
+        }
+        const double swsll2 = block_sum(t2, red);
+
+        const int rows = 2 * n1 + 2 * n2 + 4;
+        for (int kc = 0; kc < U; kc += W.cap) {
+            const int Uc = min(W.cap, U - kc);
+            const int Upad = (Uc + DM_TILE - 1) / DM_TILE * DM_TILE;
+            for (int ac = 0; ac < max(UA, 1); ac += W.cap) {
+                const int UAc = min(W.cap, UA - ac);
+                if (UAc <= 0) break;
+                const int UApad = (UAc + DM_TILE - 1) / DM_TILE * DM_TILE;
+                const bool first = (kc == 0 && ac == 0);
+                __syncthreads();
+                for (long long x = tid; x < (long long)rows * UApad; x += DM_THREADS) X[x] = 0.;
+                for (long long x = tid; x < (long long)rows * Upad; x += DM_THREADS) Y[x] = 0.;
+                __syncthreads();
+                double *Xp = X + (long long)(2 * n1 + 2 * n2) * UApad;  // P0, P2, P1, P12
+                double *Yp = Y + (long long)(2 * n1 + 2 * n2) * Upad;   // eta5, eta6, eta7, eta8
+
+                // ---------------- sweep 1: rows of forest 1
+                for (int i = tid; i < n1; i += DM_THREADS) {
+                    if (w1[i] == 0.) continue;
+                    bool i_sel = true;
+                    if (zerr_on && pb2_zerr_close(P, z1[i], zq2)) i_sel = false;
+                    int lo, hi;
+                    row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation,
+                               lo, hi);
+                    const double wi = w1[i], dli = dl1[i], fzi = f1z[i], zi = z1[i];
+                    int cA = -1, cB = -1;
+                    bool cS = false;
+                    double e1 = 0., e3 = 0., q1 = 0., q1d = 0., dg = 0., srp = 0., srt = 0., sz = 0.;
+                    double e5 = 0., e6 = 0., e7 = 0., e8 = 0.;
+                    for (int j = lo; j <= hi; j++) {
+                        DmatGeom g;
+                        g.in = false;
+                        bool sel = false;
+                        double z = 0.;
+                        if (j < hi && w2[j] != 0.) {
+                            g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                            if (g.in) {
+                                z = div_rn(add_rn(zi, z2[j]), 2.);
+                                sel = i_sel && !g.close;
+                                if (sel && ((P.has_z_min_pairs && z < P.z_min_pairs) ||
+                                            (P.has_z_max_pairs && z > P.z_max_pairs))) sel = false;
+                                if (sel && zerr_on && pb2_zerr_close(P, z2[j], zq1)) sel = false;
+                            }
+                        }
+                        const bool brk = (j == hi) || (g.in && (g.A != cA || g.B != cB || sel != cS));
+                        if (brk && cB >= 0) {  // flush the finished segment
+                            const int kb = kidx[cB] - kc;
+                            if (kb >= 0 && kb < Uc) {
+                                Y[(long long)i * Upad + kb] += e1 / sw2;                  // eta1
+                                if (order2 == 1) Y[(long long)(n1 + i) * Upad + kb] += e3 / swsll2;
+                                atomic_add_f64(Yp + 0 * (long long)Upad + kb, e5 / sw1 / sw2);
+                                if (order2 == 1) atomic_add_f64(Yp + 1 * (long long)Upad + kb, e6);
+                                if (order1 == 1) atomic_add_f64(Yp + 2 * (long long)Upad + kb, e7);
+                                if (order1 == 1 && order2 == 1)
+                                    atomic_add_f64(Yp + 3 * (long long)Upad + kb, e8);
+                            }
+                            if (cS) {
+                                const int ka = aidx[cA] - ac;
+                                if (ka >= 0 && ka < UAc) {
+                                    X[(long long)i * UApad + ka] -= wi * q1;
+                                    X[(long long)(n1 + i) * UApad + ka] -= wi * q1d;
+                                    atomic_add_f64(Xp + 0 * (long long)UApad + ka, wi * q1);
+                                    atomic_add_f64(Xp + 1 * (long long)UApad + ka, wi * q1d);
+                                    atomic_add_f64(Xp + 2 * (long long)UApad + ka, wi * dli * q1);
+                                    atomic_add_f64(Xp + 3 * (long long)UApad + ka, wi * dli * q1d);
+                                }
+                                if (first) {
+                                    atomic_add_f64(dmat + (long long)cA * nbm + cB, dg);   // cf.py:873
+                                    atomic_add_f64(weights_dmat + cA, wi * q1);            // cf.py:718
+                                    atomic_add_f64(r_par_eff + cB, srp);                   // cf.py:714
+                                    atomic_add_f64(r_trans_eff + cB, srt);
+                                    atomic_add_f64(z_eff + cB, sz);
+                                    atomic_add_f64(weight_eff + cB, wi * q1);
+                                }
+                            }
+                            e1 = e3 = q1 = q1d = dg = srp = srt = sz = e5 = e6 = e7 = e8 = 0.;
+                        }
+                        if (j == hi || !g.in) continue;
+                        cA = g.A;
+                        cB = g.B;
+                        cS = sel;
+                        const double wj = w2[j], dlj = dl2[j];
+                        const double zf = mul_rn(fzi, f2z[j]);
+                        const double w12 = mul_rn(wi, wj);
+                        e1 += zf * wj;                                   // cf.py:767
+                        e3 += zf * wj * dlj;                             // cf.py:782-787
+                        e5 += zf * w12;                                  // cf.py:775
+                        e6 += zf * wi / sw1 * (wj * dlj / swsll2);       // cf.py:793-802
+                        e7 += zf * wj / sw2 * (wi * dli / swsll1);       // cf.py:818-827
+                        e8 += zf * wi * dli * wj * dlj / swsll1 / swsll2;  // cf.py:835-843
+                        if (sel) {
+                            q1 += wj;
+                            q1d += wj * dlj;
+                            dg += w12 * zf;
+                            srp += w12 * g.rp;
+                            srt += w12 * g.rt;
+                            sz += w12 * z;
+                        }
+                    }
+                }
+
+                // ---------------- sweep 2: columns (pixels of forest 2)
+                for (int j = tid; j < n2; j += DM_THREADS) {
+                    if (w2[j] == 0.) continue;
+                    bool j_sel0 = true;
+                    if (zerr_on && pb2_zerr_close(P, z2[j], zq1)) j_sel0 = false;
+                    const double wj = w2[j], dlj = dl2[j], fzj = f2z[j], zj = z2[j];
+                    int cA = -1, cB = -1;
+                    bool cS = false;
+                    double e2 = 0., e4 = 0., q2 = 0., q2d = 0.;
+                    for (int i = 0; i <= n1; i++) {
+                        DmatGeom g;
+                        g.in = false;
+                        bool sel = false;
+                        if (i < n1 && w1[i] != 0.) {
+                            g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                            if (g.in) {
+                                sel = j_sel0 && !g.close;
+                                if (sel && zerr_on && pb2_zerr_close(P, z1[i], zq2)) sel = false;
+                                if (sel) {
+                                    const double z = div_rn(add_rn(z1[i], zj), 2.);
+                                    if ((P.has_z_min_pairs && z < P.z_min_pairs) ||
+                                        (P.has_z_max_pairs && z > P.z_max_pairs)) sel = false;
+                                }
+                            }
+                        }
+                        const bool brk = (i == n1) || (g.in && (g.A != cA || g.B != cB || sel != cS));
+                        if (brk && cB >= 0) {
+                            const int kb = kidx[cB] - kc;
+                            if (kb >= 0 && kb < Uc) {
+                                Y[(long long)(2 * n1 + j) * Upad + kb] += e2 / sw1;         // eta2
+                                if (order1 == 1)
+                                    Y[(long long)(2 * n1 + n2 + j) * Upad + kb] += e4 / swsll1;
+                            }
+                            if (cS) {
+                                const int ka = aidx[cA] - ac;
+                                if (ka >= 0 && ka < UAc) {
+                                    X[(long long)(2 * n1 + j) * UApad + ka] -= wj * q2;
+                                    X[(long long)(2 * n1 + n2 + j) * UApad + ka] -= wj * q2d;
+                                }
+                            }
+                            e2 = e4 = q2 = q2d = 0.;
+                        }
+                        if (i == n1 || !g.in) continue;
+                        cA = g.A;
+                        cB = g.B;
+                        cS = sel;
+                        const double zf = mul_rn(f1z[i], fzj);
+                        e2 += zf * w1[i];                  // cf.py:771
+                        e4 += zf * w1[i] * dl1[i];         // cf.py:808-813
+                        if (sel) {
+                            q2 += w1[i];
+                            q2d += w1[i] * dl1[i];
+                        }
+                    }
+                }
+                __syncthreads();
+                __threadfence_block();
+
+                // ---------------- contraction  C[a,k] = sum_r X[r,a] Y[r,k]
+                const int ty = tid >> 4, tx = tid & 15;
+                for (int a0 = 0; a0 < UApad; a0 += DM_TILE) {
+                    for (int k0 = 0; k0 < Upad; k0 += DM_TILE) {
+                        double c[4][4];
+#pragma unroll
+                        for (int p = 0; p < 4; p++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) c[p][q] = 0.;
+                        for (int r0 = 0; r0 < rows; r0 += DM_KCH) {
+                            __syncthreads();
+                            for (int x = tid; x < DM_KCH * DM_TILE; x += DM_THREADS) {
+                                const int rr = x / DM_TILE, cc = x % DM_TILE;
+                                const int r = r0 + rr;
+                                Xs[rr][cc] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
+                                Ys[rr][cc] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
+                            }
+                            __syncthreads();
+#pragma unroll
+                            for (int rr = 0; rr < DM_KCH; rr++) {
+                                const double4 xa = *reinterpret_cast<const double4 *>(&Xs[rr][ty * 4]);
+                                const double4 yk = *reinterpret_cast<const double4 *>(&Ys[rr][tx * 4]);
+                                const double xv[4] = {xa.x, xa.y, xa.z, xa.w};
+                                const double yv[4] = {yk.x, yk.y, yk.z, yk.w};
+#pragma unroll
+                                for (int p = 0; p < 4; p++)
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) c[p][q] = fma(xv[p], yv[q], c[p][q]);
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            const int ai = a0 + ty * 4 + p;
+                            if (ai >= UAc) continue;
+                            const long long rowp = (long long)alist[ac + ai] * nbm;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int ki = k0 + tx * 4 + q;
+                                if (ki < Uc && c[p][q] != 0.)
+                                    atomic_add_f64(dmat + rowp + klist[kc + ki], c[p][q]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forest x object: one warp per kept (forest, object) pair
+// ------------------------------------------------------------------------------------------
+
+struct XSeg {
+    int A, B;
+    double e2, e4, q2, q2d;
+};
+
+__global__ void __launch_bounds__(128)
+pb2_dmat_cross_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DmatWork W,
+                      double *__restrict__ weights_dmat, double *__restrict__ dmat,
+                      double *__restrict__ r_par_eff, double *__restrict__ r_trans_eff,
+                      double *__restrict__ z_eff, double *__restrict__ weight_eff)
+{
+    // segment lists live in the per-CTA scratch: [4 warps][seg_cap], seg_cap = max_pix1 + 1
+    // (a forest of n pixels has at most n segments)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int seg_cap = W.rows_max;
+    XSeg *segs = (XSeg *)(W.cta_base + (long long)blockIdx.x * W.cta_stride) + (long long)wid * seg_cap;
+    const int nbm = P.num_model_bins_r_par * P.num_model_bins_r_trans;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(W.count + 1, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= W.count[0]) break;
+        const long long e = W.kept[t];
+        const int k1 = pr.nb_f1[e];
+        const int f1 = pr.f1_index[k1], f2 = pr.nb_f2[e];
+        const long long a = c1.offset[f1];
+        const int n1 = (int)(c1.offset[f1 + 1] - a);
+        const long long q = c2.offset[f2];
+        const double rcq = c2.r_comov[q], dmq = c2.dist_m[q], zq = c2.z[q], wq = c2.weights[q];
+        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        const int order1 = c1.order[f1];
+        const double *rc1 = c1.r_comov + a, *dm1 = c1.dist_m + a, *z1 = c1.z + a;
+        const double *w1 = c1.weights + a, *ll1 = c1.log_lambda + a;
+        if (wq == 0. || n1 == 0) continue;  // xcf.py:516
+
+        // forest constants (xcf.py:475-486), warp reductions
+        double s = 0., sl = 0.;
+        for (int i = lane; i < n1; i += 32) {
+            s += w1[i];
+            sl += ll1[i] * w1[i];
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, m);
+            sl += __shfl_xor_sync(0xffffffffu, sl, m);
+        }
+        const double sw1 = s, mll1 = sl / s;
+        double sq = 0.;
+        for (int i = lane; i < n1; i += 32) {
+            const double d = ll1[i] - mll1;
+            sq += w1[i] * (d * d);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, m);
+        const double swsll1 = sq;
+        const double fzq = P.redshift_evolution_in_distortion_matrix
+                               ? pow((1. + zq) / (1. + P.z_ref), P.alpha2 - 1.) : 1.;  // xcf.py:544-549
+
+        // lane 0 walks the pixels (bins change every few pixels; the cost is in the outer
+        // product below, which all lanes share)
+        int nseg = 0;
+        if (lane == 0) {
+            int cA = -1, cB = -1;
+            bool cS = false;
+            double e2 = 0., e4 = 0., q2 = 0., q2d = 0., dg = 0., srp = 0., srt = 0., sz = 0.;
+            for (int i = 0; i <= n1; i++) {
+                DmatGeom g;
+                g.in = false;
+                bool sel = false;
+                double z = 0.;
+                if (i < n1 && w1[i] != 0.) {
+                    g = dmat_pair(P, rc1[i], dm1[i], rcq, dmq, ch, sh, true, false);
+                    if (g.in) {
+                        z = div_rn(add_rn(z1[i], zq), 2.);
+                        sel = !((P.has_z_min_pairs && z < P.z_min_pairs) ||
+                                (P.has_z_max_pairs && z > P.z_max_pairs));  // xcf.py:523-526
+                    }
+                }
+                const bool brk = (i == n1) || (g.in && (g.A != cA || g.B != cB || sel != cS));
+                if (brk && cB >= 0) {
+                    if (nseg < seg_cap) {
+                        XSeg sgm;
+                        sgm.A = cS ? cA : -1;
+                        sgm.B = cB;
+                        sgm.e2 = e2 / sw1;
+                        sgm.e4 = (order1 == 1) ? e4 / swsll1 : 0.;
+                        sgm.q2 = wq * q2;
+                        sgm.q2d = wq * q2d;
+                        segs[nseg++] = sgm;
+                    }
+                    if (cS) {
+                        atomic_add_f64(dmat + (long long)cA * nbm + cB, dg);  // xcf.py:666
+                        atomic_add_f64(weights_dmat + cA, wq * q2);
+                        atomic_add_f64(r_par_eff + cB, srp);
+                        atomic_add_f64(r_trans_eff + cB, srt);
+                        atomic_add_f64(z_eff + cB, sz);
+                        atomic_add_f64(weight_eff + cB, wq * q2);
+                    }
+                    e2 = e4 = q2 = q2d = dg = srp = srt = sz = 0.;
+                }
+                if (i == n1 || !g.in) continue;
+                cA = g.A;
+                cB = g.B;
+                cS = sel;
+                const double f1 = P.redshift_evolution_in_distortion_matrix
+                                      ? pow((1. + z1[i]) / (1. + P.z_ref), P.alpha - 1.) : 1.;
+                const double zf = mul_rn(f1, fzq);
+                const double dli = ll1[i] - mll1;
+                e2 += zf * w1[i];            // xcf.py:625
+                e4 += zf * w1[i] * dli;      // xcf.py:632-636
+                if (sel) {
+                    const double w12 = mul_rn(w1[i], wq);
+                    q2 += w1[i];
+                    q2d += w1[i] * dli;
+                    dg += zf * w12;
+                    srp += w12 * g.rp;
+                    srt += w12 * g.rt;
+                    sz += w12 * z;
+                }
+            }
+        }
+        nseg = __shfl_sync(0xffffffffu, nseg, 0);
+        __syncwarp();
+        // dmat[A_s, B_t] -= q2_s * e2_t + q2d_s * e4_t   for every selected segment s, segment t
+        const int total = nseg * nseg;
+        for (int x = lane; x < total; x += 32) {
+            const int sidx = x / nseg, tidx = x - sidx * nseg;
+            const XSeg sa = segs[sidx];
+            if (sa.A < 0) continue;
+            const XSeg tb = segs[tidx];
+            const double v = -(sa.q2 * tb.e2 + sa.q2d * tb.e4);
+            if (v != 0.) atomic_add_f64(dmat + (long long)sa.A * nbm + tb.B, v);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static long long auto_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
+{
+    const long long nb = (long long)par->num_bins_r_par * par->num_bins_r_trans;
+    const long long nbm = (long long)par->num_model_bins_r_par * par->num_model_bins_r_trans;
+    const long long rows = 2ll * c1->max_pix + 2ll * c2->max_pix + 4;
+    long long bytes = (2 * nb + 2 * nbm) * 4 + 64;
+    bytes += (2ll * c1->max_pix + 2ll * c2->max_pix) * 8;
+    bytes += 2 * rows * DM_CAP * 8;
+    return (bytes + 255) / 256 * 256;
+}
+
+static const int DM_AUTO_BLOCKS = 148 * 2;
+static const int DM_CROSS_BLOCKS = 148 * 8;
+
 extern "C" {
-int64_t pb2_dmat_scratch_bytes(const pb2_catalog *, const pb2_catalog *, const pb2_params *, int32_t)
+
+int64_t pb2_dmat_scratch_bytes(const pb2_catalog *cat1, const pb2_catalog *cat2,
+                               const pb2_params *par, int32_t cross)
 {
-    return 0;
+    if (!cat1 || !cat2 || !par) return 0;
+    // kept-pair list (worst case: every pair kept) is sized by the caller's pair count at launch;
+    // here: counters + per-CTA areas.  The list itself is appended after them.
+    long long bytes = 256;
+    if (cross)
+        bytes += (long long)DM_CROSS_BLOCKS * (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg));
+    else
+        bytes += (long long)DM_AUTO_BLOCKS * auto_cta_bytes(cat1, cat2, par);
+    return bytes;
 }
-int32_t pb2_dmat_auto(const pb2_catalog *, const pb2_catalog *, const pb2_params *,
-                      const pb2_pairs *, double *, double *, double *, double *, double *,
-                      double *, void *, int64_t, void *)
+
+static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                           const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
+                           double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                           double *d_weight_eff, void *d_scratch, int64_t scratch_bytes,
+                           void *stream, bool cross)
 {
-    pb2_set_error("pb2_dmat_auto: not implemented yet");
-    return PB2_ECONFIG;
+    if (!cat1 || !cat2 || !par || !pairs || !d_dmat || !d_scratch) {
+        pb2_set_error("pb2_dmat: null pointer argument");
+        return PB2_EINVAL;
+    }
+    if (par->ang_correlation) {
+        pb2_set_error("pb2_dmat: ang_correlation has no distortion matrix in the reference");
+        return PB2_ECONFIG;
+    }
+    if (!cat1->log_lambda || (!cross && !cat2->log_lambda)) {
+        pb2_set_error("pb2_dmat: catalogue has no log_lambda");
+        return PB2_EINVAL;
+    }
+    if (pairs->n_pairs <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long fixed = pb2_dmat_scratch_bytes(cat1, cat2, par, cross ? 1 : 0);
+    const long long need = fixed + pairs->n_pairs * 8;
+    if (scratch_bytes < need) {
+        pb2_set_error("pb2_dmat: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, need);
+        return PB2_EINVAL;
+    }
+    DmatWork W;
+    char *p = (char *)d_scratch;
+    W.count = (unsigned long long *)p;
+    W.cta_base = p + 256;
+    W.cta_stride = cross ? (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg))
+                         : auto_cta_bytes(cat1, cat2, par);
+    W.kept = (long long *)(p + fixed);
+    W.rows_max = cross ? (cat1->max_pix + 1) : (2 * cat1->max_pix + 2 * cat2->max_pix + 4);
+    W.cap = DM_CAP;
+    PB2_CUDA(cudaMemsetAsync(W.count, 0, 256, s));
+    pb2_timing_begin(s);
+    dmat_compact_kernel<<<(unsigned)((pairs->n_pairs + 255) / 256), 256, 0, s>>>(*pairs, W);
+    if (cross)
+        pb2_dmat_cross_kernel<<<DM_CROSS_BLOCKS, 128, 0, s>>>(*cat1, *cat2, *par, *pairs, W,
+                                                             d_weights_dmat, d_dmat, d_r_par_eff,
+                                                             d_r_trans_eff, d_z_eff, d_weight_eff);
+    else
+        pb2_dmat_auto_kernel<<<DM_AUTO_BLOCKS, DM_THREADS, 0, s>>>(*cat1, *cat2, *par, *pairs, W,
+                                                                  d_weights_dmat, d_dmat,
+                                                                  d_r_par_eff, d_r_trans_eff,
+                                                                  d_z_eff, d_weight_eff);
+    pb2_count_launch(2);
+    int32_t rc = pb2_check_launch(cross ? "pb2_dmat_cross_kernel" : "pb2_dmat_auto_kernel");
+    pb2_timing_end(s);
+    return rc;
 }
-int32_t pb2_dmat_cross(const pb2_catalog *, const pb2_catalog *, const pb2_params *,
-                       const pb2_pairs *, double *, double *, double *, double *, double *,
-                       double *, void *, int64_t, void *)
+
+int32_t pb2_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                      const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
+                      double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                      double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream)
 {
-    pb2_set_error("pb2_dmat_cross: not implemented yet");
-    return PB2_ECONFIG;
+    return dmat_launch(cat1, cat2, par, pairs, d_weights_dmat, d_dmat, d_r_par_eff, d_r_trans_eff,
+                       d_z_eff, d_weight_eff, d_scratch, scratch_bytes, stream, false);
 }
+
+int32_t pb2_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                       const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
+                       double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                       double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    return dmat_launch(cat1, objs, par, pairs, d_weights_dmat, d_dmat, d_r_par_eff, d_r_trans_eff,
+                       d_z_eff, d_weight_eff, d_scratch, scratch_bytes, stream, true);
 }
+
+}  // extern "C"

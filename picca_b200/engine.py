@@ -178,7 +178,7 @@ class Engine:
         r_par_eff, r_trans_eff, z_eff, weight_eff = z(nbm), z(nbm), z(nbm), z(nbm)
         nbytes = int(self.lib.pb2_dmat_scratch_bytes(
             ctypes.byref(cat1.struct), ctypes.byref(cat2.struct), ctypes.byref(params),
-            ctypes.c_int32(int(cross_obj))))
+            ctypes.c_int32(int(cross_obj)))) + 8 * pairs.n_pairs + 256
         scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
         ps = pairs.struct()
         fn = self.lib.pb2_dmat_cross if cross_obj else self.lib.pb2_dmat_auto

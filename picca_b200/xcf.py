@@ -1,0 +1,232 @@
+"""B200 implementation of the hot path of ``picca.xcf`` behind the reference's module API.
+
+Same module globals (reference py/picca/xcf.py:27-68), same functions, same return tuples:
+
+    fill_neighs(healpixs)                         xcf.py:71-123
+    compute_xi(healpixs) -> 6-tuple               xcf.py:126-220
+    compute_dmat(healpixs) -> 8-tuple             xcf.py:325-424
+    compute_xi_forest_pairs_fast(...)             xcf.py:223-322  (in-place accumulate)
+    compute_dmat_forest_pairs_fast(...)           xcf.py:427-674  (in-place accumulate)
+
+so that picca_xcf.py / picca_xdmat.py run unchanged once this module is importable as
+``picca.xcf``.  All arithmetic runs in the CUDA kernels of libpicca_b200.so; no Numba, no CPU
+fallback.  Globals are read at call time.
+"""
+import sys
+
+import numpy as np
+
+from . import _corr, catalog as _catalog
+from .engine import MODE_XCF, get_engine
+from .forest import Delta as _Delta, QSO as _QSO
+from .params import params_from_module
+
+
+def userprint(*args, **kwds):
+    """reference py/picca/utils.py:20-28"""
+    print(*args, **kwds)
+    sys.stdout.flush()
+
+
+# ---- module globals: names and defaults of reference xcf.py:27-68
+num_bins_r_par = None
+num_bins_r_trans = None
+num_model_bins_r_par = None
+num_model_bins_r_trans = None
+r_par_max = None
+r_par_min = None
+r_trans_max = None
+z_min_pairs = None
+z_max_pairs = None
+ang_max = None
+nside = None
+
+zerr_cut_deg = None
+zerr_cut_kms = None
+
+counter = None
+num_data = None
+
+z_ref = None
+alpha = None
+alpha_obj = None
+lambda_abs = None
+alpha_abs = None
+
+data = None
+objs = None
+
+reject = None
+lock = None
+
+cosmo = None
+rmu_binning = False
+ang_correlation = False
+
+# variables for distortion matrix
+redshift_evolution_in_distortion_matrix = True
+
+# variables used in the wick covariance matrix computation (kept for attribute parity)
+get_variance_1d = {}
+xi_1d = {}
+max_diagram = None
+xi_wick = None
+
+_THIS = sys.modules[__name__]
+_STORE = _corr.NeighbourStore()
+_XI_VARIANT = 0
+
+
+def _catalogs():
+    eng, host1, dev1 = _corr.engine_and_catalog(data, ang_correlation=ang_correlation)
+    _, host2, dev2 = _corr.engine_and_catalog(objs, is_object=True,
+                                              ang_correlation=ang_correlation)
+    return eng, host1, dev1, host2, dev2
+
+
+def fill_neighs(healpixs):
+    """Neighbouring objects of every forest of ``healpixs`` (xcf.py:71-123), incl. the optional
+    quasar-pair zerr cut (:102-115) and the r_par pre-filter (:117-121), on the device."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    index, ranges = _corr.forest_index_of(host1, healpixs)
+    pairs = eng.neighbours(dev1, dev2, params, MODE_XCF, index)
+    if _corr.HOST_ANGLES:
+        _corr.apply_host_angles(pairs, host1, host2)
+    _STORE.put(healpixs, pairs, ranges)
+    for k, f1 in enumerate(index):
+        host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
+
+
+def _pairs_for(healpixs):
+    pairs = _STORE.take(healpixs)
+    if pairs is None:
+        fill_neighs(healpixs)
+        pairs = _STORE.take(healpixs)
+    return pairs
+
+
+def compute_xi(healpixs):
+    """Cross-correlation of the forests of ``healpixs`` with their neighbouring objects
+    (xcf.py:126-220).  Returns (weights, xi, r_par, r_trans, z, num_pairs), normalised per call."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    pairs = _pairs_for(healpixs)
+    out_row = eng.torch.zeros(pairs.n_f1, dtype=eng.torch.int32, device=eng.device)
+    out = eng.xi(dev1, dev2, params, pairs, out_row, 1, cross_obj=True, variant=_XI_VARIANT,
+                 normalise=True)
+    host = out.cpu().numpy()[0]
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in pairs.f1_index.cpu().numpy():
+        setattr(host1.objs[f1], "neighbours", None)  # xcf.py:213
+    _STORE.drop(healpixs)
+    weights, xi, r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in range(5))
+    num_pairs = np.ascontiguousarray(host[5]).view(np.int64)
+    return weights, xi, r_par, r_trans, z, num_pairs
+
+
+def compute_xi_batch(healpixs, normalise=True):
+    """One launch for many HEALPix pixels: row k equals ``compute_xi([healpixs[k]])``."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    pairs = _pairs_for(healpixs)
+    rows = np.concatenate([np.full(host1.first_of(hp)[1] - host1.first_of(hp)[0], k, np.int32)
+                           for k, hp in enumerate(healpixs)]) if healpixs else np.zeros(0, np.int32)
+    out = eng.xi(dev1, dev2, params, pairs, rows, len(healpixs), cross_obj=True,
+                 variant=_XI_VARIANT, normalise=normalise)
+    host = out.cpu().numpy()
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in pairs.f1_index.cpu().numpy():
+        setattr(host1.objs[f1], "neighbours", None)
+    _STORE.drop(healpixs)
+    return host
+
+
+def _single_forest_and_objects(z1, r_comov1, dist_m1, weights1, delta1, log_lambda1, order1, z2,
+                               r_comov2, dist_m2, weights2):
+    d1 = _Delta(1, 0., 0., 0., 1, 0, 1, np.asarray(log_lambda1, dtype=np.float64),
+                np.asarray(weights1, dtype=np.float64), np.asarray(delta1, dtype=np.float64),
+                order1)
+    d1.z, d1.r_comov, d1.dist_m = (np.asarray(z1, dtype=np.float64),
+                                   np.asarray(r_comov1, dtype=np.float64),
+                                   np.asarray(dist_m1, dtype=np.float64))
+    qs = []
+    for k in range(len(z2)):
+        q = _QSO(100 + k, 0., 0., float(z2[k]), 2, 0, 2)
+        q.weights, q.r_comov, q.dist_m = float(weights2[k]), float(r_comov2[k]), float(dist_m2[k])
+        qs.append(q)
+    return d1, qs
+
+
+def _explicit_pairs(eng, ang):
+    from .engine import PairList
+    torch = eng.torch
+    ang = np.ascontiguousarray(ang, dtype=np.float64)
+    m = ang.size
+    i32 = lambda v: torch.as_tensor(np.asarray(v, dtype=np.int32), device=eng.device)
+    f64 = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64), device=eng.device)
+    return PairList(eng, i32([0]), torch.tensor([0, m], dtype=torch.int64, device=eng.device),
+                    i32(np.zeros(m)), i32(np.arange(m)), f64(ang), f64(np.cos(ang / 2)),
+                    f64(np.sin(ang / 2)))
+
+
+def compute_xi_forest_pairs_fast(z1, r_comov1, dist_m1, weights1, delta1, z2, r_comov2, dist_m2,
+                                 weights2, ang, rebin_weight, rebin_xi, rebin_r_par, rebin_r_trans,
+                                 rebin_z, rebin_num_pairs):
+    """One forest against a list of objects, accumulated in place (xcf.py:223-322).  Kept for
+    signature parity; compute_xi does not go through it."""
+    eng = get_engine()
+    d1, qs = _single_forest_and_objects(z1, r_comov1, dist_m1, weights1, delta1,
+                                        np.zeros(len(z1)), 0, z2, r_comov2, dist_m2, weights2)
+    dev1 = eng.device_catalog(_catalog.pack({0: [d1]}), cache=False)
+    dev2 = eng.device_catalog(_catalog.pack({0: qs}, is_object=True), cache=False)
+    params = params_from_module(_THIS, cross=True)
+    pairs = _explicit_pairs(eng, ang)
+    row = eng.torch.zeros(1, dtype=eng.torch.int32, device=eng.device)
+    out = eng.xi(dev1, dev2, params, pairs, row, 1, cross_obj=True,
+                 variant=_XI_VARIANT).cpu().numpy()[0]
+    rebin_weight += out[0]
+    rebin_xi += out[1]
+    rebin_r_par += out[2]
+    rebin_r_trans += out[3]
+    rebin_z += out[4]
+    rebin_num_pairs += out[5].view(np.int64)
+
+
+compute_xi_forest_pairs = compute_xi_forest_pairs_fast
+
+
+def compute_dmat(healpixs):
+    """Distortion matrix of the cross-correlation (xcf.py:325-424).  The --rej draw uses the global
+    legacy NumPy RNG in the reference's order (xcf.py:379); forests whose draw keeps nothing are
+    not counted (xcf.py:380-383).  Returns the reference's 8-tuple."""
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    pairs = _pairs_for(healpixs)
+    f1_index = pairs.f1_index.cpu().numpy()
+    if np.any(host1.arrays["order"][f1_index] < 0):
+        raise RuntimeError("Trying to compute the distortion matrix but "
+                           "order is not defined for the deltas. "
+                           "Check previous warning to solve this issue")  # xcf.py:368-373
+    offset = pairs.host_offset()
+    keep = np.random.rand(int(offset[-1])) > reject  # xcf.py:379, one stream for all forests
+    kept_per_forest = np.add.reduceat(np.append(keep.astype(np.int64), 0), offset[:-1]) \
+        if len(offset) > 1 else np.zeros(0, dtype=np.int64)
+    kept_per_forest = np.where(np.diff(offset) > 0, kept_per_forest, 0)
+    counted = kept_per_forest > 0  # xcf.py:380-383
+    num_pairs = int(np.diff(offset)[counted].sum())
+    num_pairs_used = int(kept_per_forest.sum())
+    pairs.nb_keep = eng.torch.from_numpy(keep.astype(np.uint8)).to(eng.device)
+    res = eng.dmat(dev1, dev2, params, pairs, cross_obj=True)
+    weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = (t.cpu().numpy() for t in res)
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for k, f1 in enumerate(f1_index):
+        if counted[k]:
+            setattr(host1.objs[f1], "neighbours", None)  # xcf.py:409 (skipped forests keep theirs)
+    _STORE.drop(healpixs)
+    return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
+            num_pairs_used)

@@ -1,0 +1,86 @@
+"""GPU parity of the distortion matrix: picca_b200.cf.compute_dmat / xcf.compute_dmat (CUDA)
+against the live reference's golden vectors.  NPALL / NPUSED (pair counts under the --rej draw)
+must be exact; the matrix and the effective quantities within 1e-9 relative (north_star), with an
+absolute floor of 1e-12 x the largest entry for elements that are sums of cancelling terms."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ("weights_dmat", "dmat", "r_par_eff", "r_trans_eff", "z_eff", "weight_eff")
+
+
+def check8(res, gold, prefix):
+    assert [int(res[6]), int(res[7])] == list(gold[prefix + "counts"])
+    for k, n in enumerate(NAMES):
+        want = gold[prefix + n]
+        got = np.asarray(res[k])
+        assert got.shape == want.shape
+        scale = np.abs(want).max()
+        err = np.abs(got - want)
+        tol = 1e-9 * np.abs(want) + 1e-12 * scale
+        assert np.all(err <= tol), "%s%s: max err %.3e (scale %.3e), worst rel %.3e" % (
+            prefix, n, err.max(), scale, (err / np.maximum(np.abs(want), 1e-300))[err > tol].max())
+        assert np.array_equal(got != 0, want != 0) or n != "weights_dmat"
+
+
+@pytest.mark.parametrize("name", sorted(cases.DMAT_CASES))
+def test_dmat_matches_reference_golden(name):
+    from picca_b200 import cf
+    gold = np.load(os.path.join(GOLD, "golden_dmat.npz"))
+    cfg = dict(cases.DMAT_CASES[name])
+    second = cfg.pop("second", False)
+    data, num, z_min, cosmo = cases.dmat_forests()
+    over, z_min2 = dict(cfg), None
+    if second:
+        data2, num2, z_min2, _ = cases.dmat_forests(second=True)
+        over["data2"], over["num_data2"] = data2, num2
+    helpers.configure(cf, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+    hps = sorted(data)
+    cf.fill_neighs(hps)
+    np.random.seed(hps[0])  # picca_dmat.py:36
+    res = cf.compute_dmat(hps)
+    check8(res, gold, "dmat_%s_" % name)
+
+
+@pytest.mark.parametrize("name", sorted(cases.XDMAT_CASES))
+def test_xdmat_matches_reference_golden(name):
+    from picca_b200 import xcf
+    gold = np.load(os.path.join(GOLD, "golden_xdmat.npz"))
+    cfg = cases.XDMAT_CASES[name]
+    data, num, z_min, cosmo = cases.dmat_forests()
+    objs, z_min2 = cases.quasars(cosmo)
+    helpers.configure(xcf, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), objs=objs,
+                      **cfg)
+    hps = sorted(data)
+    xcf.fill_neighs(hps)
+    np.random.seed(hps[0])  # picca_xdmat.py:37
+    res = xcf.compute_dmat(hps)
+    check8(res, gold, "xdmat_%s_" % name)
+
+
+def test_dmat_chunks_sum_like_the_script():
+    """picca_dmat.py sums the 8-tuples of its workers (:494-501): two chunks == one chunk when the
+    same pairs are kept (reject = 0 keeps every pair, no RNG dependence)."""
+    from picca_b200 import cf
+    cfg = dict(cases.DMAT_CASES["default"], reject=0.)
+    data, num, z_min, cosmo = cases.dmat_forests()
+    data = {hp: v[:6] for hp, v in data.items()}
+    helpers.configure(cf, data, num, cases.ang_max_for(cosmo, cfg, z_min), **cfg)
+    hps = sorted(data)
+    cf.fill_neighs(hps)
+    whole = cf.compute_dmat(hps)
+    half = len(hps) // 2
+    cf.fill_neighs(hps[:half])
+    a = cf.compute_dmat(hps[:half])
+    cf.fill_neighs(hps[half:])
+    b = cf.compute_dmat(hps[half:])
+    assert whole[6] == a[6] + b[6] and whole[7] == a[7] + b[7] == whole[6]
+    for k in range(6):
+        s = a[k] + b[k]
+        np.testing.assert_allclose(s, whole[k], rtol=1e-9, atol=1e-12 * np.abs(whole[k]).max())
