@@ -213,6 +213,49 @@ def compute_xi_forest_pairs_fast(z1, r_comov1, dist_m1, weights1, delta1, z_qso_
 compute_xi_forest_pairs = compute_xi_forest_pairs_fast
 
 
+def compute_dmat_forest_pairs_fast(log_lambda1, log_lambda2, r_comov1, r_comov2, dist_m1, dist_m2,
+                                   z1, z2, weights1, weights2, z_qso_1, z_qso_2, ang, weights_dmat,
+                                   dmat, r_par_eff, r_trans_eff, z_eff, weight_eff,
+                                   same_half_plate, order1, order2):
+    """One forest pair of the distortion matrix, accumulated in place into the caller's arrays
+    (cf.py:520-887; ``dmat`` is the flat [nb * nbm] array of cf.py:410-415).  Kept for signature
+    parity; compute_dmat does not go through it."""
+    from .engine import PairList
+    eng = get_engine()
+    torch = eng.torch
+
+    def one(ll, z, rc, dm, w, zq, plate, order):
+        d = _Delta(1, 0., 0., zq, plate, 0, 1, np.asarray(ll, dtype=np.float64),
+                   np.asarray(w, dtype=np.float64), np.zeros(len(z)), int(order))
+        d.z, d.r_comov, d.dist_m = (np.asarray(z, dtype=np.float64),
+                                    np.asarray(rc, dtype=np.float64),
+                                    np.asarray(dm, dtype=np.float64))
+        return d
+
+    d1 = one(log_lambda1, z1, r_comov1, dist_m1, weights1, z_qso_1, 1, order1)
+    d2 = one(log_lambda2, z2, r_comov2, dist_m2, weights2, z_qso_2, 1 if same_half_plate else 2,
+             order2)
+    dev1 = eng.device_catalog(_catalog.pack({0: [d1]}), cache=False)
+    dev2 = eng.device_catalog(_catalog.pack({0: [d2]}), cache=False)
+    params = params_from_module(_THIS)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=eng.device)
+    f64 = lambda v: torch.tensor(v, dtype=torch.float64, device=eng.device)
+    ang = float(ang)
+    pairs = PairList(eng, i32([0]), torch.tensor([0, 1], dtype=torch.int64, device=eng.device),
+                     i32([0]), i32([0]), f64([ang]), f64([np.cos(ang / 2)]),
+                     f64([np.sin(ang / 2)]))
+    res = [t.cpu().numpy() for t in eng.dmat(dev1, dev2, params, pairs)]
+    weights_dmat += res[0]
+    dmat += res[1].reshape(dmat.shape)
+    r_par_eff += res[2]
+    r_trans_eff += res[3]
+    z_eff += res[4]
+    weight_eff += res[5]
+
+
+compute_dmat_forest_pairs = compute_dmat_forest_pairs_fast
+
+
 def compute_dmat(healpixs):
     """Distortion matrix of the forests of ``healpixs`` (cf.py:390-517).  The --rej draw uses the
     global legacy NumPy RNG in the reference's order (cf.py:444), so results match the reference

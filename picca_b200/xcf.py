@@ -199,6 +199,30 @@ def compute_xi_forest_pairs_fast(z1, r_comov1, dist_m1, weights1, delta1, z2, r_
 compute_xi_forest_pairs = compute_xi_forest_pairs_fast
 
 
+def compute_dmat_forest_pairs_fast(log_lambda1, r_comov1, dist_m1, z1, weights1, r_comov2, dist_m2,
+                                   z2, weights2, ang, weights_dmat, dmat, r_par_eff, r_trans_eff,
+                                   z_eff, weight_eff, order1):
+    """One forest against its kept objects, accumulated in place (xcf.py:427-674; ``dmat`` is the
+    flat [nb * nbm] array).  Kept for signature parity; compute_dmat does not go through it."""
+    eng = get_engine()
+    d1, qs = _single_forest_and_objects(z1, r_comov1, dist_m1, weights1, np.zeros(len(z1)),
+                                        log_lambda1, int(order1), z2, r_comov2, dist_m2, weights2)
+    dev1 = eng.device_catalog(_catalog.pack({0: [d1]}), cache=False)
+    dev2 = eng.device_catalog(_catalog.pack({0: qs}, is_object=True), cache=False)
+    params = params_from_module(_THIS, cross=True)
+    pairs = _explicit_pairs(eng, ang)
+    res = [t.cpu().numpy() for t in eng.dmat(dev1, dev2, params, pairs, cross_obj=True)]
+    weights_dmat += res[0]
+    dmat += res[1].reshape(dmat.shape)
+    r_par_eff += res[2]
+    r_trans_eff += res[3]
+    z_eff += res[4]
+    weight_eff += res[5]
+
+
+compute_dmat_forest_pairs = compute_dmat_forest_pairs_fast
+
+
 def compute_dmat(healpixs):
     """Distortion matrix of the cross-correlation (xcf.py:325-424).  The --rej draw uses the global
     legacy NumPy RNG in the reference's order (xcf.py:379); forests whose draw keeps nothing are

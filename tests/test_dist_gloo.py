@@ -1,0 +1,66 @@
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic -- LPT partition of HEALPix pixels,
+gather of per-pixel blocks to rank 0, sum-reduction of the distortion-matrix accumulators."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from picca_b200 import catalog, dist as pdist
+from tests import helpers
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data, num, z_min, _, cosmo = helpers.small_sample(n=120, seed=7, max_pix=40)
+    host = catalog.pack(data)
+    work = pdist.estimate_work(host, host, 0.02)
+    parts = pdist.lpt_partition(work, world)
+    mine = parts[rank]
+    nb = 9
+    # stand-in for the per-pixel blocks a rank's GPU would produce: a function of the pixel index
+    local = torch.stack([torch.full((6, nb), float(k + 1), dtype=torch.float64) for k in mine]) \
+        if len(mine) else torch.zeros((0, 6, nb), dtype=torch.float64)
+    full = pdist.gather_rows(local, mine, len(host.healpixs))
+    dm = torch.full((4, 5), float(rank + 1), dtype=torch.float64)
+    pdist.allreduce_dmat([dm])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "full.npy"), full.numpy())
+        np.save(os.path.join(out_dir, "dm.npy"), dm.numpy())
+        np.save(os.path.join(out_dir, "loads.npy"),
+                np.array([work[p].sum() for p in parts]))
+    else:
+        assert full is None
+    dist.destroy_process_group()
+
+
+def test_partition_gather_and_reduce_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    full = np.load(tmp_path / "full.npy")
+    n_hp = full.shape[0]
+    assert np.array_equal(full[:, 0, 0], np.arange(1, n_hp + 1, dtype=np.float64))
+    assert np.all(np.load(tmp_path / "dm.npy") == 3.0)
+    loads = np.load(tmp_path / "loads.npy")
+    assert loads.max() / loads.mean() < 1.35  # LPT keeps the shards balanced
+
+
+def test_lpt_is_a_partition_and_balanced():
+    rng = np.random.default_rng(0)
+    work = rng.pareto(1.5, 500) + 0.1
+    parts = pdist.lpt_partition(work, 8)
+    allidx = np.sort(np.concatenate(parts))
+    assert np.array_equal(allidx, np.arange(500))
+    loads = np.array([work[p].sum() for p in parts])
+    assert loads.max() <= loads.mean() + work.max()

@@ -1,0 +1,72 @@
+"""CPU, this container only: the overlay makes the reference's UNMODIFIED scripts bind the B200
+modules as picca.cf / picca.xcf while everything else stays the reference's, and the product
+fails loudly (no CPU fallback) when no CUDA device is present."""
+import importlib
+import sys
+
+import pytest
+
+from tests.refharness import shims
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not shims.reference_available(), reason="needs /root/reference")]
+
+
+@pytest.fixture()
+def overlay_on():
+    shims.install()
+    from picca_b200 import overlay
+    saved = {k: v for k, v in sys.modules.items() if k == "picca" or k.startswith("picca.")}
+    saved_path = list(sys.path)
+    overlay.activate(shims.REFERENCE_PY)
+    yield
+    for name in [m for m in sys.modules if m == "picca" or m.startswith("picca.")]:
+        del sys.modules[name]
+    sys.modules.update(saved)
+    sys.path[:] = saved_path
+
+
+def test_scripts_bind_b200_modules(overlay_on):
+    import picca_b200.cf
+    import picca_b200.xcf
+    cf_script = importlib.import_module("picca.bin.picca_cf")
+    dmat_script = importlib.import_module("picca.bin.picca_dmat")
+    xcf_script = importlib.import_module("picca.bin.picca_xcf")
+    xdmat_script = importlib.import_module("picca.bin.picca_xdmat")
+    assert cf_script.cf is picca_b200.cf and dmat_script.cf is picca_b200.cf
+    assert xcf_script.xcf is picca_b200.xcf and xdmat_script.xcf is picca_b200.xcf
+    import picca.io
+    import picca.constants
+    assert picca.io.__file__.startswith(shims.REFERENCE_PY)
+    assert picca.constants.__file__.startswith(shims.REFERENCE_PY)
+    # reload (used by the reference's tests, test_3_cor.py:233) keeps working
+    again = importlib.reload(sys.modules["picca.cf"])
+    assert again.compute_xi is not None
+
+
+def test_exports_every_global_and_function_of_the_reference(overlay_on):
+    """every module global of reference cf.py:28-79 / xcf.py:27-68 and the hot-path functions"""
+    import ast
+    import picca_b200.cf
+    import picca_b200.xcf
+    for name, mod in (("cf", picca_b200.cf), ("xcf", picca_b200.xcf)):
+        tree = ast.parse(open(shims.REFERENCE_PY + "/picca/%s.py" % name).read())
+        for node in tree.body:
+            if isinstance(node, ast.Assign):
+                for tgt in node.targets:
+                    assert hasattr(mod, tgt.id), (name, tgt.id)
+        for fn in ("fill_neighs", "compute_xi", "compute_dmat", "compute_xi_forest_pairs_fast",
+                   "compute_dmat_forest_pairs_fast"):
+            assert callable(getattr(mod, fn)), (name, fn)
+
+
+def test_product_fails_loudly_without_cuda(overlay_on):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import picca_b200.cf as cf
+    from tests import helpers
+    data, num, z_min, _, cosmo = helpers.small_sample(n=20, seed=2, max_pix=30)
+    helpers.configure(cf, data, num, 0.01)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cf.fill_neighs(sorted(data)[:1])
