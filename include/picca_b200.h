@@ -134,8 +134,9 @@ int32_t pb2_neigh_fill(const pb2_catalog *cat1, const pb2_catalog *cat2, const p
  * d_out is [n_rows][6][np*nt]: un-normalised sums of weight, xi, r_par, r_trans, z (fp64) and
  * num_pairs (int64 stored in the same 8-byte slots); it is accumulated into (caller zeroes it).
  * d_out_row[k] is the output row of f1_index[k].  The per-call normalisation of cf.py:242-246
- * is pb2_xi_normalise.  `variant`: 0 = tiled diagonal-sweep kernel (product), 1 = brute-force
- * validation kernel (same results, used by tests to cross-check). */
+ * is pb2_xi_normalise.  `variant`: 0 = product (diagonal-sweep kernel; a specialised instance for
+ * the standard binning without per-pair cuts, the general one otherwise), 1 = brute-force
+ * validation kernel, 2 = force the general diagonal-sweep kernel (same results; tests). */
 int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
                     const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                     double *d_out, int32_t variant, void *stream);

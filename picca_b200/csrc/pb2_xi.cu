@@ -498,6 +498,20 @@ static int32_t launch_tiled(const pb2_catalog *c1, const pb2_catalog *c2, const 
     return pb2_check_launch("pb2_xi_auto_tiled");
 }
 
+int32_t pb2_launch_xi_fast(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
+                           const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
+                           cudaStream_t s);
+
+// the specialised kernel (pb2_xi_fast.cu) covers the standard binning without per-pair cuts
+static bool fast_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
+{
+    return !par->rmu_binning && !par->ang_correlation && c1->sorted && c2->sorted &&
+           !par->has_z_min_pairs && !par->has_z_max_pairs && !par->has_zerr_cut &&
+           !par->remove_same_half_plate_close_pairs && par->num_bins_r_par <= 4096 &&
+           par->num_bins_r_trans <= 4096 && par->r_par_max > par->r_par_min &&
+           par->r_trans_max > 0.;
+}
+
 extern "C" {
 
 int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
@@ -520,6 +534,8 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
                                                            d_out);
         pb2_count_launch(1);
         rc = pb2_check_launch("pb2_xi_auto_brute");
+    } else if (variant == 0 && fast_eligible(cat1, cat2, par)) {
+        rc = pb2_launch_xi_fast(cat1, cat2, par, pairs, d_out_row, d_out, s);
     } else {
         rc = launch_tiled<2>(cat1, cat2, par, pairs, d_out_row, d_out, s);
     }

@@ -1,2 +1,2 @@
 set -x
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pb2_xi_auto_tiled -c 1 -o gpurun_out/prof_xi_r1b python scripts/perf_probe.py --n 1200 --side 7.6 --brute 0 --reps 1 2>&1 | tail -3
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KERNEL:-pb2_xi_auto} -c 1 -o gpurun_out/${OUT:-prof} python scripts/perf_probe.py --n 1200 --side 7.6 --brute 0 --reps 1 2>&1 | tail -3
