@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 4
+#define PB2_ABI_VERSION 5
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
@@ -75,6 +75,11 @@ typedef struct pb2_catalog {
     const double *delta_w;    /* Delta.delta * Delta.weights, 0 where weights == 0 */
     const double *z_w;        /* Delta.z * Delta.weights */
     const double *log_lambda; /* Delta.log_lambda (distortion matrix only; may be NULL) */
+    /* interleaved-by-2 copies used by the diagonal-lane xi kernel: pixel j of a line of sight
+     * with n pixels sits at perm_offset[los] + (j & 1) * S + (j >> 1), S = (n + 1) / 2; padding
+     * slots hold r_comov = -1e300 and zeros elsewhere */
+    const int64_t *perm_offset;  /* [n_los+1] */
+    const double *r_comov_p, *dist_m_p, *z_p, *weights_p, *delta_w_p;
     /* per line of sight */
     const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;
     const int64_t *thingid, *plate, *fiberid;
@@ -134,9 +139,10 @@ int32_t pb2_neigh_fill(const pb2_catalog *cat1, const pb2_catalog *cat2, const p
  * d_out is [n_rows][6][np*nt]: un-normalised sums of weight, xi, r_par, r_trans, z (fp64) and
  * num_pairs (int64 stored in the same 8-byte slots); it is accumulated into (caller zeroes it).
  * d_out_row[k] is the output row of f1_index[k].  The per-call normalisation of cf.py:242-246
- * is pb2_xi_normalise.  `variant`: 0 = product (diagonal-sweep kernel; a specialised instance for
- * the standard binning without per-pair cuts, the general one otherwise), 1 = brute-force
- * validation kernel, 2 = force the general diagonal-sweep kernel (same results; tests). */
+ * is pb2_xi_normalise.  `variant`: 0 = product (diagonal-lane kernel for the standard binning
+ * without per-pair cuts, the general row-tile kernel otherwise), 1 = brute-force validation
+ * kernel, 2 = force the general row-tile kernel, 3 = force the specialised row-tile kernel
+ * (same results; used by tests and for comparison). */
 int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
                     const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                     double *d_out, int32_t variant, void *stream);

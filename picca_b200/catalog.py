@@ -14,6 +14,7 @@ import numpy as np
 from . import _lib
 
 _PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
+_PERM_FIELDS = ("r_comov_p", "dist_m_p", "z_p", "weights_p", "delta_w_p")
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
 _LOS_I64 = ("thingid", "plate", "fiberid")
 
@@ -142,6 +143,26 @@ def pack(data, is_object=False, ang_correlation=False):
     lengths = np.diff(offset)
     cat.max_pix = int(lengths.max()) if n else 0
 
+    # interleaved-by-2 copies of the column fields (diagonal-lane xi kernel): pixel j of a forest
+    # of n pixels -> perm_offset + (j & 1) * S + (j >> 1), S = ceil(n / 2)
+    stride = (lengths + 1) // 2
+    perm_offset = np.zeros(n + 1, dtype=np.int64)
+    perm_offset[1:] = np.cumsum(2 * stride)
+    A["perm_offset"] = perm_offset
+    total = int(perm_offset[-1])
+    if cat.n_pix:
+        los = np.repeat(np.arange(n, dtype=np.int64), lengths)
+        j = np.arange(cat.n_pix, dtype=np.int64) - offset[:-1][los]
+        pos = perm_offset[:-1][los] + (j & 1) * stride[los] + (j >> 1)
+    else:
+        pos = np.zeros(0, dtype=np.int64)
+    for name in ("r_comov", "dist_m", "z", "weights", "delta_w"):
+        out = np.zeros(total, dtype=np.float64)
+        if name == "r_comov":
+            out[:] = -1e300
+        out[pos] = A[name]
+        A[name + "_p"] = out
+
     # sortedness inside each forest (enables the column windows of the pair kernel)
     cat.sorted = 1
     if not is_object and cat.n_pix > 1:
@@ -195,7 +216,7 @@ def build_struct(host, tensors):
     c = _lib.Catalog()
     c.n_los = host.n_los
     c.n_pix = host.n_pix
-    for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
+    for name in ("offset", "perm_offset") + _PIXEL_FIELDS + _PERM_FIELDS + _LOS_F64 + _LOS_I64 + (
             "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
         setattr(c, name, tensors[name].data_ptr())
     c.n_hp = len(host.healpixs)

@@ -502,7 +502,12 @@ int32_t pb2_launch_xi_fast(const pb2_catalog *c1, const pb2_catalog *c2, const p
                            const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
                            cudaStream_t s);
 
-// the specialised kernel (pb2_xi_fast.cu) covers the standard binning without per-pair cuts
+int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
+                           const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
+                           cudaStream_t s);
+
+// the specialised kernels (pb2_xi_diag.cu, pb2_xi_fast.cu) cover the standard binning without
+// per-pair cuts
 static bool fast_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
 {
     return !par->rmu_binning && !par->ang_correlation && c1->sorted && c2->sorted &&
@@ -534,7 +539,9 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
                                                            d_out);
         pb2_count_launch(1);
         rc = pb2_check_launch("pb2_xi_auto_brute");
-    } else if (variant == 0 && fast_eligible(cat1, cat2, par)) {
+    } else if (variant == 0 && fast_eligible(cat1, cat2, par) && cat2->r_comov_p != nullptr) {
+        rc = pb2_launch_xi_diag(cat1, cat2, par, pairs, d_out_row, d_out, s);
+    } else if ((variant == 0 || variant == 3) && fast_eligible(cat1, cat2, par)) {
         rc = pb2_launch_xi_fast(cat1, cat2, par, pairs, d_out_row, d_out, s);
     } else {
         rc = launch_tiled<2>(cat1, cat2, par, pairs, d_out_row, d_out, s);

@@ -33,7 +33,7 @@ print("fp64 peak %.3e op/s" % peak)
 hps = sorted(data)
 eng.lib.pb2_set_timing(1)
 res = {}
-for variant in ([0, 1] if args.brute else [0]):
+for variant in ([0, 3, 1] if args.brute == 1 else ([0, 3] if args.brute == 2 else [0])):
     cf._XI_VARIANT = variant
     for rep in range(args.reps):
         torch.cuda.synchronize()
@@ -51,7 +51,7 @@ for variant in ([0, 1] if args.brute else [0]):
                                                  npairs / (kms * 1e-3),
                                                  30. * npairs / (kms * 1e-3) / peak))
     res[variant] = out
-if args.brute:
+if args.brute == 1:
     a, b = res[0], res[1]
     print("counts equal:", np.array_equal(a[:, 5].view(np.int64), b[:, 5].view(np.int64)))
     for k in range(5):

@@ -15,7 +15,7 @@ def sample():
     return data, num, ang_max
 
 
-@pytest.mark.parametrize("variant", [1, 2, 0])
+@pytest.mark.parametrize("variant", [1, 2, 3, 0])
 @pytest.mark.parametrize("over", [
     dict(),
     dict(remove_same_half_plate_close_pairs=True),
