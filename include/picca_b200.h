@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 5
+#define PB2_ABI_VERSION 6
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
@@ -79,7 +79,12 @@ typedef struct pb2_catalog {
      * with n pixels sits at perm_offset[los] + (j & 1) * S + (j >> 1), S = (n + 1) / 2; padding
      * slots hold r_comov = -1e300 and zeros elsewhere */
     const int64_t *perm_offset;  /* [n_los+1] */
-    const double *r_comov_p, *dist_m_p, *z_p, *weights_p, *delta_w_p;
+    const double *z_p;           /* z, interleaved */
+    const double *rcdm_p;        /* (r_comov, dist_m) pairs, interleaved, 16-byte elements */
+    const double *wdw_p;         /* (weights, delta_w) pairs, interleaved, 16-byte elements */
+    /* natural-order packed pairs for the uniform row loads of the same kernel */
+    const double *rcdm;          /* (r_comov, dist_m) per pixel */
+    const double *wdw;           /* (weights, delta_w) per pixel */
     /* per line of sight */
     const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;
     const int64_t *thingid, *plate, *fiberid;

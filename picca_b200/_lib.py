@@ -57,11 +57,11 @@ class Catalog(ctypes.Structure):
         ("z_w", c_void_p),
         ("log_lambda", c_void_p),
         ("perm_offset", c_void_p),
-        ("r_comov_p", c_void_p),
-        ("dist_m_p", c_void_p),
         ("z_p", c_void_p),
-        ("weights_p", c_void_p),
-        ("delta_w_p", c_void_p),
+        ("rcdm_p", c_void_p),
+        ("wdw_p", c_void_p),
+        ("rcdm", c_void_p),
+        ("wdw", c_void_p),
         ("x_cart", c_void_p),
         ("y_cart", c_void_p),
         ("z_cart", c_void_p),
@@ -110,7 +110,7 @@ EXPORTS = [
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 def lib():

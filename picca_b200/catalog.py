@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 
 _PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
-_PERM_FIELDS = ("r_comov_p", "dist_m_p", "z_p", "weights_p", "delta_w_p")
+_PERM_FIELDS = ("z_p", "rcdm_p", "wdw_p", "rcdm", "wdw")
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
 _LOS_I64 = ("thingid", "plate", "fiberid")
 
@@ -156,12 +156,21 @@ def pack(data, is_object=False, ang_correlation=False):
         pos = perm_offset[:-1][los] + (j & 1) * stride[los] + (j >> 1)
     else:
         pos = np.zeros(0, dtype=np.int64)
-    for name in ("r_comov", "dist_m", "z", "weights", "delta_w"):
-        out = np.zeros(total, dtype=np.float64)
-        if name == "r_comov":
-            out[:] = -1e300
-        out[pos] = A[name]
-        A[name + "_p"] = out
+    zp = np.zeros(total, dtype=np.float64)
+    zp[pos] = A["z"]
+    A["z_p"] = zp
+    rcdm_p = np.zeros((total, 2), dtype=np.float64)
+    rcdm_p[:, 0] = -1e300  # padding slots: the kernel's "column outside the forest" marker
+    rcdm_p[pos, 0] = A["r_comov"]
+    rcdm_p[pos, 1] = A["dist_m"]
+    A["rcdm_p"] = rcdm_p.reshape(-1)
+    wdw_p = np.zeros((total, 2), dtype=np.float64)
+    wdw_p[pos, 0] = A["weights"]
+    wdw_p[pos, 1] = A["delta_w"]
+    A["wdw_p"] = wdw_p.reshape(-1)
+    # natural-order packed pairs (one 128-bit uniform load per pair of fields for the rows)
+    A["rcdm"] = np.ascontiguousarray(np.stack([A["r_comov"], A["dist_m"]], axis=1)).reshape(-1)
+    A["wdw"] = np.ascontiguousarray(np.stack([A["weights"], A["delta_w"]], axis=1)).reshape(-1)
 
     # sortedness inside each forest (enables the column windows of the pair kernel)
     cat.sorted = 1

@@ -539,7 +539,7 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
                                                            d_out);
         pb2_count_launch(1);
         rc = pb2_check_launch("pb2_xi_auto_brute");
-    } else if (variant == 0 && fast_eligible(cat1, cat2, par) && cat2->r_comov_p != nullptr) {
+    } else if (variant == 0 && fast_eligible(cat1, cat2, par) && cat2->rcdm_p != nullptr && cat1->rcdm != nullptr) {
         rc = pb2_launch_xi_diag(cat1, cat2, par, pairs, d_out_row, d_out, s);
     } else if ((variant == 0 || variant == 3) && fast_eligible(cat1, cat2, par)) {
         rc = pb2_launch_xi_fast(cat1, cat2, par, pairs, d_out_row, d_out, s);

@@ -61,11 +61,15 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
 }
 
 // ---- per-diagonal state on named scalars (r = 0, 1)
+// The five sums and the count are RUNNING totals over the whole diagonal (never cleared, also
+// advanced while the diagonal is in a dead run); a run's contribution is total - snapshot, the
+// snapshot being taken when the run starts.  This keeps the per-pair path free of predication
+// and the run-change path free of writes to the accumulators.
 #define DG_DECL(r)                                                                       \
     double lo_##r = 1e299, hi_##r = inf, thi_##r = inf; /* dead run: column outside */   \
     double sw_##r = 0., sxi_##r = 0., srp_##r = 0., srt_##r = 0., sz_##r = 0.;           \
-    int bp_##r = -1, bt_##r = 0, cnt_##r = 0; /* bp < 0: dead run */                     \
-    bool fresh_##r = false; /* the run was just flushed: the next pair overwrites the sums */
+    double qw_##r = 0., qxi_##r = 0., qrp_##r = 0., qrt_##r = 0., qz_##r = 0.;           \
+    int bp_##r = -1, bt_##r = 0, cnt_##r = 0, qcnt_##r = 0; /* bp < 0: dead run */
 
 #define DG_COLS(c)  double c##_rc, c##_dm, c##_w, c##_dw, c##_z;
 
@@ -77,11 +81,13 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
         c##_dm = c##_w = c##_dw = c##_z = 0.;                                            \
         if (jj >= 0 && jj < n2) {                                                        \
             const int pos = ((jb) & 1) * S2 + ((jb) >> 1) + lane;                        \
-            c##_rc = __ldg(p_rc2 + pos);                                                 \
-            c##_dm = __ldg(p_dm2 + pos);                                                 \
-            c##_w = __ldg(p_w2 + pos);                                                   \
-            c##_dw = __ldg(p_dw2 + pos);                                                 \
+            const double2 a2 = __ldg(p_rcdm2 + pos);                                     \
+            const double2 b2 = __ldg(p_wdw2 + pos);                                      \
             c##_z = __ldg(p_z2 + pos);                                                   \
+            c##_rc = a2.x;                                                               \
+            c##_dm = a2.y;                                                               \
+            c##_w = b2.x;                                                                \
+            c##_dw = b2.y;                                                               \
         }                                                                                \
     }
 
@@ -91,20 +97,26 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
     const double t_##r = add_rn(dm1, c##_dm);                                            \
     const bool p_##r = (v_##r >= lo_##r) && (v_##r < hi_##r) && (t_##r < thi_##r);
 
-// add the finished run to its bin.  The sums are NOT cleared here: `fresh` makes the next pair
-// overwrite them, so that the (rarely taken) run-change path never redefines the accumulators
-// and the compiler keeps them in place.
+// opaque copy: keeps the compiler from turning the snapshot into a loop-carried register rotation
+#define DG_SNAP(q, v) asm volatile("mov.f64 %0, %1;" : "=d"(q) : "d"(v));
+
+// add the finished run (totals - snapshot) to its bin and take the snapshot for the next run
 #define DG_RED(r)                                                                        \
-    if (bp_##r >= 0 && !fresh_##r && cnt_##r > 0) {                                      \
+    if (bp_##r >= 0 && cnt_##r > qcnt_##r) {                                             \
         double *const dst = orow + (bt_##r + nt_i * bp_##r);                             \
-        atomic_add_f64(dst + 0 * (size_t)nb, sw_##r);                                    \
-        atomic_add_f64(dst + 1 * (size_t)nb, sxi_##r);                                   \
-        atomic_add_f64(dst + 2 * (size_t)nb, srp_##r * ch);                              \
-        atomic_add_f64(dst + 3 * (size_t)nb, srt_##r * sh);                              \
-        atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * sz_##r);                              \
-        atomic_add_i64(dst + 5 * (size_t)nb, (long long)cnt_##r);                        \
+        atomic_add_f64(dst + 0 * (size_t)nb, sw_##r - qw_##r);                           \
+        atomic_add_f64(dst + 1 * (size_t)nb, sxi_##r - qxi_##r);                         \
+        atomic_add_f64(dst + 2 * (size_t)nb, (srp_##r - qrp_##r) * ch);                  \
+        atomic_add_f64(dst + 3 * (size_t)nb, (srt_##r - qrt_##r) * sh);                  \
+        atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * (sz_##r - qz_##r));                   \
+        atomic_add_i64(dst + 5 * (size_t)nb, (long long)(cnt_##r - qcnt_##r));           \
     }                                                                                    \
-    fresh_##r = true;
+    DG_SNAP(qw_##r, sw_##r)                                                              \
+    DG_SNAP(qxi_##r, sxi_##r)                                                            \
+    DG_SNAP(qrp_##r, srp_##r)                                                            \
+    DG_SNAP(qrt_##r, srt_##r)                                                            \
+    DG_SNAP(qz_##r, sz_##r)                                                              \
+    asm volatile("mov.s32 %0, %1;" : "=r"(qcnt_##r) : "r"(cnt_##r));
 
 // The pair left its run.  Common case, handled first: a live run steps into the ADJACENT r_par
 // bin (or the next r_trans bin) and the pair lies outside the guard band of the new bin, which
@@ -195,35 +207,24 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
     }
 
 #define DG_ACC(r, c)                                                                     \
-    if (bp_##r >= 0) {                                                                  \
+    {                                                                                    \
         const double w12 = mul_rn(w1, c##_w);                                            \
-        const double zz = add_rn(z1, c##_z);                                             \
-        const int one = row_ok & ((__double2hiint(c##_w) != 0) ? 1 : 0);                 \
-        if (fresh_##r) {                                                                 \
-            sw_##r = w12;                                                                \
-            sxi_##r = dw1 * c##_dw;                                                      \
-            srp_##r = v_##r * w12;                                                       \
-            srt_##r = t_##r * w12;                                                       \
-            sz_##r = zz * w12;                                                           \
-            cnt_##r = one;                                                               \
-            fresh_##r = false;                                                           \
-        } else {                                                                         \
-            sw_##r += w12;                                                               \
-            sxi_##r = fma(dw1, c##_dw, sxi_##r);                                         \
-            srp_##r = fma(v_##r, w12, srp_##r);                                          \
-            srt_##r = fma(t_##r, w12, srt_##r);                                          \
-            sz_##r = fma(zz, w12, sz_##r);                                               \
-            cnt_##r += one;                                                              \
-        }                                                                                \
+        sw_##r += w12;                                                                   \
+        sxi_##r = fma(dw1, c##_dw, sxi_##r);                                             \
+        srp_##r = fma(v_##r, w12, srp_##r);                                              \
+        srt_##r = fma(t_##r, w12, srt_##r);                                              \
+        sz_##r = fma(add_rn(z1, c##_z), w12, sz_##r);                                    \
+        if (row_ok && __double2hiint(c##_w) != 0) cnt_##r += 1;                          \
     }
 
 // row ii against the lane's two diagonals, which meet columns ca (d = D0 + 2 lane) and cb (+1)
 #define DG_STEP(ii, ca, cb)                                                              \
     {                                                                                    \
-        const double rc1 = __ldg(p_rc1 + (ii)), dm1 = __ldg(p_dm1 + (ii));               \
-        const double w1 = __ldg(p_w1 + (ii)), dw1 = __ldg(p_dw1 + (ii));                 \
+        const double2 ra = __ldg(p_rcdm1 + (ii));                                        \
+        const double2 rb = __ldg(p_wdw1 + (ii));                                         \
         const double z1 = __ldg(p_z1 + (ii));                                            \
-        const int row_ok = (w1 != 0.) ? 1 : 0;                                           \
+        const double rc1 = ra.x, dm1 = ra.y, w1 = rb.x, dw1 = rb.y;                      \
+        const bool row_ok = (w1 != 0.);                                                  \
         DG_TEST(0, ca)                                                                   \
         DG_TEST(1, cb)                                                                   \
         if (__any_sync(0xffffffffu, !(p_0 && p_1))) {                                    \
@@ -272,8 +273,6 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         const double *__restrict__ p_rc1 = c1.r_comov + a;
         const double *__restrict__ p_dm1 = c1.dist_m + a;
         const double *__restrict__ p_z1 = c1.z + a;
-        const double *__restrict__ p_w1 = c1.weights + a;
-        const double *__restrict__ p_dw1 = c1.delta_w + a;
 
         // ---- diagonal range of the forest pair and row range of this block (supersets).
         // lane = segment of L consecutive rows; columns of row i in range: [jlo(i), jhi(i))
@@ -314,11 +313,11 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         if (ibeg >= iend) continue;
 
         const long long pb = c2.perm_offset[f2];
-        const double *__restrict__ p_rc2 = c2.r_comov_p + pb;
-        const double *__restrict__ p_dm2 = c2.dist_m_p + pb;
-        const double *__restrict__ p_w2 = c2.weights_p + pb;
-        const double *__restrict__ p_dw2 = c2.delta_w_p + pb;
+        const double2 *__restrict__ p_rcdm2 = reinterpret_cast<const double2 *>(c2.rcdm_p) + pb;
+        const double2 *__restrict__ p_wdw2 = reinterpret_cast<const double2 *>(c2.wdw_p) + pb;
         const double *__restrict__ p_z2 = c2.z_p + pb;
+        const double2 *__restrict__ p_rcdm1 = reinterpret_cast<const double2 *>(c1.rcdm) + a;
+        const double2 *__restrict__ p_wdw1 = reinterpret_cast<const double2 *>(c1.wdw) + a;
         const int S2 = (n2 + 1) >> 1;
         double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
         // bin edges in units of d and t, and the absolute part of the guard band
