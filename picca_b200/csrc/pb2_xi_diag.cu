@@ -73,17 +73,15 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
 
 #define DG_COLS(c)  double c##_rc, c##_dm, c##_w, c##_dw, c##_z;
 
-// column j = jb + 2 lane of forest 2 (interleaved layout: even pixels first, then odd ones)
-#define DG_LOAD(c, jb)                                                                   \
+// one column element of forest 2 (interleaved layout), `pos` = slot, `jj` = its pixel index
+#define DG_LOAD(c, pos, jj)                                                              \
     {                                                                                    \
-        const int jj = (jb) + 2 * lane;                                                  \
         c##_rc = DG_DEAD_RC;                                                             \
         c##_dm = c##_w = c##_dw = c##_z = 0.;                                            \
-        if (jj >= 0 && jj < n2) {                                                        \
-            const int pos = ((jb) & 1) * S2 + ((jb) >> 1) + lane;                        \
-            const double2 a2 = __ldg(p_rcdm2 + pos);                                     \
-            const double2 b2 = __ldg(p_wdw2 + pos);                                      \
-            c##_z = __ldg(p_z2 + pos);                                                   \
+        if ((jj) >= 0 && (jj) < n2) {                                                    \
+            const double2 a2 = __ldg(p_rcdm2 + (pos));                                   \
+            const double2 b2 = __ldg(p_wdw2 + (pos));                                    \
+            c##_z = __ldg(p_z2 + (pos));                                                 \
             c##_rc = a2.x;                                                               \
             c##_dm = a2.y;                                                               \
             c##_w = b2.x;                                                                \
@@ -328,16 +326,25 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         DG_DECL(1)
         DG_COLS(c0)
         DG_COLS(c1)
-        // c0 / c1 = columns i + D0 + 2 lane + {0, 1}; each step the window slides by one column
-        DG_LOAD(c0, ibeg + D0)
-        DG_LOAD(c1, ibeg + D0 + 1)
+        // c0 / c1 = columns i + D0 + 2 lane + {0, 1}; each step the window slides by one column.
+        // i advances by 2 per iteration, so c0 always reads one parity half of the interleaved
+        // copy and c1 the other: two slot counters that advance by one per iteration.
+        const int jb = ibeg + D0;
+        int pos0 = (jb & 1) * S2 + (jb >> 1) + lane;              // slot of column jb + 2 lane
+        int pos1 = ((jb + 1) & 1) * S2 + ((jb + 1) >> 1) + lane;  // slot of column jb + 1 + 2 lane
+        int jj0 = jb + 2 * lane;
+        DG_LOAD(c0, pos0, jj0)
+        DG_LOAD(c1, pos1, jj0 + 1)
         for (int i = ibeg; i < iend; i += 2) {
             DG_STEP(i, c0, c1)
-            DG_LOAD(c0, i + D0 + 2)
+            pos0 += 1;
+            DG_LOAD(c0, pos0, jj0 + 2)
             if (i + 1 < iend) {
                 DG_STEP(i + 1, c1, c0)
-                DG_LOAD(c1, i + D0 + 3)
+                pos1 += 1;
+                DG_LOAD(c1, pos1, jj0 + 3)
             }
+            jj0 += 2;
         }
         DG_RED(0)
         DG_RED(1)
