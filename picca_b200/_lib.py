@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpicca_b200.so")
+LIB_PATH = os.environ.get("PICCA_B200_LIB", os.path.join(_HERE, "libpicca_b200.so"))
 _LIB = None
 
 c_i32p = ctypes.c_void_p

@@ -20,8 +20,12 @@
 // slides in a register) from an interleaved-by-2 copy of forest 2, which makes the load coalesced.
 #include "pb2_common.cuh"
 
+#ifndef DG_THREADS
 #define DG_THREADS 384
+#endif
+#ifndef DG_CHUNK
 #define DG_CHUNK 8
+#endif
 #define DG_BLOCK 64
 #define DG_EPS 1e-12
 #define DG_DEAD_RC (-1e300)
