@@ -325,7 +325,7 @@ def run_cuda(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tops/s (1 DFMA = 1 op)", "frac": achieved / peak_ops,
-                         "traffic": None, "kernel": "pb2_xi_auto_tiled", "kernel_ms": kms,
+                         "traffic": None, "kernel": "pb2_xi_auto_diag", "kernel_ms": kms,
                          "peak_source": "pb2_fp64_peak DFMA microbenchmark, measured in this run",
                          "ops_per_pair": FLOPS_PER_PAIR},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9,
