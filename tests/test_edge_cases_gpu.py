@@ -1,0 +1,120 @@
+"""GPU parity on the edge cases the reference's loops handle implicitly: forests with no usable
+pixel, single-pixel forests, ragged lengths, forests longer than any tile, unsorted pixels
+(falls back to the general kernel), duplicate sky positions (small-angle branch of
+get_angle_between, data.py:158-161), empty neighbour lists, production binning for a
+delta x delta cross-correlation, and the maximum bin counts of the xcf defaults."""
+import copy
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(data, num, ang_max, **over):
+    from oracle import cf as ocf
+    from picca_b200 import cf
+    helpers.configure(ocf, data, num, ang_max, **over)
+    helpers.configure(cf, data, num, ang_max, **over)
+    total = 0
+    for hp in sorted(data):
+        ocf.fill_neighs([hp])
+        want_n = [[d2.thingid for d2 in d.neighbours] for d in data[hp]]
+        want = ocf.compute_xi([hp])
+        cf.fill_neighs([hp])
+        got_n = [[d2.thingid for d2 in d.neighbours] for d in data[hp]]
+        assert got_n == want_n
+        got = cf.compute_xi([hp])
+        helpers.assert_xi_close(got, want, tag="hp %d" % hp)
+        total += int(want[5].sum())
+    return total
+
+
+@pytest.fixture()
+def base():
+    from picca_b200 import synth
+    data, num, z_min, _, cosmo = helpers.small_sample(n=120, seed=77, max_pix=90, side_deg=4.)
+    data = {hp: [copy.copy(d) for d in v] for hp, v in data.items()}
+    return data, num, synth.compute_ang_max(cosmo, 60., z_min)
+
+
+def test_zero_weight_and_tiny_forests(base):
+    data, num, ang_max = base
+    flat = [d for hp in sorted(data) for d in data[hp]]
+    flat[0].weights = np.zeros_like(flat[0].weights)            # nothing usable
+    for name in ("weights", "delta", "z", "r_comov", "dist_m", "log_lambda"):
+        setattr(flat[1], name, getattr(flat[1], name)[:1].copy())  # one pixel
+        setattr(flat[2], name, getattr(flat[2], name)[:2].copy())  # two pixels
+    flat[3].weights = flat[3].weights.copy()
+    flat[3].weights[::2] = 0.                                   # every other pixel masked
+    assert run_both(data, num, ang_max) > 0
+
+
+def test_ragged_and_long_forests():
+    from picca_b200 import synth
+    # forests up to ~1400 pixels: longer than one row tile / several diagonal blocks
+    data, num, z_min, _, cosmo = synth.make_forests(
+        40, seed=5, nside=16, ra_deg=(10., 12.), dec_deg=(5., 7.), rest_range=(1000., 1250.),
+        dlambda=0.4)
+    lens = [len(d.weights) for hp in data for d in data[hp]]
+    assert max(lens) > 1100 and min(lens) < max(lens)
+    ang_max = synth.compute_ang_max(cosmo, 60., z_min)
+    assert run_both(data, num, ang_max) > 0
+    assert run_both(data, num, ang_max, num_bins_r_par=50, num_bins_r_trans=50, r_par_max=200.,
+                    r_trans_max=200.) > 0
+
+
+def test_unsorted_forest_uses_general_kernel(base):
+    data, num, ang_max = base
+    flat = [d for hp in sorted(data) for d in data[hp]]
+    d = flat[5]
+    perm = np.random.default_rng(0).permutation(len(d.weights))
+    for name in ("weights", "delta", "z", "r_comov", "dist_m", "log_lambda"):
+        setattr(d, name, getattr(d, name)[perm].copy())
+    from picca_b200 import catalog
+    assert catalog.pack(data).sorted == 0
+    assert run_both(data, num, ang_max) > 0
+
+
+def test_duplicate_positions_small_angle_branch(base):
+    data, num, ang_max = base
+    hp = sorted(data)[0]
+    a = data[hp][0]
+    twin = copy.copy(a)
+    twin.thingid = twin.los_id = 999001
+    twin.ra = a.ra + 1e-7          # within 2 arcsec: sqrt(ddec^2 + (cos_dec dra)^2) branch
+    twin.dec = a.dec - 2e-7
+    twin.x_cart = np.cos(twin.ra) * np.cos(twin.dec)
+    twin.y_cart = np.sin(twin.ra) * np.cos(twin.dec)
+    twin.z_cart = np.sin(twin.dec)
+    twin.cos_dec = np.cos(twin.dec)
+    data[hp].append(twin)
+    assert run_both(data, num + 1, ang_max) > 0
+
+
+def test_isolated_forest_has_no_neighbours():
+    from picca_b200 import cf, synth
+    data, num, z_min, _, cosmo = helpers.small_sample(n=3, seed=1, max_pix=30, side_deg=30.)
+    ang_max = synth.compute_ang_max(cosmo, 60., z_min)
+    helpers.configure(cf, data, num, ang_max)
+    for hp in sorted(data):
+        cf.fill_neighs([hp])
+        res = cf.compute_xi([hp])
+        assert all(len(r) == 225 for r in res)
+    # at least one of the three widely separated forests has an empty list and gives zeros
+    assert any(int(cf.compute_xi_batch([hp])[0, 5].view(np.int64).sum()) == 0
+               for hp in sorted(data) if not cf.fill_neighs([hp]))
+
+
+def test_cross_correlation_production_binning(base):
+    data, num, ang_max = base
+    from picca_b200 import synth
+    data2, num2, z_min2, _, cosmo = helpers.small_sample(n=90, seed=78, max_pix=80, side_deg=4.,
+                                                        id_offset=7000)
+    ang_max = synth.compute_ang_max(cosmo, 200., 1.96, z_min2)
+    total = run_both(data, num, ang_max, data2=data2, num_data2=num2, x_correlation=True,
+                     r_par_min=-200., r_par_max=200., r_trans_max=200., num_bins_r_par=100,
+                     num_bins_r_trans=50)
+    assert total > 10**6
