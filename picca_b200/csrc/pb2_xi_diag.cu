@@ -21,8 +21,9 @@
 #include "pb2_common.cuh"
 
 #ifndef DG_THREADS
-#define DG_THREADS 384
+#define DG_THREADS 512
 #endif
+#define DG_WARPS (DG_THREADS / 32)
 #ifndef DG_CHUNK
 #define DG_CHUNK 8
 #endif
@@ -72,8 +73,10 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
 #define DG_DECL(r)                                                                       \
     double lo_##r = 1e299, hi_##r = inf, thi_##r = inf; /* dead run: column outside */   \
     double sw_##r = 0., sxi_##r = 0., srp_##r = 0., srt_##r = 0., sz_##r = 0.;           \
-    double qw_##r = 0., qxi_##r = 0., qrp_##r = 0., qrt_##r = 0., qz_##r = 0.;           \
-    int bp_##r = -1, bt_##r = 0, cnt_##r = 0, qcnt_##r = 0; /* bp < 0: dead run */
+    int bp_##r = -1, bt_##r = 0, cnt_##r = 0; /* bp < 0: dead run */                     \
+    snap[r][0][lane] = snap[r][1][lane] = snap[r][2][lane] = snap[r][3][lane] =          \
+        snap[r][4][lane] = 0.;                                                           \
+    qcnt[r][lane] = 0;
 
 #define DG_COLS(c)  double c##_rc, c##_dm, c##_w, c##_dw, c##_z;
 
@@ -99,26 +102,27 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
     const double t_##r = add_rn(dm1, c##_dm);                                            \
     const bool p_##r = (v_##r >= lo_##r) && (v_##r < hi_##r) && (t_##r < thi_##r);
 
-// opaque copy: keeps the compiler from turning the snapshot into a loop-carried register rotation
-#define DG_SNAP(q, v) asm volatile("mov.f64 %0, %1;" : "=d"(q) : "d"(v));
-
-// add the finished run (totals - snapshot) to its bin and take the snapshot for the next run
+// add the finished run (totals - snapshot) to its bin and take the snapshot for the next run;
+// snapshots live in lane-private shared-memory slots (only this rare path touches them)
 #define DG_RED(r)                                                                        \
-    if (bp_##r >= 0 && cnt_##r > qcnt_##r) {                                             \
-        double *const dst = orow + (bt_##r + nt_i * bp_##r);                             \
-        atomic_add_f64(dst + 0 * (size_t)nb, sw_##r - qw_##r);                           \
-        atomic_add_f64(dst + 1 * (size_t)nb, sxi_##r - qxi_##r);                         \
-        atomic_add_f64(dst + 2 * (size_t)nb, (srp_##r - qrp_##r) * ch);                  \
-        atomic_add_f64(dst + 3 * (size_t)nb, (srt_##r - qrt_##r) * sh);                  \
-        atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * (sz_##r - qz_##r));                   \
-        atomic_add_i64(dst + 5 * (size_t)nb, (long long)(cnt_##r - qcnt_##r));           \
-    }                                                                                    \
-    DG_SNAP(qw_##r, sw_##r)                                                              \
-    DG_SNAP(qxi_##r, sxi_##r)                                                            \
-    DG_SNAP(qrp_##r, srp_##r)                                                            \
-    DG_SNAP(qrt_##r, srt_##r)                                                            \
-    DG_SNAP(qz_##r, sz_##r)                                                              \
-    asm volatile("mov.s32 %0, %1;" : "=r"(qcnt_##r) : "r"(cnt_##r));
+    {                                                                                    \
+        const int dc = cnt_##r - qcnt[r][lane];                                          \
+        if (bp_##r >= 0 && dc > 0) {                                                     \
+            double *const dst = orow + (bt_##r + nt_i * bp_##r);                         \
+            atomic_add_f64(dst + 0 * (size_t)nb, sw_##r - snap[r][0][lane]);             \
+            atomic_add_f64(dst + 1 * (size_t)nb, sxi_##r - snap[r][1][lane]);            \
+            atomic_add_f64(dst + 2 * (size_t)nb, (srp_##r - snap[r][2][lane]) * edge[5]); \
+            atomic_add_f64(dst + 3 * (size_t)nb, (srt_##r - snap[r][3][lane]) * edge[6]); \
+            atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * (sz_##r - snap[r][4][lane]));     \
+            atomic_add_i64(dst + 5 * (size_t)nb, (long long)dc);                         \
+        }                                                                                \
+        snap[r][0][lane] = sw_##r;                                                       \
+        snap[r][1][lane] = sxi_##r;                                                      \
+        snap[r][2][lane] = srp_##r;                                                      \
+        snap[r][3][lane] = srt_##r;                                                      \
+        snap[r][4][lane] = sz_##r;                                                       \
+        qcnt[r][lane] = cnt_##r;                                                         \
+    }
 
 // The pair left its run.  Common case, handled first: a live run steps into the ADJACENT r_par
 // bin (or the next r_trans bin) and the pair lies outside the guard band of the new bin, which
@@ -128,6 +132,8 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
         double nlo = lo_##r, nhi = hi_##r, nthi = thi_##r;                               \
         int nbp = bp_##r, nbt = bt_##r;                                                  \
         bool done = false;                                                               \
+        const double e0 = edge[0], ep = edge[1], et = edge[2];                           \
+        const double abs_p = edge[3], abs_t = edge[4];                                   \
         if (bp_##r >= 0) {                                                               \
             const bool up = v_##r >= hi_##r, dn = v_##r < lo_##r, tup = t_##r >= thi_##r; \
             if (!tup && (up != dn)) { /* adjacent r_par bin */                           \
@@ -162,6 +168,7 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
             if (c##_rc == DG_DEAD_RC) {                                                  \
                 nlo = 1e299;                                                             \
             } else {                                                                     \
+                const double ch = edge[5], sh = edge[6];                                 \
                 const double rp = mul_rn(v_##r, ch); /* |fl(d ch)| == fl(|d| ch) */      \
                 const double rt = mul_rn(t_##r, sh);                                     \
                 const double x = sub_rn(rp, P.r_par_min);                                \
@@ -243,9 +250,15 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                  const int32_t *__restrict__ out_row, double *__restrict__ out)
 {
     __shared__ unsigned s_ctr;
+    __shared__ double s_snap[DG_WARPS][2][5][32];
+    __shared__ int s_qcnt[DG_WARPS][2][32];
+    __shared__ double s_edge[DG_WARPS][8];
     if (threadIdx.x == 0) s_ctr = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    double (*snap)[5][32] = s_snap[threadIdx.x >> 5];
+    int (*qcnt)[32] = s_qcnt[threadIdx.x >> 5];
+    double *edge = s_edge[threadIdx.x >> 5];
     const int nb = P.num_bins_r_par * P.num_bins_r_trans;
     const int np_i = P.num_bins_r_par, nt_i = P.num_bins_r_trans;
     const unsigned gmax = (unsigned)C.gmax;
@@ -322,12 +335,19 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         const double2 *__restrict__ p_wdw1 = reinterpret_cast<const double2 *>(c1.wdw) + a;
         const int S2 = (n2 + 1) >> 1;
         double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
-        // bin edges in units of d and t, and the absolute part of the guard band
-        const double e0 = P.r_par_min * inv_c, ep = C.dbin_p * inv_c, et = C.dbin_t * inv_s;
-        const double abs_p = DG_EPS * C.rp_scale * inv_c, abs_t = DG_EPS * P.r_trans_max * inv_s;
-
+        __syncwarp();
+        if (lane == 0) {  // bin edges in units of d and t, guard band, cos / sin of ang/2
+            edge[0] = P.r_par_min * inv_c;
+            edge[1] = C.dbin_p * inv_c;
+            edge[2] = C.dbin_t * inv_s;
+            edge[3] = DG_EPS * C.rp_scale * inv_c;
+            edge[4] = DG_EPS * P.r_trans_max * inv_s;
+            edge[5] = ch;
+            edge[6] = sh;
+        }
         DG_DECL(0)
         DG_DECL(1)
+        __syncwarp();
         DG_COLS(c0)
         DG_COLS(c1)
         // c0 / c1 = columns i + D0 + 2 lane + {0, 1}; each step the window slides by one column.
