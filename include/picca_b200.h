@@ -24,7 +24,14 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 6
+#define PB2_ABI_VERSION 8
+
+/* layout constants of the packed copies read by the diagonal-lane xi kernel */
+#ifndef PB2_DIAG_LANES
+#define PB2_DIAG_LANES 4                     /* adjacent diagonals per lane */
+#endif
+#define PB2_DIAG_PAD (34 * PB2_DIAG_LANES)   /* dummy pixels either side, interleaved copy */
+#define PB2_DIAG_ROW_PAD 8                   /* dummy pixels after a line of sight, natural copy */
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
@@ -75,16 +82,31 @@ typedef struct pb2_catalog {
     const double *delta_w;    /* Delta.delta * Delta.weights, 0 where weights == 0 */
     const double *z_w;        /* Delta.z * Delta.weights */
     const double *log_lambda; /* Delta.log_lambda (distortion matrix only; may be NULL) */
-    /* interleaved-by-2 copies used by the diagonal-lane xi kernel: pixel j of a line of sight
-     * with n pixels sits at perm_offset[los] + (j & 1) * S + (j >> 1), S = (n + 1) / 2; padding
-     * slots hold r_comov = -1e300 and zeros elsewhere */
-    const int64_t *perm_offset;  /* [n_los+1] */
-    const double *z_p;           /* z, interleaved */
-    const double *rcdm_p;        /* (r_comov, dist_m) pairs, interleaved, 16-byte elements */
-    const double *wdw_p;         /* (weights, delta_w) pairs, interleaved, 16-byte elements */
-    /* natural-order packed pairs for the uniform row loads of the same kernel */
-    const double *rcdm;          /* (r_comov, dist_m) per pixel */
-    const double *wdw;           /* (weights, delta_w) per pixel */
+    /* ---- packed copies read by the diagonal-lane xi kernel (pb2_xi_diag.cu); NULL for object
+     * catalogues.  Zero-weight pixels (never counted by the reference, cf.py:318,331) are
+     * compacted away; dg_count[f] pixels of line of sight f remain.
+     * Natural order (row loads, window searches): pixel i of line of sight f sits at
+     * dg_offset[f] + i, followed by PB2_DIAG_ROW_PAD dummies (+Inf distances, zeros elsewhere). */
+    const int64_t *dg_offset;    /* [n_los] */
+    const int32_t *dg_count;     /* [n_los] */
+    const double *dg_rcdm;       /* (r_comov, dist_m) pairs, 16-byte elements */
+    const double *dg_wdw;        /* (weights, delta_w) pairs, 16-byte elements */
+    const double *dg_z;          /* z */
+    /* Interleaved by PB2_DIAG_LANES (column loads): with jp = j + PB2_DIAG_PAD, pixel j of line of
+     * sight f sits in plane jp % PB2_DIAG_LANES at il_offset[f] + jp / PB2_DIAG_LANES; plane p of
+     * an array starts il_total elements after plane p - 1.  Every line of sight is padded with
+     * PB2_DIAG_PAD dummies (+Inf distances, zeros elsewhere) on both sides, so a warp may read a
+     * whole diagonal block past either end without a bounds check. */
+    const int64_t *il_offset;    /* [n_los] */
+    int64_t il_total;            /* elements per plane */
+    const double *il_rcdm;       /* (r_comov, dist_m) */
+    const double *il_wdw;        /* (weights, delta_w) */
+    const double *il_z;          /* z */
+    int32_t dg_lanes;            /* PB2_DIAG_LANES the copies were packed for */
+    int32_t dg_max_pix;          /* longest compacted line of sight */
+    int32_t dg_ok;               /* 1 if every r_comov, dist_m, z, weight, delta_w is finite */
+    int32_t dg_reserved;
+    double dg_reach;             /* max(|r_comov|, |dist_m|) over the catalogue */
     /* per line of sight */
     const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;
     const int64_t *thingid, *plate, *fiberid;
@@ -122,6 +144,7 @@ const char *pb2_last_error(void);
 int32_t pb2_sizeof_params(void);
 int32_t pb2_sizeof_catalog(void);
 int32_t pb2_sizeof_pairs(void);
+int32_t pb2_diag_lanes(void); /* PB2_DIAG_LANES the library was built with */
 
 /* ---- neighbour search: replaces cf.fill_neighs (cf.py:82-135) and xcf.fill_neighs
  * (xcf.py:71-123), including QSO.get_angle_between (data.py:106-162).

@@ -56,12 +56,21 @@ class Catalog(ctypes.Structure):
         ("delta_w", c_void_p),
         ("z_w", c_void_p),
         ("log_lambda", c_void_p),
-        ("perm_offset", c_void_p),
-        ("z_p", c_void_p),
-        ("rcdm_p", c_void_p),
-        ("wdw_p", c_void_p),
-        ("rcdm", c_void_p),
-        ("wdw", c_void_p),
+        ("dg_offset", c_void_p),
+        ("dg_count", c_void_p),
+        ("dg_rcdm", c_void_p),
+        ("dg_wdw", c_void_p),
+        ("dg_z", c_void_p),
+        ("il_offset", c_void_p),
+        ("il_total", ctypes.c_int64),
+        ("il_rcdm", c_void_p),
+        ("il_wdw", c_void_p),
+        ("il_z", c_void_p),
+        ("dg_lanes", ctypes.c_int32),
+        ("dg_max_pix", ctypes.c_int32),
+        ("dg_ok", ctypes.c_int32),
+        ("dg_reserved", ctypes.c_int32),
+        ("dg_reach", ctypes.c_double),
         ("x_cart", c_void_p),
         ("y_cart", c_void_p),
         ("z_cart", c_void_p),
@@ -105,12 +114,12 @@ class Pairs(ctypes.Structure):
 # every symbol include/picca_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "pb2_abi_version", "pb2_last_error", "pb2_sizeof_params", "pb2_sizeof_catalog",
-    "pb2_sizeof_pairs", "pb2_neigh_count", "pb2_neigh_fill", "pb2_xi_auto", "pb2_xi_cross",
+    "pb2_sizeof_pairs", "pb2_diag_lanes", "pb2_neigh_count", "pb2_neigh_fill", "pb2_xi_auto", "pb2_xi_cross",
     "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross",
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 6
+ABI_VERSION = 8
 
 
 def lib():

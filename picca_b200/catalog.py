@@ -14,7 +14,10 @@ import numpy as np
 from . import _lib
 
 _PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
-_PERM_FIELDS = ("z_p", "rcdm_p", "wdw_p", "rcdm", "wdw")
+_DIAG_FIELDS = ("dg_offset", "dg_count", "dg_rcdm", "dg_wdw", "dg_z",
+                "il_offset", "il_rcdm", "il_wdw", "il_z")
+DIAG_DUMMY_COL = 1e300   # distance of the dummy pixels around a line of sight (interleaved copy)
+DIAG_DUMMY_ROW = 1e299   # ... and after it in the natural-order copy
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
 _LOS_I64 = ("thingid", "plate", "fiberid")
 
@@ -32,6 +35,11 @@ class HostCatalog:
         self.max_pix = 0
         self.ids_are_int = True
         self.is_object = False
+        self.il_total = 0         # diagonal-lane copies (see _pack_diag_copies)
+        self.dg_lanes = 0
+        self.dg_max_pix = 0
+        self.dg_ok = 0
+        self.dg_reach = 0.0
 
     def first_of(self, healpix):
         k = self.hp_index[healpix]
@@ -52,6 +60,72 @@ def _as_int64(values):
     except (TypeError, ValueError):
         pass
     return np.zeros(len(values), dtype=np.int64), False
+
+
+def diag_layout():
+    """(lanes, pad, row_pad) of the packed copies the diagonal-lane xi kernel reads
+    (PB2_DIAG_LANES, PB2_DIAG_PAD, PB2_DIAG_ROW_PAD of include/picca_b200.h)."""
+    lanes = int(_lib.lib().pb2_diag_lanes())
+    return lanes, 34 * lanes, 8
+
+
+def _pack_diag_copies(cat, offset):
+    """Packed copies for the diagonal-lane xi kernel (layout: include/picca_b200.h, pb2_catalog).
+
+    Zero-weight pixels are dropped (the reference never counts them, cf.py:318,331).  Natural
+    order with ROW_PAD dummies after every line of sight, and a copy interleaved by LANES with PAD
+    dummies either side.  Dummies have weight 0 and a distance of 1e300 / 1e299: they add zeros to
+    every sum and fall in no bin."""
+    A = cat.arrays
+    lanes, pad, row_pad = diag_layout()
+    n = cat.n_los
+    keep = A["weights"] != 0
+    lengths = np.diff(offset)
+    los_all = np.repeat(np.arange(n, dtype=np.int64), lengths)
+    count = np.bincount(los_all[keep], minlength=n).astype(np.int64) if n else np.zeros(0, np.int64)
+    los = los_all[keep]
+    rc, dm, z = A["r_comov"][keep], A["dist_m"][keep], A["z"][keep]
+    w, dw = A["weights"][keep], A["delta_w"][keep]
+    first = np.zeros(n + 1, dtype=np.int64)
+    first[1:] = np.cumsum(count)
+    rank = np.arange(len(los), dtype=np.int64) - first[:-1][los]   # pixel index inside its forest
+
+    # natural order
+    dg_offset = first[:-1] + row_pad * np.arange(n, dtype=np.int64)
+    total = int(first[-1]) + row_pad * n
+    pos = dg_offset[los] + rank
+    rcdm = np.full((total, 2), DIAG_DUMMY_ROW, dtype=np.float64)
+    rcdm[pos, 0], rcdm[pos, 1] = rc, dm
+    wdw = np.zeros((total, 2), dtype=np.float64)
+    wdw[pos, 0], wdw[pos, 1] = w, dw
+    zz = np.zeros(total, dtype=np.float64)
+    zz[pos] = z
+    A["dg_offset"] = np.ascontiguousarray(dg_offset)
+    A["dg_count"] = count.astype(np.int32)
+    A["dg_rcdm"], A["dg_wdw"], A["dg_z"] = rcdm.reshape(-1), wdw.reshape(-1), zz
+
+    # interleaved by `lanes`
+    per_plane = (count + lanes - 1) // lanes + 2 * pad // lanes
+    il_offset = np.zeros(n + 1, dtype=np.int64)
+    il_offset[1:] = np.cumsum(per_plane)
+    il_total = int(il_offset[-1])
+    jp = rank + pad
+    pos = (jp % lanes) * il_total + il_offset[:-1][los] + jp // lanes
+    rcdm = np.full((lanes * il_total, 2), DIAG_DUMMY_COL, dtype=np.float64)
+    rcdm[pos, 0], rcdm[pos, 1] = rc, dm
+    wdw = np.zeros((lanes * il_total, 2), dtype=np.float64)
+    wdw[pos, 0], wdw[pos, 1] = w, dw
+    zz = np.zeros(lanes * il_total, dtype=np.float64)
+    zz[pos] = z
+    A["il_offset"] = np.ascontiguousarray(il_offset[:-1])
+    A["il_rcdm"], A["il_wdw"], A["il_z"] = rcdm.reshape(-1), wdw.reshape(-1), zz
+    cat.il_total = il_total
+    cat.dg_lanes = lanes
+    cat.dg_max_pix = int(count.max()) if n else 0
+    finite = all(bool(np.all(np.isfinite(x))) for x in (rc, dm, z, w, dw))
+    # 32-bit element indices in the kernel
+    cat.dg_ok = int(finite and total < 2**31 and lanes * il_total < 2**31)
+    cat.dg_reach = float(max(np.abs(rc).max(), np.abs(dm).max())) if len(rc) and finite else 0.0
 
 
 def pack(data, is_object=False, ang_correlation=False):
@@ -143,34 +217,8 @@ def pack(data, is_object=False, ang_correlation=False):
     lengths = np.diff(offset)
     cat.max_pix = int(lengths.max()) if n else 0
 
-    # interleaved-by-2 copies of the column fields (diagonal-lane xi kernel): pixel j of a forest
-    # of n pixels -> perm_offset + (j & 1) * S + (j >> 1), S = ceil(n / 2)
-    stride = (lengths + 1) // 2
-    perm_offset = np.zeros(n + 1, dtype=np.int64)
-    perm_offset[1:] = np.cumsum(2 * stride)
-    A["perm_offset"] = perm_offset
-    total = int(perm_offset[-1])
-    if cat.n_pix:
-        los = np.repeat(np.arange(n, dtype=np.int64), lengths)
-        j = np.arange(cat.n_pix, dtype=np.int64) - offset[:-1][los]
-        pos = perm_offset[:-1][los] + (j & 1) * stride[los] + (j >> 1)
-    else:
-        pos = np.zeros(0, dtype=np.int64)
-    zp = np.zeros(total, dtype=np.float64)
-    zp[pos] = A["z"]
-    A["z_p"] = zp
-    rcdm_p = np.zeros((total, 2), dtype=np.float64)
-    rcdm_p[:, 0] = -1e300  # padding slots: the kernel's "column outside the forest" marker
-    rcdm_p[pos, 0] = A["r_comov"]
-    rcdm_p[pos, 1] = A["dist_m"]
-    A["rcdm_p"] = rcdm_p.reshape(-1)
-    wdw_p = np.zeros((total, 2), dtype=np.float64)
-    wdw_p[pos, 0] = A["weights"]
-    wdw_p[pos, 1] = A["delta_w"]
-    A["wdw_p"] = wdw_p.reshape(-1)
-    # natural-order packed pairs (one 128-bit uniform load per pair of fields for the rows)
-    A["rcdm"] = np.ascontiguousarray(np.stack([A["r_comov"], A["dist_m"]], axis=1)).reshape(-1)
-    A["wdw"] = np.ascontiguousarray(np.stack([A["weights"], A["delta_w"]], axis=1)).reshape(-1)
+    if not is_object:
+        _pack_diag_copies(cat, offset)
 
     # sortedness inside each forest (enables the column windows of the pair kernel)
     cat.sorted = 1
@@ -225,9 +273,17 @@ def build_struct(host, tensors):
     c = _lib.Catalog()
     c.n_los = host.n_los
     c.n_pix = host.n_pix
-    for name in ("offset", "perm_offset") + _PIXEL_FIELDS + _PERM_FIELDS + _LOS_F64 + _LOS_I64 + (
+    for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
             "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
         setattr(c, name, tensors[name].data_ptr())
+    if "dg_rcdm" in tensors:
+        for name in _DIAG_FIELDS:
+            setattr(c, name, tensors[name].data_ptr())
+        c.il_total = host.il_total
+        c.dg_lanes = host.dg_lanes
+        c.dg_max_pix = host.dg_max_pix
+        c.dg_ok = host.dg_ok
+        c.dg_reach = host.dg_reach
     c.n_hp = len(host.healpixs)
     c.sorted = host.sorted
     c.max_pix = host.max_pix

@@ -74,6 +74,7 @@ const char *pb2_last_error(void) { return g_err; }
 int32_t pb2_sizeof_params(void) { return (int32_t)sizeof(pb2_params); }
 int32_t pb2_sizeof_catalog(void) { return (int32_t)sizeof(pb2_catalog); }
 int32_t pb2_sizeof_pairs(void) { return (int32_t)sizeof(pb2_pairs); }
+int32_t pb2_diag_lanes(void) { return PB2_DIAG_LANES; }
 int64_t pb2_launch_count(void) { return g_launches.load(); }
 int32_t pb2_set_timing(int32_t enable) { g_timing = enable; return 0; }
 double pb2_last_kernel_ms(void) { return g_last_ms; }

@@ -502,6 +502,8 @@ int32_t pb2_launch_xi_fast(const pb2_catalog *c1, const pb2_catalog *c2, const p
                            const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
                            cudaStream_t s);
 
+bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
+                          int64_t n_rows);
 int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                            const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
                            cudaStream_t s);
@@ -527,7 +529,6 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
         pb2_set_error("pb2_xi_auto: null pointer argument");
         return PB2_EINVAL;
     }
-    (void)n_rows;
     if (pairs->n_pairs <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     pb2_timing_begin(s);
@@ -539,7 +540,8 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
                                                            d_out);
         pb2_count_launch(1);
         rc = pb2_check_launch("pb2_xi_auto_brute");
-    } else if (variant == 0 && fast_eligible(cat1, cat2, par) && cat2->rcdm_p != nullptr && cat1->rcdm != nullptr) {
+    } else if (variant == 0 && fast_eligible(cat1, cat2, par) &&
+               pb2_xi_diag_eligible(cat1, cat2, par, n_rows)) {
         rc = pb2_launch_xi_diag(cat1, cat2, par, pairs, d_out_row, d_out, s);
     } else if ((variant == 0 || variant == 3) && fast_eligible(cat1, cat2, par)) {
         rc = pb2_launch_xi_fast(cat1, cat2, par, pairs, d_out_row, d_out, s);

@@ -1,269 +1,110 @@
 // Auto / delta x delta pixel-pair histogram, standard (r_par, r_trans) binning, no per-pair cuts:
-// "diagonal lanes" kernel.  Replaces cf.compute_xi's pair loop + cf.compute_xi_forest_pairs_fast
-// (reference py/picca/cf.py:161-240, 250-387).
+// "diagonal lanes" kernel -- the product path of picca_cf.py's default mode.  Replaces
+// cf.compute_xi's pair loop + cf.compute_xi_forest_pairs_fast (reference py/picca/cf.py:161-240,
+// 250-387).
 //
-// For one forest pair the pixel pairs (i, j) are visited along diagonals d = j - i.  On a diagonal
-// r_par = (rc1[i] - rc2[j]) cos(ang/2) is nearly constant and r_trans = (dm1[i] + dm2[j]) sin(ang/2)
-// grows slowly, so a diagonal stays in ONE (r_par, r_trans) bin for ~100 consecutive pairs.  Each
-// lane owns two adjacent diagonals and keeps, per diagonal, the current bin ("run"), its partial
-// sums and three thresholds bounding the run in registers:
-//   per pair   d = rc1 - rc2, t = dm1 + dm2, three compares against the thresholds and seven
-//              accumulate instructions -- 12 FP64 instructions, no division, no bin arithmetic;
-//   run change (about once per 100 pairs per diagonal) the lane flushes the finished run with
-//              native red.global.add.f64 and finds the new bin with the sandwich test of
-//              pb2_xi.cu (reference expression with true divisions when it cannot prove the bin);
-//              the new thresholds are the bin's edges mapped to d and t, shrunk by a 1e-12 guard
-//              band -- a pair inside the guard band becomes a one-value run, so every bin
-//              assignment is either proven or computed by the reference expression: bit-exact.
-// Work unit = (forest pair, block of 64 diagonals), one warp.  The warp walks the rows; the row's
-// five values are uniform loads; each lane fetches ONE new column element per step (the other
-// slides in a register) from an interleaved-by-2 copy of forest 2, which makes the load coalesced.
+// For one forest pair the pixel pairs (i, j) are visited along diagonals j - i = const.  On a
+// diagonal r_par = (rc1[i] - rc2[j]) cos(ang/2) is nearly constant and r_trans = (dm1[i] + dm2[j])
+// sin(ang/2) grows slowly, so a diagonal stays in ONE (r_par, r_trans) bin for ~80 consecutive
+// pairs (a "run").  Each lane owns DG_C adjacent diagonals and keeps, per diagonal, the bin of the
+// current run and five running totals in registers.
+//   per pair    d = rc1 - rc2, t = dm1 + dm2, then the bin straight from four round-down FMAs
+//               against 2^52 + 2^51 (floor(x K (1 -+ 2^-40)) in the low word): when the two r_par
+//               values agree and the two r_trans values agree, the reference's
+//               floor((r - min) / (max - min) * n) (cf.py:372-376) is sandwiched and the bin is
+//               proven, and "0 <= value < n" is the reference's range test (cf.py:364).  Four
+//               integer compares of the low words with the run's bin, seven FP64 instructions to
+//               accumulate: 13 FP64 instructions, no division, no predication, no bounds check
+//               and no pair counter -- zero-weight pixels (skipped by the reference,
+//               cf.py:318,331) are compacted away in the packed copies, so num_pairs of a run is
+//               its length, and columns outside forest 2 read dummies (distance 1e300, weight 0)
+//               that add zeros and land in no bin.
+//   run change  (about once per 40-80 pairs per diagonal) the lane adds its five sums and the run
+//               length to the finished run's bin with six native red.global.add.f64 / .u64 into
+//               the L2-resident per-HEALPix histogram (~30 instructions).  The sums restart through
+//               six selects in the MAIN path (high word := 0 when the bin changed, which leaves
+//               at most a 1e-314 denormal behind): the accumulators are then written only by the
+//               accumulate instructions and ptxas keeps them in place -- clearing them inside the
+//               branch costs ten register moves per pair, snapshots in shared memory saturate the
+//               L1 data pipe.  When the two FMAs of a dimension disagree (pair within 2^-40 of a
+//               bin edge, ~1e-10 of the pairs) the bin comes from the reference expression with
+//               IEEE divisions.
+// Work unit = (forest pair, block of 32 * DG_C diagonals), one warp.  The warp walks the rows: the
+// row's values are uniform 128-bit loads; each lane loads ONE new column element per row (the
+// other DG_C - 1 slide through registers, statically renamed by unrolling DG_C rows) from a copy
+// of forest 2 interleaved by DG_C, which makes that load coalesced.
 #include "pb2_common.cuh"
 
+#define DG_C PB2_DIAG_LANES
 #ifndef DG_THREADS
-#define DG_THREADS 512
+#define DG_THREADS 384
 #endif
-#define DG_WARPS (DG_THREADS / 32)
 #ifndef DG_CHUNK
 #define DG_CHUNK 8
 #endif
-#define DG_BLOCK 64
-#define DG_EPS 1e-12
-#define DG_DEAD_RC (-1e300)
+#define DG_WARPS (DG_THREADS / 32)
+#define DG_BLOCK (32 * DG_C)
+#define DG_DEAD_START 0x3fffffff
+#define DG_MAGIC 6755399441055744.0  // 2^52 + 2^51
+#define DG_MAGIC_HI 0x43380000       // its high word: unchanged by adding 0 <= bin < 2^31
+#define DG_NO_BIN ((int)0x80000000)
 
 struct DiagConst {
-    double dbin_p;   // (r_par_max - r_par_min) / np
-    double dbin_t;   // r_trans_max / nt
-    double rp_scale; // max(|r_par_min|, |r_par_max|)
-    double kp_lo, kp_hi, kt_lo, kt_hi, magic;  // sandwich constants (see pb2_xi.cu)
-    int gmax;        // diagonal blocks per forest pair (longest forests)
+    double kp_lo, kp_hi, kt_lo, kt_hi;  // n / range * (1 -+ 2^-40)
+    int gmax;                           // diagonal blocks per forest pair (longest forests)
 };
 
-__device__ __forceinline__ double dg_next_up(double v)
-{
-    if (v == 0.) return 4.9406564584124654e-324;
-    const long long b = __double_as_longlong(v);
-    return __longlong_as_double(v > 0. ? b + 1 : b - 1);
-}
-
-__device__ __forceinline__ int dg_exact_bin(const pb2_params &P, double rc1, double dm1, double rc2,
-                                         double dm2, double ang, double ch, double sh)
-{
-    return pb2_pair_exact(P, rc1, dm1, rc2, dm2, ang, ch, sh, false, false).bin;
-}
-
-// first index in non-decreasing a[0..n) with a[idx] > v (strict) or a[idx] >= v
+// first index in non-decreasing a[0], a[2], a[4] ... (n values, stride 2 doubles) with
+// a[idx] > v (strict) or a[idx] >= v
 __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, double v, bool strict)
 {
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const double x = __ldg(a + mid);
+        const double x = __ldg(a + 2 * mid);
         if (strict ? (x <= v) : (x < v)) lo = mid + 1;
         else hi = mid;
     }
     return lo;
 }
 
-// ---- per-diagonal state on named scalars (r = 0, 1)
-// The five sums and the count are RUNNING totals over the whole diagonal (never cleared, also
-// advanced while the diagonal is in a dead run); a run's contribution is total - snapshot, the
-// snapshot being taken when the run starts.  This keeps the per-pair path free of predication
-// and the run-change path free of writes to the accumulators.
-#define DG_DECL(r)                                                                       \
-    double lo_##r = 1e299, hi_##r = inf, thi_##r = inf; /* dead run: column outside */   \
-    double sw_##r = 0., sxi_##r = 0., srp_##r = 0., srt_##r = 0., sz_##r = 0.;           \
-    int bp_##r = -1, bt_##r = 0, cnt_##r = 0; /* bp < 0: dead run */                     \
-    snap[r][0][lane] = snap[r][1][lane] = snap[r][2][lane] = snap[r][3][lane] =          \
-        snap[r][4][lane] = 0.;                                                           \
-    qcnt[r][lane] = 0;
+// reference bin of a pair too close to a bin edge for the sandwich; (DG_NO_BIN, .) when rejected
+__device__ __noinline__ int2 dg_exact_bin(const pb2_params &P, double rc1, double dm1, double rc2,
+                                          double dm2, double ang, double ch, double sh)
+{
+    const int bin = pb2_pair_exact(P, rc1, dm1, rc2, dm2, ang, ch, sh, false, false).bin;
+    if (bin < 0) return make_int2(DG_NO_BIN, 0);
+    const int bp = bin / P.num_bins_r_trans;
+    return make_int2(bp, bin - bp * P.num_bins_r_trans);
+}
 
-#define DG_COLS(c)  double c##_rc, c##_dm, c##_w, c##_dw, c##_z;
+__device__ __forceinline__ void dg_emit(double *__restrict__ dst, int nb, int cnt, double a0,
+                                        double a1, double a2, double a3, double a4)
+{
+    atomic_add_f64(dst, a0);
+    atomic_add_f64(dst + (size_t)nb, a1);
+    atomic_add_f64(dst + 2 * (size_t)nb, a2);
+    atomic_add_f64(dst + 3 * (size_t)nb, a3);
+    atomic_add_f64(dst + 4 * (size_t)nb, a4);
+    atomic_add_i64(dst + 5 * (size_t)nb, (long long)cnt);
+}
 
-// one column element of forest 2 (interleaved layout), `pos` = slot, `jj` = its pixel index
-#define DG_LOAD(c, pos, jj)                                                              \
-    {                                                                                    \
-        c##_rc = DG_DEAD_RC;                                                             \
-        c##_dm = c##_w = c##_dw = c##_z = 0.;                                            \
-        if ((jj) >= 0 && (jj) < n2) {                                                    \
-            const double2 a2 = __ldg(p_rcdm2 + (pos));                                   \
-            const double2 b2 = __ldg(p_wdw2 + (pos));                                    \
-            c##_z = __ldg(p_z2 + (pos));                                                 \
-            c##_rc = a2.x;                                                               \
-            c##_dm = a2.y;                                                               \
-            c##_w = b2.x;                                                                \
-            c##_dw = b2.y;                                                               \
-        }                                                                                \
-    }
-
-#define DG_TEST(r, c)                                                                    \
-    const double d_##r = sub_rn(rc1, c##_rc);                                            \
-    const double v_##r = XCORR ? d_##r : fabs(d_##r);                                    \
-    const double t_##r = add_rn(dm1, c##_dm);                                            \
-    const bool p_##r = (v_##r >= lo_##r) && (v_##r < hi_##r) && (t_##r < thi_##r);
-
-// add the finished run (totals - snapshot) to its bin and take the snapshot for the next run;
-// snapshots live in lane-private shared-memory slots (only this rare path touches them)
-#define DG_RED(r)                                                                        \
-    {                                                                                    \
-        const int dc = cnt_##r - qcnt[r][lane];                                          \
-        if (bp_##r >= 0 && dc > 0) {                                                     \
-            double *const dst = orow + (bt_##r + nt_i * bp_##r);                         \
-            atomic_add_f64(dst + 0 * (size_t)nb, sw_##r - snap[r][0][lane]);             \
-            atomic_add_f64(dst + 1 * (size_t)nb, sxi_##r - snap[r][1][lane]);            \
-            atomic_add_f64(dst + 2 * (size_t)nb, (srp_##r - snap[r][2][lane]) * edge[5]); \
-            atomic_add_f64(dst + 3 * (size_t)nb, (srt_##r - snap[r][3][lane]) * edge[6]); \
-            atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * (sz_##r - snap[r][4][lane]));     \
-            atomic_add_i64(dst + 5 * (size_t)nb, (long long)dc);                         \
-        }                                                                                \
-        snap[r][0][lane] = sw_##r;                                                       \
-        snap[r][1][lane] = sxi_##r;                                                      \
-        snap[r][2][lane] = srp_##r;                                                      \
-        snap[r][3][lane] = srt_##r;                                                      \
-        snap[r][4][lane] = sz_##r;                                                       \
-        qcnt[r][lane] = cnt_##r;                                                         \
-    }
-
-// The pair left its run.  Common case, handled first: a live run steps into the ADJACENT r_par
-// bin (or the next r_trans bin) and the pair lies outside the guard band of the new bin, which
-// proves the new bin without evaluating it.  Otherwise: sandwich test / reference expression.
-#define DG_LEAVE(r, c)                                                                   \
-    if (!p_##r) {                                                                        \
-        double nlo = lo_##r, nhi = hi_##r, nthi = thi_##r;                               \
-        int nbp = bp_##r, nbt = bt_##r;                                                  \
-        bool done = false;                                                               \
-        const double e0 = edge[0], ep = edge[1], et = edge[2];                           \
-        const double abs_p = edge[3], abs_t = edge[4];                                   \
-        if (bp_##r >= 0) {                                                               \
-            const bool up = v_##r >= hi_##r, dn = v_##r < lo_##r, tup = t_##r >= thi_##r; \
-            if (!tup && (up != dn)) { /* adjacent r_par bin */                           \
-                const int cb = bp_##r + (up ? 1 : -1);                                   \
-                const double e_lo = fma((double)cb, ep, e0), e_hi = e_lo + ep;           \
-                double a_lo = e_lo + fma(fabs(e_lo), DG_EPS, abs_p);                     \
-                const double a_hi = e_hi - fma(fabs(e_hi), DG_EPS, abs_p);               \
-                if (!XCORR && e_lo <= 0.) a_lo = -1.;                                    \
-                if (cb >= 0 && cb < np_i && v_##r >= a_lo && v_##r < a_hi) {             \
-                    nbp = cb;                                                            \
-                    nlo = a_lo;                                                          \
-                    nhi = a_hi;                                                          \
-                    done = true;                                                         \
-                }                                                                        \
-            } else if (tup && !up && !dn) { /* next r_trans bin */                       \
-                const double t_lo = (double)(bt_##r + 1) * et, t_hi = t_lo + et;         \
-                const double b_lo = t_lo + fma(t_lo, DG_EPS, abs_t);                     \
-                const double b_hi = t_hi - fma(t_hi, DG_EPS, abs_t);                     \
-                if (bt_##r + 1 < nt_i && t_##r >= b_lo && t_##r < b_hi) {                \
-                    nbt = bt_##r + 1;                                                    \
-                    nthi = b_hi;                                                         \
-                    done = true;                                                         \
-                }                                                                        \
-            }                                                                            \
-        }                                                                                \
-        if (!done) {                                                                     \
-            nlo = -inf;                                                                  \
-            nhi = inf;                                                                   \
-            nthi = inf;                                                                  \
-            nbp = -1;                                                                    \
-            nbt = 0;                                                                     \
-            if (c##_rc == DG_DEAD_RC) {                                                  \
-                nlo = 1e299;                                                             \
-            } else {                                                                     \
-                const double ch = edge[5], sh = edge[6];                                 \
-                const double rp = mul_rn(v_##r, ch); /* |fl(d ch)| == fl(|d| ch) */      \
-                const double rt = mul_rn(t_##r, sh);                                     \
-                const double x = sub_rn(rp, P.r_par_min);                                \
-                const int bpl = __double2loint(__fma_rd(x, C.kp_lo, C.magic));           \
-                const int bph = __double2loint(__fma_rd(x, C.kp_hi, C.magic));           \
-                const int btl = __double2loint(__fma_rd(rt, C.kt_lo, C.magic));          \
-                const int bth = __double2loint(__fma_rd(rt, C.kt_hi, C.magic));          \
-                if (bpl != bph || btl != bth || !(fabs(x) < 1e15) || !(rt < 1e15)) {     \
-                    const int bin = dg_exact_bin(P, rc1, dm1, c##_rc, c##_dm, ang, ch, sh); \
-                    if (bin >= 0) {                                                      \
-                        nbp = bin / nt_i;                                                \
-                        nbt = bin - nbp * nt_i;                                          \
-                    }                                                                    \
-                    nlo = v_##r;                                                         \
-                    nhi = dg_next_up(v_##r);                                             \
-                    nthi = dg_next_up(t_##r);                                            \
-                } else if (btl < nt_i) { /* else r_trans >= max: dead for good */        \
-                    const int bc = max(-1, min(bpl, np_i)); /* -1, np: rejected sides */ \
-                    const double e_lo = fma((double)bc, ep, e0), e_hi = e_lo + ep;       \
-                    if (bc >= 0) nlo = e_lo + fma(fabs(e_lo), DG_EPS, abs_p);            \
-                    if (bc < np_i) nhi = e_hi - fma(fabs(e_hi), DG_EPS, abs_p);          \
-                    if (!XCORR && e_lo <= 0.) nlo = -1.; /* |r_par| >= 0 always */       \
-                    if (bc >= 0 && bc < np_i) {                                          \
-                        const double t_hi = (double)(btl + 1) * et;                      \
-                        nthi = isfinite(t_hi) ? t_hi - fma(t_hi, DG_EPS, abs_t) : inf;   \
-                        if (!(t_##r < nthi)) nthi = dg_next_up(t_##r);                   \
-                        nbp = bc;                                                        \
-                        nbt = btl;                                                       \
-                    }                                                                    \
-                    if (!(v_##r >= nlo && v_##r < nhi)) { /* guard band: one-value run */ \
-                        nlo = v_##r;                                                     \
-                        nhi = dg_next_up(v_##r);                                         \
-                    }                                                                    \
-                }                                                                        \
-            }                                                                            \
-        }                                                                                \
-        if (nbp != bp_##r || nbt != bt_##r) {                                            \
-            DG_RED(r)                                                                    \
-            bp_##r = nbp;                                                                \
-            bt_##r = nbt;                                                                \
-        }                                                                                \
-        lo_##r = nlo;                                                                    \
-        hi_##r = nhi;                                                                    \
-        thi_##r = nthi;                                                                  \
-    }
-
-#define DG_ACC(r, c)                                                                     \
-    {                                                                                    \
-        const double w12 = mul_rn(w1, c##_w);                                            \
-        sw_##r += w12;                                                                   \
-        sxi_##r = fma(dw1, c##_dw, sxi_##r);                                             \
-        srp_##r = fma(v_##r, w12, srp_##r);                                              \
-        srt_##r = fma(t_##r, w12, srt_##r);                                              \
-        sz_##r = fma(add_rn(z1, c##_z), w12, sz_##r);                                    \
-        if (row_ok && __double2hiint(c##_w) != 0) cnt_##r += 1;                          \
-    }
-
-// row ii against the lane's two diagonals, which meet columns ca (d = D0 + 2 lane) and cb (+1)
-#define DG_STEP(ii, ca, cb)                                                              \
-    {                                                                                    \
-        const double2 ra = __ldg(p_rcdm1 + (ii));                                        \
-        const double2 rb = __ldg(p_wdw1 + (ii));                                         \
-        const double z1 = __ldg(p_z1 + (ii));                                            \
-        const double rc1 = ra.x, dm1 = ra.y, w1 = rb.x, dw1 = rb.y;                      \
-        const bool row_ok = (w1 != 0.);                                                  \
-        DG_TEST(0, ca)                                                                   \
-        DG_TEST(1, cb)                                                                   \
-        if (__any_sync(0xffffffffu, !(p_0 && p_1))) {                                    \
-            DG_LEAVE(0, ca)                                                              \
-            DG_LEAVE(1, cb)                                                              \
-        }                                                                                \
-        DG_ACC(0, ca)                                                                    \
-        DG_ACC(1, cb)                                                                    \
-    }
-
-template <bool XCORR>
+// ABS: auto-correlation (r_par = |r_par|, cf.py:361-362).  FOLD: r_par_min == 0, so the r_par bin
+// is floor(|d| * (cos * K)) and cos folds into the constant; otherwise x = fl(fl(d cos) - min) is
+// formed exactly as the reference does (cf.py:356,372).
+template <bool ABS, bool FOLD>
 __global__ void __launch_bounds__(DG_THREADS, 1)
 pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DiagConst C,
                  const int32_t *__restrict__ out_row, double *__restrict__ out)
 {
     __shared__ unsigned s_ctr;
-    __shared__ double s_snap[DG_WARPS][2][5][32];
-    __shared__ int s_qcnt[DG_WARPS][2][32];
-    __shared__ double s_edge[DG_WARPS][8];
     if (threadIdx.x == 0) s_ctr = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    double (*snap)[5][32] = s_snap[threadIdx.x >> 5];
-    int (*qcnt)[32] = s_qcnt[threadIdx.x >> 5];
-    double *edge = s_edge[threadIdx.x >> 5];
     const int nb = P.num_bins_r_par * P.num_bins_r_trans;
     const int np_i = P.num_bins_r_par, nt_i = P.num_bins_r_trans;
     const unsigned gmax = (unsigned)C.gmax;
     const unsigned units_per_chunk = DG_CHUNK * gmax;
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
 
     for (;;) {
         unsigned u = 0;
@@ -276,34 +117,30 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         if (e >= pr.n_pairs) continue;
         const int g = (int)(local % gmax);
 
-        const int k = pr.nb_f1[e];
-        const int f1 = pr.f1_index[k];
+        const int k1 = pr.nb_f1[e];
+        const int f1 = pr.f1_index[k1];
         const int f2 = pr.nb_f2[e];
-        const long long a = c1.offset[f1];
-        const int n1 = (int)(c1.offset[f1 + 1] - a);
-        const long long b = c2.offset[f2];
-        const int n2 = (int)(c2.offset[f2 + 1] - b);
+        const int n1 = c1.dg_count[f1], n2 = c2.dg_count[f2];
         if (n1 == 0 || n2 == 0) continue;
-        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e], ang = pr.nb_ang[e];
-        const double *__restrict__ p_rc1 = c1.r_comov + a;
-        const double *__restrict__ p_dm1 = c1.dist_m + a;
-        const double *__restrict__ p_z1 = c1.z + a;
+        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        const double *__restrict__ p_rc1 = c1.dg_rcdm + 2 * c1.dg_offset[f1];  // (rc, dm) pairs
+        const double *__restrict__ p_rc2 = c2.dg_rcdm + 2 * c2.dg_offset[f2];
 
         // ---- diagonal range of the forest pair and row range of this block (supersets).
         // lane = segment of L consecutive rows; columns of row i in range: [jlo(i), jhi(i))
         const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
         const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
         const double dmin = P.r_par_min * inv_c;
-        const double dlow = XCORR ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
+        const double dlow = ABS ? -dmax : (dmin - fabs(dmin) * 1e-9 - 1e-9);
         const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
         const int L = (n1 + 31) >> 5;
         const int s0 = lane * L, s1 = min(n1, s0 + L) - 1;
         int dlo = 0x7fffffff, dhi = -0x7fffffff;
         if (s0 < n1) {
-            const int jlo = dg_bound(c2.r_comov + b, n2, __ldg(p_rc1 + s0) - dmax, true);
-            int jhi = dg_bound(c2.r_comov + b, n2, __ldg(p_rc1 + s1) - dlow, false);
+            const int jlo = dg_bound(p_rc2, n2, __ldg(p_rc1 + 2 * s0) - dmax, true);
+            int jhi = dg_bound(p_rc2, n2, __ldg(p_rc1 + 2 * s1) - dlow, false);
             if (isfinite(tsum))
-                jhi = min(jhi, dg_bound(c2.dist_m + b, n2, tsum - __ldg(p_dm1 + s0), false));
+                jhi = min(jhi, dg_bound(p_rc2 + 1, n2, tsum - __ldg(p_rc1 + 2 * s0 + 1), false));
             if (jhi > jlo) {
                 dlo = jlo - s1;
                 dhi = jhi - 1 - s0;
@@ -316,63 +153,170 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
             Dmax = max(Dmax, __shfl_xor_sync(0xffffffffu, Dmax, m));
         }
         if (Dmin > Dmax) continue;
-        const int D0 = Dmin + DG_BLOCK * g;
+        // blocks start at a multiple of DG_C (the interleaved copy is addressed by phase)
+        const int Dbase = Dmin - (((Dmin % DG_C) + DG_C) % DG_C);
+        const int D0 = Dbase + DG_BLOCK * g;
         if (D0 > Dmax) continue;
-        const int D1 = min(D0 + DG_BLOCK - 1, Dmax);
+        const int D1 = D0 + DG_BLOCK - 1;
         const unsigned segs = __ballot_sync(0xffffffffu, dlo <= D1 && dhi >= D0);
         if (!segs) continue;
         int ibeg = (__ffs(segs) - 1) * L;
         int iend = min(n1, (32 - __clz(segs)) * L);
-        ibeg = max(ibeg, max(0, -D1));
+        // lanes read columns i + D0 .. i + D0 + DG_BLOCK - 1: rows whose whole span lies outside
+        // forest 2 are skipped; everything else stays inside the padding of the packed copies
+        ibeg = max(ibeg, max(0, -D0 - (DG_BLOCK - 1)));
         iend = min(iend, n2 - D0);
         if (ibeg >= iend) continue;
+        ibeg -= ibeg % DG_C;
 
-        const long long pb = c2.perm_offset[f2];
-        const double2 *__restrict__ p_rcdm2 = reinterpret_cast<const double2 *>(c2.rcdm_p) + pb;
-        const double2 *__restrict__ p_wdw2 = reinterpret_cast<const double2 *>(c2.wdw_p) + pb;
-        const double *__restrict__ p_z2 = c2.z_p + pb;
-        const double2 *__restrict__ p_rcdm1 = reinterpret_cast<const double2 *>(c1.rcdm) + a;
-        const double2 *__restrict__ p_wdw1 = reinterpret_cast<const double2 *>(c1.wdw) + a;
-        const int S2 = (n2 + 1) >> 1;
-        double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
-        __syncwarp();
-        if (lane == 0) {  // bin edges in units of d and t, guard band, cos / sin of ang/2
-            edge[0] = P.r_par_min * inv_c;
-            edge[1] = C.dbin_p * inv_c;
-            edge[2] = C.dbin_t * inv_s;
-            edge[3] = DG_EPS * C.rp_scale * inv_c;
-            edge[4] = DG_EPS * P.r_trans_max * inv_s;
-            edge[5] = ch;
-            edge[6] = sh;
+        double *__restrict__ const orow = out + (size_t)out_row[k1] * 6 * nb;
+        const double ang = pr.nb_ang[e];
+        // bin constants of this forest pair
+        const double kpl = FOLD ? mul_rn(ch, C.kp_lo) : C.kp_lo;
+        const double kph = FOLD ? mul_rn(ch, C.kp_hi) : C.kp_hi;
+        const double ktl = mul_rn(sh, C.kt_lo), kth = mul_rn(sh, C.kt_hi);
+
+        // per diagonal: sums of the current run, the step it started at, the low words of its
+        // bin; `lv` bit k = the run of diagonal k is in range.  No run is open at the start.
+        double a0[DG_C], a1[DG_C], a2[DG_C], a3[DG_C], a4[DG_C];
+        int curp[DG_C], curt[DG_C], start[DG_C];
+        unsigned lv = 0;
+#pragma unroll
+        for (int k = 0; k < DG_C; k++) {
+            a0[k] = a1[k] = a2[k] = a3[k] = a4[k] = 0.;
+            curp[k] = DG_NO_BIN;
+            curt[k] = 0;
+            start[k] = 0;
         }
-        DG_DECL(0)
-        DG_DECL(1)
-        __syncwarp();
-        DG_COLS(c0)
-        DG_COLS(c1)
-        // c0 / c1 = columns i + D0 + 2 lane + {0, 1}; each step the window slides by one column.
-        // i advances by 2 per iteration, so c0 always reads one parity half of the interleaved
-        // copy and c1 the other: two slot counters that advance by one per iteration.
-        const int jb = ibeg + D0;
-        int pos0 = (jb & 1) * S2 + (jb >> 1) + lane;              // slot of column jb + 2 lane
-        int pos1 = ((jb + 1) & 1) * S2 + ((jb + 1) >> 1) + lane;  // slot of column jb + 1 + 2 lane
-        int jj0 = jb + 2 * lane;
-        DG_LOAD(c0, pos0, jj0)
-        DG_LOAD(c1, pos1, jj0 + 1)
-        for (int i = ibeg; i < iend; i += 2) {
-            DG_STEP(i, c0, c1)
-            pos0 += 1;
-            DG_LOAD(c0, pos0, jj0 + 2)
-            if (i + 1 < iend) {
-                DG_STEP(i + 1, c1, c0)
-                pos1 += 1;
-                DG_LOAD(c1, pos1, jj0 + 3)
+
+        // rows: natural-order packed copy of forest 1 (uniform loads).  32-bit element indices
+        // (checked by pb2_xi_diag_eligible) keep the address registers few.
+        const unsigned ra = (unsigned)c1.dg_offset[f1];
+        const double2 *__restrict__ p_r1 = reinterpret_cast<const double2 *>(c1.dg_rcdm);
+        const double2 *__restrict__ p_w1 = reinterpret_cast<const double2 *>(c1.dg_wdw);
+        const double *__restrict__ p_z1 = c1.dg_z;
+        // columns: copy of forest 2 interleaved by DG_C; padded column jp = j + PB2_DIAG_PAD sits
+        // in plane jp % DG_C at il_offset[f2] + jp / DG_C.  This lane's first column is
+        // ibeg + D0 + DG_C * lane (a multiple of DG_C after padding).
+        const unsigned plane = (unsigned)c2.il_total;
+        unsigned cpos = (unsigned)c2.il_offset[f2] + (unsigned)((ibeg + D0 + PB2_DIAG_PAD) / DG_C + lane);
+        const double2 *__restrict__ q_r2 = reinterpret_cast<const double2 *>(c2.il_rcdm);
+        const double2 *__restrict__ q_w2 = reinterpret_cast<const double2 *>(c2.il_wdw);
+        const double *__restrict__ q_z2 = c2.il_z;
+
+        double2 cr[DG_C], cw[DG_C];
+        double cz[DG_C];
+#pragma unroll
+        for (int k = 0; k < DG_C - 1; k++) {
+            cr[k] = __ldg(q_r2 + (k * plane + cpos));
+            cw[k] = __ldg(q_w2 + (k * plane + cpos));
+            cz[k] = __ldg(q_z2 + (k * plane + cpos));
+        }
+
+        for (int s = ibeg; s < iend; s += DG_C) {
+#pragma unroll
+            for (int uu = 0; uu < DG_C; uu++) {
+                const unsigned rat = ra + (unsigned)(s + uu);
+                const double2 r1 = __ldg(p_r1 + rat);  // (rc1, dm1), uniform
+                const double2 w1 = __ldg(p_w1 + rat);  // (w1, delta1 w1), uniform
+                const double z1 = __ldg(p_z1 + rat);
+                {
+                    // the new column of this row: ibeg.. + DG_C * lane + uu + DG_C - 1
+                    const int pl = (uu + DG_C - 1) % DG_C;
+                    const unsigned at = pl * plane + cpos + (uu + DG_C - 1) / DG_C;
+                    cr[pl] = __ldg(q_r2 + at);
+                    cw[pl] = __ldg(q_w2 + at);
+                    cz[pl] = __ldg(q_z2 + at);
+                }
+#pragma unroll
+                for (int k = 0; k < DG_C; k++) {
+                    const int sl = (uu + k) % DG_C;
+                    const double d = sub_rn(r1.x, cr[sl].x);
+                    const double v = ABS ? fabs(d) : d;
+                    const double t = add_rn(r1.y, cr[sl].y);
+                    const double x = FOLD ? v : sub_rn(mul_rn(v, ch), P.r_par_min);
+                    const double upl = __fma_rd(x, kpl, DG_MAGIC), uph = __fma_rd(x, kph, DG_MAGIC);
+                    const double utl = __fma_rd(t, ktl, DG_MAGIC), uth = __fma_rd(t, kth, DG_MAGIC);
+                    const int bpl = __double2loint(upl), bph = __double2loint(uph);
+                    const int btl = __double2loint(utl), bth = __double2loint(uth);
+                    const bool chg = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
+                                      ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
+                    const int sidx = s + uu;
+                    if (chg) {
+                        // ---- diagonal k left its run: add the run to its bin
+                        if (lv & (1u << k))
+                            dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, sidx - start[k], a0[k],
+                                    a1[k], a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
+                        // ---- the new run: proven bin, or the reference expression.  Dummy pixels
+                        // (distance 1e300) leave the high word of the r_trans FMA off 2^52 + 2^51
+                        const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
+                        int nbp = bpl, nbt = btl;
+                        bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
+                                    (unsigned)btl < (unsigned)nt_i;
+                        if (fmt && (bpl != bph || btl != bth)) {
+                            const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang, ch, sh);
+                            nbp = b.x;
+                            nbt = b.y;
+                            live = b.x != DG_NO_BIN;
+                        }
+                        curp[k] = nbp;
+                        curt[k] = nbt;
+                        lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
+                    }
+                    // restart the sums in the main path (see the header)
+                    start[k] = chg ? sidx : start[k];
+                    a0[k] = __hiloint2double(chg ? 0 : __double2hiint(a0[k]), __double2loint(a0[k]));
+                    a1[k] = __hiloint2double(chg ? 0 : __double2hiint(a1[k]), __double2loint(a1[k]));
+                    a2[k] = __hiloint2double(chg ? 0 : __double2hiint(a2[k]), __double2loint(a2[k]));
+                    a3[k] = __hiloint2double(chg ? 0 : __double2hiint(a3[k]), __double2loint(a3[k]));
+                    a4[k] = __hiloint2double(chg ? 0 : __double2hiint(a4[k]), __double2loint(a4[k]));
+                    const double w12 = mul_rn(w1.x, cw[sl].x);
+                    a0[k] += w12;
+                    a1[k] = fma(w1.y, cw[sl].y, a1[k]);
+                    a2[k] = fma(v, w12, a2[k]);
+                    a3[k] = fma(t, w12, a3[k]);
+                    a4[k] = fma(add_rn(z1, cz[sl]), w12, a4[k]);
+                }
             }
-            jj0 += 2;
+            cpos += 1;
         }
-        DG_RED(0)
-        DG_RED(1)
+        // ---- last runs of the unit's diagonals (rows were walked up to a multiple of DG_C)
+        const int send = ibeg + ((iend - ibeg + DG_C - 1) / DG_C) * DG_C;
+#pragma unroll
+        for (int k = 0; k < DG_C; k++) {
+            if (lv & (1u << k))
+                dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, send - start[k], a0[k], a1[k],
+                        a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
+        }
     }
+}
+
+template <bool ABS, bool FOLD>
+static int32_t dg_launch(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
+                         const pb2_pairs *pairs, const DiagConst &C, const int32_t *d_out_row,
+                         double *d_out, int blocks, cudaStream_t s)
+{
+    pb2_xi_auto_diag<ABS, FOLD><<<blocks, DG_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, C,
+                                                                  d_out_row, d_out);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_xi_auto_diag");
+}
+
+// can this launch use the diagonal-lane kernel?  (the caller has checked the binning mode)
+bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
+                          int64_t n_rows)
+{
+    if (!c1->dg_rcdm || !c2->il_rcdm || c1->dg_lanes != DG_C || c2->dg_lanes != DG_C) return false;
+    if (!c1->dg_ok || !c2->dg_ok) return false;
+    const double nb6 = 6. * par->num_bins_r_par * par->num_bins_r_trans;
+    if ((double)n_rows * nb6 >= 4294967296.) return false;  // 32-bit histogram offsets
+    // low-word bins: |x K| must stay far below 2^31 for every real pair
+    const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
+    const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
+    const double reach = c1->dg_reach + c2->dg_reach;
+    const double rmin = par->r_par_min < 0 ? -par->r_par_min : par->r_par_min;
+    if (!((reach + rmin) * kp < 1e9) || !(reach * kt < 1e9)) return false;
+    return true;
 }
 
 int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
@@ -380,13 +324,7 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
                            cudaStream_t s)
 {
     DiagConst C;
-    C.dbin_p = (par->r_par_max - par->r_par_min) / par->num_bins_r_par;
-    C.dbin_t = par->r_trans_max / par->num_bins_r_trans;
-    const double a0 = par->r_par_min < 0 ? -par->r_par_min : par->r_par_min;
-    const double a1 = par->r_par_max < 0 ? -par->r_par_max : par->r_par_max;
-    C.rp_scale = a0 > a1 ? a0 : a1;
-    C.gmax = (c1->max_pix + c2->max_pix + DG_BLOCK - 1) / DG_BLOCK;
-    if (C.gmax < 1) C.gmax = 1;
+    C.gmax = (c1->dg_max_pix + c2->dg_max_pix + DG_C + DG_BLOCK - 1) / DG_BLOCK + 1;
     const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
     const double eps = 9.094947017729282e-13;  // 2^-40
@@ -394,7 +332,6 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
     C.kp_hi = kp * (1. + eps);
     C.kt_lo = kt * (1. - eps);
     C.kt_hi = kt * (1. + eps);
-    C.magic = 6755399441055744.0;  // 2^52 + 2^51
     int dev = 0, sms = 0;
     PB2_CUDA(cudaGetDevice(&dev));
     PB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -402,9 +339,8 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
     int blocks = (int)(want < sms ? want : sms);
     if (blocks < 1) blocks = 1;
     if (par->x_correlation)
-        pb2_xi_auto_diag<true><<<blocks, DG_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, C, d_out_row, d_out);
-    else
-        pb2_xi_auto_diag<false><<<blocks, DG_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, C, d_out_row, d_out);
-    pb2_count_launch(1);
-    return pb2_check_launch("pb2_xi_auto_diag");
+        return dg_launch<false, false>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
+    if (par->r_par_min != 0.)
+        return dg_launch<true, false>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
+    return dg_launch<true, true>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
 }
