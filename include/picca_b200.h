@@ -28,7 +28,7 @@ extern "C" {
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
-#define PB2_DIAG_LANES 4                     /* adjacent diagonals per lane */
+#define PB2_DIAG_LANES 2                     /* adjacent diagonals per lane */
 #endif
 #define PB2_DIAG_PAD (34 * PB2_DIAG_LANES)   /* dummy pixels either side, interleaved copy */
 #define PB2_DIAG_ROW_PAD 8                   /* dummy pixels after a line of sight, natural copy */

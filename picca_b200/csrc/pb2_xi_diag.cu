@@ -37,7 +37,7 @@
 
 #define DG_C PB2_DIAG_LANES
 #ifndef DG_THREADS
-#define DG_THREADS 384
+#define DG_THREADS 512
 #endif
 #ifndef DG_CHUNK
 #define DG_CHUNK 8
@@ -228,53 +228,81 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                     cw[pl] = __ldg(q_w2 + at);
                     cz[pl] = __ldg(q_z2 + at);
                 }
+                // phase 1: geometry and bins of the DG_C pairs of this row (independent chains)
+                const int sidx = s + uu;
+                double v[DG_C], t[DG_C];
+                bool chg[DG_C];
+                bool any = false;
 #pragma unroll
                 for (int k = 0; k < DG_C; k++) {
                     const int sl = (uu + k) % DG_C;
                     const double d = sub_rn(r1.x, cr[sl].x);
-                    const double v = ABS ? fabs(d) : d;
-                    const double t = add_rn(r1.y, cr[sl].y);
-                    const double x = FOLD ? v : sub_rn(mul_rn(v, ch), P.r_par_min);
-                    const double upl = __fma_rd(x, kpl, DG_MAGIC), uph = __fma_rd(x, kph, DG_MAGIC);
-                    const double utl = __fma_rd(t, ktl, DG_MAGIC), uth = __fma_rd(t, kth, DG_MAGIC);
-                    const int bpl = __double2loint(upl), bph = __double2loint(uph);
-                    const int btl = __double2loint(utl), bth = __double2loint(uth);
-                    const bool chg = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
-                                      ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
-                    const int sidx = s + uu;
-                    if (chg) {
-                        // ---- diagonal k left its run: add the run to its bin
-                        if (lv & (1u << k))
-                            dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, sidx - start[k], a0[k],
-                                    a1[k], a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
-                        // ---- the new run: proven bin, or the reference expression.  Dummy pixels
-                        // (distance 1e300) leave the high word of the r_trans FMA off 2^52 + 2^51
-                        const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
-                        int nbp = bpl, nbt = btl;
-                        bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
-                                    (unsigned)btl < (unsigned)nt_i;
-                        if (fmt && (bpl != bph || btl != bth)) {
-                            const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang, ch, sh);
-                            nbp = b.x;
-                            nbt = b.y;
-                            live = b.x != DG_NO_BIN;
+                    v[k] = ABS ? fabs(d) : d;
+                    t[k] = add_rn(r1.y, cr[sl].y);
+                    const double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
+                    const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
+                    const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
+                    const int btl = __double2loint(__fma_rd(t[k], ktl, DG_MAGIC));
+                    const int bth = __double2loint(__fma_rd(t[k], kth, DG_MAGIC));
+                    chg[k] = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
+                              ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
+                    any = any || chg[k];
+                }
+                // phase 2: run changes (one branch per row in the common case)
+                if (any) {
+#pragma unroll
+                    for (int k = 0; k < DG_C; k++) {
+                        if (chg[k]) {
+                            const int sl = (uu + k) % DG_C;
+                            // ---- diagonal k left its run: add the run to its bin
+                            if (lv & (1u << k))
+                                dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, sidx - start[k], a0[k],
+                                        a1[k], a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
+                            // ---- the new run: proven bin, or the reference expression.  Dummy
+                            // pixels (distance 1e300) leave the high word of the r_trans FMA off
+                            // 2^52 + 2^51
+                            // (recomputed behind an opaque copy: keeping phase 1's values alive
+                            // for this rare path costs four register moves per pair)
+                            double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
+                            double tt = t[k];
+                            asm volatile("" : "+d"(x), "+d"(tt));
+                            const double utl = __fma_rd(tt, ktl, DG_MAGIC);
+                            const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
+                            const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
+                            const int btl = __double2loint(utl);
+                            const int bth = __double2loint(__fma_rd(tt, kth, DG_MAGIC));
+                            const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
+                            int nbp = bpl, nbt = btl;
+                            bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
+                                        (unsigned)btl < (unsigned)nt_i;
+                            if (fmt && (bpl != bph || btl != bth)) {
+                                const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang,
+                                                            ch, sh);
+                                nbp = b.x;
+                                nbt = b.y;
+                                live = b.x != DG_NO_BIN;
+                            }
+                            curp[k] = nbp;
+                            curt[k] = nbt;
+                            start[k] = sidx;
+                            lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
                         }
-                        curp[k] = nbp;
-                        curt[k] = nbt;
-                        lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
                     }
-                    // restart the sums in the main path (see the header)
-                    start[k] = chg ? sidx : start[k];
-                    a0[k] = __hiloint2double(chg ? 0 : __double2hiint(a0[k]), __double2loint(a0[k]));
-                    a1[k] = __hiloint2double(chg ? 0 : __double2hiint(a1[k]), __double2loint(a1[k]));
-                    a2[k] = __hiloint2double(chg ? 0 : __double2hiint(a2[k]), __double2loint(a2[k]));
-                    a3[k] = __hiloint2double(chg ? 0 : __double2hiint(a3[k]), __double2loint(a3[k]));
-                    a4[k] = __hiloint2double(chg ? 0 : __double2hiint(a4[k]), __double2loint(a4[k]));
+                }
+                // phase 3: restart the sums of changed runs (see the header) and accumulate
+#pragma unroll
+                for (int k = 0; k < DG_C; k++) {
+                    const int sl = (uu + k) % DG_C;
+                    a0[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a0[k]), __double2loint(a0[k]));
+                    a1[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a1[k]), __double2loint(a1[k]));
+                    a2[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a2[k]), __double2loint(a2[k]));
+                    a3[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a3[k]), __double2loint(a3[k]));
+                    a4[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a4[k]), __double2loint(a4[k]));
                     const double w12 = mul_rn(w1.x, cw[sl].x);
                     a0[k] += w12;
                     a1[k] = fma(w1.y, cw[sl].y, a1[k]);
-                    a2[k] = fma(v, w12, a2[k]);
-                    a3[k] = fma(t, w12, a3[k]);
+                    a2[k] = fma(v[k], w12, a2[k]);
+                    a3[k] = fma(t[k], w12, a3[k]);
                     a4[k] = fma(add_rn(z1, cz[sl]), w12, a4[k]);
                 }
             }
