@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 8
+#define PB2_ABI_VERSION 9
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -32,6 +32,7 @@ extern "C" {
 #endif
 #define PB2_DIAG_PAD (34 * PB2_DIAG_LANES)   /* dummy pixels either side, interleaved copy */
 #define PB2_DIAG_ROW_PAD 8                   /* dummy pixels after a line of sight, natural copy */
+#define PB2_DIAG_CHUNK_ROWS 32               /* rows staged in shared memory per TMA bulk copy */
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */
@@ -84,24 +85,23 @@ typedef struct pb2_catalog {
     const double *log_lambda; /* Delta.log_lambda (distortion matrix only; may be NULL) */
     /* ---- packed copies read by the diagonal-lane xi kernel (pb2_xi_diag.cu); NULL for object
      * catalogues.  Zero-weight pixels (never counted by the reference, cf.py:318,331) are
-     * compacted away; dg_count[f] pixels of line of sight f remain.
-     * Natural order (row loads, window searches): pixel i of line of sight f sits at
-     * dg_offset[f] + i, followed by PB2_DIAG_ROW_PAD dummies (+Inf distances, zeros elsewhere). */
+     * compacted away; dg_count[f] pixels of line of sight f remain.  A pixel is a 48-byte record
+     * (r_comov, dist_m, weights, delta_w, z / 2, 0).
+     * Natural order (row records, window searches): pixel i of line of sight f is record
+     * dg_offset[f] + i of dg_rec, followed by PB2_DIAG_ROW_PAD dummies (distance 1e299, zeros
+     * elsewhere); PB2_DIAG_CHUNK_ROWS more dummies end the array. */
     const int64_t *dg_offset;    /* [n_los] */
     const int32_t *dg_count;     /* [n_los] */
-    const double *dg_rcdm;       /* (r_comov, dist_m) pairs, 16-byte elements */
-    const double *dg_wdw;        /* (weights, delta_w) pairs, 16-byte elements */
-    const double *dg_z;          /* z */
-    /* Interleaved by PB2_DIAG_LANES (column loads): with jp = j + PB2_DIAG_PAD, pixel j of line of
-     * sight f sits in plane jp % PB2_DIAG_LANES at il_offset[f] + jp / PB2_DIAG_LANES; plane p of
-     * an array starts il_total elements after plane p - 1.  Every line of sight is padded with
-     * PB2_DIAG_PAD dummies (+Inf distances, zeros elsewhere) on both sides, so a warp may read a
-     * whole diagonal block past either end without a bounds check. */
+    const double *dg_rec;
+    /* Interleaved by PB2_DIAG_LANES (column records): with jp = j + PB2_DIAG_PAD, pixel j of line
+     * of sight f is record il_offset[f] + jp / PB2_DIAG_LANES of plane jp % PB2_DIAG_LANES; plane
+     * p starts at record p * il_total of il_rec.  Every line of sight is padded with PB2_DIAG_PAD
+     * dummies (distance 1e300, zeros elsewhere) on both sides, and every plane ends with
+     * PB2_DIAG_CHUNK_ROWS + 64 more, so a warp may copy whole chunks of a diagonal block past
+     * either end without a bounds check. */
     const int64_t *il_offset;    /* [n_los] */
-    int64_t il_total;            /* elements per plane */
-    const double *il_rcdm;       /* (r_comov, dist_m) */
-    const double *il_wdw;        /* (weights, delta_w) */
-    const double *il_z;          /* z */
+    int64_t il_total;            /* records per plane */
+    const double *il_rec;
     int32_t dg_lanes;            /* PB2_DIAG_LANES the copies were packed for */
     int32_t dg_max_pix;          /* longest compacted line of sight */
     int32_t dg_ok;               /* 1 if every r_comov, dist_m, z, weight, delta_w is finite */

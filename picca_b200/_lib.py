@@ -58,14 +58,10 @@ class Catalog(ctypes.Structure):
         ("log_lambda", c_void_p),
         ("dg_offset", c_void_p),
         ("dg_count", c_void_p),
-        ("dg_rcdm", c_void_p),
-        ("dg_wdw", c_void_p),
-        ("dg_z", c_void_p),
+        ("dg_rec", c_void_p),
         ("il_offset", c_void_p),
         ("il_total", ctypes.c_int64),
-        ("il_rcdm", c_void_p),
-        ("il_wdw", c_void_p),
-        ("il_z", c_void_p),
+        ("il_rec", c_void_p),
         ("dg_lanes", ctypes.c_int32),
         ("dg_max_pix", ctypes.c_int32),
         ("dg_ok", ctypes.c_int32),
@@ -119,7 +115,7 @@ EXPORTS = [
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 def lib():

@@ -14,8 +14,7 @@ import numpy as np
 from . import _lib
 
 _PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
-_DIAG_FIELDS = ("dg_offset", "dg_count", "dg_rcdm", "dg_wdw", "dg_z",
-                "il_offset", "il_rcdm", "il_wdw", "il_z")
+_DIAG_FIELDS = ("dg_offset", "dg_count", "dg_rec", "il_offset", "il_rec")
 DIAG_DUMMY_COL = 1e300   # distance of the dummy pixels around a line of sight (interleaved copy)
 DIAG_DUMMY_ROW = 1e299   # ... and after it in the natural-order copy
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
@@ -63,69 +62,64 @@ def _as_int64(values):
 
 
 def diag_layout():
-    """(lanes, pad, row_pad) of the packed copies the diagonal-lane xi kernel reads
-    (PB2_DIAG_LANES, PB2_DIAG_PAD, PB2_DIAG_ROW_PAD of include/picca_b200.h)."""
+    """(lanes, pad, row_pad, chunk_rows) of the packed copies the diagonal-lane xi kernel reads
+    (PB2_DIAG_LANES, PB2_DIAG_PAD, PB2_DIAG_ROW_PAD, PB2_DIAG_CHUNK_ROWS of
+    include/picca_b200.h)."""
     lanes = int(_lib.lib().pb2_diag_lanes())
-    return lanes, 34 * lanes, 8
+    return lanes, 34 * lanes, 8, 32
 
 
 def _pack_diag_copies(cat, offset):
     """Packed copies for the diagonal-lane xi kernel (layout: include/picca_b200.h, pb2_catalog).
 
-    Zero-weight pixels are dropped (the reference never counts them, cf.py:318,331).  Natural
-    order with ROW_PAD dummies after every line of sight, and a copy interleaved by LANES with PAD
-    dummies either side.  Dummies have weight 0 and a distance of 1e300 / 1e299: they add zeros to
-    every sum and fall in no bin."""
+    Zero-weight pixels are dropped (the reference never counts them, cf.py:318,331).  A pixel is
+    a record of six doubles (r_comov, dist_m, weights, delta*weights, z/2, 0).  Natural order with
+    ROW_PAD dummies after every line of sight, and a copy interleaved by LANES with PAD dummies
+    either side.  Dummies have weight 0 and a distance of 1e300 / 1e299: they add zeros to every
+    sum and fall in no bin."""
     A = cat.arrays
-    lanes, pad, row_pad = diag_layout()
+    lanes, pad, row_pad, chunk = diag_layout()
     n = cat.n_los
     keep = A["weights"] != 0
     lengths = np.diff(offset)
     los_all = np.repeat(np.arange(n, dtype=np.int64), lengths)
     count = np.bincount(los_all[keep], minlength=n).astype(np.int64) if n else np.zeros(0, np.int64)
     los = los_all[keep]
-    rc, dm, z = A["r_comov"][keep], A["dist_m"][keep], A["z"][keep]
-    w, dw = A["weights"][keep], A["delta_w"][keep]
+    rec = np.zeros((len(los), 6), dtype=np.float64)
+    rec[:, 0], rec[:, 1] = A["r_comov"][keep], A["dist_m"][keep]
+    rec[:, 2], rec[:, 3] = A["weights"][keep], A["delta_w"][keep]
+    rec[:, 4] = 0.5 * A["z"][keep]
     first = np.zeros(n + 1, dtype=np.int64)
     first[1:] = np.cumsum(count)
     rank = np.arange(len(los), dtype=np.int64) - first[:-1][los]   # pixel index inside its forest
 
     # natural order
     dg_offset = first[:-1] + row_pad * np.arange(n, dtype=np.int64)
-    total = int(first[-1]) + row_pad * n
-    pos = dg_offset[los] + rank
-    rcdm = np.full((total, 2), DIAG_DUMMY_ROW, dtype=np.float64)
-    rcdm[pos, 0], rcdm[pos, 1] = rc, dm
-    wdw = np.zeros((total, 2), dtype=np.float64)
-    wdw[pos, 0], wdw[pos, 1] = w, dw
-    zz = np.zeros(total, dtype=np.float64)
-    zz[pos] = z
+    total = int(first[-1]) + row_pad * n + chunk
+    dg_rec = np.zeros((total, 6), dtype=np.float64)
+    dg_rec[:, 0] = dg_rec[:, 1] = DIAG_DUMMY_ROW
+    dg_rec[dg_offset[los] + rank] = rec
     A["dg_offset"] = np.ascontiguousarray(dg_offset)
     A["dg_count"] = count.astype(np.int32)
-    A["dg_rcdm"], A["dg_wdw"], A["dg_z"] = rcdm.reshape(-1), wdw.reshape(-1), zz
+    A["dg_rec"] = dg_rec.reshape(-1)
 
     # interleaved by `lanes`
     per_plane = (count + lanes - 1) // lanes + 2 * pad // lanes
     il_offset = np.zeros(n + 1, dtype=np.int64)
     il_offset[1:] = np.cumsum(per_plane)
-    il_total = int(il_offset[-1])
+    il_total = int(il_offset[-1]) + chunk + 64
     jp = rank + pad
-    pos = (jp % lanes) * il_total + il_offset[:-1][los] + jp // lanes
-    rcdm = np.full((lanes * il_total, 2), DIAG_DUMMY_COL, dtype=np.float64)
-    rcdm[pos, 0], rcdm[pos, 1] = rc, dm
-    wdw = np.zeros((lanes * il_total, 2), dtype=np.float64)
-    wdw[pos, 0], wdw[pos, 1] = w, dw
-    zz = np.zeros(lanes * il_total, dtype=np.float64)
-    zz[pos] = z
+    il_rec = np.zeros((lanes * il_total, 6), dtype=np.float64)
+    il_rec[:, 0] = il_rec[:, 1] = DIAG_DUMMY_COL
+    il_rec[(jp % lanes) * il_total + il_offset[:-1][los] + jp // lanes] = rec
     A["il_offset"] = np.ascontiguousarray(il_offset[:-1])
-    A["il_rcdm"], A["il_wdw"], A["il_z"] = rcdm.reshape(-1), wdw.reshape(-1), zz
+    A["il_rec"] = il_rec.reshape(-1)
     cat.il_total = il_total
     cat.dg_lanes = lanes
     cat.dg_max_pix = int(count.max()) if n else 0
-    finite = all(bool(np.all(np.isfinite(x))) for x in (rc, dm, z, w, dw))
-    # 32-bit element indices in the kernel
-    cat.dg_ok = int(finite and total < 2**31 and lanes * il_total < 2**31)
-    cat.dg_reach = float(max(np.abs(rc).max(), np.abs(dm).max())) if len(rc) and finite else 0.0
+    finite = bool(np.all(np.isfinite(rec)))
+    cat.dg_ok = int(finite)
+    cat.dg_reach = float(np.abs(rec[:, :2]).max()) if len(rec) and finite else 0.0
 
 
 def pack(data, is_object=False, ang_correlation=False):
@@ -276,7 +270,7 @@ def build_struct(host, tensors):
     for name in ("offset",) + _PIXEL_FIELDS + _LOS_F64 + _LOS_I64 + (
             "order", "row", "hp_first", "cap_x", "cap_y", "cap_z", "cap_rad"):
         setattr(c, name, tensors[name].data_ptr())
-    if "dg_rcdm" in tensors:
+    if "dg_rec" in tensors:
         for name in _DIAG_FIELDS:
             setattr(c, name, tensors[name].data_ptr())
         c.il_total = host.il_total

@@ -505,8 +505,8 @@ int32_t pb2_launch_xi_fast(const pb2_catalog *c1, const pb2_catalog *c2, const p
 bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                           int64_t n_rows);
 int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
-                           const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
-                           cudaStream_t s);
+                           const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
+                           double *d_out, cudaStream_t s);
 
 // the specialised kernels (pb2_xi_diag.cu, pb2_xi_fast.cu) cover the standard binning without
 // per-pair cuts
@@ -542,7 +542,7 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
         rc = pb2_check_launch("pb2_xi_auto_brute");
     } else if (variant == 0 && fast_eligible(cat1, cat2, par) &&
                pb2_xi_diag_eligible(cat1, cat2, par, n_rows)) {
-        rc = pb2_launch_xi_diag(cat1, cat2, par, pairs, d_out_row, d_out, s);
+        rc = pb2_launch_xi_diag(cat1, cat2, par, pairs, d_out_row, n_rows, d_out, s);
     } else if ((variant == 0 || variant == 3) && fast_eligible(cat1, cat2, par)) {
         rc = pb2_launch_xi_fast(cat1, cat2, par, pairs, d_out_row, d_out, s);
     } else {

@@ -29,13 +29,21 @@
 //               L1 data pipe.  When the two FMAs of a dimension disagree (pair within 2^-40 of a
 //               bin edge, ~1e-10 of the pairs) the bin comes from the reference expression with
 //               IEEE divisions.
-// Work unit = (forest pair, block of 32 * DG_C diagonals), one warp.  The warp walks the rows: the
-// row's values are uniform 128-bit loads; each lane loads ONE new column element per row (the
-// other DG_C - 1 slide through registers, statically renamed by unrolling DG_C rows) from a copy
-// of forest 2 interleaved by DG_C, which makes that load coalesced.
+// Work unit = (forest pair, block of 32 * DG_C diagonals), one warp.  The warp walks the rows in
+// chunks of DG_R: one lane issues TMA bulk copies (cp.async.bulk, completion on an mbarrier) of the
+// chunk's row records and of the column records it needs from a copy of forest 2 interleaved by
+// DG_C, into a two-stage per-warp buffer in shared memory, one chunk ahead of the arithmetic.
+// Pixels are 48-byte records (r_comov, dist_m, weight, delta*weight, z/2, 0).  Per row the warp
+// reads the row's record with broadcast loads and each lane ONE new column record (the other
+// DG_C - 1 slide through registers, statically renamed by unrolling DG_C rows); all addresses are a
+// running shared-memory pointer plus immediates.
+// The histogram is accumulated in a [row][bin][8]-slot scratch (the six sums of a bin share one
+// 64-byte line: one address per run change) and folded into the caller's [row][6][bin] layout by
+// pb2_xi_diag_fold.
 #include "pb2_common.cuh"
 
 #define DG_C PB2_DIAG_LANES
+#define DG_R PB2_DIAG_CHUNK_ROWS
 #ifndef DG_THREADS
 #define DG_THREADS 512
 #endif
@@ -44,24 +52,77 @@
 #endif
 #define DG_WARPS (DG_THREADS / 32)
 #define DG_BLOCK (32 * DG_C)
-#define DG_DEAD_START 0x3fffffff
 #define DG_MAGIC 6755399441055744.0  // 2^52 + 2^51
 #define DG_MAGIC_HI 0x43380000       // its high word: unchanged by adding 0 <= bin < 2^31
 #define DG_NO_BIN ((int)0x80000000)
+#define DG_GMAX 48                                  // diagonal blocks per forest pair, at most
+#define DG_REC 48                                   // bytes per pixel record
+#define DG_ROW_BYTES (DG_R * DG_REC)                // row records of a chunk
+#define DG_PLANE_REC (DG_R / DG_C + 33)             // column records of a chunk, per plane
+#define DG_PLANE_BYTES (DG_PLANE_REC * DG_REC)
+#define DG_STAGE_BYTES (DG_ROW_BYTES + DG_C * DG_PLANE_BYTES)
+
+static_assert(DG_R % DG_C == 0, "chunk rows must be a multiple of the diagonals per lane");
+static_assert(PB2_DIAG_PAD % DG_C == 0, "padding must be a multiple of the diagonals per lane");
 
 struct DiagConst {
     double kp_lo, kp_hi, kt_lo, kt_hi;  // n / range * (1 -+ 2^-40)
     int gmax;                           // diagonal blocks per forest pair (longest forests)
 };
 
-// first index in non-decreasing a[0], a[2], a[4] ... (n values, stride 2 doubles) with
+// ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier)
+__device__ __forceinline__ unsigned dg_saddr(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void dg_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dg_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void dg_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void dg_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DG_DONE;\n"
+        "bra DG_WAIT;\n"
+        "DG_DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// plain (schedulable) shared-memory loads at a byte offset of the dynamic buffer
+__device__ __forceinline__ double2 dg_lds128(const unsigned char *p)
+{
+    return *reinterpret_cast<const double2 *>(p);
+}
+__device__ __forceinline__ double dg_lds64(const unsigned char *p)
+{
+    return *reinterpret_cast<const double *>(p);
+}
+
+// first index in non-decreasing a[0], a[6], a[12] ... (n records of 6 doubles) with
 // a[idx] > v (strict) or a[idx] >= v
 __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, double v, bool strict)
 {
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const double x = __ldg(a + 2 * mid);
+        const double x = __ldg(a + 6 * mid);
         if (strict ? (x <= v) : (x < v)) lo = mid + 1;
         else hi = mid;
     }
@@ -78,15 +139,16 @@ __device__ __noinline__ int2 dg_exact_bin(const pb2_params &P, double rc1, doubl
     return make_int2(bp, bin - bp * P.num_bins_r_trans);
 }
 
-__device__ __forceinline__ void dg_emit(double *__restrict__ dst, int nb, int cnt, double a0,
-                                        double a1, double a2, double a3, double a4)
+// one finished run -> the six sums of its bin (one 64-byte line of the scratch histogram)
+__device__ __forceinline__ void dg_emit(double *__restrict__ dst, int cnt, double a0, double a1,
+                                        double a2, double a3, double a4)
 {
     atomic_add_f64(dst, a0);
-    atomic_add_f64(dst + (size_t)nb, a1);
-    atomic_add_f64(dst + 2 * (size_t)nb, a2);
-    atomic_add_f64(dst + 3 * (size_t)nb, a3);
-    atomic_add_f64(dst + 4 * (size_t)nb, a4);
-    atomic_add_i64(dst + 5 * (size_t)nb, (long long)cnt);
+    atomic_add_f64(dst + 1, a1);
+    atomic_add_f64(dst + 2, a2);
+    atomic_add_f64(dst + 3, a3);
+    atomic_add_f64(dst + 4, a4);
+    atomic_add_i64(dst + 5, (long long)cnt);
 }
 
 // ABS: auto-correlation (r_par = |r_par|, cf.py:361-362).  FOLD: r_par_min == 0, so the r_par bin
@@ -95,27 +157,40 @@ __device__ __forceinline__ void dg_emit(double *__restrict__ dst, int nb, int cn
 template <bool ABS, bool FOLD>
 __global__ void __launch_bounds__(DG_THREADS, 1)
 pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DiagConst C,
-                 const int32_t *__restrict__ out_row, double *__restrict__ out)
+                 const int32_t *__restrict__ out_row, double *__restrict__ scr)
 {
+    extern __shared__ __align__(128) unsigned char dg_smem[];
     __shared__ unsigned s_ctr;
-    if (threadIdx.x == 0) s_ctr = 0;
-    __syncthreads();
+    __shared__ __align__(8) unsigned long long s_bar[DG_WARPS][2];
+    __shared__ int2 s_tb[DG_WARPS][DG_GMAX];
     const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_ctr = 0;
+    if (lane == 0) {
+        dg_mbar_init(dg_saddr(&s_bar[wid][0]), 1);
+        dg_mbar_init(dg_saddr(&s_bar[wid][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned bar0 = dg_saddr(&s_bar[wid][0]);                 // stage t: bar0 + 8 t
+    const unsigned buf0 = dg_saddr(dg_smem) + wid * (2 * DG_STAGE_BYTES);  // stage t: + t STAGE
     const int nb = P.num_bins_r_par * P.num_bins_r_trans;
     const int np_i = P.num_bins_r_par, nt_i = P.num_bins_r_trans;
-    const unsigned gmax = (unsigned)C.gmax;
-    const unsigned units_per_chunk = DG_CHUNK * gmax;
+    const double *__restrict__ rec1 = c1.dg_rec;
+    const double *__restrict__ rec2 = c2.il_rec;
+    int2 *const tb = s_tb[wid];  // per block of the current forest pair: (first row, walked rows)
+    unsigned stage = 0;  // stage of the next chunk to consume (warp-uniform)
+    unsigned phase = 0;  // bit t: parity to wait for on stage t
 
     for (;;) {
+        // ---- claim a forest pair (warps of a CTA take neighbouring pairs: they share forest 1)
         unsigned u = 0;
         if (lane == 0) u = atomicAdd(&s_ctr, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        const long long chunk = (long long)blockIdx.x + (long long)(u / units_per_chunk) * gridDim.x;
-        if (chunk * DG_CHUNK >= pr.n_pairs) break;
-        const unsigned local = u % units_per_chunk;
-        const long long e = chunk * DG_CHUNK + local / gmax;
+        const long long e = ((long long)blockIdx.x + (long long)(u / DG_CHUNK) * gridDim.x) * DG_CHUNK +
+                            u % DG_CHUNK;
+        if (e - u % DG_CHUNK >= pr.n_pairs) break;
         if (e >= pr.n_pairs) continue;
-        const int g = (int)(local % gmax);
 
         const int k1 = pr.nb_f1[e];
         const int f1 = pr.f1_index[k1];
@@ -123,10 +198,11 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         const int n1 = c1.dg_count[f1], n2 = c2.dg_count[f2];
         if (n1 == 0 || n2 == 0) continue;
         const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
-        const double *__restrict__ p_rc1 = c1.dg_rcdm + 2 * c1.dg_offset[f1];  // (rc, dm) pairs
-        const double *__restrict__ p_rc2 = c2.dg_rcdm + 2 * c2.dg_offset[f2];
+        const long long ra = c1.dg_offset[f1];
+        const double *__restrict__ p_rc1 = rec1 + 6 * ra;  // records (rc, dm, w, dw, z/2, 0)
+        const double *__restrict__ p_rc2 = c2.dg_rec + 6 * c2.dg_offset[f2];
 
-        // ---- diagonal range of the forest pair and row range of this block (supersets).
+        // ---- diagonal range of the forest pair and row range of every block (supersets).
         // lane = segment of L consecutive rows; columns of row i in range: [jlo(i), jhi(i))
         const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
         const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
@@ -137,10 +213,10 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         const int s0 = lane * L, s1 = min(n1, s0 + L) - 1;
         int dlo = 0x7fffffff, dhi = -0x7fffffff;
         if (s0 < n1) {
-            const int jlo = dg_bound(p_rc2, n2, __ldg(p_rc1 + 2 * s0) - dmax, true);
-            int jhi = dg_bound(p_rc2, n2, __ldg(p_rc1 + 2 * s1) - dlow, false);
+            const int jlo = dg_bound(p_rc2, n2, __ldg(p_rc1 + 6 * s0) - dmax, true);
+            int jhi = dg_bound(p_rc2, n2, __ldg(p_rc1 + 6 * s1) - dlow, false);
             if (isfinite(tsum))
-                jhi = min(jhi, dg_bound(p_rc2 + 1, n2, tsum - __ldg(p_rc1 + 2 * s0 + 1), false));
+                jhi = min(jhi, dg_bound(p_rc2 + 1, n2, tsum - __ldg(p_rc1 + 6 * s0 + 1), false));
             if (jhi > jlo) {
                 dlo = jlo - s1;
                 dhi = jhi - 1 - s0;
@@ -155,27 +231,69 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         if (Dmin > Dmax) continue;
         // blocks start at a multiple of DG_C (the interleaved copy is addressed by phase)
         const int Dbase = Dmin - (((Dmin % DG_C) + DG_C) % DG_C);
-        const int D0 = Dbase + DG_BLOCK * g;
-        if (D0 > Dmax) continue;
-        const int D1 = D0 + DG_BLOCK - 1;
-        const unsigned segs = __ballot_sync(0xffffffffu, dlo <= D1 && dhi >= D0);
-        if (!segs) continue;
-        int ibeg = (__ffs(segs) - 1) * L;
-        int iend = min(n1, (32 - __clz(segs)) * L);
-        // lanes read columns i + D0 .. i + D0 + DG_BLOCK - 1: rows whose whole span lies outside
-        // forest 2 are skipped; everything else stays inside the padding of the packed copies
-        ibeg = max(ibeg, max(0, -D0 - (DG_BLOCK - 1)));
-        iend = min(iend, n2 - D0);
-        if (ibeg >= iend) continue;
-        ibeg -= ibeg % DG_C;
+        const int G = min((Dmax - Dbase) / DG_BLOCK + 1, DG_GMAX);
+        __syncwarp();
+        for (int g = 0; g < G; g++) {
+            const int D0 = Dbase + DG_BLOCK * g, D1 = D0 + DG_BLOCK - 1;
+            const unsigned segs = __ballot_sync(0xffffffffu, dlo <= D1 && dhi >= D0);
+            int ibeg = 0, nrows = 0;
+            if (segs) {
+                ibeg = (__ffs(segs) - 1) * L;
+                int iend = min(n1, (32 - __clz(segs)) * L);
+                // lanes read columns i + D0 .. i + D0 + DG_BLOCK - 1: rows whose whole span lies
+                // outside forest 2 are skipped; everything else stays inside the padding of the
+                // packed copies
+                ibeg = max(ibeg, max(0, -D0 - (DG_BLOCK - 1)));
+                iend = min(iend, n2 - D0);
+                ibeg -= ibeg % DG_C;
+                if (iend > ibeg) nrows = ((iend - ibeg + DG_C - 1) / DG_C) * DG_C;  // walked rows
+            }
+            if (lane == 0) tb[g] = make_int2(ibeg, nrows);
+        }
+        __syncwarp();
 
-        double *__restrict__ const orow = out + (size_t)out_row[k1] * 6 * nb;
+        // ---- chunk c of block g: rows ibeg + c DG_R ..., and per plane the column records from
+        // this lane-0 position on.  Padded column jp = j + PB2_DIAG_PAD sits in plane jp % DG_C at
+        // il_offset[f2] + jp / DG_C; lane l's first column is ibeg + D0 + DG_C l.  The two-stage
+        // pipeline runs across the blocks of the forest pair: (pg, pc) = next chunk to request.
+        const double *__restrict__ g_row = rec1 + 6 * ra;
+        const double *__restrict__ g_col = rec2 + 6 * (c2.il_offset[f2] + (Dbase + PB2_DIAG_PAD) / DG_C);
+        const long long plane6 = 6 * c2.il_total;
+        int pg = 0, pc = 0;
+        auto request = [&](unsigned t) {  // all lanes advance (pg, pc); lane 0 issues the copies
+            while (pg < G && pc * DG_R >= tb[pg].y) {
+                pg++;
+                pc = 0;
+            }
+            if (pg >= G) return;
+            if (lane == 0) {
+                const int ib = tb[pg].x;
+                const unsigned bar = bar0 + 8 * t, dst = buf0 + t * DG_STAGE_BYTES;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                dg_mbar_expect_tx(bar, DG_STAGE_BYTES);
+                dg_bulk_g2s(dst, g_row + (size_t)(ib + pc * DG_R) * 6, DG_ROW_BYTES, bar);
+                const size_t col = (size_t)((ib + pg * DG_BLOCK) / DG_C + pc * (DG_R / DG_C)) * 6;
+#pragma unroll
+                for (int p = 0; p < DG_C; p++)
+                    dg_bulk_g2s(dst + DG_ROW_BYTES + p * DG_PLANE_BYTES, g_col + p * plane6 + col,
+                                DG_PLANE_BYTES, bar);
+            }
+            pc++;
+        };
+        request(stage);
+        request(stage ^ 1u);
+
+        double *__restrict__ const srow = scr + (size_t)out_row[k1] * nb * 8;
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
         const double kpl = FOLD ? mul_rn(ch, C.kp_lo) : C.kp_lo;
         const double kph = FOLD ? mul_rn(ch, C.kp_hi) : C.kp_hi;
         const double ktl = mul_rn(sh, C.kt_lo), kth = mul_rn(sh, C.kt_hi);
 
+        for (int g = 0; g < G; g++) {
+        const int ibeg = tb[g].x, nrows = tb[g].y;
+        if (nrows == 0) continue;
+        const int nchunk = (nrows + DG_R - 1) / DG_R;
         // per diagonal: sums of the current run, the step it started at, the low words of its
         // bin; `lv` bit k = the run of diagonal k is in range.  No run is open at the start.
         double a0[DG_C], a1[DG_C], a2[DG_C], a3[DG_C], a4[DG_C];
@@ -188,144 +306,168 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
             curt[k] = 0;
             start[k] = 0;
         }
-
-        // rows: natural-order packed copy of forest 1 (uniform loads).  32-bit element indices
-        // (checked by pb2_xi_diag_eligible) keep the address registers few.
-        const unsigned ra = (unsigned)c1.dg_offset[f1];
-        const double2 *__restrict__ p_r1 = reinterpret_cast<const double2 *>(c1.dg_rcdm);
-        const double2 *__restrict__ p_w1 = reinterpret_cast<const double2 *>(c1.dg_wdw);
-        const double *__restrict__ p_z1 = c1.dg_z;
-        // columns: copy of forest 2 interleaved by DG_C; padded column jp = j + PB2_DIAG_PAD sits
-        // in plane jp % DG_C at il_offset[f2] + jp / DG_C.  This lane's first column is
-        // ibeg + D0 + DG_C * lane (a multiple of DG_C after padding).
-        const unsigned plane = (unsigned)c2.il_total;
-        unsigned cpos = (unsigned)c2.il_offset[f2] + (unsigned)((ibeg + D0 + PB2_DIAG_PAD) / DG_C + lane);
-        const double2 *__restrict__ q_r2 = reinterpret_cast<const double2 *>(c2.il_rcdm);
-        const double2 *__restrict__ q_w2 = reinterpret_cast<const double2 *>(c2.il_wdw);
-        const double *__restrict__ q_z2 = c2.il_z;
-
         double2 cr[DG_C], cw[DG_C];
         double cz[DG_C];
-#pragma unroll
-        for (int k = 0; k < DG_C - 1; k++) {
-            cr[k] = __ldg(q_r2 + (k * plane + cpos));
-            cw[k] = __ldg(q_w2 + (k * plane + cpos));
-            cz[k] = __ldg(q_z2 + (k * plane + cpos));
-        }
+        int s = ibeg;  // row of the next step
 
-        for (int s = ibeg; s < iend; s += DG_C) {
+        for (int c = 0; c < nchunk; c++) {
+            dg_mbar_wait(bar0 + 8 * stage, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            // row record of the next step; this lane's column records
+            const unsigned char *rp = dg_smem + (wid * 2 + stage) * DG_STAGE_BYTES;
+            const unsigned char *cp = rp + DG_ROW_BYTES + lane * DG_REC;
+            if (c == 0) {
 #pragma unroll
-            for (int uu = 0; uu < DG_C; uu++) {
-                const unsigned rat = ra + (unsigned)(s + uu);
-                const double2 r1 = __ldg(p_r1 + rat);  // (rc1, dm1), uniform
-                const double2 w1 = __ldg(p_w1 + rat);  // (w1, delta1 w1), uniform
-                const double z1 = __ldg(p_z1 + rat);
-                {
-                    // the new column of this row: ibeg.. + DG_C * lane + uu + DG_C - 1
-                    const int pl = (uu + DG_C - 1) % DG_C;
-                    const unsigned at = pl * plane + cpos + (uu + DG_C - 1) / DG_C;
-                    cr[pl] = __ldg(q_r2 + at);
-                    cw[pl] = __ldg(q_w2 + at);
-                    cz[pl] = __ldg(q_z2 + at);
-                }
-                // phase 1: geometry and bins of the DG_C pairs of this row (independent chains)
-                const int sidx = s + uu;
-                double v[DG_C], t[DG_C];
-                bool chg[DG_C];
-                bool any = false;
-#pragma unroll
-                for (int k = 0; k < DG_C; k++) {
-                    const int sl = (uu + k) % DG_C;
-                    const double d = sub_rn(r1.x, cr[sl].x);
-                    v[k] = ABS ? fabs(d) : d;
-                    t[k] = add_rn(r1.y, cr[sl].y);
-                    const double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
-                    const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
-                    const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
-                    const int btl = __double2loint(__fma_rd(t[k], ktl, DG_MAGIC));
-                    const int bth = __double2loint(__fma_rd(t[k], kth, DG_MAGIC));
-                    chg[k] = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
-                              ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
-                    any = any || chg[k];
-                }
-                // phase 2: run changes (one branch per row in the common case)
-                if (any) {
-#pragma unroll
-                    for (int k = 0; k < DG_C; k++) {
-                        if (chg[k]) {
-                            const int sl = (uu + k) % DG_C;
-                            // ---- diagonal k left its run: add the run to its bin
-                            if (lv & (1u << k))
-                                dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, sidx - start[k], a0[k],
-                                        a1[k], a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
-                            // ---- the new run: proven bin, or the reference expression.  Dummy
-                            // pixels (distance 1e300) leave the high word of the r_trans FMA off
-                            // 2^52 + 2^51
-                            // (recomputed behind an opaque copy: keeping phase 1's values alive
-                            // for this rare path costs four register moves per pair)
-                            double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
-                            double tt = t[k];
-                            asm volatile("" : "+d"(x), "+d"(tt));
-                            const double utl = __fma_rd(tt, ktl, DG_MAGIC);
-                            const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
-                            const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
-                            const int btl = __double2loint(utl);
-                            const int bth = __double2loint(__fma_rd(tt, kth, DG_MAGIC));
-                            const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
-                            int nbp = bpl, nbt = btl;
-                            bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
-                                        (unsigned)btl < (unsigned)nt_i;
-                            if (fmt && (bpl != bph || btl != bth)) {
-                                const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang,
-                                                            ch, sh);
-                                nbp = b.x;
-                                nbt = b.y;
-                                live = b.x != DG_NO_BIN;
-                            }
-                            curp[k] = nbp;
-                            curt[k] = nbt;
-                            start[k] = sidx;
-                            lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
-                        }
-                    }
-                }
-                // phase 3: restart the sums of changed runs (see the header) and accumulate
-#pragma unroll
-                for (int k = 0; k < DG_C; k++) {
-                    const int sl = (uu + k) % DG_C;
-                    a0[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a0[k]), __double2loint(a0[k]));
-                    a1[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a1[k]), __double2loint(a1[k]));
-                    a2[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a2[k]), __double2loint(a2[k]));
-                    a3[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a3[k]), __double2loint(a3[k]));
-                    a4[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a4[k]), __double2loint(a4[k]));
-                    const double w12 = mul_rn(w1.x, cw[sl].x);
-                    a0[k] += w12;
-                    a1[k] = fma(w1.y, cw[sl].y, a1[k]);
-                    a2[k] = fma(v[k], w12, a2[k]);
-                    a3[k] = fma(t[k], w12, a3[k]);
-                    a4[k] = fma(add_rn(z1, cz[sl]), w12, a4[k]);
+                for (int k = 0; k < DG_C - 1; k++) {
+                    cr[k] = dg_lds128(cp + k * DG_PLANE_BYTES);
+                    cw[k] = dg_lds128(cp + k * DG_PLANE_BYTES + 16);
+                    cz[k] = dg_lds64(cp + k * DG_PLANE_BYTES + 32);
                 }
             }
-            cpos += 1;
+            const int nit = min(DG_R, nrows - c * DG_R) / DG_C;
+            for (int it = 0; it < nit; it++) {
+#pragma unroll
+                for (int uu = 0; uu < DG_C; uu++) {
+                    const double2 r1 = dg_lds128(rp + uu * DG_REC);       // (rc1, dm1), broadcast
+                    const double2 w1 = dg_lds128(rp + uu * DG_REC + 16);  // (w1, delta1 w1)
+                    const double z1 = dg_lds64(rp + uu * DG_REC + 32);    // z1 / 2
+                    {
+                        // the new column of this row: row + D0 + DG_C * lane + DG_C - 1
+                        const int pl = (uu + DG_C - 1) % DG_C;
+                        const unsigned char *at = cp + pl * DG_PLANE_BYTES + ((uu + DG_C - 1) / DG_C) * DG_REC;
+                        cr[pl] = dg_lds128(at);
+                        cw[pl] = dg_lds128(at + 16);
+                        cz[pl] = dg_lds64(at + 32);
+                    }
+                    // phase 1: geometry and bins of the DG_C pairs of this row (independent chains)
+                    const int sidx = s + uu;
+                    double v[DG_C], t[DG_C];
+                    bool chg[DG_C];
+                    bool any = false;
+#pragma unroll
+                    for (int k = 0; k < DG_C; k++) {
+                        const int sl = (uu + k) % DG_C;
+                        const double d = sub_rn(r1.x, cr[sl].x);
+                        v[k] = ABS ? fabs(d) : d;
+                        t[k] = add_rn(r1.y, cr[sl].y);
+                        const double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
+                        const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
+                        const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
+                        const int btl = __double2loint(__fma_rd(t[k], ktl, DG_MAGIC));
+                        const int bth = __double2loint(__fma_rd(t[k], kth, DG_MAGIC));
+                        chg[k] = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
+                                  ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
+                        any = any || chg[k];
+                    }
+                    // phase 2: run changes (one branch per row in the common case)
+                    if (any) {
+#pragma unroll
+                        for (int k = 0; k < DG_C; k++) {
+                            if (chg[k]) {
+                                const int sl = (uu + k) % DG_C;
+                                // ---- diagonal k left its run: add the run to its bin
+                                if (lv & (1u << k))
+                                    dg_emit(srow + (size_t)(curp[k] * nt_i + curt[k]) * 8,
+                                            sidx - start[k], a0[k], a1[k], a2[k] * ch, a3[k] * sh,
+                                            a4[k]);
+                                // ---- the new run: proven bin, or the reference expression.
+                                // Dummy pixels (distance 1e300) leave the high word of the
+                                // r_trans FMA off 2^52 + 2^51.  (Recomputed behind an opaque
+                                // copy: keeping phase 1's values alive for this rare path costs
+                                // four register moves per pair.)
+                                double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
+                                double tt = t[k];
+                                asm volatile("" : "+d"(x), "+d"(tt));
+                                const double utl = __fma_rd(tt, ktl, DG_MAGIC);
+                                const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
+                                const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
+                                const int btl = __double2loint(utl);
+                                const int bth = __double2loint(__fma_rd(tt, kth, DG_MAGIC));
+                                const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
+                                int nbp = bpl, nbt = btl;
+                                bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
+                                            (unsigned)btl < (unsigned)nt_i;
+                                if (fmt && (bpl != bph || btl != bth)) {
+                                    const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y,
+                                                                ang, ch, sh);
+                                    nbp = b.x;
+                                    nbt = b.y;
+                                    live = b.x != DG_NO_BIN;
+                                }
+                                curp[k] = nbp;
+                                curt[k] = nbt;
+                                start[k] = sidx;
+                                lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
+                            }
+                        }
+                    }
+                    // phase 3: restart the sums of changed runs (see the header) and accumulate
+#pragma unroll
+                    for (int k = 0; k < DG_C; k++) {
+                        const int sl = (uu + k) % DG_C;
+                        a0[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a0[k]), __double2loint(a0[k]));
+                        a1[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a1[k]), __double2loint(a1[k]));
+                        a2[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a2[k]), __double2loint(a2[k]));
+                        a3[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a3[k]), __double2loint(a3[k]));
+                        a4[k] = __hiloint2double(chg[k] ? 0 : __double2hiint(a4[k]), __double2loint(a4[k]));
+                        const double w12 = mul_rn(w1.x, cw[sl].x);
+                        a0[k] += w12;
+                        a1[k] = fma(w1.y, cw[sl].y, a1[k]);
+                        a2[k] = fma(v[k], w12, a2[k]);
+                        a3[k] = fma(t[k], w12, a3[k]);
+                        a4[k] = fma(add_rn(z1, cz[sl]), w12, a4[k]);
+                    }
+                }
+                s += DG_C;
+                rp += DG_C * DG_REC;
+                cp += DG_REC;
+            }
+            // the stage is free again: refill it with the chunk after the next one
+            __syncwarp();
+            request(stage);
+            stage ^= 1u;
         }
-        // ---- last runs of the unit's diagonals (rows were walked up to a multiple of DG_C)
-        const int send = ibeg + ((iend - ibeg + DG_C - 1) / DG_C) * DG_C;
+        // ---- last runs of the block's diagonals
 #pragma unroll
         for (int k = 0; k < DG_C; k++) {
             if (lv & (1u << k))
-                dg_emit(orow + (curp[k] * nt_i + curt[k]), nb, send - start[k], a0[k], a1[k],
-                        a2[k] * ch, a3[k] * sh, a4[k] * 0.5);
+                dg_emit(srow + (size_t)(curp[k] * nt_i + curt[k]) * 8, s - start[k], a0[k], a1[k],
+                        a2[k] * ch, a3[k] * sh, a4[k]);
         }
+        }  // blocks of the forest pair
     }
+}
+
+// scratch [row][bin][8] -> the caller's [row][6][bin] (accumulated; slot 5 is an int64 count)
+__global__ void pb2_xi_diag_fold(const double *__restrict__ scr, double *__restrict__ out,
+                                 long long n_rows, int nb)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * nb) return;
+    const long long row = idx / nb;
+    const int bin = (int)(idx - row * nb);
+    const double2 *src = reinterpret_cast<const double2 *>(scr + idx * 8);
+    const double2 v01 = src[0], v23 = src[1], v45 = src[2];
+    double *dst = out + row * 6 * (long long)nb + bin;
+    dst[0] += v01.x;
+    dst[(size_t)nb] += v01.y;
+    dst[2 * (size_t)nb] += v23.x;
+    dst[3 * (size_t)nb] += v23.y;
+    dst[4 * (size_t)nb] += v45.x;
+    long long *cnt = reinterpret_cast<long long *>(dst + 5 * (size_t)nb);
+    *cnt += __double_as_longlong(v45.y);
 }
 
 template <bool ABS, bool FOLD>
 static int32_t dg_launch(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                          const pb2_pairs *pairs, const DiagConst &C, const int32_t *d_out_row,
-                         double *d_out, int blocks, cudaStream_t s)
+                         double *d_scr, int blocks, cudaStream_t s)
 {
-    pb2_xi_auto_diag<ABS, FOLD><<<blocks, DG_THREADS, 0, s>>>(*c1, *c2, *par, *pairs, C,
-                                                                  d_out_row, d_out);
+    const size_t smem = (size_t)DG_WARPS * 2 * DG_STAGE_BYTES;
+    PB2_CUDA(cudaFuncSetAttribute(pb2_xi_auto_diag<ABS, FOLD>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pb2_xi_auto_diag<ABS, FOLD><<<blocks, DG_THREADS, smem, s>>>(*c1, *c2, *par, *pairs, C,
+                                                                  d_out_row, d_scr);
     pb2_count_launch(1);
     return pb2_check_launch("pb2_xi_auto_diag");
 }
@@ -334,10 +476,12 @@ static int32_t dg_launch(const pb2_catalog *c1, const pb2_catalog *c2, const pb2
 bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                           int64_t n_rows)
 {
-    if (!c1->dg_rcdm || !c2->il_rcdm || c1->dg_lanes != DG_C || c2->dg_lanes != DG_C) return false;
+    if (!c1->dg_rec || !c2->dg_rec || !c2->il_rec || c1->dg_lanes != DG_C || c2->dg_lanes != DG_C)
+        return false;
     if (!c1->dg_ok || !c2->dg_ok) return false;
+    if ((c1->dg_max_pix + c2->dg_max_pix + DG_C) / DG_BLOCK + 2 > DG_GMAX) return false;
     const double nb6 = 6. * par->num_bins_r_par * par->num_bins_r_trans;
-    if ((double)n_rows * nb6 >= 4294967296.) return false;  // 32-bit histogram offsets
+    if ((double)n_rows * nb6 >= 2147483648.) return false;  // 32-bit bin arithmetic
     // low-word bins: |x K| must stay far below 2^31 for every real pair
     const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
@@ -348,11 +492,11 @@ bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb
 }
 
 int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
-                           const pb2_pairs *pairs, const int32_t *d_out_row, double *d_out,
-                           cudaStream_t s)
+                           const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
+                           double *d_out, cudaStream_t s)
 {
     DiagConst C;
-    C.gmax = (c1->dg_max_pix + c2->dg_max_pix + DG_C + DG_BLOCK - 1) / DG_BLOCK + 1;
+    C.gmax = 0;
     const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
     const double eps = 9.094947017729282e-13;  // 2^-40
@@ -366,9 +510,33 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
     long long want = (pairs->n_pairs + DG_CHUNK - 1) / DG_CHUNK;
     int blocks = (int)(want < sms ? want : sms);
     if (blocks < 1) blocks = 1;
+    // scratch histogram [row][bin][8], folded into d_out after the pair kernel
+    const int nb = par->num_bins_r_par * par->num_bins_r_trans;
+    const size_t scr_bytes = (size_t)n_rows * nb * 8 * sizeof(double);
+    double *d_scr = nullptr;
+    {
+        // keep the stream-ordered pool's memory across calls (the default releases it at every
+        // synchronisation, which costs ~0.5 s per call for a few hundred MB)
+        cudaMemPool_t pool;
+        PB2_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        PB2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    PB2_CUDA(cudaMallocAsync((void **)&d_scr, scr_bytes, s));
+    PB2_CUDA(cudaMemsetAsync(d_scr, 0, scr_bytes, s));
+    int32_t rc;
     if (par->x_correlation)
-        return dg_launch<false, false>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
-    if (par->r_par_min != 0.)
-        return dg_launch<true, false>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
-    return dg_launch<true, true>(c1, c2, par, pairs, C, d_out_row, d_out, blocks, s);
+        rc = dg_launch<false, false>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+    else if (par->r_par_min != 0.)
+        rc = dg_launch<true, false>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+    else
+        rc = dg_launch<true, true>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+    if (rc == 0) {
+        const long long total = (long long)n_rows * nb;
+        pb2_xi_diag_fold<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_scr, d_out, n_rows, nb);
+        pb2_count_launch(1);
+        rc = pb2_check_launch("pb2_xi_diag_fold");
+    }
+    cudaFreeAsync(d_scr, s);
+    return rc;
 }
