@@ -32,7 +32,9 @@ extern "C" {
 #endif
 #define PB2_DIAG_PAD (34 * PB2_DIAG_LANES)   /* dummy pixels either side, interleaved copy */
 #define PB2_DIAG_ROW_PAD 8                   /* dummy pixels after a line of sight, natural copy */
+#ifndef PB2_DIAG_CHUNK_ROWS
 #define PB2_DIAG_CHUNK_ROWS 32               /* rows staged in shared memory per TMA bulk copy */
+#endif
 
 #define PB2_EINVAL (-1)   /* bad argument */
 #define PB2_ECONFIG (-2)  /* configuration not supported by the kernels (message says which) */

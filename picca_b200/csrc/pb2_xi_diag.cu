@@ -66,7 +66,7 @@ static_assert(DG_R % DG_C == 0, "chunk rows must be a multiple of the diagonals 
 static_assert(PB2_DIAG_PAD % DG_C == 0, "padding must be a multiple of the diagonals per lane");
 
 struct DiagConst {
-    double kp_lo, kp_hi, kt_lo, kt_hi;  // n / range * (1 -+ 2^-40)
+    double kp16, kt16;  // 65536 n / range
     int gmax;                           // diagonal blocks per forest pair (longest forests)
 };
 
@@ -129,14 +129,11 @@ __device__ __forceinline__ int dg_bound(const double *__restrict__ a, int n, dou
     return lo;
 }
 
-// reference bin of a pair too close to a bin edge for the sandwich; (DG_NO_BIN, .) when rejected
-__device__ __noinline__ int2 dg_exact_bin(const pb2_params &P, double rc1, double dm1, double rc2,
-                                          double dm2, double ang, double ch, double sh)
+// reference bin (flat; -1 when rejected) of a pair too close to a bin edge for the proof
+__device__ __noinline__ int dg_exact_bin(const pb2_params &P, double rc1, double dm1, double rc2,
+                                         double dm2, double ang, double ch, double sh)
 {
-    const int bin = pb2_pair_exact(P, rc1, dm1, rc2, dm2, ang, ch, sh, false, false).bin;
-    if (bin < 0) return make_int2(DG_NO_BIN, 0);
-    const int bp = bin / P.num_bins_r_trans;
-    return make_int2(bp, bin - bp * P.num_bins_r_trans);
+    return pb2_pair_exact(P, rc1, dm1, rc2, dm2, ang, ch, sh, false, false).bin;
 }
 
 // one finished run -> the six sums of its bin (one 64-byte line of the scratch histogram)
@@ -286,24 +283,23 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         double *__restrict__ const srow = scr + (size_t)out_row[k1] * nb * 8;
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
-        const double kpl = FOLD ? mul_rn(ch, C.kp_lo) : C.kp_lo;
-        const double kph = FOLD ? mul_rn(ch, C.kp_hi) : C.kp_hi;
-        const double ktl = mul_rn(sh, C.kt_lo), kth = mul_rn(sh, C.kt_hi);
+        const double kpf = FOLD ? mul_rn(ch, C.kp16) : C.kp16;
+        const double ktf = mul_rn(sh, C.kt16);
 
         for (int g = 0; g < G; g++) {
         const int ibeg = tb[g].x, nrows = tb[g].y;
         if (nrows == 0) continue;
         const int nchunk = (nrows + DG_R - 1) / DG_R;
-        // per diagonal: sums of the current run, the step it started at, the low words of its
-        // bin; `lv` bit k = the run of diagonal k is in range.  No run is open at the start.
+        // per diagonal: sums of the current run, the step it started at, its flat bin (-1: out
+        // of range) and, per dimension, 65536 * bin + 1: a pair stays in the run while both
+        // (unsigned)(low word - that) < 65534.  No run is open at the start.
         double a0[DG_C], a1[DG_C], a2[DG_C], a3[DG_C], a4[DG_C];
-        int curp[DG_C], curt[DG_C], start[DG_C];
-        unsigned lv = 0;
+        int bp1[DG_C], bt1[DG_C], cb[DG_C], start[DG_C];
 #pragma unroll
         for (int k = 0; k < DG_C; k++) {
             a0[k] = a1[k] = a2[k] = a3[k] = a4[k] = 0.;
-            curp[k] = DG_NO_BIN;
-            curt[k] = 0;
+            bp1[k] = bt1[k] = DG_NO_BIN;
+            cb[k] = -1;
             start[k] = 0;
         }
         double2 cr[DG_C], cw[DG_C];
@@ -351,12 +347,9 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                         v[k] = ABS ? fabs(d) : d;
                         t[k] = add_rn(r1.y, cr[sl].y);
                         const double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
-                        const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
-                        const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
-                        const int btl = __double2loint(__fma_rd(t[k], ktl, DG_MAGIC));
-                        const int bth = __double2loint(__fma_rd(t[k], kth, DG_MAGIC));
-                        chg[k] = (((bpl ^ curp[k]) | (bph ^ curp[k])) |
-                                  ((btl ^ curt[k]) | (bth ^ curt[k]))) != 0;
+                        const int lp = __double2loint(__fma_rd(x, kpf, DG_MAGIC));
+                        const int lt = __double2loint(__fma_rd(t[k], ktf, DG_MAGIC));
+                        chg[k] = (unsigned)(lp - bp1[k]) >= 65534u || (unsigned)(lt - bt1[k]) >= 65534u;
                         any = any || chg[k];
                     }
                     // phase 2: run changes (one branch per row in the common case)
@@ -366,38 +359,45 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                             if (chg[k]) {
                                 const int sl = (uu + k) % DG_C;
                                 // ---- diagonal k left its run: add the run to its bin
-                                if (lv & (1u << k))
-                                    dg_emit(srow + (size_t)(curp[k] * nt_i + curt[k]) * 8,
-                                            sidx - start[k], a0[k], a1[k], a2[k] * ch, a3[k] * sh,
-                                            a4[k]);
-                                // ---- the new run: proven bin, or the reference expression.
-                                // Dummy pixels (distance 1e300) leave the high word of the
-                                // r_trans FMA off 2^52 + 2^51.  (Recomputed behind an opaque
-                                // copy: keeping phase 1's values alive for this rare path costs
-                                // four register moves per pair.)
+                                if (cb[k] >= 0)
+                                    dg_emit(srow + (size_t)cb[k] * 8, sidx - start[k], a0[k], a1[k],
+                                            a2[k] * ch, a3[k] * sh, a4[k]);
+                                // ---- the new run.  The low words hold floor(65536 x K): bin in
+                                // the upper, a 16-bit fraction in the lower half.  (Recomputed
+                                // behind an opaque copy: keeping phase 1's values alive for this
+                                // path costs register moves on every pair.)
                                 double x = FOLD ? v[k] : sub_rn(mul_rn(v[k], ch), P.r_par_min);
                                 double tt = t[k];
                                 asm volatile("" : "+d"(x), "+d"(tt));
-                                const double utl = __fma_rd(tt, ktl, DG_MAGIC);
-                                const int bpl = __double2loint(__fma_rd(x, kpl, DG_MAGIC));
-                                const int bph = __double2loint(__fma_rd(x, kph, DG_MAGIC));
-                                const int btl = __double2loint(utl);
-                                const int bth = __double2loint(__fma_rd(tt, kth, DG_MAGIC));
-                                const bool fmt = __double2hiint(utl) == DG_MAGIC_HI;
-                                int nbp = bpl, nbt = btl;
-                                bool live = fmt && (unsigned)bpl < (unsigned)np_i &&
-                                            (unsigned)btl < (unsigned)nt_i;
-                                if (fmt && (bpl != bph || btl != bth)) {
-                                    const int2 b = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y,
-                                                                ang, ch, sh);
-                                    nbp = b.x;
-                                    nbt = b.y;
-                                    live = b.x != DG_NO_BIN;
+                                const double ut = __fma_rd(tt, ktf, DG_MAGIC);
+                                const int lp = __double2loint(__fma_rd(x, kpf, DG_MAGIC));
+                                const int lt = __double2loint(ut);
+                                // dummy pixels (distance 1e300) leave the high word off 2^52 + 2^51
+                                const bool fmt = __double2hiint(ut) == DG_MAGIC_HI;
+                                const unsigned bp = (unsigned)lp >> 16, bt = (unsigned)lt >> 16;
+                                // (branch-free: dummies stay quiet and have no bin).  Bin 0
+                                // accepts a zero fraction: its lower edge is x = 0 itself, which
+                                // pixels of a common wavelength grid hit exactly (d = 0).
+                                const int hp = lp & (int)0xffff0000, ht = lt & (int)0xffff0000;
+                                int nb1p = fmt ? (hp ? hp + 1 : 0) : lp - 1;
+                                int nb1t = fmt ? (ht ? ht + 1 : 0) : lt - 1;
+                                int ncb = (fmt && bp < (unsigned)np_i && bt < (unsigned)nt_i)
+                                              ? (int)(bp * nt_i + bt) : -1;
+                                // a fraction of 65535, or of 0 above bin 0: within 2^-16 of a bin
+                                // edge -> the reference expression decides, and the pair is a run
+                                // of its own
+                                const unsigned fp = ((unsigned)lp + 1u) & 0xffffu, ft = ((unsigned)lt + 1u) & 0xffffu;
+                                const bool edge = fp == 0u || (fp == 1u && hp != 0) || ft == 0u ||
+                                                  (ft == 1u && ht != 0);
+                                if (fmt && edge) {
+                                    ncb = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang, ch, sh);
+                                    nb1p = lp ^ DG_NO_BIN;
+                                    nb1t = lt ^ DG_NO_BIN;
                                 }
-                                curp[k] = nbp;
-                                curt[k] = nbt;
+                                bp1[k] = nb1p;
+                                bt1[k] = nb1t;
+                                cb[k] = ncb;
                                 start[k] = sidx;
-                                lv = live ? (lv | (1u << k)) : (lv & ~(1u << k));
                             }
                         }
                     }
@@ -430,9 +430,9 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         // ---- last runs of the block's diagonals
 #pragma unroll
         for (int k = 0; k < DG_C; k++) {
-            if (lv & (1u << k))
-                dg_emit(srow + (size_t)(curp[k] * nt_i + curt[k]) * 8, s - start[k], a0[k], a1[k],
-                        a2[k] * ch, a3[k] * sh, a4[k]);
+            if (cb[k] >= 0)
+                dg_emit(srow + (size_t)cb[k] * 8, s - start[k], a0[k], a1[k], a2[k] * ch, a3[k] * sh,
+                        a4[k]);
         }
         }  // blocks of the forest pair
     }
@@ -487,7 +487,9 @@ bool pb2_xi_diag_eligible(const pb2_catalog *c1, const pb2_catalog *c2, const pb
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
     const double reach = c1->dg_reach + c2->dg_reach;
     const double rmin = par->r_par_min < 0 ? -par->r_par_min : par->r_par_min;
-    if (!((reach + rmin) * kp < 1e9) || !(reach * kt < 1e9)) return false;
+    // floor(65536 x K) must stay far below 2^31 for every real pair: bins < 8192
+    if (!((reach + rmin) * kp < 8192.) || !(reach * kt < 8192.)) return false;
+    if (par->num_bins_r_par > 4096 || par->num_bins_r_trans > 4096) return false;
     return true;
 }
 
@@ -499,11 +501,8 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
     C.gmax = 0;
     const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
-    const double eps = 9.094947017729282e-13;  // 2^-40
-    C.kp_lo = kp * (1. - eps);
-    C.kp_hi = kp * (1. + eps);
-    C.kt_lo = kt * (1. - eps);
-    C.kt_hi = kt * (1. + eps);
+    C.kp16 = kp * 65536.;
+    C.kt16 = kt * 65536.;
     int dev = 0, sms = 0;
     PB2_CUDA(cudaGetDevice(&dev));
     PB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
