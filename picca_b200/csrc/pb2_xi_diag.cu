@@ -48,7 +48,7 @@
 #define DG_THREADS 512
 #endif
 #ifndef DG_CHUNK
-#define DG_CHUNK 8
+#define DG_CHUNK 4
 #endif
 #define DG_WARPS (DG_THREADS / 32)
 #define DG_BLOCK (32 * DG_C)
