@@ -118,3 +118,38 @@ def test_cross_correlation_production_binning(base):
                      r_par_min=-200., r_par_max=200., r_trans_max=200., num_bins_r_par=100,
                      num_bins_r_trans=50)
     assert total > 10**6
+
+
+def _grid_forest(los_id, ra, dec, first, n, rng):
+    """A forest whose comoving distances sit on a 0.5 Mpc/h grid: with bins of 4 Mpc/h many pixel
+    pairs fall EXACTLY on r_par bin edges (and on r_par = 0)."""
+    from picca_b200.forest import Delta
+    rc = 3000. + 0.5 * (first + np.arange(n, dtype=np.float64))
+    d = Delta(los_id, ra, dec, 2.5, los_id, los_id, los_id, np.log10(3600. + np.arange(n)),
+              rng.uniform(0.5, 2., n), rng.normal(0., 0.3, n), 1)
+    d.weights[rng.random(n) < 0.1] = 0.
+    d.z = 2. + 1e-3 * (first + np.arange(n, dtype=np.float64))
+    d.r_comov = rc
+    d.dist_m = rc.copy()
+    return d
+
+
+def test_pairs_exactly_on_bin_edges():
+    """Bin-edge pairs: the diagonal-lane kernel must take the reference expression for them
+    (fraction 0 or 65535 of its fixed-point bin value) and still count every pair once."""
+    rng = np.random.default_rng(4)
+    forests = []
+    # same sky position (ang = 0: cos = 1, sin = 0 -> r_par on the grid, r_trans = 0), a 1e-4 rad
+    # neighbour, and shifted grids so that forests overlap only partially
+    for k, (dra, ddec, first, n) in enumerate([(0., 0., 0, 150), (0., 0., 40, 97), (1e-4, 0., 3, 200),
+                                               (2e-4, 1e-4, 90, 130), (0., 1.5e-4, 16, 64)]):
+        forests.append(_grid_forest(500 + k, 0.3 + dra, 0.1 + ddec, first, n, rng))
+    data = {7: forests}
+    ang_max = 1e-3
+    total = run_both(data, len(forests), ang_max, num_bins_r_par=15, num_bins_r_trans=15,
+                     r_par_max=60., r_trans_max=60.)
+    assert total > 10**4
+    # production binning (4 Mpc/h bins, every eighth grid point is an edge)
+    total = run_both(data, len(forests), ang_max, num_bins_r_par=50, num_bins_r_trans=50,
+                     r_par_max=200., r_trans_max=200.)
+    assert total > 10**4

@@ -105,3 +105,63 @@ def test_ang2pix_ring_known_values():
     theta = np.arccos(vec[:, 2])
     phi = np.arctan2(vec[:, 1], vec[:, 0])
     assert np.array_equal(synth.ang2pix_ring(nside, theta, phi), np.arange(12 * nside * nside))
+
+
+def test_diag_copies_layout(sample):
+    """The packed copies the diagonal-lane xi kernel reads (include/picca_b200.h, pb2_catalog):
+    zero-weight pixels dropped, 48-byte records, natural order + copy interleaved by LANES, dummy
+    pixels (weight 0, distance 1e299 / 1e300) everywhere else."""
+    import copy
+    data = {hp: list(v) for hp, v in sample[0].items()}
+    hp0 = sorted(data)[0]
+    d = copy.copy(data[hp0][0])
+    d.weights = d.weights.copy()
+    d.weights[[2, 5]] = 0.
+    data[hp0][0] = d
+    cat = catalog.pack(data)
+    lanes, pad, row_pad, chunk = catalog.diag_layout()
+    assert cat.dg_lanes == lanes and cat.dg_ok == 1
+    A = cat.arrays
+    flat = [x for hp in sorted(data) for x in data[hp]]
+    rec = A["dg_rec"].reshape(-1, 6)
+    il = A["il_rec"].reshape(lanes, cat.il_total, 6)
+    assert A["dg_count"][0] == int((d.weights != 0).sum()) < len(d.weights) - 1
+    assert cat.dg_max_pix == int(A["dg_count"].max())
+    seen = np.zeros(il.shape[:2], dtype=bool)
+    for f in (0, 1, 57, 199):
+        x = flat[f]
+        keep = x.weights != 0
+        n = int(keep.sum())
+        assert A["dg_count"][f] == n
+        want = np.stack([x.r_comov[keep], x.dist_m[keep], x.weights[keep],
+                         (x.delta * x.weights)[keep], 0.5 * x.z[keep], np.zeros(n)], axis=1)
+        a = A["dg_offset"][f]
+        assert np.array_equal(rec[a:a + n], want)
+        # dummies after the forest: weight 0, distance 1e299
+        assert np.all(rec[a + n:a + n + row_pad, 2:] == 0)
+        assert np.all(rec[a + n:a + n + row_pad, :2] == catalog.DIAG_DUMMY_ROW)
+        # interleaved copy: pixel j -> plane (j + pad) % lanes, record il_offset + (j + pad) // lanes
+        jp = np.arange(n) + pad
+        got = il[jp % lanes, A["il_offset"][f] + jp // lanes]
+        assert np.array_equal(got, want)
+        seen[jp % lanes, A["il_offset"][f] + jp // lanes] = True
+        # pad dummies either side
+        for j in (-pad, -1, n, n + pad - lanes):
+            q = j + pad
+            r = il[q % lanes, A["il_offset"][f] + q // lanes]
+            assert r[2] == 0 and r[0] == catalog.DIAG_DUMMY_COL
+    # a whole chunk of records may be read past the last forest in every plane
+    last = A["il_offset"][-1] + (int(A["dg_count"][-1]) + 2 * pad + lanes - 1) // lanes
+    assert cat.il_total >= last + chunk
+    assert rec.shape[0] >= A["dg_offset"][-1] + A["dg_count"][-1] + row_pad + chunk
+
+
+def test_diag_copies_flag_non_finite(sample):
+    import copy
+    data = {hp: list(v) for hp, v in sample[0].items()}
+    hp0 = sorted(data)[0]
+    d = copy.copy(data[hp0][0])
+    d.z = d.z.copy()
+    d.z[1] = np.inf
+    data[hp0][0] = d
+    assert catalog.pack(data).dg_ok == 0
