@@ -139,10 +139,10 @@ def test_pairs_exactly_on_bin_edges():
     (fraction 0 or 65535 of its fixed-point bin value) and still count every pair once."""
     rng = np.random.default_rng(4)
     forests = []
-    # same sky position (ang = 0: cos = 1, sin = 0 -> r_par on the grid, r_trans = 0), a 1e-4 rad
-    # neighbour, and shifted grids so that forests overlap only partially
-    for k, (dra, ddec, first, n) in enumerate([(0., 0., 0, 150), (0., 0., 40, 97), (1e-4, 0., 3, 200),
-                                               (2e-4, 1e-4, 90, 130), (0., 1.5e-4, 16, 64)]):
+    # nearly the same sky position (ang ~ 1e-9: cos(ang/2) rounds to 1 -> r_par exactly on the
+    # grid, r_trans ~ 0), 1e-4 rad neighbours, and shifted grids so that forests overlap partially
+    for k, (dra, ddec, first, n) in enumerate([(0., 0., 0, 150), (1e-9, 0., 40, 97), (1e-4, 0., 3, 200),
+                                               (2e-4, 1e-4, 90, 130), (2e-9, 1.5e-4, 16, 64)]):
         forests.append(_grid_forest(500 + k, 0.3 + dra, 0.1 + ddec, first, n, rng))
     data = {7: forests}
     ang_max = 1e-3
