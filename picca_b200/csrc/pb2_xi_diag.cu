@@ -55,7 +55,7 @@
 #define DG_MAGIC 6755399441055744.0  // 2^52 + 2^51
 #define DG_MAGIC_HI 0x43380000       // its high word: unchanged by adding 0 <= bin < 2^31
 #define DG_NO_BIN ((int)0x80000000)
-#define DG_GMAX 48                                  // diagonal blocks per forest pair, at most
+#define DG_GMAX 96                                  // diagonal blocks per forest pair, at most
 #define DG_REC 48                                   // bytes per pixel record
 #define DG_ROW_BYTES (DG_R * DG_REC)                // row records of a chunk
 #define DG_PLANE_REC (DG_R / DG_C + 33)             // column records of a chunk, per plane
