@@ -283,6 +283,7 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         double *__restrict__ const srow = scr + (size_t)out_row[k1] * nb * 8;
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
+        const unsigned np16 = (unsigned)np_i << 16, nt16 = (unsigned)nt_i << 16;
         const double kpf = FOLD ? mul_rn(ch, C.kp16) : C.kp16;
         const double ktf = mul_rn(sh, C.kt16);
 
@@ -374,22 +375,23 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                                 const int lt = __double2loint(ut);
                                 // dummy pixels (distance 1e300) leave the high word off 2^52 + 2^51
                                 const bool fmt = __double2hiint(ut) == DG_MAGIC_HI;
-                                const unsigned bp = (unsigned)lp >> 16, bt = (unsigned)lt >> 16;
-                                // (branch-free: dummies stay quiet and have no bin).  Bin 0
-                                // accepts a zero fraction: its lower edge is x = 0 itself, which
-                                // pixels of a common wavelength grid hit exactly (d = 0).
+                                // new window per dimension: 65536 bin + 1 (bin 0 also accepts a
+                                // zero fraction: its lower edge is x = 0 itself, which pixels of
+                                // a common wavelength grid hit exactly with d = 0)
                                 const int hp = lp & (int)0xffff0000, ht = lt & (int)0xffff0000;
-                                int nb1p = fmt ? (hp ? hp + 1 : 0) : lp - 1;
-                                int nb1t = fmt ? (ht ? ht + 1 : 0) : lt - 1;
-                                int ncb = (fmt && bp < (unsigned)np_i && bt < (unsigned)nt_i)
-                                              ? (int)(bp * nt_i + bt) : -1;
-                                // a fraction of 65535, or of 0 above bin 0: within 2^-16 of a bin
-                                // edge -> the reference expression decides, and the pair is a run
-                                // of its own
-                                const unsigned fp = ((unsigned)lp + 1u) & 0xffffu, ft = ((unsigned)lt + 1u) & 0xffffu;
-                                const bool edge = fp == 0u || (fp == 1u && hp != 0) || ft == 0u ||
-                                                  (ft == 1u && ht != 0);
-                                if (fmt && edge) {
+                                int nb1p = hp + (hp != 0), nb1t = ht + (ht != 0);
+                                const unsigned bp = (unsigned)lp >> 16, bt = (unsigned)lt >> 16;
+                                int ncb = (int)(bp * (unsigned)nt_i + bt);
+                                if ((unsigned)lp >= np16 || (unsigned)lt >= nt16) ncb = -1;
+                                if (!fmt) {  // dummy pixel: no bin, and quiet while it lasts
+                                    nb1p = lp - 1;
+                                    nb1t = lt - 1;
+                                    ncb = -1;
+                                }
+                                // outside its own window: a fraction of 65535 (65534), or of 0
+                                // above bin 0 -> within 2^-16 of a bin edge: the reference
+                                // expression decides, and the pair is a run of its own
+                                if (max((unsigned)(lp - nb1p), (unsigned)(lt - nb1t)) >= 65534u) {
                                     ncb = dg_exact_bin(P, r1.x, r1.y, cr[sl].x, cr[sl].y, ang, ch, sh);
                                     nb1p = lp ^ DG_NO_BIN;
                                     nb1t = lt ^ DG_NO_BIN;
