@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 9
+#define PB2_ABI_VERSION 10
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -109,6 +109,11 @@ typedef struct pb2_catalog {
     int32_t dg_ok;               /* 1 if every r_comov, dist_m, z, weight, delta_w is finite */
     int32_t dg_reserved;
     double dg_reach;             /* max(|r_comov|, |dist_m|) over the catalogue */
+    /* ---- per-forest prefix sums read by the forest x object kernel (pb2_xcf.cu), filled by
+     * pb2_build_prefix; may be NULL.  Entry offset[f] + f + i (six doubles) = sums over pixels
+     * [0, i) of line of sight f of weights, delta_w, (r_comov - r_comov[0]) weights,
+     * (dist_m - dist_m[0]) weights, z_w and the number of non-zero weights; n + 1 entries. */
+    const double *px_rec;
     /* per line of sight */
     const double *x_cart, *y_cart, *z_cart, *ra, *dec, *cos_dec, *z_qso;
     const int64_t *thingid, *plate, *fiberid;
@@ -182,6 +187,10 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
 int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
                      const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                      double *d_out, int32_t variant, void *stream);
+
+/* Fill the prefix records of a delta catalogue: d_px_rec holds 6 * (n_pix + n_los) doubles (see
+ * pb2_catalog.px_rec); the caller then stores the pointer in the catalogue it passes on. */
+int32_t pb2_build_prefix(const pb2_catalog *cat, double *d_px_rec, void *stream);
 
 /* xi, r_par, r_trans, z /= weights where weights > 0, per row (cf.py:242-246, xcf.py:215-219). */
 int32_t pb2_xi_normalise(int64_t n_rows, int32_t nb, double *d_out, void *stream);

@@ -67,6 +67,7 @@ class Catalog(ctypes.Structure):
         ("dg_ok", ctypes.c_int32),
         ("dg_reserved", ctypes.c_int32),
         ("dg_reach", ctypes.c_double),
+        ("px_rec", c_void_p),
         ("x_cart", c_void_p),
         ("y_cart", c_void_p),
         ("z_cart", c_void_p),
@@ -111,11 +112,11 @@ class Pairs(ctypes.Structure):
 EXPORTS = [
     "pb2_abi_version", "pb2_last_error", "pb2_sizeof_params", "pb2_sizeof_catalog",
     "pb2_sizeof_pairs", "pb2_diag_lanes", "pb2_neigh_count", "pb2_neigh_fill", "pb2_xi_auto", "pb2_xi_cross",
-    "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross",
+    "pb2_build_prefix", "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross",
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 def lib():

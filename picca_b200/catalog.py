@@ -260,6 +260,15 @@ class DeviceCatalog:
             self.tensors[name] = t.to(device, non_blocking=pin)
             self.h2d_bytes += arr.nbytes
         self.struct = build_struct(host, self.tensors)
+        if not host.is_object and host.n_los:
+            # per-forest prefix sums for the forest x object kernel, built on the device
+            import ctypes
+            self.tensors["px_rec"] = torch.empty(6 * (host.n_pix + host.n_los), dtype=torch.float64,
+                                                 device=device)
+            _lib.check(_lib.lib().pb2_build_prefix(
+                ctypes.byref(self.struct), ctypes.c_void_p(self.tensors["px_rec"].data_ptr()),
+                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "pb2_build_prefix")
+            self.struct.px_rec = self.tensors["px_rec"].data_ptr()
 
 
 def build_struct(host, tensors):

@@ -1,6 +1,18 @@
 // Forest x object (quasar) pixel-pair histogram: replaces xcf.compute_xi's loop and
 // xcf.compute_xi_forest_pairs_fast (reference py/picca/xcf.py:149-213, 223-322).
 //
+// Product path (pb2_xi_cross_chunk): for a fixed object the pixels of a forest walk monotonically
+// through the (r_par, r_trans) bins in runs of ~7, and every sum of the reference over a run
+// factorises into (object constants) x (sums over the run's pixels of w, delta w, r_comov w,
+// dist_m w, z w and a count).  Those come from per-forest PREFIX SUMS (pb2_build_prefix), so a
+// run costs two record loads instead of a loop over its pixels.  One warp takes a forest; lane l
+// first prepares neighbouring object l of a batch of 32 (its constants and pixel window, by
+// binary search); then the warp handles the 32 objects in turn, 32 consecutive pixels at a time:
+// lane = pixel evaluates the pixel's bin (coalesced loads, same proven-or-exact bins as below), a
+// ballot marks where the bin changes, and the last lane of every run adds the run to its bin
+// with six native reductions.  The run boundaries are therefore exact, pixel by pixel.
+//
+// General path (pb2_xi_cross_kernel; every mode, and the validation variant):
 // One warp per forest; lane l owns one neighbouring object (its r_comov, dist_m, z, weight and
 // cos/sin of half the separation stay in registers) and the warp sweeps the forest's pixels, every
 // lane reading the same pixel (broadcast loads).  For a fixed object the pixels walk monotonically
@@ -179,6 +191,191 @@ pb2_xi_cross_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// prefix records: entry offset[f] + f + i of px_rec = sums over pixels [0, i) of forest f of
+// (w, delta w, (r_comov - r_comov[0]) w, (dist_m - dist_m[0]) w, z w, [w != 0]); n + 1 entries.
+__global__ void pb2_build_prefix_kernel(pb2_catalog c, double *__restrict__ px)
+{
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= c.n_los) return;
+    const long long a = c.offset[f];
+    const int n = (int)(c.offset[f + 1] - a);
+    double *o = px + 6 * (a + f);
+    double s0 = 0., s1 = 0., s2 = 0., s3 = 0., s4 = 0., cnt = 0.;
+    const double rc0 = n ? c.r_comov[a] : 0., dm0 = n ? c.dist_m[a] : 0.;
+    for (int i = 0; i <= n; i++) {
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4; o[5] = cnt;
+        o += 6;
+        if (i < n) {
+            const double w = c.weights[a + i];
+            s0 += w;
+            s1 += c.delta_w[a + i];
+            s2 = fma(sub_rn(c.r_comov[a + i], rc0), w, s2);
+            s3 = fma(sub_rn(c.dist_m[a + i], dm0), w, s3);
+            s4 += c.z_w[a + i];
+            cnt += (w != 0.) ? 1. : 0.;
+        }
+    }
+}
+
+// first index in the non-decreasing a[0..n).x (.y) with value > v (strict) / >= v; shared memory
+__device__ __forceinline__ int smem_upper_bound(const double2 *a, int n, double v, bool strict,
+                                                bool second)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double x = second ? a[mid].y : a[mid].x;
+        const bool left = strict ? (x <= v) : (x < v);
+        if (left) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// One CTA per forest: its (r_comov, dist_m) pairs and prefix records are staged in shared memory
+// once, then the warps take batches of 32 neighbouring objects.
+__global__ void __launch_bounds__(256)
+pb2_xi_cross_chunk(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, XcfFast F,
+                   const int32_t *__restrict__ out_row, double *__restrict__ out,
+                   unsigned long long *__restrict__ counter)
+{
+    extern __shared__ __align__(16) double2 xs[];  // [n1] (rc, dm), then 3 (n1 + 1) prefix halves
+    __shared__ unsigned long long s_k;
+    __shared__ unsigned s_batch;
+    const int lane = threadIdx.x & 31;
+    const int nb = P.num_bins_r_par * P.num_bins_r_trans;
+    const unsigned np_u = (unsigned)P.num_bins_r_par, nt_u = (unsigned)P.num_bins_r_trans;
+    const double magic = F.magic;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_k = atomicAdd(counter, 1ull);
+            s_batch = 0;
+        }
+        __syncthreads();
+        const unsigned long long k = s_k;
+        if ((long long)k >= pr.n_f1) break;
+        const int f1 = pr.f1_index[k];
+        const long long a = c1.offset[f1];
+        const int n1 = (int)(c1.offset[f1 + 1] - a);
+        const long long e0 = pr.nb_offset[k], e1 = pr.nb_offset[k + 1];
+        if (n1 == 0 || e1 == e0) continue;  // xcf.py:157
+        double *__restrict__ orow = out + (size_t)out_row[k] * 6 * nb;
+        double2 *const s_px = xs + n1;
+        {
+            const double *__restrict__ g_rc = c1.r_comov + a;
+            const double *__restrict__ g_dm = c1.dist_m + a;
+            const double2 *__restrict__ g_px = reinterpret_cast<const double2 *>(c1.px_rec) + 3 * (a + f1);
+            for (int i = threadIdx.x; i < n1; i += blockDim.x) xs[i] = make_double2(__ldg(g_rc + i), __ldg(g_dm + i));
+            for (int i = threadIdx.x; i < 3 * (n1 + 1); i += blockDim.x) s_px[i] = __ldg(g_px + i);
+        }
+        __syncthreads();
+        const double rc0 = xs[0].x, dm0 = xs[0].y;
+
+        for (;;) {
+            unsigned bidx = 0;
+            if (lane == 0) bidx = atomicAdd(&s_batch, 1u);
+            bidx = __shfl_sync(0xffffffffu, bidx, 0);
+            const long long eb = e0 + 32ll * bidx;
+            if (eb >= e1) break;
+            // ---- lane l prepares object eb + l: constants and pixel window (a superset)
+            const long long e = eb + lane;
+            const bool have = e < e1;
+            double rcq = 0., dmq = 0., zq = 0., wq = 0., ang = 0., ch = 1., sh = 0.;
+            if (have) {
+                const int f2 = pr.nb_f2[e];
+                const long long q = c2.offset[f2];
+                rcq = c2.r_comov[q];
+                dmq = c2.dist_m[q];
+                zq = c2.z[q];
+                wq = c2.weights[q];
+                ang = pr.nb_ang[e];
+                ch = pr.nb_cos[e];
+                sh = pr.nb_sin[e];
+            }
+            int ilo = n1, ihi = 0;
+            if (have && wq != 0.) {  // xcf.py:283
+                // r_par_min < (rc1 - rcq) ch < r_par_max  and  (dm1 + dmq) sh < r_trans_max
+                const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
+                const double hi_rc = rcq + P.r_par_max * inv_c;
+                const double lo_rc = rcq + P.r_par_min * inv_c;
+                ilo = smem_upper_bound(xs, n1, lo_rc - fabs(lo_rc) * 1e-9 - 1e-9, false, false);
+                ihi = smem_upper_bound(xs, n1, hi_rc + fabs(hi_rc) * 1e-9 + 1e-9, true, false);
+                const double tsum = P.r_trans_max * inv_s;
+                if (isfinite(tsum))
+                    ihi = min(ihi, smem_upper_bound(xs, n1, (tsum - dmq) * (1. + 1e-9) + 1e-9, true, true));
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, ihi > ilo);
+
+            // ---- the warp takes the prepared objects in turn
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const double q_rc = __shfl_sync(0xffffffffu, rcq, src);
+                const double q_dm = __shfl_sync(0xffffffffu, dmq, src);
+                const double q_z = __shfl_sync(0xffffffffu, zq, src);
+                const double q_w = __shfl_sync(0xffffffffu, wq, src);
+                const double q_ang = __shfl_sync(0xffffffffu, ang, src);
+                const double q_ch = __shfl_sync(0xffffffffu, ch, src);
+                const double q_sh = __shfl_sync(0xffffffffu, sh, src);
+                const int q_lo = __shfl_sync(0xffffffffu, ilo, src);
+                const int q_hi = __shfl_sync(0xffffffffu, ihi, src);
+                for (int base = q_lo & ~31; base < q_hi; base += 32) {
+                    const int i = base + lane;
+                    // ---- bin of pixel i (lane = pixel): -1 = rejected / outside the window
+                    int key = -1;
+                    if (i >= q_lo && i < q_hi) {
+                        const double2 p1 = xs[i];
+                        const double rp = mul_rn(sub_rn(p1.x, q_rc), q_ch);
+                        const double rt = mul_rn(add_rn(p1.y, q_dm), q_sh);
+                        const double x = sub_rn(rp, P.r_par_min);
+                        const int bpl = __double2loint(__fma_rd(x, F.kp_lo, magic));
+                        const int bph = __double2loint(__fma_rd(x, F.kp_hi, magic));
+                        const int btl = __double2loint(__fma_rd(rt, F.kt_lo, magic));
+                        const int bth = __double2loint(__fma_rd(rt, F.kt_hi, magic));
+                        // x == 0 exactly is rejected by the reference (r_par <= r_par_min, xcf.py:305)
+                        if ((bpl == bph) && (btl == bth) && (x != 0.)) {
+                            if (((unsigned)bpl < np_u) && ((unsigned)btl < nt_u)) key = btl + (int)nt_u * bpl;
+                        } else {
+                            key = pb2_pair_exact(P, p1.x, p1.y, q_rc, q_dm, q_ang, q_ch, q_sh, true, false).bin;
+                        }
+                    }
+                    // ---- runs of equal bins inside the chunk: a lane starts a run when its bin
+                    // differs from its left neighbour's; the last lane of a run adds it up
+                    const int left = __shfl_up_sync(0xffffffffu, key, 1);
+                    const bool starts = (lane == 0) || (key != left);
+                    const unsigned smask = __ballot_sync(0xffffffffu, starts);
+                    const bool last = (lane == 31) || ((smask >> ((lane + 1) & 31)) & 1u);
+                    if (last && key >= 0) {
+                        const int first = 31 - __clz(smask & (0xffffffffu >> (31 - lane)));
+                        const double2 *pa = s_px + 3 * (base + first);
+                        const double2 *pb = s_px + 3 * (i + 1);
+                        const double2 a01 = pa[0], a23 = pa[1], a45 = pa[2];
+                        const double2 b01 = pb[0], b23 = pb[1], b45 = pb[2];
+                        const int cnt = (int)(b45.y - a45.y);
+                        if (cnt > 0) {
+                            const double sw = b01.x - a01.x, sdw = b01.y - a01.y;
+                            const double src2 = b23.x - a23.x, sdm = b23.y - a23.y, szw = b45.x - a45.x;
+                            const double we = q_w * sw;
+                            double *dst = orow + key;
+                            atomic_add_f64(dst, we);                                       // xcf.py:318
+                            atomic_add_f64(dst + (size_t)nb, q_w * sdw);                   // :308,:317
+                            atomic_add_f64(dst + 2 * (size_t)nb,
+                                           q_w * q_ch * fma(rc0 - q_rc, sw, src2));        // :319
+                            atomic_add_f64(dst + 3 * (size_t)nb,
+                                           q_w * q_sh * fma(dm0 + q_dm, sw, sdm));         // :320
+                            atomic_add_f64(dst + 4 * (size_t)nb, 0.5 * (q_w * szw + q_z * we));  // :286,:321
+                            atomic_add_i64(dst + 5 * (size_t)nb, (long long)cnt);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 extern "C" {
 
 int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
@@ -202,12 +399,35 @@ int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2
     F.kt_hi = kt * (1. + eps);
     F.magic = PB2_MAGIC;
     // variant 1 = validation: every pair through the reference expression, no windows
-    F.fast = (variant == 0 && !par->rmu_binning && !par->ang_correlation && cat1->sorted &&
+    F.fast = (variant != 1 && !par->rmu_binning && !par->ang_correlation && cat1->sorted &&
               par->num_bins_r_par <= 4096 && par->num_bins_r_trans <= 4096 &&
               par->r_par_max > par->r_par_min && par->r_trans_max > 0.) ? 1 : 0;
     long long blocks = (pairs->n_f1 + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     pb2_timing_begin(s);
+    // variant 0: prefix-sum kernel when the catalogue carries prefix records and no per-pair
+    // z cut is set (the cut is per pixel pair, xcf.py:286-291); variant 2 forces the lane = object
+    // kernel
+    const size_t chunk_smem = (size_t)64 * (cat1->max_pix + 1);
+    if (variant == 0 && F.fast && cat1->px_rec && !par->has_z_min_pairs && !par->has_z_max_pairs &&
+        chunk_smem <= 100 * 1024) {
+        // forest-claim counter: one per device, reset on the stream before every launch
+        static unsigned long long *d_ctr[64] = {nullptr};
+        int dev = 0;
+        PB2_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) dev = 0;
+        if (!d_ctr[dev]) PB2_CUDA(cudaMalloc((void **)&d_ctr[dev], sizeof(unsigned long long)));
+        PB2_CUDA(cudaMemsetAsync(d_ctr[dev], 0, sizeof(unsigned long long), s));
+        PB2_CUDA(cudaFuncSetAttribute(pb2_xi_cross_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)chunk_smem));
+        long long ctas = pairs->n_f1 < 148 * 4 ? pairs->n_f1 : 148 * 4;
+        pb2_xi_cross_chunk<<<(unsigned)ctas, 256, chunk_smem, s>>>(*cat1, *objs, *par, *pairs, F,
+                                                                   d_out_row, d_out, d_ctr[dev]);
+        pb2_count_launch(1);
+        int32_t rc2 = pb2_check_launch("pb2_xi_cross_chunk");
+        pb2_timing_end(s);
+        return rc2;
+    }
     if (F.fast)
         pb2_xi_cross_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(*cat1, *objs, *par, *pairs, F,
                                                                     d_out_row, d_out);
@@ -218,6 +438,19 @@ int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2
     int32_t rc = pb2_check_launch("pb2_xi_cross_kernel");
     pb2_timing_end(s);
     return rc;
+}
+
+int32_t pb2_build_prefix(const pb2_catalog *cat, double *d_px_rec, void *stream)
+{
+    if (!cat || !d_px_rec) {
+        pb2_set_error("pb2_build_prefix: null pointer argument");
+        return PB2_EINVAL;
+    }
+    if (cat->n_los <= 0) return 0;
+    pb2_build_prefix_kernel<<<(unsigned)((cat->n_los + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        *cat, d_px_rec);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_build_prefix");
 }
 
 }  // extern "C"
