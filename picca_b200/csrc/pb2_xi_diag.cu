@@ -5,38 +5,42 @@
 //
 // For one forest pair the pixel pairs (i, j) are visited along diagonals j - i = const.  On a
 // diagonal r_par = (rc1[i] - rc2[j]) cos(ang/2) is nearly constant and r_trans = (dm1[i] + dm2[j])
-// sin(ang/2) grows slowly, so a diagonal stays in ONE (r_par, r_trans) bin for ~80 consecutive
-// pairs (a "run").  Each lane owns DG_C adjacent diagonals and keeps, per diagonal, the bin of the
-// current run and five running totals in registers.
-//   per pair    d = rc1 - rc2, t = dm1 + dm2, then the bin straight from four round-down FMAs
-//               against 2^52 + 2^51 (floor(x K (1 -+ 2^-40)) in the low word): when the two r_par
-//               values agree and the two r_trans values agree, the reference's
-//               floor((r - min) / (max - min) * n) (cf.py:372-376) is sandwiched and the bin is
-//               proven, and "0 <= value < n" is the reference's range test (cf.py:364).  Four
-//               integer compares of the low words with the run's bin, seven FP64 instructions to
-//               accumulate: 13 FP64 instructions, no division, no predication, no bounds check
-//               and no pair counter -- zero-weight pixels (skipped by the reference,
-//               cf.py:318,331) are compacted away in the packed copies, so num_pairs of a run is
-//               its length, and columns outside forest 2 read dummies (distance 1e300, weight 0)
-//               that add zeros and land in no bin.
-//   run change  (about once per 40-80 pairs per diagonal) the lane adds its five sums and the run
-//               length to the finished run's bin with six native red.global.add.f64 / .u64 into
-//               the L2-resident per-HEALPix histogram (~30 instructions).  The sums restart through
-//               six selects in the MAIN path (high word := 0 when the bin changed, which leaves
-//               at most a 1e-314 denormal behind): the accumulators are then written only by the
-//               accumulate instructions and ptxas keeps them in place -- clearing them inside the
-//               branch costs ten register moves per pair, snapshots in shared memory saturate the
-//               L1 data pipe.  When the two FMAs of a dimension disagree (pair within 2^-40 of a
-//               bin edge, ~1e-10 of the pairs) the bin comes from the reference expression with
-//               IEEE divisions.
-// Work unit = (forest pair, block of 32 * DG_C diagonals), one warp.  The warp walks the rows in
-// chunks of DG_R: one lane issues TMA bulk copies (cp.async.bulk, completion on an mbarrier) of the
-// chunk's row records and of the column records it needs from a copy of forest 2 interleaved by
-// DG_C, into a two-stage per-warp buffer in shared memory, one chunk ahead of the arithmetic.
-// Pixels are 48-byte records (r_comov, dist_m, weight, delta*weight, z/2, 0).  Per row the warp
-// reads the row's record with broadcast loads and each lane ONE new column record (the other
-// DG_C - 1 slide through registers, statically renamed by unrolling DG_C rows); all addresses are a
-// running shared-memory pointer plus immediates.
+// sin(ang/2) grows slowly, so a diagonal stays in ONE (r_par, r_trans) bin for a "run" of ~45
+// consecutive pairs.  Each lane owns DG_C adjacent diagonals and keeps, per diagonal, five sums
+// of the current run and its bin window in registers.
+//   per pair    d = rc1 - rc2, t = dm1 + dm2, then ONE round-down FMA per dimension against
+//               2^52 + 2^51 leaves floor(65536 x K) in the low word of the result: the bin in the
+//               upper half, a 16-bit fraction in the lower (K = n / range, with cos or sin of the
+//               half angle folded in).  The reference's floor((r - min) / (max - min) * n)
+//               (cf.py:372-376) carries a rounding error below 1e-11 bins, so a fraction in
+//               [1, 65534] -- the exact product at least 2^-16 bins from an edge -- proves the
+//               bin, and "bin < n" is then the reference's range test (cf.py:364).  The pair stays
+//               in its run while (unsigned)(low word - (65536 bin + 1)) < 65534 in both
+//               dimensions: two integer subtractions and one compare.  With w1 w2 and six
+//               accumulate instructions that is 11 FP64 instructions per pair, no division, no
+//               predication, no bounds check and no pair counter: zero-weight pixels (skipped by
+//               the reference, cf.py:318,331) are compacted away in the packed copies, so
+//               num_pairs of a run is its length, and columns outside forest 2 read dummies
+//               (distance 1e300, weight 0) that add zeros and land in no bin.
+//   run change  the lane adds its five sums and the run length to the finished run's bin with six
+//               native red.global.add.f64 / .u64 (~40 instructions, divergent).  The sums restart
+//               through five selects in the MAIN path (high word := 0 when the bin changed, which
+//               leaves at most a 1e-314 denormal behind): the accumulators are then written only
+//               by the accumulate instructions and ptxas keeps them in place -- clearing them
+//               inside the branch costs ten register moves per pair, snapshots in shared memory
+//               saturate the L1 data pipe.  A pair whose fraction is 65535, or 0 above bin 0, lies
+//               within 2^-16 of a bin edge (exactly on it when the spectra share a wavelength
+//               grid): its bin comes from the reference expression with IEEE divisions
+//               (dg_exact_bin) and it forms a run of its own.  Bin 0 accepts a zero fraction: its
+//               lower edge is x = 0 itself (d = 0 for equal wavelengths).
+// Work unit = forest pair, one warp; inside it, blocks of 32 * DG_C diagonals.  The warp walks a
+// block's rows in chunks of DG_R: one lane issues TMA bulk copies (cp.async.bulk, completion on an
+// mbarrier) of the chunk's row records and of the column records it needs from a copy of forest 2
+// interleaved by DG_C, into a two-stage per-warp buffer in shared memory, one chunk ahead of the
+// arithmetic and across block boundaries.  Pixels are 48-byte records (r_comov, dist_m, weight,
+// delta*weight, z/2, 0).  Per row the warp reads the row's record with broadcast loads and each
+// lane ONE new column record (the other DG_C - 1 slide through registers, statically renamed by
+// unrolling DG_C rows); all addresses are a running shared-memory pointer plus immediates.
 // The histogram is accumulated in a [row][bin][8]-slot scratch (the six sums of a bin share one
 // 64-byte line: one address per run change) and folded into the caller's [row][6][bin] layout by
 // pb2_xi_diag_fold.
@@ -67,7 +71,6 @@ static_assert(PB2_DIAG_PAD % DG_C == 0, "padding must be a multiple of the diago
 
 struct DiagConst {
     double kp16, kt16;  // 65536 n / range
-    int gmax;                           // diagonal blocks per forest pair (longest forests)
 };
 
 // ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier)
@@ -500,7 +503,6 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
                            double *d_out, cudaStream_t s)
 {
     DiagConst C;
-    C.gmax = 0;
     const double kp = (double)par->num_bins_r_par / (par->r_par_max - par->r_par_min);
     const double kt = (double)par->num_bins_r_trans / par->r_trans_max;
     C.kp16 = kp * 65536.;
