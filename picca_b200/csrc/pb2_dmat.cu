@@ -39,10 +39,21 @@ struct DmatGeom {
     double rp, rt;
 };
 
-// exact evaluation of one pixel pair for the distortion matrix (cf.py:660-700 / xcf.py:528-564)
-__device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, double rc1, double dm1,
-                                              double rc2, double dm2, double ch, double sh,
-                                              bool cross_obj, bool shp)
+// bin constants n / range * (1 -+ 2^-40) of the data and model grids, for the division-free proof
+// of a pixel pair's bins (same sandwich as the xi kernels: both round-down products against
+// 2^52 + 2^51 must agree, otherwise the reference expression below decides)
+struct DmatFast {
+    double kp_lo, kp_hi, kt_lo, kt_hi;  // data grid
+    double mp_lo, mp_hi, mt_lo, mt_hi;  // model grid
+    int same;                           // model grid == data grid (coefficient 1)
+};
+#define DM_MAGIC 6755399441055744.0  // 2^52 + 2^51
+
+// evaluation of one pixel pair for the distortion matrix (cf.py:660-700 / xcf.py:528-564): bins
+// proven by the sandwich, else the reference expression with IEEE divisions
+__device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, const DmatFast &F, double rc1,
+                                              double dm1, double rc2, double dm2, double ch,
+                                              double sh, bool cross_obj, bool shp)
 {
     DmatGeom g;
     g.in = false;
@@ -60,6 +71,29 @@ __device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, double rc1, d
     if (r_par >= P.r_par_max || r_trans >= P.r_trans_max || r_par < P.r_par_min) return g;
     const double span = sub_rn(P.r_par_max, P.r_par_min);
     if (shp && fabs(r_par) < div_rn(span, (double)P.num_bins_r_par)) g.close = true;
+    {
+        const double x = sub_rn(r_par, P.r_par_min);
+        const int bpl = __double2loint(__fma_rd(x, F.kp_lo, DM_MAGIC));
+        const int bph = __double2loint(__fma_rd(x, F.kp_hi, DM_MAGIC));
+        const int btl = __double2loint(__fma_rd(r_trans, F.kt_lo, DM_MAGIC));
+        const int bth = __double2loint(__fma_rd(r_trans, F.kt_hi, DM_MAGIC));
+        int mpl = bpl, mph = bph, mtl = btl, mth = bth;
+        if (!F.same) {
+            mpl = __double2loint(__fma_rd(x, F.mp_lo, DM_MAGIC));
+            mph = __double2loint(__fma_rd(x, F.mp_hi, DM_MAGIC));
+            mtl = __double2loint(__fma_rd(r_trans, F.mt_lo, DM_MAGIC));
+            mth = __double2loint(__fma_rd(r_trans, F.mt_hi, DM_MAGIC));
+        }
+        if (bpl == bph && btl == bth && mpl == mph && mtl == mth &&
+            (unsigned)bpl < (unsigned)P.num_bins_r_par && (unsigned)btl < (unsigned)P.num_bins_r_trans &&
+            (unsigned)mpl < (unsigned)P.num_model_bins_r_par &&
+            (unsigned)mtl < (unsigned)P.num_model_bins_r_trans) {
+            g.in = true;
+            g.A = btl + P.num_bins_r_trans * bpl;
+            g.B = mtl + P.num_model_bins_r_trans * mpl;
+            return g;
+        }
+    }
     const double fp = div_rn(sub_rn(r_par, P.r_par_min), span);
     const double ft = div_rn(r_trans, P.r_trans_max);
     const double bp = floor(mul_rn(fp, (double)P.num_bins_r_par));
@@ -131,6 +165,48 @@ __device__ __forceinline__ void row_window(const pb2_params &P, bool windows, do
     }
 }
 
+// conservative row window of a column: rows i with rc1[i] - rc_j in [dlow, dmax] and
+// dm1[i] + dm_j below the r_trans limit (the mirror image of row_window)
+__device__ __forceinline__ void col_window(const pb2_params &P, bool windows, double rc_j,
+                                           double dm_j, const double *rc1, const double *dm1,
+                                           int n1, double ch, double sh, bool signed_rp, int &lo,
+                                           int &hi)
+{
+    lo = 0;
+    hi = n1;
+    if (!windows) return;
+    const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
+    const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
+    const double dmin = P.r_par_min * inv_c;
+    const double dlow = signed_rp ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
+    // rc1 >= rc_j + dlow, rc1 <= rc_j + dmax, dm1 < r_trans_max/sh - dm_j
+    int a = 0, b = n1;
+    const double v0 = rc_j + dlow;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (rc1[m] < v0) a = m + 1; else b = m;
+    }
+    lo = a;
+    b = n1;
+    const double v1 = rc_j + dmax;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (rc1[m] <= v1) a = m + 1; else b = m;
+    }
+    hi = a;
+    const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
+    if (isfinite(tsum)) {
+        a = lo;
+        b = hi;
+        const double v2 = tsum - dm_j;
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (dm1[m] < v2) a = m + 1; else b = m;
+        }
+        hi = a;
+    }
+}
+
 struct DmatWork {
     long long *kept;            // kept pair indices
     unsigned long long *count;  // [0] number of kept pairs, [1] claim counter
@@ -138,6 +214,7 @@ struct DmatWork {
     long long cta_stride;
     int rows_max;               // 2*max_pix1 + 2*max_pix2 + 4
     int cap;                    // DM_CAP
+    DmatFast fast;
 };
 
 __global__ void dmat_compact_kernel(pb2_pairs pr, DmatWork W)
@@ -224,7 +301,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                 row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation, lo, hi);
                 for (int j = lo; j < hi; j++) {
                     if (w2[j] == 0.) continue;
-                    DmatGeom g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                    DmatGeom g = dmat_pair(P, W.fast, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
                     if (!g.in) continue;
                     cnt_in++;
                     if (!g.close) cnt_nc++;
@@ -323,7 +400,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         bool sel = false;
                         double z = 0.;
                         if (j < hi && w2[j] != 0.) {
-                            g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                            g = dmat_pair(P, W.fast, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
                             if (g.in) {
                                 z = div_rn(add_rn(zi, z2[j]), 2.);
                                 sel = i_sel && !g.close;
@@ -398,12 +475,15 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                     int cA = -1, cB = -1;
                     bool cS = false;
                     double e2 = 0., e4 = 0., q2 = 0., q2d = 0.;
-                    for (int i = 0; i <= n1; i++) {
+                    int ilo, ihi;
+                    col_window(P, windows, rc2[j], dm2[j], rc1, dm1, n1, ch, sh, P.x_correlation, ilo,
+                               ihi);
+                    for (int i = ilo; i <= ihi; i++) {
                         DmatGeom g;
                         g.in = false;
                         bool sel = false;
-                        if (i < n1 && w1[i] != 0.) {
-                            g = dmat_pair(P, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
+                        if (i < ihi && w1[i] != 0.) {
+                            g = dmat_pair(P, W.fast, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
                             if (g.in) {
                                 sel = j_sel0 && !g.close;
                                 if (sel && zerr_on && pb2_zerr_close(P, z1[i], zq2)) sel = false;
@@ -414,7 +494,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                                 }
                             }
                         }
-                        const bool brk = (i == n1) || (g.in && (g.A != cA || g.B != cB || sel != cS));
+                        const bool brk = (i == ihi) || (g.in && (g.A != cA || g.B != cB || sel != cS));
                         if (brk && cB >= 0) {
                             const int kb = kidx[cB] - kc;
                             if (kb >= 0 && kb < Uc) {
@@ -431,7 +511,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             }
                             e2 = e4 = q2 = q2d = 0.;
                         }
-                        if (i == n1 || !g.in) continue;
+                        if (i == ihi || !g.in) continue;
                         cA = g.A;
                         cB = g.B;
                         cS = sel;
@@ -572,7 +652,7 @@ pb2_dmat_cross_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr
                 bool sel = false;
                 double z = 0.;
                 if (i < n1 && w1[i] != 0.) {
-                    g = dmat_pair(P, rc1[i], dm1[i], rcq, dmq, ch, sh, true, false);
+                    g = dmat_pair(P, W.fast, rc1[i], dm1[i], rcq, dmq, ch, sh, true, false);
                     if (g.in) {
                         z = div_rn(add_rn(z1[i], zq), 2.);
                         sel = !((P.has_z_min_pairs && z < P.z_min_pairs) ||
@@ -704,6 +784,19 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
     W.kept = (long long *)(p + fixed);
     W.rows_max = cross ? (cat1->max_pix + 1) : (2 * cat1->max_pix + 2 * cat2->max_pix + 4);
     W.cap = DM_CAP;
+    {
+        const double eps = 9.094947017729282e-13;  // 2^-40
+        const double span = par->r_par_max - par->r_par_min;
+        const double kp = (double)par->num_bins_r_par / span, kt = (double)par->num_bins_r_trans / par->r_trans_max;
+        const double mp = (double)par->num_model_bins_r_par / span;
+        const double mt = (double)par->num_model_bins_r_trans / par->r_trans_max;
+        W.fast.kp_lo = kp * (1. - eps); W.fast.kp_hi = kp * (1. + eps);
+        W.fast.kt_lo = kt * (1. - eps); W.fast.kt_hi = kt * (1. + eps);
+        W.fast.mp_lo = mp * (1. - eps); W.fast.mp_hi = mp * (1. + eps);
+        W.fast.mt_lo = mt * (1. - eps); W.fast.mt_hi = mt * (1. + eps);
+        W.fast.same = (par->num_model_bins_r_par == par->num_bins_r_par &&
+                       par->num_model_bins_r_trans == par->num_bins_r_trans) ? 1 : 0;
+    }
     PB2_CUDA(cudaMemsetAsync(W.count, 0, 256, s));
     pb2_timing_begin(s);
     dmat_compact_kernel<<<(unsigned)((pairs->n_pairs + 255) / 256), 256, 0, s>>>(*pairs, W);
