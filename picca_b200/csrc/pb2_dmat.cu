@@ -111,6 +111,13 @@ __device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, const DmatFas
     return g;
 }
 
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
 __device__ __forceinline__ double block_sum(double v, double *red)
 {
     __syncthreads();
@@ -293,13 +300,22 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
         __syncthreads();
         {
             int cnt_nc = 0, cnt_in = 0;
-            for (int i = tid; i < n1; i += DM_THREADS) {
-                if (w1[i] == 0.) continue;
+            // (every pair loop of this kernel runs a warp-uniform number of iterations with a
+            // __syncwarp() on top: without it the lanes of a warp, whose rows have different
+            // windows and flush points, end up executing the loop one or two lanes at a time)
+            for (int ib = 0; ib < n1; ib += DM_THREADS) {
+                const int i = min(ib + tid, n1 - 1);
+                const bool rowok = (ib + tid < n1) && (w1[i] != 0.);
                 bool i_sel = true;
                 if (zerr_on && pb2_zerr_close(P, z1[i], zq2)) i_sel = false;
-                int lo, hi;
-                row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation, lo, hi);
-                for (int j = lo; j < hi; j++) {
+                int lo = 0, hi = 0;
+                if (rowok)
+                    row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation, lo, hi);
+                const int len = hi - lo, maxlen = warp_max(len);
+                for (int t = 0; t < maxlen; t++) {
+                    __syncwarp();
+                    if (t >= len) continue;
+                    const int j = lo + t;
                     if (w2[j] == 0.) continue;
                     DmatGeom g = dmat_pair(P, W.fast, rc1[i], dm1[i], rc2[j], dm2[j], ch, sh, false, shp);
                     if (!g.in) continue;
@@ -382,19 +398,25 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                 double *Yp = Y + (long long)(2 * n1 + 2 * n2) * Upad;   // eta5, eta6, eta7, eta8
 
                 // ---------------- sweep 1: rows of forest 1
-                for (int i = tid; i < n1; i += DM_THREADS) {
-                    if (w1[i] == 0.) continue;
+                for (int ib = 0; ib < n1; ib += DM_THREADS) {
+                    const int i = min(ib + tid, n1 - 1);
+                    const bool rowok = (ib + tid < n1) && (w1[i] != 0.);
                     bool i_sel = true;
                     if (zerr_on && pb2_zerr_close(P, z1[i], zq2)) i_sel = false;
-                    int lo, hi;
-                    row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation,
-                               lo, hi);
+                    int lo = 0, hi = -1;
+                    if (rowok)
+                        row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation,
+                                   lo, hi);
                     const double wi = w1[i], dli = dl1[i], fzi = f1z[i], zi = z1[i];
                     int cA = -1, cB = -1;
                     bool cS = false;
                     double e1 = 0., e3 = 0., q1 = 0., q1d = 0., dg = 0., srp = 0., srt = 0., sz = 0.;
                     double e5 = 0., e6 = 0., e7 = 0., e8 = 0.;
-                    for (int j = lo; j <= hi; j++) {
+                    const int len = hi - lo + 1, maxlen = warp_max(len);
+                    for (int t = 0; t < maxlen; t++) {
+                        __syncwarp();
+                        if (t >= len) continue;
+                        const int j = lo + t;
                         DmatGeom g;
                         g.in = false;
                         bool sel = false;
@@ -467,18 +489,24 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                 }
 
                 // ---------------- sweep 2: columns (pixels of forest 2)
-                for (int j = tid; j < n2; j += DM_THREADS) {
-                    if (w2[j] == 0.) continue;
+                for (int jb = 0; jb < n2; jb += DM_THREADS) {
+                    const int j = min(jb + tid, n2 - 1);
+                    const bool colok = (jb + tid < n2) && (w2[j] != 0.);
                     bool j_sel0 = true;
                     if (zerr_on && pb2_zerr_close(P, z2[j], zq1)) j_sel0 = false;
                     const double wj = w2[j], dlj = dl2[j], fzj = f2z[j], zj = z2[j];
                     int cA = -1, cB = -1;
                     bool cS = false;
                     double e2 = 0., e4 = 0., q2 = 0., q2d = 0.;
-                    int ilo, ihi;
-                    col_window(P, windows, rc2[j], dm2[j], rc1, dm1, n1, ch, sh, P.x_correlation, ilo,
-                               ihi);
-                    for (int i = ilo; i <= ihi; i++) {
+                    int ilo = 0, ihi = -1;
+                    if (colok)
+                        col_window(P, windows, rc2[j], dm2[j], rc1, dm1, n1, ch, sh, P.x_correlation,
+                                   ilo, ihi);
+                    const int len = ihi - ilo + 1, maxlen = warp_max(len);
+                    for (int t = 0; t < maxlen; t++) {
+                        __syncwarp();
+                        if (t >= len) continue;
+                        const int i = ilo + t;
                         DmatGeom g;
                         g.in = false;
                         bool sel = false;
