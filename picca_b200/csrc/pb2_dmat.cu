@@ -29,7 +29,7 @@
 
 #define DM_THREADS 256
 #define DM_TILE 64
-#define DM_KCH 16
+#define DM_KCH 32
 #define DM_CAP 512  // compact bins handled per chunk (padded to DM_TILE)
 
 struct DmatGeom {
@@ -564,15 +564,35 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         for (int p = 0; p < 4; p++)
 #pragma unroll
                             for (int q = 0; q < 4; q++) c[p][q] = 0.;
+                        // software pipeline: the next K chunk of X and Y is fetched into
+                        // registers while the current one is multiplied out of shared memory
+                        constexpr int PER = DM_KCH * DM_TILE / DM_THREADS;
+                        double px[PER], py[PER];
+#pragma unroll
+                        for (int m = 0; m < PER; m++) {
+                            const int x = tid + m * DM_THREADS;
+                            const int r = x / DM_TILE, cc = x % DM_TILE;
+                            px[m] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
+                            py[m] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
+                        }
                         for (int r0 = 0; r0 < rows; r0 += DM_KCH) {
                             __syncthreads();
-                            for (int x = tid; x < DM_KCH * DM_TILE; x += DM_THREADS) {
-                                const int rr = x / DM_TILE, cc = x % DM_TILE;
-                                const int r = r0 + rr;
-                                Xs[rr][cc] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
-                                Ys[rr][cc] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
+#pragma unroll
+                            for (int m = 0; m < PER; m++) {
+                                const int x = tid + m * DM_THREADS;
+                                Xs[x / DM_TILE][x % DM_TILE] = px[m];
+                                Ys[x / DM_TILE][x % DM_TILE] = py[m];
                             }
                             __syncthreads();
+                            if (r0 + DM_KCH < rows) {
+#pragma unroll
+                                for (int m = 0; m < PER; m++) {
+                                    const int x = tid + m * DM_THREADS;
+                                    const int r = r0 + DM_KCH + x / DM_TILE, cc = x % DM_TILE;
+                                    px[m] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
+                                    py[m] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
+                                }
+                            }
 #pragma unroll
                             for (int rr = 0; rr < DM_KCH; rr++) {
                                 const double4 xa = *reinterpret_cast<const double4 *>(&Xs[rr][ty * 4]);
