@@ -397,6 +397,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                 double *Xp = X + (long long)(2 * n1 + 2 * n2) * UApad;  // P0, P2, P1, P12
                 double *Yp = Y + (long long)(2 * n1 + 2 * n2) * Upad;   // eta5, eta6, eta7, eta8
 
+                // (the X / Y updates below are fire-and-forget reductions rather than load-add-store:
+                // a row is owned by one thread, but the round trip to the scratch in L2 would stall it)
                 // ---------------- sweep 1: rows of forest 1
                 for (int ib = 0; ib < n1; ib += DM_THREADS) {
                     const int i = min(ib + tid, n1 - 1);
@@ -435,8 +437,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         if (brk && cB >= 0) {  // flush the finished segment
                             const int kb = kidx[cB] - kc;
                             if (kb >= 0 && kb < Uc) {
-                                Y[(long long)i * Upad + kb] += e1 / sw2;                  // eta1
-                                if (order2 == 1) Y[(long long)(n1 + i) * Upad + kb] += e3 / swsll2;
+                                atomic_add_f64(&Y[(long long)i * Upad + kb], e1 / sw2);                  // eta1
+                                if (order2 == 1) atomic_add_f64(&Y[(long long)(n1 + i) * Upad + kb], e3 / swsll2);
                                 atomic_add_f64(Yp + 0 * (long long)Upad + kb, e5 / sw1 / sw2);
                                 if (order2 == 1) atomic_add_f64(Yp + 1 * (long long)Upad + kb, e6);
                                 if (order1 == 1) atomic_add_f64(Yp + 2 * (long long)Upad + kb, e7);
@@ -446,8 +448,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             if (cS) {
                                 const int ka = aidx[cA] - ac;
                                 if (ka >= 0 && ka < UAc) {
-                                    X[(long long)i * UApad + ka] -= wi * q1;
-                                    X[(long long)(n1 + i) * UApad + ka] -= wi * q1d;
+                                    atomic_add_f64(&X[(long long)i * UApad + ka], -(wi * q1));
+                                    atomic_add_f64(&X[(long long)(n1 + i) * UApad + ka], -(wi * q1d));
                                     atomic_add_f64(Xp + 0 * (long long)UApad + ka, wi * q1);
                                     atomic_add_f64(Xp + 1 * (long long)UApad + ka, wi * q1d);
                                     atomic_add_f64(Xp + 2 * (long long)UApad + ka, wi * dli * q1);
@@ -526,15 +528,15 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         if (brk && cB >= 0) {
                             const int kb = kidx[cB] - kc;
                             if (kb >= 0 && kb < Uc) {
-                                Y[(long long)(2 * n1 + j) * Upad + kb] += e2 / sw1;         // eta2
+                                atomic_add_f64(&Y[(long long)(2 * n1 + j) * Upad + kb], e2 / sw1);         // eta2
                                 if (order1 == 1)
-                                    Y[(long long)(2 * n1 + n2 + j) * Upad + kb] += e4 / swsll1;
+                                    atomic_add_f64(&Y[(long long)(2 * n1 + n2 + j) * Upad + kb], e4 / swsll1);
                             }
                             if (cS) {
                                 const int ka = aidx[cA] - ac;
                                 if (ka >= 0 && ka < UAc) {
-                                    X[(long long)(2 * n1 + j) * UApad + ka] -= wj * q2;
-                                    X[(long long)(2 * n1 + n2 + j) * UApad + ka] -= wj * q2d;
+                                    atomic_add_f64(&X[(long long)(2 * n1 + j) * UApad + ka], -(wj * q2));
+                                    atomic_add_f64(&X[(long long)(2 * n1 + n2 + j) * UApad + ka], -(wj * q2d));
                                 }
                             }
                             e2 = e4 = q2 = q2d = 0.;
