@@ -31,6 +31,7 @@
 #define DM_TILE 64
 #define DM_KCH 32
 #define DM_CAP 512  // compact bins handled per chunk (padded to DM_TILE)
+#define DM_MAXCH 256  // K chunks of rows with a column range (more: no tile skipping)
 
 struct DmatGeom {
     bool in;       // inside the model range (cf.py:667)
@@ -247,6 +248,9 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
     __shared__ long long s_e;
     __shared__ int s_cnt[2];   // in-range pairs that are not close, in-range pairs
     __shared__ int s_U, s_UA;
+    __shared__ int s_cxlo[DM_MAXCH], s_cxhi[DM_MAXCH], s_cylo[DM_MAXCH], s_cyhi[DM_MAXCH];
+    __shared__ int s_act[DM_MAXCH];
+    __shared__ int s_nact;
     __shared__ __align__(16) double Xs[DM_KCH][DM_TILE];
     __shared__ __align__(16) double Ys[DM_KCH][DM_TILE];
 
@@ -268,6 +272,11 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
     double *dl2 = dl1 + c1.max_pix;              // [max_pix2]
     double *X = dl2 + c2.max_pix;                // [rows_max][cap]
     double *Y = X + (long long)W.rows_max * W.cap;
+    // per pixel (forest 1 then forest 2): first / last compact column written in X and in Y
+    int *xlo = (int *)(Y + (long long)W.rows_max * W.cap);
+    int *xhi = xlo + (c1.max_pix + c2.max_pix);
+    int *ylo = xhi + (c1.max_pix + c2.max_pix);
+    int *yhi = ylo + (c1.max_pix + c2.max_pix);
 
     for (;;) {
         __syncthreads();
@@ -338,15 +347,24 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
         __syncthreads();
         if (s_cnt[0] == 0) continue;  // cf.py:570-571
 
-        // compact indices in ascending bin order (np.unique order, cf.py:846-848)
+        // compact indices of the touched bins (the set of np.unique, cf.py:846-848), ordered
+        // r_trans-major: a pixel row meets every r_par bin but only two or three r_trans bins, so
+        // its non-zeros in X and Y then sit in a few contiguous column ranges and the contraction
+        // can skip the tiles a K chunk of rows does not touch
         if (tid == 0) {
             int u = 0;
-            for (int x = 0; x < nbm; x++)
-                if (kidx[x] == 0) { kidx[x] = u; klist[u++] = x; }
+            for (int t = 0; t < P.num_model_bins_r_trans; t++)
+                for (int q = 0; q < P.num_model_bins_r_par; q++) {
+                    const int x = t + P.num_model_bins_r_trans * q;
+                    if (kidx[x] == 0) { kidx[x] = u; klist[u++] = x; }
+                }
             s_U = u;
             u = 0;
-            for (int x = 0; x < nb; x++)
-                if (aidx[x] == 0) { aidx[x] = u; alist[u++] = x; }
+            for (int t = 0; t < P.num_bins_r_trans; t++)
+                for (int q = 0; q < P.num_bins_r_par; q++) {
+                    const int x = t + P.num_bins_r_trans * q;
+                    if (aidx[x] == 0) { aidx[x] = u; alist[u++] = x; }
+                }
             s_UA = u;
         }
         __syncthreads();
@@ -410,6 +428,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         row_window(P, windows, rc1[i], dm1[i], rc2, dm2, n2, ch, sh, P.x_correlation,
                                    lo, hi);
                     const double wi = w1[i], dli = dl1[i], fzi = f1z[i], zi = z1[i];
+                    int rxl = 0x7fffffff, rxh = -1, ryl = 0x7fffffff, ryh = -1;
                     int cA = -1, cB = -1;
                     bool cS = false;
                     double e1 = 0., e3 = 0., q1 = 0., q1d = 0., dg = 0., srp = 0., srt = 0., sz = 0.;
@@ -437,6 +456,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         if (brk && cB >= 0) {  // flush the finished segment
                             const int kb = kidx[cB] - kc;
                             if (kb >= 0 && kb < Uc) {
+                                ryl = min(ryl, kb);
+                                ryh = max(ryh, kb);
                                 atomic_add_f64(&Y[(long long)i * Upad + kb], e1 / sw2);                  // eta1
                                 if (order2 == 1) atomic_add_f64(&Y[(long long)(n1 + i) * Upad + kb], e3 / swsll2);
                                 atomic_add_f64(Yp + 0 * (long long)Upad + kb, e5 / sw1 / sw2);
@@ -448,6 +469,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             if (cS) {
                                 const int ka = aidx[cA] - ac;
                                 if (ka >= 0 && ka < UAc) {
+                                    rxl = min(rxl, ka);
+                                    rxh = max(rxh, ka);
                                     atomic_add_f64(&X[(long long)i * UApad + ka], -(wi * q1));
                                     atomic_add_f64(&X[(long long)(n1 + i) * UApad + ka], -(wi * q1d));
                                     atomic_add_f64(Xp + 0 * (long long)UApad + ka, wi * q1);
@@ -488,6 +511,12 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             sz += w12 * z;
                         }
                     }
+                    if (ib + tid < n1) {
+                        xlo[i] = rxl;
+                        xhi[i] = rxh;
+                        ylo[i] = ryl;
+                        yhi[i] = ryh;
+                    }
                 }
 
                 // ---------------- sweep 2: columns (pixels of forest 2)
@@ -499,6 +528,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                     const double wj = w2[j], dlj = dl2[j], fzj = f2z[j], zj = z2[j];
                     int cA = -1, cB = -1;
                     bool cS = false;
+                    int rxl = 0x7fffffff, rxh = -1, ryl = 0x7fffffff, ryh = -1;
                     double e2 = 0., e4 = 0., q2 = 0., q2d = 0.;
                     int ilo = 0, ihi = -1;
                     if (colok)
@@ -528,6 +558,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         if (brk && cB >= 0) {
                             const int kb = kidx[cB] - kc;
                             if (kb >= 0 && kb < Uc) {
+                                ryl = min(ryl, kb);
+                                ryh = max(ryh, kb);
                                 atomic_add_f64(&Y[(long long)(2 * n1 + j) * Upad + kb], e2 / sw1);         // eta2
                                 if (order1 == 1)
                                     atomic_add_f64(&Y[(long long)(2 * n1 + n2 + j) * Upad + kb], e4 / swsll1);
@@ -535,6 +567,8 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             if (cS) {
                                 const int ka = aidx[cA] - ac;
                                 if (ka >= 0 && ka < UAc) {
+                                    rxl = min(rxl, ka);
+                                    rxh = max(rxh, ka);
                                     atomic_add_f64(&X[(long long)(2 * n1 + j) * UApad + ka], -(wj * q2));
                                     atomic_add_f64(&X[(long long)(2 * n1 + n2 + j) * UApad + ka], -(wj * q2d));
                                 }
@@ -553,14 +587,70 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             q2d += w1[i] * dl1[i];
                         }
                     }
+                    if (jb + tid < n2) {
+                        xlo[n1 + j] = rxl;
+                        xhi[n1 + j] = rxh;
+                        ylo[n1 + j] = ryl;
+                        yhi[n1 + j] = ryh;
+                    }
                 }
                 __syncthreads();
                 __threadfence_block();
+
+                // ---------------- column ranges of every K chunk of rows.  Rows: [0, n1) and
+                // [n1, 2 n1) belong to the pixels of forest 1, the next 2 n2 to forest 2, the last
+                // four (P0, P2, P1, P12 / eta5..8) are dense.
+                const int nch = (rows + DM_KCH - 1) / DM_KCH;
+                const bool skipping = nch <= DM_MAXCH;
+                if (skipping) {
+                    for (int cch = tid; cch < nch; cch += DM_THREADS) {
+                        int cxl = 0x7fffffff, cxh = -1, cyl = 0x7fffffff, cyh = -1;
+                        for (int r = cch * DM_KCH; r < min(rows, (cch + 1) * DM_KCH); r++) {
+                            if (r >= 2 * n1 + 2 * n2) {
+                                cxl = cyl = 0;
+                                cxh = cyh = 0x7ffffff0;
+                                break;
+                            }
+                            const int px = r < n1 ? r : r < 2 * n1 ? r - n1
+                                           : r < 2 * n1 + n2 ? r - n1 : r - n1 - n2;
+                            const bool used = px < n1 ? (w1[px] != 0.) : (w2[px - n1] != 0.);
+                            if (!used) continue;  // rows of zero-weight pixels were never written
+                            cxl = min(cxl, xlo[px]);
+                            cxh = max(cxh, xhi[px]);
+                            cyl = min(cyl, ylo[px]);
+                            cyh = max(cyh, yhi[px]);
+                        }
+                        s_cxlo[cch] = cxl;
+                        s_cxhi[cch] = cxh;
+                        s_cylo[cch] = cyl;
+                        s_cyhi[cch] = cyh;
+                    }
+                }
+                __syncthreads();
 
                 // ---------------- contraction  C[a,k] = sum_r X[r,a] Y[r,k]
                 const int ty = tid >> 4, tx = tid & 15;
                 for (int a0 = 0; a0 < UApad; a0 += DM_TILE) {
                     for (int k0 = 0; k0 < Upad; k0 += DM_TILE) {
+                        // K chunks whose rows touch both column tiles, in ascending order
+                        __syncthreads();
+                        if (tid < 32) {
+                            int cnt = 0;
+                            for (int cb = 0; cb < nch; cb += 32) {
+                                const int cch = cb + tid;
+                                const bool on = cch < nch &&
+                                    (!skipping || (s_cxlo[cch] < a0 + DM_TILE && s_cxhi[cch] >= a0 &&
+                                                   s_cylo[cch] < k0 + DM_TILE && s_cyhi[cch] >= k0));
+                                const unsigned m = __ballot_sync(0xffffffffu, on);
+                                if (on && cnt + __popc(m & ((1u << tid) - 1u)) < DM_MAXCH)
+                                    s_act[cnt + __popc(m & ((1u << tid) - 1u))] = cch;
+                                cnt += __popc(m);
+                            }
+                            if (tid == 0) s_nact = cnt;
+                        }
+                        __syncthreads();
+                        const int nact = s_nact;
+                        if (nact == 0) continue;
                         double c[4][4];
 #pragma unroll
                         for (int p = 0; p < 4; p++)
@@ -570,14 +660,19 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                         // registers while the current one is multiplied out of shared memory
                         constexpr int PER = DM_KCH * DM_TILE / DM_THREADS;
                         double px[PER], py[PER];
+                        auto fetch = [&](int r0) {
 #pragma unroll
-                        for (int m = 0; m < PER; m++) {
-                            const int x = tid + m * DM_THREADS;
-                            const int r = x / DM_TILE, cc = x % DM_TILE;
-                            px[m] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
-                            py[m] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
-                        }
-                        for (int r0 = 0; r0 < rows; r0 += DM_KCH) {
+                            for (int m = 0; m < PER; m++) {
+                                const int x = tid + m * DM_THREADS;
+                                const int r = r0 + x / DM_TILE, cc = x % DM_TILE;
+                                px[m] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
+                                py[m] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
+                            }
+                        };
+                        // (without skipping the list may be cut at DM_MAXCH: then walk all chunks)
+                        const int nloop = skipping ? nact : nch;
+                        fetch((skipping ? s_act[0] : 0) * DM_KCH);
+                        for (int n = 0; n < nloop; n++) {
                             __syncthreads();
 #pragma unroll
                             for (int m = 0; m < PER; m++) {
@@ -586,15 +681,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                                 Ys[x / DM_TILE][x % DM_TILE] = py[m];
                             }
                             __syncthreads();
-                            if (r0 + DM_KCH < rows) {
-#pragma unroll
-                                for (int m = 0; m < PER; m++) {
-                                    const int x = tid + m * DM_THREADS;
-                                    const int r = r0 + DM_KCH + x / DM_TILE, cc = x % DM_TILE;
-                                    px[m] = (r < rows) ? X[(long long)r * UApad + a0 + cc] : 0.;
-                                    py[m] = (r < rows) ? Y[(long long)r * Upad + k0 + cc] : 0.;
-                                }
-                            }
+                            if (n + 1 < nloop) fetch((skipping ? s_act[n + 1] : n + 1) * DM_KCH);
 #pragma unroll
                             for (int rr = 0; rr < DM_KCH; rr++) {
                                 const double4 xa = *reinterpret_cast<const double4 *>(&Xs[rr][ty * 4]);
@@ -777,6 +864,7 @@ static long long auto_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, co
     long long bytes = (2 * nb + 2 * nbm) * 4 + 64;
     bytes += (2ll * c1->max_pix + 2ll * c2->max_pix) * 8;
     bytes += 2 * rows * DM_CAP * 8;
+    bytes += 4ll * (c1->max_pix + c2->max_pix) * 4;
     return (bytes + 255) / 256 * 256;
 }
 
