@@ -223,6 +223,9 @@ struct DmatWork {
     int rows_max;               // 2*max_pix1 + 2*max_pix2 + 4
     int cap;                    // DM_CAP
     DmatFast fast;
+    // per pixel / per line of sight constants of cf.py:577-594, 680-685 (filled by dmat_prologue)
+    double *fz1, *dl1, *fz2, *dl2;  // ((1+z)/(1+z_ref))^(alpha-1), log_lambda - <log_lambda>_w
+    double2 *fs1, *fs2;             // (sum w, sum w dll^2) per line of sight
 };
 
 __global__ void dmat_compact_kernel(pb2_pairs pr, DmatWork W)
@@ -238,6 +241,41 @@ __global__ void dmat_compact_kernel(pb2_pairs pr, DmatWork W)
 // ------------------------------------------------------------------------------------------
 // auto / delta x delta
 // ------------------------------------------------------------------------------------------
+// per-forest constants of the projection (cf.py:577-594) and the per-pixel redshift-evolution
+// factor (cf.py:680-685), once per call instead of once per forest pair.  One warp per forest.
+__global__ void dmat_prologue_kernel(pb2_catalog c, pb2_params P, double alpha, double *__restrict__ fz,
+                                     double *__restrict__ dl, double2 *__restrict__ fs)
+{
+    const int lane = threadIdx.x & 31;
+    const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= c.n_los) return;
+    const long long a = c.offset[f];
+    const int n = (int)(c.offset[f + 1] - a);
+    const double *w = c.weights + a, *ll = c.log_lambda + a, *z = c.z + a;
+    double t = 0., u = 0.;
+    for (int i = lane; i < n; i += 32) {
+        t += w[i];
+        u += ll[i] * w[i];
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, m);
+        u += __shfl_xor_sync(0xffffffffu, u, m);
+    }
+    const double mll = u / t;
+    double q = 0.;
+    for (int i = lane; i < n; i += 32) {
+        const double d = ll[i] - mll;
+        dl[a + i] = d;
+        q += w[i] * (d * d);
+        fz[a + i] = P.redshift_evolution_in_distortion_matrix
+                        ? pow((1. + z[i]) / (1. + P.z_ref), alpha - 1.) : 1.;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
+    if (lane == 0) fs[f] = make_double2(t, q);
+}
+
 __global__ void __launch_bounds__(DM_THREADS, 2)
 pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DmatWork W,
                      double *__restrict__ weights_dmat, double *__restrict__ dmat,
@@ -266,11 +304,7 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
     int *aidx = kidx + nbm;                      // [nb]
     int *klist = aidx + nb;                      // [nbm]
     int *alist = klist + nbm;                    // [nb]
-    double *f1z = (double *)(((uintptr_t)(alist + nb) + 15) & ~(uintptr_t)15);  // [max_pix1]
-    double *f2z = f1z + c1.max_pix;              // [max_pix2]
-    double *dl1 = f2z + c2.max_pix;              // [max_pix1] log_lambda - mean
-    double *dl2 = dl1 + c1.max_pix;              // [max_pix2]
-    double *X = dl2 + c2.max_pix;                // [rows_max][cap]
+    double *X = (double *)(((uintptr_t)(alist + nb) + 15) & ~(uintptr_t)15);  // [rows_max][cap]
     double *Y = X + (long long)W.rows_max * W.cap;
     // per pixel (forest 1 then forest 2): first / last compact column written in X and in Y
     int *xlo = (int *)(Y + (long long)W.rows_max * W.cap);
@@ -370,34 +404,11 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
         __syncthreads();
         const int U = s_U, UA = s_UA;
 
-        // ---------------- per-forest constants (cf.py:577-594)
-        double t1 = 0., t2 = 0.;
-        for (int i = tid; i < n1; i += DM_THREADS) t1 += w1[i];
-        const double sw1 = block_sum(t1, red);
-        for (int j = tid; j < n2; j += DM_THREADS) t2 += w2[j];
-        const double sw2 = block_sum(t2, red);
-        t1 = t2 = 0.;
-        for (int i = tid; i < n1; i += DM_THREADS) t1 += ll1[i] * w1[i];
-        const double mll1 = block_sum(t1, red) / sw1;
-        for (int j = tid; j < n2; j += DM_THREADS) t2 += ll2[j] * w2[j];
-        const double mll2 = block_sum(t2, red) / sw2;
-        t1 = t2 = 0.;
-        for (int i = tid; i < n1; i += DM_THREADS) {
-            const double d = ll1[i] - mll1;
-            dl1[i] = d;
-            t1 += w1[i] * (d * d);
-            f1z[i] = P.redshift_evolution_in_distortion_matrix
-                         ? pow((1. + z1[i]) / (1. + P.z_ref), P.alpha - 1.) : 1.;  // cf.py:680-685
-        }
-        const double swsll1 = block_sum(t1, red);
-        for (int j = tid; j < n2; j += DM_THREADS) {
-            const double d = ll2[j] - mll2;
-            dl2[j] = d;
-            t2 += w2[j] * (d * d);
-            f2z[j] = P.redshift_evolution_in_distortion_matrix
-                         ? pow((1. + z2[j]) / (1. + P.z_ref), P.alpha2 - 1.) : 1.;
-        }
-        const double swsll2 = block_sum(t2, red);
+        // ---------------- per-forest constants (cf.py:577-594), from the prologue
+        const double sw1 = W.fs1[f1].x, swsll1 = W.fs1[f1].y;
+        const double sw2 = W.fs2[f2].x, swsll2 = W.fs2[f2].y;
+        const double *__restrict__ f1z = W.fz1 + a, *__restrict__ dl1 = W.dl1 + a;
+        const double *__restrict__ f2z = W.fz2 + b, *__restrict__ dl2 = W.dl2 + b;
 
         const int rows = 2 * n1 + 2 * n2 + 4;
         for (int kc = 0; kc < U; kc += W.cap) {
@@ -868,6 +879,13 @@ static long long auto_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, co
     return (bytes + 255) / 256 * 256;
 }
 
+// per-pixel (fz, dl) and per-forest (sum w, sum w dll^2) constants of both catalogues
+static long long auto_prologue_bytes(const pb2_catalog *c1, const pb2_catalog *c2)
+{
+    const long long b = 16 * (c1->n_pix + c2->n_pix) + 16 * (c1->n_los + c2->n_los) + 256;
+    return (b + 255) / 256 * 256;
+}
+
 static const int DM_AUTO_BLOCKS = 148 * 2;
 static const int DM_CROSS_BLOCKS = 148 * 8;
 
@@ -883,7 +901,8 @@ int64_t pb2_dmat_scratch_bytes(const pb2_catalog *cat1, const pb2_catalog *cat2,
     if (cross)
         bytes += (long long)DM_CROSS_BLOCKS * (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg));
     else
-        bytes += (long long)DM_AUTO_BLOCKS * auto_cta_bytes(cat1, cat2, par);
+        bytes += (long long)DM_AUTO_BLOCKS * auto_cta_bytes(cat1, cat2, par) +
+                 auto_prologue_bytes(cat1, cat2);
     return bytes;
 }
 
@@ -937,6 +956,23 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
     }
     PB2_CUDA(cudaMemsetAsync(W.count, 0, 256, s));
     pb2_timing_begin(s);
+    if (!cross) {
+        // prologue arrays sit between the per-CTA areas and the kept-pair list
+        char *q = p + 256 + (long long)DM_AUTO_BLOCKS * W.cta_stride;
+        W.fs1 = (double2 *)q;
+        W.fs2 = W.fs1 + cat1->n_los;
+        W.fz1 = (double *)(W.fs2 + cat2->n_los);
+        W.dl1 = W.fz1 + cat1->n_pix;
+        W.fz2 = W.dl1 + cat1->n_pix;
+        W.dl2 = W.fz2 + cat2->n_pix;
+        if (cat1->n_los > 0)
+            dmat_prologue_kernel<<<(unsigned)((cat1->n_los * 32 + 255) / 256), 256, 0, s>>>(
+                *cat1, *par, par->alpha, W.fz1, W.dl1, W.fs1);
+        if (cat2->n_los > 0)
+            dmat_prologue_kernel<<<(unsigned)((cat2->n_los * 32 + 255) / 256), 256, 0, s>>>(
+                *cat2, *par, par->alpha2, W.fz2, W.dl2, W.fs2);
+        pb2_count_launch(2);
+    }
     dmat_compact_kernel<<<(unsigned)((pairs->n_pairs + 255) / 256), 256, 0, s>>>(*pairs, W);
     if (cross)
         pb2_dmat_cross_kernel<<<DM_CROSS_BLOCKS, 128, 0, s>>>(*cat1, *cat2, *par, *pairs, W,
