@@ -84,3 +84,50 @@ def test_dmat_chunks_sum_like_the_script():
     for k in range(6):
         s = a[k] + b[k]
         np.testing.assert_allclose(s, whole[k], rtol=1e-9, atol=1e-12 * np.abs(whole[k]).max())
+
+
+def _dmat_vs_oracle(data, num, ang_max, **cfg):
+    from oracle import cf as ocf
+    from picca_b200 import cf
+    helpers.configure(ocf, data, num, ang_max, **cfg)
+    helpers.configure(cf, data, num, ang_max, **cfg)
+    hps = sorted(data)
+    ocf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    want = ocf.compute_dmat(hps)
+    cf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    got = cf.compute_dmat(hps)
+    assert (int(got[6]), int(got[7])) == (int(want[6]), int(want[7]))
+    for k, n in enumerate(NAMES):
+        w, g = np.asarray(want[k]), np.asarray(got[k])
+        err = np.abs(g - w)
+        tol = 1e-9 * np.abs(w) + 1e-12 * np.abs(w).max()
+        assert np.all(err <= tol), "%s: max err %.3e (scale %.3e)" % (n, err.max(), np.abs(w).max())
+    return int(want[7])
+
+
+def test_dmat_production_binning_matches_oracle():
+    """50 x 50 bins, r < 200: several hundred touched bins per forest pair (compact-bin chunks,
+    r_trans-major tiles and the tile skipping of the contraction)."""
+    from picca_b200 import synth
+    data, num, z_min, _, cosmo = helpers.small_sample(n=60, seed=91, max_pix=260, side_deg=3.)
+    ang_max = synth.compute_ang_max(cosmo, 200., z_min)
+    used = _dmat_vs_oracle(data, num, ang_max, num_bins_r_par=50, num_bins_r_trans=50,
+                           num_model_bins_r_par=50, num_model_bins_r_trans=50, r_par_max=200.,
+                           r_trans_max=200., reject=0.9)
+    assert used > 20
+
+
+def test_dmat_long_forests_without_tile_skipping():
+    """Forests of ~2200 pixels: more K chunks of rows than the kernel keeps column ranges for, so
+    the contraction walks every chunk."""
+    from picca_b200 import synth
+    data, num, z_min, _, cosmo = synth.make_forests(
+        5, seed=6, nside=16, ra_deg=(10., 10.6), dec_deg=(5., 5.6), rest_range=(1000., 1250.),
+        dlambda=0.25)
+    lens = [len(d.weights) for hp in data for d in data[hp]]
+    assert 2 * sorted(lens)[-1] + 2 * sorted(lens)[-2] > 256 * 32 > 4 * min(lens)
+    ang_max = synth.compute_ang_max(cosmo, 60., z_min)
+    used = _dmat_vs_oracle(data, num, ang_max, reject=0.)
+    assert used >= 3
