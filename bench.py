@@ -36,6 +36,7 @@ WORKLOADS = {
 }
 CF_CFG = dict(num_bins_r_par=50, num_bins_r_trans=50, r_par_max=200., r_par_min=0.,
               r_trans_max=200., nside=32)
+DMAT_REJECT = 0.99  # BASELINE.json configs[3]
 FLOPS_PER_PAIR = 30.  # algorithmic FP64 ops per binned pair (cf)
 
 
@@ -282,6 +283,75 @@ def run_cuda(args):
         step_e2e()
     e2e_ms, _ = timed(step_e2e, args.steps)
 
+    # ---- distortion-matrix leg (BASELINE config 4: --rej 0.99 on the same sample, one reference
+    # chunk seeded with the first HEALPix pixel as picca_dmat.py --nproc 1 does, :36,:471-485)
+    dmat_info = None
+    if not args.no_dmat:
+        all_f1 = torch.as_tensor(np.arange(host.n_los, dtype=np.int32), device=eng.device)
+        row_of_f1 = np.repeat(np.arange(len(hps)), np.diff(host.arrays["hp_first"]))
+        row_owner = np.zeros(len(hps), dtype=np.int64)
+        for r_, part in enumerate(pdist.lpt_partition(work, world)):
+            row_owner[part] = r_
+        cf.reject = DMAT_REJECT
+        dparams = params_from_module(cf)
+        dm_counts = {}
+
+        def dmat_step(dev_cat):
+            # neighbour search is replicated (ms); the draw is identical on every rank (Q6);
+            # the kernels run on this rank's share; one NCCL all-reduce sums the accumulators
+            prs = eng.neighbours(dev_cat, dev_cat, dparams, MODE_AUTO, all_f1)
+            keep = pdist.draw_keep_mask(prs.n_pairs, DMAT_REJECT, hps[0])
+            dm_counts["npall"], dm_counts["npused"] = int(prs.n_pairs), int(keep.sum())
+            if world > 1:
+                f1_of_pair = prs.nb_f1.cpu().numpy()
+                keep = pdist.shard_keep_mask(keep, row_of_f1[f1_of_pair], row_owner, rank)
+            return pdist.dmat_sharded(eng, dev_cat, dev_cat, dparams, prs, keep, world=world)
+
+        dmat_step(dev)
+        eng.lib.pb2_set_timing(1)
+        dm_kernel_ms = []
+
+        def dmat_resident():
+            r_ = dmat_step(dev)
+            dm_kernel_ms.append(eng.lib.pb2_last_kernel_ms())
+            return r_
+        dl0 = eng.launch_count()
+        dm_ms, dm_res = timed(dmat_resident, args.dmat_steps)
+        dm_launches = eng.launch_count() - dl0
+        eng.lib.pb2_set_timing(0)
+        dm_nbytes = int(sum(t.numel() * 8 for t in dm_res))
+        dm_host = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in dm_res]
+
+        def dmat_e2e():
+            fresh = catalog.DeviceCatalog.__new__(catalog.DeviceCatalog)
+            fresh.host, fresh.device, fresh.tensors = host, eng.device, {}
+            for k, v in pinned.items():
+                fresh.tensors[k] = v.to(eng.device, non_blocking=True)
+            fresh.struct = catalog.build_struct(host, fresh.tensors)
+            r_ = dmat_step(fresh)
+            if rank == 0:
+                for h_, t_ in zip(dm_host, r_):
+                    h_.copy_(t_, non_blocking=True)
+            return r_
+        dm_e2e_ms, _ = timed(dmat_e2e, args.dmat_steps)
+        used = dm_counts["npused"]
+        dmat_info = {
+            "metric": "used forest pairs/sec (distortion matrix, --rej %.2f)" % DMAT_REJECT,
+            "value": used / (dm_ms / args.dmat_steps * 1e-3), "unit": "forest pairs/s",
+            "steps": args.dmat_steps, "ms_per_step": dm_ms / args.dmat_steps,
+            "kernel_ms": float(np.mean(dm_kernel_ms)), "gpu_launches": int(dm_launches),
+            "NPALL": dm_counts["npall"], "NPUSED": used,
+            "dmat_shape": [int(dm_res[1].shape[0]), int(dm_res[1].shape[1])],
+            "sum_dmat": float(dm_res[1].sum().item()),
+            "sum_weights_dmat": float(dm_res[0].sum().item()),
+            "e2e": {"value": used / (dm_e2e_ms / args.dmat_steps * 1e-3),
+                    "unit": "forest pairs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": dm_nbytes},
+            "parallelism": "kept forest pairs sharded by owning HEALPix row x%d, "
+                           "NCCL all-reduce(SUM) of dmat + 5 vectors" % world if world > 1 else
+                           "one GPU, one reference chunk",
+        }
+
     # ---- totals (all ranks processed the whole sample between them)
     local_pairs = torch.tensor([0], dtype=torch.int64, device=eng.device)
     if world == 1:
@@ -308,6 +378,15 @@ def run_cuda(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # DRAM bytes of one launch of the dominant kernel on this workload, from an ncu capture
+        # (scripts/gpu_traffic.sh -> profiles/r01_traffic.json); null if no capture matches
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("workload") == args.workload and world == 1:
+                traffic = tr.get("dram_bytes_per_launch")
+        except Exception:
+            pass
         alg_bytes = 48.0 * host.n_pix + n_rows * 6 * nb * 8.0
         line = {
             "metric": "binned forest-pixel pairs/sec (cf auto-correlation)",
@@ -325,7 +404,7 @@ def run_cuda(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tops/s (1 DFMA = 1 op)", "frac": achieved / peak_ops,
-                         "traffic": None, "kernel": "pb2_xi_auto_diag", "kernel_ms": kms,
+                         "traffic": traffic, "kernel": "pb2_xi_auto_diag", "kernel_ms": kms,
                          "peak_source": "pb2_fp64_peak DFMA microbenchmark, measured in this run",
                          "ops_per_pair": FLOPS_PER_PAIR},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9,
@@ -338,6 +417,8 @@ def run_cuda(args):
             cpairs, cdt, cdesc = cpu_sample_run(data, num, ang_max, args.cpu_healpix, threads)
             line["cpu_baseline"] = {"value": cpairs / cdt, "unit": "pairs/s", "cores": threads,
                                     "kind": "port", "sample": cdesc}
+        if dmat_info is not None:
+            line["dmat"] = dmat_info
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -352,6 +433,8 @@ def main():
     ap.add_argument("--workload", default="c2_100k", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-healpix", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dmat", action="store_true", help="skip the distortion-matrix leg")
+    ap.add_argument("--dmat-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

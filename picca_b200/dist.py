@@ -81,3 +81,31 @@ def allreduce_dmat(tensors, group=None):
     for t in tensors:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return tensors
+
+
+def draw_keep_mask(n_pairs, reject, seed):
+    """The ``--rej`` draw of one reference chunk: ``np.random.seed(healpixs[0])``
+    (picca_dmat.py:36) followed by ``rand(len(neighbours)) > reject`` per forest in catalogue
+    order (cf.py:444).  Consecutive ``rand(n)`` calls consume the legacy MT19937 stream exactly
+    like one ``rand(sum n)``, so one call reproduces the whole chunk; every rank draws the same
+    mask from the same seed."""
+    state = np.random.RandomState(seed)
+    return state.rand(int(n_pairs)) > reject
+
+
+def shard_keep_mask(keep, pair_row, row_owner, rank):
+    """Restrict the chunk-wide keep mask to the forest pairs whose owning HEALPix row belongs to
+    ``rank`` (``row_owner[row]`` = rank).  The union over ranks is the chunk's mask and the
+    shards are disjoint, so the all-reduced distortion matrix equals the single-process one."""
+    return keep & (np.asarray(row_owner)[np.asarray(pair_row)] == rank)
+
+
+def dmat_sharded(eng, dev1, dev2, params, pairs, keep_local, group=None, world=1):
+    """Distortion matrix of this rank's share of the kept forest pairs, then ONE all-reduce(SUM)
+    per accumulator across ranks (the NumPy ``.sum(axis=0)`` of picca_dmat.py:494-501)."""
+    torch = eng.torch
+    pairs.nb_keep = torch.from_numpy(np.ascontiguousarray(keep_local, dtype=np.uint8)).to(eng.device)
+    res = list(eng.dmat(dev1, dev2, params, pairs))
+    if world > 1:
+        allreduce_dmat(res, group=group)
+    return res

@@ -64,3 +64,21 @@ def test_lpt_is_a_partition_and_balanced():
     assert np.array_equal(allidx, np.arange(500))
     loads = np.array([work[p].sum() for p in parts])
     assert loads.max() <= loads.mean() + work.max()
+
+
+def test_keep_mask_draw_and_shards():
+    """The chunk-wide --rej draw equals the reference's per-forest draws after
+    np.random.seed(healpixs[0]) (picca_dmat.py:36, cf.py:444); its per-rank shards are disjoint
+    and their union is the chunk's mask, so all-reduced sums equal the one-process sums."""
+    counts = [3, 0, 7, 1, 12, 5]
+    seed, reject = 1234, 0.6
+    np.random.seed(seed)
+    want = np.concatenate([np.random.rand(n) > reject for n in counts])
+    got = pdist.draw_keep_mask(sum(counts), reject, seed)
+    assert np.array_equal(got, want)
+    pair_row = np.repeat([0, 0, 1, 2, 2, 3], counts)
+    owner = np.array([1, 0, 1, 0])
+    shards = [pdist.shard_keep_mask(got, pair_row, owner, r) for r in range(2)]
+    assert not np.any(shards[0] & shards[1])
+    assert np.array_equal(shards[0] | shards[1], got)
+    assert np.array_equal(shards[1], got & np.isin(pair_row, [0, 2]))
