@@ -293,6 +293,8 @@ def run_cuda(args):
         for r_, part in enumerate(pdist.lpt_partition(work, world)):
             row_owner[part] = r_
         cf.reject = DMAT_REJECT
+        cf.num_model_bins_r_par = CF_CFG["num_bins_r_par"]      # picca_dmat.py:114-122: coef 1
+        cf.num_model_bins_r_trans = CF_CFG["num_bins_r_trans"]
         dparams = params_from_module(cf)
         dm_counts = {}
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 10
+#define PB2_ABI_VERSION 11
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -210,6 +210,29 @@ int32_t pb2_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const p
                        const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
                        double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
                        double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* ---- sub-sample covariance of the per-HEALPix blocks (the consumer of the WE/DA columns the
+ * pair kernels produce).
+ * pb2_cov_subsample replaces utils.compute_cov (py/picca/utils.py:100-128): d_xi, d_weights are
+ * [n_samples][nb] row-major fp64 (one row per HEALPix pixel); outputs d_cov [nb][nb],
+ * d_mean_xi [nb] (weighted mean, utils.py:113-116) and d_sum_weights [nb].  Workspace of
+ * pb2_cov_scratch_bytes(n_samples, nb) bytes.
+ * pb2_cov_smooth replaces utils.smooth_cov (py/picca/utils.py:153-249) for a covariance without
+ * zero variances (the caller handles the reference's early return, utils.py:187-190): the
+ * correlation coefficient is averaged over bin pairs with equal
+ * (round(|dr_par|/delta_r_par), round(|dr_trans|/delta_r_trans)) and, with per_r_par, equal
+ * int(r_par/delta_r_par).  n_dp, n_dt: extents of the two rounded differences; rp_lo, n_rp: lowest
+ * value and extent of int(r_par/delta_r_par) (per_r_par only).  d_table_sum / d_table_count:
+ * n_rp*n_dp*n_dt entries of workspace; *d_bad is set to 1 if a key fell outside the extents. */
+int64_t pb2_cov_scratch_bytes(int64_t n_samples, int32_t nb);
+int32_t pb2_cov_subsample(int64_t n_samples, int32_t nb, const double *d_xi, const double *d_weights,
+                          double *d_cov, double *d_mean_xi, double *d_sum_weights, void *d_scratch,
+                          int64_t scratch_bytes, void *stream);
+int32_t pb2_cov_smooth(int32_t nb, const double *d_cov, const double *d_r_par,
+                       const double *d_r_trans, double delta_r_par, double delta_r_trans,
+                       int32_t per_r_par, int32_t n_dp, int32_t n_dt, int32_t rp_lo, int32_t n_rp,
+                       double *d_table_sum, uint64_t *d_table_count, int32_t *d_bad,
+                       double *d_cov_smooth, void *stream);
 
 /* ---- measurement helpers
  * pb2_fp64_peak: dependent-free DFMA microbenchmark; returns achieved FP64 op/s (1 DFMA = 1 op,

@@ -157,15 +157,14 @@ __device__ __forceinline__ void dg_emit(double *__restrict__ dst, int cnt, doubl
 template <bool ABS, bool FOLD>
 __global__ void __launch_bounds__(DG_THREADS, 1)
 pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DiagConst C,
-                 const int32_t *__restrict__ out_row, double *__restrict__ scr)
+                 const int32_t *__restrict__ out_row, double *__restrict__ scr,
+                 unsigned long long *__restrict__ work_ctr)
 {
     extern __shared__ __align__(128) unsigned char dg_smem[];
-    __shared__ unsigned s_ctr;
     __shared__ __align__(8) unsigned long long s_bar[DG_WARPS][2];
     __shared__ int2 s_tb[DG_WARPS][DG_GMAX];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_ctr = 0;
     if (lane == 0) {
         dg_mbar_init(dg_saddr(&s_bar[wid][0]), 1);
         dg_mbar_init(dg_saddr(&s_bar[wid][1]), 1);
@@ -183,14 +182,15 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
     unsigned phase = 0;  // bit t: parity to wait for on stage t
 
     for (;;) {
-        // ---- claim a forest pair (warps of a CTA take neighbouring pairs: they share forest 1)
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(&s_ctr, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        const long long e = ((long long)blockIdx.x + (long long)(u / DG_CHUNK) * gridDim.x) * DG_CHUNK +
-                            u % DG_CHUNK;
-        if (e - u % DG_CHUNK >= pr.n_pairs) break;
-        if (e >= pr.n_pairs) continue;
+        // ---- claim the next forest pair of the list from ONE device-wide counter: at any time
+        // the warps of the whole grid work inside a window of a few thousand consecutive forest
+        // pairs (a handful of forests 1 and their shared neighbours), which stays in L2.  A static
+        // split lets the CTAs drift apart by a few per cent of the list -- hundreds of MB of
+        // records -- and re-reads the catalogue from DRAM ~50 times (ncu: 454 GB per launch).
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(work_ctr, 1ull);
+        const long long e = (long long)__shfl_sync(0xffffffffu, u, 0);
+        if (e >= pr.n_pairs) break;
 
         const int k1 = pr.nb_f1[e];
         const int f1 = pr.f1_index[k1];
@@ -466,13 +466,13 @@ __global__ void pb2_xi_diag_fold(const double *__restrict__ scr, double *__restr
 template <bool ABS, bool FOLD>
 static int32_t dg_launch(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par,
                          const pb2_pairs *pairs, const DiagConst &C, const int32_t *d_out_row,
-                         double *d_scr, int blocks, cudaStream_t s)
+                         double *d_scr, unsigned long long *d_ctr, int blocks, cudaStream_t s)
 {
     const size_t smem = (size_t)DG_WARPS * 2 * DG_STAGE_BYTES;
     PB2_CUDA(cudaFuncSetAttribute(pb2_xi_auto_diag<ABS, FOLD>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pb2_xi_auto_diag<ABS, FOLD><<<blocks, DG_THREADS, smem, s>>>(*c1, *c2, *par, *pairs, C,
-                                                                  d_out_row, d_scr);
+                                                                  d_out_row, d_scr, d_ctr);
     pb2_count_launch(1);
     return pb2_check_launch("pb2_xi_auto_diag");
 }
@@ -525,15 +525,18 @@ int32_t pb2_launch_xi_diag(const pb2_catalog *c1, const pb2_catalog *c2, const p
         uint64_t keep = UINT64_MAX;
         PB2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    PB2_CUDA(cudaMallocAsync((void **)&d_scr, scr_bytes, s));
-    PB2_CUDA(cudaMemsetAsync(d_scr, 0, scr_bytes, s));
+    // + the work counter behind the histogram (zeroed by the same memset)
+    PB2_CUDA(cudaMallocAsync((void **)&d_scr, scr_bytes + 256, s));
+    PB2_CUDA(cudaMemsetAsync(d_scr, 0, scr_bytes + 256, s));
+    unsigned long long *d_ctr = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<unsigned char *>(d_scr) + scr_bytes);
     int32_t rc;
     if (par->x_correlation)
-        rc = dg_launch<false, false>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+        rc = dg_launch<false, false>(c1, c2, par, pairs, C, d_out_row, d_scr, d_ctr, blocks, s);
     else if (par->r_par_min != 0.)
-        rc = dg_launch<true, false>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+        rc = dg_launch<true, false>(c1, c2, par, pairs, C, d_out_row, d_scr, d_ctr, blocks, s);
     else
-        rc = dg_launch<true, true>(c1, c2, par, pairs, C, d_out_row, d_scr, blocks, s);
+        rc = dg_launch<true, true>(c1, c2, par, pairs, C, d_out_row, d_scr, d_ctr, blocks, s);
     if (rc == 0) {
         const long long total = (long long)n_rows * nb;
         pb2_xi_diag_fold<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_scr, d_out, n_rows, nb);

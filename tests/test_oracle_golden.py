@@ -122,3 +122,46 @@ def test_xdmat(name):
     np.random.seed(hps[0])
     res = oxcf.compute_dmat(hps)
     check8(res, gold, "xdmat_%s_" % name, rtol=1e-12)
+
+
+# ---- covariance step (oracle/export.py against the live reference's outputs)
+def _cov_close(got, want, rtol):
+    """covariance entries compared on the scale of the two variances (an off-diagonal entry is a
+    cancelling sum, its own magnitude is not a scale)"""
+    sd = np.sqrt(np.abs(np.diagonal(want)))
+    scale = np.maximum(sd[:, None] * sd[None, :], np.abs(want))
+    assert got.shape == want.shape
+    assert np.all(np.abs(got - want) <= rtol * scale + 1e-300), \
+        "max scaled error %.3e" % np.max(np.abs(got - want) / np.maximum(scale, 1e-300))
+
+
+@pytest.mark.parametrize("name", ["small", "ragged", "per_r_par", "xcf_like", "empty_bin"])
+def test_export_covariance(name):
+    from oracle import export as oexp
+    from tests.golden import cases_export
+    gold = load("export")
+    cfg = cases_export.CASES[name]
+    xi, we, rp, rt = cases_export.inputs(cfg)
+    cov = oexp.compute_cov(xi, we)
+    _cov_close(cov, gold["%s_cov" % name], 1e-12)
+    smooth = oexp.smooth_cov(xi, we, rp, rt, delta_r_trans=cfg["delta_r_trans"],
+                             delta_r_par=cfg["delta_r_par"], covariance=gold["%s_cov" % name],
+                             per_r_par=cfg.get("per_r_par", False))
+    _cov_close(smooth, gold["%s_smooth" % name], 1e-12)
+    if name == "empty_bin":  # zero variance: the reference returns the covariance unsmoothed
+        assert np.array_equal(smooth, gold["%s_cov" % name])
+
+
+def test_export_covariance_reference_fixture():
+    """cf.fits.gz -> exported_cf.fits.gz, the reference's own golden pair (test_3_cor.py:443-456,
+    compared there at rtol 1e-5): sub-sample covariance + smoothing with the script's bin widths
+    (picca_export.py:271-293)."""
+    from oracle import export as oexp
+    gold = load("export")
+    n_p, n_t, rp_min, rp_max, rt_max = gold["fixture_bins"]
+    cov = oexp.compute_cov(gold["fixture_da"], gold["fixture_we"])
+    smooth = oexp.smooth_cov(None, None, gold["fixture_rp"], gold["fixture_rt"],
+                             delta_r_trans=(rt_max - 0.) / n_t,
+                             delta_r_par=(rp_max - rp_min) / n_p, covariance=cov)
+    np.testing.assert_allclose(smooth, gold["fixture_co"], rtol=1e-5, atol=1e-8 * np.abs(
+        gold["fixture_co"]).max())

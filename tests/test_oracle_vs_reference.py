@@ -160,3 +160,25 @@ def test_unmodified_script_on_oracle_matches_golden_fits(tmp_path, script, doubl
     finally:
         setattr(mod, double, saved)
     _compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz")
+
+
+@pytest.mark.parametrize("name", ["small", "ragged", "per_r_par", "xcf_like", "empty_bin"])
+def test_export_covariance_equals_live_reference(name):
+    """oracle/export.py against the live utils.compute_cov / utils.smooth_cov
+    (py/picca/utils.py:100-128, :153-249) on the seeded cases: same NumPy calls in the same
+    order, so bit for bit."""
+    from oracle import export as oexp
+    from tests.golden import cases_export
+    from tests.refharness import load
+    _, _, _, _, utils = load.reference_modules()
+    utils.userprint = lambda *a, **k: None
+    cfg = cases_export.CASES[name]
+    xi, we, rp, rt = cases_export.inputs(cfg)
+    want = utils.compute_cov(xi, we)
+    got = oexp.compute_cov(xi, we)
+    assert np.array_equal(got, want)
+    kw = dict(delta_r_trans=cfg["delta_r_trans"], delta_r_par=cfg["delta_r_par"],
+              per_r_par=cfg.get("per_r_par", False))
+    want_s = utils.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
+    got_s = oexp.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
+    assert np.array_equal(got_s, want_s)

@@ -70,3 +70,20 @@ def test_product_fails_loudly_without_cuda(overlay_on):
     helpers.configure(cf, data, num, 0.01)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cf.fill_neighs(sorted(data)[:1])
+
+
+def test_export_script_binds_b200_covariance(overlay_on):
+    """picca_export.py does `from picca.utils import smooth_cov, compute_cov` (picca_export.py:17):
+    through the overlay these are picca_b200.export's, the rest of picca.utils is the reference's
+    own code."""
+    import picca_b200.export
+    script = importlib.import_module("picca.bin.picca_export")
+    assert script.compute_cov is picca_b200.export.compute_cov
+    assert script.smooth_cov is picca_b200.export.smooth_cov
+    import picca.utils
+    assert picca.utils.__file__.startswith(shims.REFERENCE_PY)
+    assert callable(picca.utils.reference_compute_cov) and callable(picca.utils.compute_ang_max)
+    # no CUDA device in this container: the product path must raise, never fall back
+    import numpy as np
+    with pytest.raises(RuntimeError):
+        script.compute_cov(np.ones((3, 4)), np.ones((3, 4)))
