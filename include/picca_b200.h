@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 11
+#define PB2_ABI_VERSION 12
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -233,6 +233,40 @@ int32_t pb2_cov_smooth(int32_t nb, const double *d_cov, const double *d_r_par,
                        int32_t per_r_par, int32_t n_dp, int32_t n_dt, int32_t rp_lo, int32_t n_rp,
                        double *d_table_sum, uint64_t *d_table_count, int32_t *d_bad,
                        double *d_cov_smooth, void *stream);
+
+/* ---- delta loader: FITS delta files -> the SoA CSR buffers.
+ * Host side (plain C, no GPU): pb2_fits_scan walks the HDUs of a decompressed FITS buffer,
+ * info[h] = {header_off, data_off, data_bytes, bitpix, naxis, naxis1, naxis2, tfields}; returns the
+ * number of HDUs or -1.  pb2_fits_cards extracts header cards of many HDUs (keys: n_keys x 8 blank-
+ * padded characters; per HDU and key: kind 0 missing / 1 number / 2 string / 3 logical, value as
+ * double, as int64 for integer literals, and as a 24-character string).  Together they replace the
+ * per-HDU fitsio calls of io.read_delta_file (py/picca/io.py:354-360) and Delta.from_fitsio
+ * (py/picca/data.py:392-474).
+ * pb2_delta_unpack: big-endian BinTable rows (the raw file bytes, uploaded as they are) -> native
+ * fp64 arrays at the CSR offsets: forest f has rows at d_raw + d_row0[f], d_row_bytes[f] apart,
+ * with the wavelength (LOGLAM or LAMBDA), DELTA and WEIGHT columns at d_col_off[3f..3f+2].
+ * pb2_delta_prepare: the per-forest loop of io.read_deltas (py/picca/io.py:493-507): z =
+ * 10^log_lambda / lambda_abs - 1 (or d_z_in when given: parity mode with the host's power),
+ * r_comov / dist_m by linear interpolation on the n_table-point cosmology table exactly as
+ * scipy's interp1d evaluates it (py/picca/constants.py:211-229; skipped when d_tab_z is NULL, the
+ * reference's cosmo=None), weights *= ((1+z)/(1+z_ref))^(alpha-1), Delta.project
+ * (py/picca/data.py:622-655) when project != 0 (d_order: 0/1 per forest), d_z_range[2f..2f+1] =
+ * min/max z of forest f.  *d_status = 1 if a redshift fell outside the table (interp1d raises). */
+int64_t pb2_fits_scan(const uint8_t *buf, int64_t len, int64_t max_hdu, int64_t *info);
+int32_t pb2_fits_cards(const uint8_t *buf, int64_t len, int64_t n_hdu, const int64_t *header_off,
+                       int32_t n_keys, const char *keys, int32_t *kind, double *num, int64_t *inum,
+                       char *str);
+int32_t pb2_delta_unpack(int64_t n_los, const uint8_t *d_raw, const int64_t *d_row0,
+                         const int32_t *d_row_bytes, const int32_t *d_col_off,
+                         const int64_t *d_offset, double *d_log_lambda, double *d_delta,
+                         double *d_weights, void *stream);
+int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t *d_order,
+                          double lambda_abs, double alpha, double z_ref, int32_t n_table,
+                          const double *d_tab_z, const double *d_tab_r_comov,
+                          const double *d_tab_dist_m, int32_t project, int32_t wave_is_lambda,
+                          const double *d_z_in, double *d_log_lambda, double *d_delta,
+                          double *d_weights, double *d_z, double *d_r_comov, double *d_dist_m,
+                          double *d_z_range, int32_t *d_status, void *stream);
 
 /* ---- measurement helpers
  * pb2_fp64_peak: dependent-free DFMA microbenchmark; returns achieved FP64 op/s (1 DFMA = 1 op,

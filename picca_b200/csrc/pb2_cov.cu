@@ -8,10 +8,10 @@
 // an fp64 rank-n_s update of an nb x nb matrix (2500^2 x 1400 x 2 = 1.8e10 flop at config 2).
 // B200 runs FP64 through the ordinary DFMA pipe (the fp64 tensor path is no faster on sm_100a), so
 // this is a register-tiled DFMA kernel:
-//   * pb2_cov_prepare: one thread per bin walks the sub-samples in order -- the same association
-//     as NumPy's axis-0 reduction, so <xi> and W are bit-equal to the reference's -- and writes M
-//     once into a zero-padded scratch [ks][ld] (ld, ks multiples of the tile sizes: no bounds
-//     checks anywhere in the contraction);
+//   * pb2_cov_colstats: one thread per bin adds the sub-samples in order -- the same association
+//     as NumPy's axis-0 reduction, so <xi> and W are bit-equal to the reference's;
+//     pb2_cov_build_m writes M once into a zero-padded scratch [ks][ld] (ld, ks multiples of the
+//     tile sizes: no bounds checks anywhere in the contraction);
 //   * pb2_cov_syrk: upper-triangular 64x64 tiles, 128 threads x (8 x 4) accumulators, K chunks of
 //     16 sub-samples staged by TMA bulk copies (cp.async.bulk + mbarrier, 3 stages, one producer
 //     thread), epilogue divides by W_i W_j where positive and writes the tile and its mirror.
@@ -62,21 +62,32 @@ __device__ __forceinline__ void cv_mbar_wait(unsigned bar, unsigned parity)
         : "memory");
 }
 
-// ---- column statistics + the weighted, mean-subtracted matrix M (utils.py:113-118)
-__global__ void pb2_cov_prepare(int n_s, int nb, int ld, int ks, const double *__restrict__ xi,
-                                const double *__restrict__ we, double *__restrict__ mean_xi,
-                                double *__restrict__ sum_w, double *__restrict__ M)
+// ---- column statistics (utils.py:113-116): one thread per bin, the sub-samples added in order
+// like NumPy's axis-0 reduction (bit-equal means and weight sums).  The loads of 16 sub-samples are
+// issued together, only the additions are sequential.
+#define CV_BATCH 16
+__global__ void pb2_cov_colstats(int n_s, int nb, const double *__restrict__ xi,
+                                 const double *__restrict__ we, double *__restrict__ mean_xi,
+                                 double *__restrict__ sum_w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ld) return;
-    if (i >= nb) {  // padding columns
-        for (int s = 0; s < ks; ++s) M[(size_t)s * ld + i] = 0.;
-        return;
-    }
-    // mean_xi = (xi * weights).sum(axis=0); sum_weights = weights.sum(axis=0): NumPy adds the rows
-    // in order, one product rounded per term (no FMA)
+    if (i >= nb) return;
     double sx = 0., sw = 0.;
-    for (int s = 0; s < n_s; ++s) {
+    int s = 0;
+    for (; s + CV_BATCH <= n_s; s += CV_BATCH) {
+        double x[CV_BATCH], w[CV_BATCH];
+#pragma unroll
+        for (int k = 0; k < CV_BATCH; ++k) {
+            x[k] = __ldg(xi + (size_t)(s + k) * nb + i);
+            w[k] = __ldg(we + (size_t)(s + k) * nb + i);
+        }
+#pragma unroll
+        for (int k = 0; k < CV_BATCH; ++k) {
+            sx = add_rn(sx, mul_rn(x[k], w[k]));  // one rounded product per term, no FMA
+            sw = add_rn(sw, w[k]);
+        }
+    }
+    for (; s < n_s; ++s) {
         const double w = we[(size_t)s * nb + i];
         sx = add_rn(sx, mul_rn(xi[(size_t)s * nb + i], w));
         sw = add_rn(sw, w);
@@ -84,9 +95,20 @@ __global__ void pb2_cov_prepare(int n_s, int nb, int ld, int ks, const double *_
     if (sw > 0.) sx = div_rn(sx, sw);  // mean_xi[w] /= sum_weights[w]
     mean_xi[i] = sx;
     sum_w[i] = sw;
-    for (int s = 0; s < n_s; ++s)
-        M[(size_t)s * ld + i] = mul_rn(we[(size_t)s * nb + i], sub_rn(xi[(size_t)s * nb + i], sx));
-    for (int s = n_s; s < ks; ++s) M[(size_t)s * ld + i] = 0.;
+}
+
+// ---- M[s][i] = weights * (xi - mean_xi) (utils.py:118) into the zero-padded scratch [ks][ld]
+__global__ void pb2_cov_build_m(int n_s, int nb, int ld, const double *__restrict__ xi,
+                                const double *__restrict__ we, const double *__restrict__ mean_xi,
+                                double *__restrict__ M)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= ld) return;
+    double v = 0.;
+    if (i < nb && s < n_s)
+        v = mul_rn(we[(size_t)s * nb + i], sub_rn(xi[(size_t)s * nb + i], mean_xi[i]));
+    M[(size_t)s * ld + i] = v;
 }
 
 // ---- C = M^T M / (W W^T), upper-triangular tiles + mirror
@@ -282,10 +304,15 @@ int32_t pb2_cov_subsample(int64_t n_samples, int32_t nb, const double *d_xi, con
     const int n_tiles = ld / CV_TILE;
     double *M = (double *)d_scratch;
     pb2_timing_begin(s);
-    pb2_cov_prepare<<<(ld + 127) / 128, 128, 0, s>>>((int)n_samples, nb, ld, ks, d_xi, d_weights,
-                                                     d_mean_xi, d_sum_weights, M);
+    pb2_cov_colstats<<<(nb + 31) / 32, 32, 0, s>>>((int)n_samples, nb, d_xi, d_weights, d_mean_xi,
+                                                   d_sum_weights);
     pb2_count_launch(1);
-    int32_t rc = pb2_check_launch("pb2_cov_prepare");
+    int32_t rc = pb2_check_launch("pb2_cov_colstats");
+    if (rc) return rc;
+    pb2_cov_build_m<<<dim3((ld + 255) / 256, ks), 256, 0, s>>>((int)n_samples, nb, ld, d_xi,
+                                                                d_weights, d_mean_xi, M);
+    pb2_count_launch(1);
+    rc = pb2_check_launch("pb2_cov_build_m");
     if (rc) return rc;
     const int smem = CV_STAGES * CV_STAGE_BYTES;
     PB2_CUDA(cudaFuncSetAttribute(pb2_cov_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -1,0 +1,410 @@
+"""B200 delta loader: ``read_deltas`` with the reference's signature and return tuple
+(py/picca/io.py:383-512), reading the BinTable delta files straight into the SoA CSR buffers of
+the pair kernels.
+
+What the reference does per forest in Python -- one fitsio HDU object, four column reads, one
+``Delta`` constructor, ``10**log_lambda``, two scipy interpolations, the weight evolution and
+``project()`` (io.py:354-360, :493-507; data.py:375-474, :622-655) -- happens here per FILE:
+
+  host   gunzip + ``pb2_fits_scan`` / ``pb2_fits_cards`` (plain C): HDU table and header cards;
+  H2D    the raw big-endian file bytes, as they are;
+  device ``pb2_delta_unpack`` (byte swap + de-interleave into log_lambda / delta / weights at the
+         CSR offsets) and ``pb2_delta_prepare`` (z, r_comov, dist_m, weight evolution, projection).
+
+The returned ``data`` is the reference's ``dict[healpix] -> list[Delta]``; every array attribute of
+a ``Delta`` is a view into one contiguous host array per field.  There is no CPU fallback: without
+the CUDA library or a device the call raises.
+
+Parity: the table interpolation follows scipy's ``interp1d`` operation by operation, so r_comov
+and dist_m are bit-equal to the reference's GIVEN the same z; ``10**x`` on the device (``exp10``)
+can differ from NumPy's power in the last ulp, so by default z, r_comov and dist_m agree with the
+reference within 2 ulp.  ``PICCA_B200_HOST_POW=1`` (parity mode, used by the golden tests)
+evaluates ``10**log_lambda / lambda_abs - 1`` with NumPy on the host instead; then z, r_comov and
+dist_m are bit-equal.  Weights and projected deltas are within 1e-13 relative either way (``pow``
+and re-associated sums).  Not implemented: ``rebin_factor`` and the ImageHDU flavour
+(``Delta.from_image``) -- both raise NotImplementedError.
+"""
+import ctypes
+import glob
+import gzip
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from configparser import ConfigParser
+
+import numpy as np
+
+from . import _lib
+from .engine import get_engine
+from .forest import Delta
+from .synth import ang2pix_ring
+
+_KEYS = (["EXTNAME", "RA", "DEC", "Z", "THING_ID", "PLATE", "MJD", "FIBERID", "LOS_ID",
+          "BLINDING", "XTENSION"] + ["TTYPE%d" % k for k in range(1, 9)] +
+         ["TFORM%d" % k for k in range(1, 9)])
+_KEY_BYTES = "".join(k.ljust(8) for k in _KEYS).encode("ascii")
+_K = {k: i for i, k in enumerate(_KEYS)}
+_TFORM_BYTES = {"D": 8, "E": 4, "K": 8, "J": 4, "I": 2, "B": 1, "L": 1, "A": 1}
+_UPLOAD_BATCH = 256 << 20  # raw bytes staged per H2D copy
+
+
+def userprint(*args, **kwds):
+    """reference py/picca/utils.py:31-40"""
+    print(*args, **kwds)
+    sys.stdout.flush()
+
+
+# ------------------------------------------------------------------------------------ FITS (host)
+def _file_bytes(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    return np.frombuffer(raw, dtype=np.uint8)
+
+
+def _scan(buf):
+    """HDU table of a FITS buffer: int64 [n_hdu, 8] (see pb2_fits_scan)."""
+    lib = _lib.lib()
+    cap = max(16, buf.size // 2880 + 1)
+    info = np.zeros((cap, 8), dtype=np.int64)
+    n = lib.pb2_fits_scan(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size),
+                          ctypes.c_int64(cap), info.ctypes.data_as(ctypes.c_void_p))
+    if n < 0:
+        raise OSError("picca_b200: " + lib.pb2_last_error().decode("utf-8", "replace"))
+    return info[:n]
+
+
+def _cards(buf, header_off):
+    """Header cards _KEYS of the HDUs starting at ``header_off``: (kind, num, inum, strings)."""
+    lib = _lib.lib()
+    n, nk = len(header_off), len(_KEYS)
+    kind = np.zeros((n, nk), dtype=np.int32)
+    num = np.zeros((n, nk), dtype=np.float64)
+    inum = np.zeros((n, nk), dtype=np.int64)
+    strs = np.zeros((n, nk), dtype="S24")
+    header_off = np.ascontiguousarray(header_off, dtype=np.int64)
+    _lib.check(lib.pb2_fits_cards(
+        buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size), ctypes.c_int64(n),
+        header_off.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(nk),
+        ctypes.c_char_p(_KEY_BYTES), kind.ctypes.data_as(ctypes.c_void_p),
+        num.ctypes.data_as(ctypes.c_void_p), inum.ctypes.data_as(ctypes.c_void_p),
+        strs.ctypes.data_as(ctypes.c_void_p)), "pb2_fits_cards")
+    return kind, num, inum, strs
+
+
+def _column_offsets(ttypes, tforms):
+    """name -> (byte offset, type letter, repeat) of a BinTable row."""
+    out, pos = {}, 0
+    for name, form in zip(ttypes, tforms):
+        if not form:
+            break
+        form = form.strip()
+        digits = "".join(c for c in form if c.isdigit())
+        letter = form[len(digits):len(digits) + 1]
+        if letter not in _TFORM_BYTES:
+            raise NotImplementedError("picca_b200.io: TFORM %r is not supported" % form)
+        rep = int(digits) if digits else 1
+        out[name.strip().upper()] = (pos, letter, rep)
+        pos += rep * _TFORM_BYTES[letter]
+    return out, pos
+
+
+class _FileForests:
+    """What one delta file contributes: per kept forest the row geometry and the header values."""
+
+    def __init__(self, path, z_min_qso, z_max_qso):
+        self.path = path
+        buf = _file_bytes(path)
+        info = _scan(buf)
+        kind, num, inum, strs = _cards(buf, info[:, 0])
+        names = [s.decode("ascii", "replace") for s in strs[:, _K["EXTNAME"]]]
+        if "LAMBDA" in names:  # io.py:356: `'LAMBDA' in hdul` selects Delta.from_image
+            raise NotImplementedError(
+                "picca_b200.io: ImageHDU delta files (Delta.from_image, data.py:519-620) are not "
+                "implemented; file %s" % path)
+        hdus = np.arange(1, len(info))  # hdul[1:]
+        z = num[hdus, _K["Z"]]
+        if np.any(kind[hdus, _K["Z"]] != 1):
+            raise KeyError("Z")
+        keep = hdus[(z_min_qso < z) & (z < z_max_qso)]  # io.py:359-360, strict
+        self.buf = buf
+        self.n = len(keep)
+        self.row0 = info[keep, 1]
+        self.row_bytes = info[keep, 5].astype(np.int32)
+        self.n_pix = info[keep, 6]
+        self.ra = num[keep, _K["RA"]]
+        self.dec = num[keep, _K["DEC"]]
+        self.z_qso = num[keep, _K["Z"]]
+        if np.any(kind[keep, _K["RA"]] != 1) or np.any(kind[keep, _K["DEC"]] != 1):
+            raise KeyError("RA")
+        has_thing = kind[keep, _K["THING_ID"]] == 1
+        has_los = kind[keep, _K["LOS_ID"]] == 1
+        if np.any(~has_thing & ~has_los):
+            raise Exception("Could not find THING_ID or LOS_ID")  # data.py:462-463
+        pick = lambda key: np.where(has_thing, inum[keep, _K[key]], inum[keep, _K["LOS_ID"]])
+        self.los_id = pick("THING_ID")
+        self.plate, self.mjd, self.fiberid = pick("PLATE"), pick("MJD"), pick("FIBERID")
+        # column layout: usually one per file; computed once per distinct (TTYPE, TFORM) set
+        t0, f0 = _K["TTYPE1"], _K["TFORM1"]
+        layout = np.concatenate([strs[keep, t0:t0 + 8], strs[keep, f0:f0 + 8],
+                                 strs[keep, _K["BLINDING"]][:, None]], axis=1)
+        self.col_off = np.zeros((self.n, 3), dtype=np.int32)
+        self.wave_is_lambda = np.zeros(self.n, dtype=bool)
+        uniq, inverse = np.unique(layout, axis=0, return_inverse=True) if self.n else ([], [])
+        inverse = np.asarray(inverse).reshape(-1)
+        for u, row in enumerate(uniq):
+            dec = [s.decode("ascii", "replace") for s in row]
+            cols, width = _column_offsets(dec[:8], dec[8:16])
+            blinding = dec[16] if dec[16] else "none"            # data.py:395-400
+            delta_name = "DELTA" if blinding == "none" else "DELTA_BLIND"
+            if delta_name not in cols:
+                raise KeyError(delta_name)
+            if "LOGLAM" in cols:                                   # data.py:409-414
+                wave, is_lambda = "LOGLAM", False
+            elif "LAMBDA" in cols:
+                wave, is_lambda = "LAMBDA", True
+            else:
+                raise KeyError("Did not find LOGLAM or LAMBDA in delta file")
+            if "WEIGHT" not in cols:
+                raise KeyError("WEIGHT")
+            for name in (wave, delta_name, "WEIGHT"):
+                if cols[name][1] != "D" or cols[name][2] != 1:
+                    raise NotImplementedError("picca_b200.io: column %s is not a scalar fp64 "
+                                              "column" % name)
+            sel = inverse == u
+            if np.any(self.row_bytes[sel] != width):
+                raise OSError("picca_b200.io: NAXIS1 does not match the TFORM widths in %s" % path)
+            self.col_off[sel] = (cols[wave][0], cols[delta_name][0], cols["WEIGHT"][0])
+            self.wave_is_lambda[sel] = is_lambda
+
+
+def find_order(in_dir, delta_attributes):
+    """Order of the continuum polynomial from the delta-attributes file (io.py:31-112): header card
+    FITORDER of HDU FIT_METADATA, else of STACK_DELTAS, else ``[expected flux] order`` of
+    ``in_dir/../.config.ini``, else None."""
+    if delta_attributes is None:
+        delta_attributes = in_dir + "/../Log/delta_attributes.fits.gz"
+        userprint(f"WARNING: delta_attributes file not given, setting to {delta_attributes}")
+    userprint(f"Reading delta attributes from {delta_attributes}")
+
+    def from_config():
+        config = ConfigParser()
+        config.read(in_dir + "/../.config.ini")
+        if "expected flux" in config and "order" in config["expected flux"]:
+            return config["expected flux"].getint("order")
+        userprint("WARNING: `order` not found in delta config file")
+        return None
+
+    try:
+        buf = _file_bytes(delta_attributes)
+    except OSError as e:
+        userprint(f"WARNING: OSError encountered: {str(e)}")
+        order = from_config()
+    else:
+        info = _scan(buf)
+        lib = _lib.lib()
+        keys = "".join(k.ljust(8) for k in ("EXTNAME", "FITORDER")).encode("ascii")
+        n = len(info)
+        kind = np.zeros((n, 2), dtype=np.int32)
+        num = np.zeros((n, 2))
+        inum = np.zeros((n, 2), dtype=np.int64)
+        strs = np.zeros((n, 2), dtype="S24")
+        off = np.ascontiguousarray(info[:, 0])
+        _lib.check(lib.pb2_fits_cards(
+            buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size), ctypes.c_int64(n),
+            off.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(2), ctypes.c_char_p(keys),
+            kind.ctypes.data_as(ctypes.c_void_p), num.ctypes.data_as(ctypes.c_void_p),
+            inum.ctypes.data_as(ctypes.c_void_p), strs.ctypes.data_as(ctypes.c_void_p)),
+            "pb2_fits_cards")
+        order = None
+        for ext in (b"FIT_METADATA", b"STACK_DELTAS"):
+            hit = [h for h in range(n) if strs[h, 0] == ext and kind[h, 1] == 1]
+            if hit:
+                order = int(inum[hit[0], 1])
+                break
+        else:
+            userprint("WARNING: FITORDER not found in the delta attributes file")
+            order = from_config()
+    userprint(f"Setting order={order} for the polynomial used for the continuum fitting")
+    return order
+
+
+def _cosmo_tables(cosmo):
+    """(z, r_comov, dist_m) tables behind ``cosmo.get_r_comov`` / ``cosmo.get_dist_m``: scipy
+    ``interp1d`` objects in the reference (constants.py:211-229), ``table()`` on our own class."""
+    if hasattr(cosmo, "table"):
+        return tuple(np.ascontiguousarray(t, dtype=np.float64) for t in cosmo.table())
+    f_r, f_m = cosmo.get_r_comov, cosmo.get_dist_m
+    if not (hasattr(f_r, "x") and hasattr(f_r, "y") and hasattr(f_m, "x") and hasattr(f_m, "y")):
+        raise TypeError("picca_b200.io: cannot find the distance tables of this cosmology object")
+    if not np.array_equal(f_r.x, f_m.x):
+        raise TypeError("picca_b200.io: r_comov and dist_m tables use different redshift grids")
+    return (np.ascontiguousarray(f_r.x, dtype=np.float64),
+            np.ascontiguousarray(f_r.y, dtype=np.float64),
+            np.ascontiguousarray(f_m.y, dtype=np.float64))
+
+
+def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=None,
+                no_project=False, nproc=None, rebin_factor=None, z_min_qso=0, z_max_qso=10,
+                delta_attributes=None):
+    """Reads deltas and computes their redshifts, distances, evolved weights and projection
+    (io.py:383-512).  Same arguments; returns ``(data, num_data, z_min, z_max)``.
+
+    Raises:
+        AssertionError: if no healpix numbers are found (io.py:489-490)
+        RuntimeError: projecting without a continuum order (data.py:628-633); CUDA errors
+        ValueError: a redshift outside the cosmology table (scipy interp1d bounds error)
+    """
+    if rebin_factor is not None:
+        raise NotImplementedError("picca_b200.io.read_deltas: rebin_factor is not implemented")
+    in_dir = os.path.expandvars(in_dir)
+    if len(in_dir) > 8 and in_dir[-8:] == '.fits.gz':
+        files = sorted(glob.glob(in_dir))
+    elif len(in_dir) > 5 and in_dir[-5:] == '.fits':
+        files = sorted(glob.glob(in_dir))
+    else:
+        files = sorted(glob.glob(in_dir + '/*.fits') + glob.glob(in_dir + '/*.fits.gz'))
+    order = find_order(in_dir, delta_attributes)
+
+    eng = get_engine()  # raises without a device: no CPU fallback
+    torch = eng.torch
+    workers = nproc if nproc else (os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=max(1, min(workers, 32))) as pool:
+        parts = list(pool.map(lambda f: _FileForests(f, z_min_qso, z_max_qso), files))
+
+    # truncate like io.py:467-480: files are consumed in order until max_num_spec is exceeded
+    if max_num_spec is not None:
+        kept, total = [], 0
+        for p in parts:
+            kept.append(p)
+            total += p.n
+            if total > max_num_spec:
+                break
+        parts = kept
+    n_los = sum(p.n for p in parts)
+    if max_num_spec is not None:
+        n_los = min(n_los, max_num_spec)
+    if n_los == 0:
+        raise AssertionError('ERROR: No data in {}'.format(in_dir))  # io.py:489-490
+
+    cat = lambda name, dt: np.concatenate([np.asarray(getattr(p, name)) for p in parts]
+                                          )[:n_los].astype(dt)
+    ra, dec, z_qso = cat("ra", np.float64), cat("dec", np.float64), cat("z_qso", np.float64)
+    los_id, plate = cat("los_id", np.int64), cat("plate", np.int64)
+    mjd, fiberid = cat("mjd", np.int64), cat("fiberid", np.int64)
+    n_pix = cat("n_pix", np.int64)
+    wave_is_lambda = cat("wave_is_lambda", bool)
+    if wave_is_lambda.any() and not wave_is_lambda.all():
+        raise NotImplementedError("picca_b200.io: mixed LOGLAM / LAMBDA delta files")
+    if not no_project and order is None:
+        raise RuntimeError("Trying to project but order is not defined for the deltas. "
+                           "Check previous warning to solve this issue")  # data.py:628-633
+    offset = np.zeros(n_los + 1, dtype=np.int64)
+    np.cumsum(n_pix, out=offset[1:])
+    total_pix = int(offset[-1])
+
+    dev = eng.device
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
+    d_ll, d_delta, d_w = f64(total_pix), f64(total_pix), f64(total_pix)
+    d_offset = torch.from_numpy(offset).to(dev)
+
+    # ---- H2D of the raw file bytes in batches + unpack at the CSR offsets
+    def flush(batch, first):
+        if not batch:
+            return
+        sizes = [p.buf.size for p in batch]
+        base = np.concatenate([[0], np.cumsum(sizes)])
+        staged = torch.empty(int(base[-1]), dtype=torch.uint8).pin_memory()
+        host = staged.numpy()
+        for p, b in zip(batch, base[:-1]):
+            host[b:b + p.buf.size] = p.buf
+        d_raw = staged.to(dev, non_blocking=True)
+        n_b = min(sum(p.n for p in batch), n_los - first)
+        row0 = np.concatenate([p.row0 + b for p, b in zip(batch, base[:-1])])[:n_b]
+        row_bytes = np.concatenate([p.row_bytes for p in batch])[:n_b]
+        col_off = np.concatenate([p.col_off for p in batch])[:n_b]
+        d_row0 = torch.from_numpy(np.ascontiguousarray(row0, dtype=np.int64)).to(dev)
+        d_rb = torch.from_numpy(np.ascontiguousarray(row_bytes, dtype=np.int32)).to(dev)
+        d_co = torch.from_numpy(np.ascontiguousarray(col_off, dtype=np.int32)).to(dev)
+        _lib.check(eng.lib.pb2_delta_unpack(
+            ctypes.c_int64(n_b), ctypes.c_void_p(d_raw.data_ptr()),
+            ctypes.c_void_p(d_row0.data_ptr()), ctypes.c_void_p(d_rb.data_ptr()),
+            ctypes.c_void_p(d_co.data_ptr()),
+            ctypes.c_void_p(d_offset.data_ptr() + 8 * first), ctypes.c_void_p(d_ll.data_ptr()),
+            ctypes.c_void_p(d_delta.data_ptr()), ctypes.c_void_p(d_w.data_ptr()),
+            eng.stream_ptr()), "pb2_delta_unpack")
+        torch.cuda.current_stream().synchronize()  # the staging buffers die with this scope
+
+    batch, batch_bytes, first, done = [], 0, 0, 0
+    for p in parts:
+        if done >= n_los:
+            break
+        batch.append(p)
+        batch_bytes += p.buf.size
+        done += p.n
+        if batch_bytes >= _UPLOAD_BATCH:
+            flush(batch, first)
+            first, batch, batch_bytes = min(done, n_los), [], 0
+    flush(batch, first)
+    for p in parts:
+        p.buf = None
+
+    # ---- z, distances, weight evolution, projection (io.py:493-507)
+    d_z, d_range = f64(total_pix), f64(2 * n_los)
+    d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_order = torch.full((n_los,), -1 if order is None else int(order), dtype=torch.int32,
+                         device=dev)
+    if cosmo is not None:
+        tz, tr, tm = _cosmo_tables(cosmo)
+        d_tz, d_tr, d_tm = (torch.from_numpy(t).to(dev) for t in (tz, tr, tm))
+        d_rc, d_dm = f64(total_pix), f64(total_pix)
+        tabs = (ctypes.c_int32(len(tz)), ctypes.c_void_p(d_tz.data_ptr()),
+                ctypes.c_void_p(d_tr.data_ptr()), ctypes.c_void_p(d_tm.data_ptr()))
+        dist = (ctypes.c_void_p(d_rc.data_ptr()), ctypes.c_void_p(d_dm.data_ptr()))
+    else:  # io.py:500: distances only `if not cosmo is None`
+        d_rc = d_dm = None
+        tabs = (ctypes.c_int32(0), None, None, None)
+        dist = (None, None)
+    d_z_in = None
+    if os.environ.get("PICCA_B200_HOST_POW", "0") == "1":
+        ll_host = d_ll.cpu().numpy()
+        if wave_is_lambda.any():
+            ll_host = np.log10(ll_host)
+        d_z_in = torch.from_numpy(10**ll_host / lambda_abs - 1.).to(dev)  # io.py:496, NumPy power
+    _lib.check(eng.lib.pb2_delta_prepare(
+        ctypes.c_int64(n_los), ctypes.c_void_p(d_offset.data_ptr()),
+        ctypes.c_void_p(d_order.data_ptr()), ctypes.c_double(lambda_abs), ctypes.c_double(alpha),
+        ctypes.c_double(z_ref), *tabs, ctypes.c_int32(0 if no_project else 1),
+        ctypes.c_int32(int(wave_is_lambda.any())),
+        ctypes.c_void_p(d_z_in.data_ptr()) if d_z_in is not None else None,
+        ctypes.c_void_p(d_ll.data_ptr()), ctypes.c_void_p(d_delta.data_ptr()),
+        ctypes.c_void_p(d_w.data_ptr()), ctypes.c_void_p(d_z.data_ptr()), *dist,
+        ctypes.c_void_p(d_range.data_ptr()), ctypes.c_void_p(d_status.data_ptr()),
+        eng.stream_ptr()), "pb2_delta_prepare")
+    if int(d_status.item()):
+        raise ValueError("A value in x_new is outside the interpolation range of the cosmology "
+                         "table (scipy interp1d bounds error in the reference)")
+
+    # ---- back to the reference's data model: dict[healpix] -> list[Delta] of array views
+    h = {name: t.cpu().numpy() for name, t in (("log_lambda", d_ll), ("delta", d_delta),
+                                               ("weights", d_w), ("z", d_z))}
+    if d_rc is not None:
+        h["r_comov"], h["dist_m"] = d_rc.cpu().numpy(), d_dm.cpu().numpy()
+    z_range = d_range.cpu().numpy().reshape(n_los, 2)
+    filled = n_pix > 0
+    z_min = float(z_range[filled, 0].min())
+    z_max = max(0., float(z_range[filled, 1].max()))  # io.py:493: z_max starts at 0
+    healpixs = ang2pix_ring(nside, np.pi / 2. - dec, ra)  # io.py:486-488
+    data = {}
+    for f in range(n_los):
+        a, b = offset[f], offset[f + 1]
+        d = Delta(int(los_id[f]), float(ra[f]), float(dec[f]), float(z_qso[f]), int(plate[f]),
+                  int(mjd[f]), int(fiberid[f]), h["log_lambda"][a:b], h["weights"][a:b],
+                  h["delta"][a:b], order)
+        d.z = h["z"][a:b]
+        if d_rc is not None:
+            d.r_comov, d.dist_m = h["r_comov"][a:b], h["dist_m"][a:b]
+        data.setdefault(int(healpixs[f]), []).append(d)
+    userprint("\n")
+    return data, n_los, z_min, z_max

@@ -31,6 +31,10 @@ class FlatLCDM:
 
     get_dist_m = get_r_comov
 
+    def table(self):
+        """(z, r_comov, dist_m) tables (flat: dist_m = r_comov, constants.py:214-215)"""
+        return self._z, self._r, self._r
+
 
 def compute_ang_max(cosmo, r_trans_max, z_min, z_min2=None):
     """reference py/picca/utils.py:419-450"""

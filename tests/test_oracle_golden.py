@@ -165,3 +165,37 @@ def test_export_covariance_reference_fixture():
                              delta_r_par=(rp_max - rp_min) / n_p, covariance=cov)
     np.testing.assert_allclose(smooth, gold["fixture_co"], rtol=1e-5, atol=1e-8 * np.abs(
         gold["fixture_co"]).max())
+
+
+# ---- delta loader (oracle/io.py against the live reference's io.read_deltas outputs)
+IO_RUNS = {"fixture": None, "sdss": {}, "desi": {}, "blind": {},
+           "sdss_noproject": dict(no_project=True), "sdss_max30": dict(max_num_spec=30),
+           "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0)}
+
+
+def io_inputs(tag, tmp_path):
+    from tests.golden import cases_io
+    if tag == "fixture":
+        fx = os.path.join(GOLD, "fixtures")
+        return os.path.join(fx, "delta-272.fits.gz"), os.path.join(fx, "delta_attributes.fits.gz")
+    return cases_io.write_case(str(tmp_path), tag.split("_")[0])
+
+
+@pytest.mark.parametrize("tag", sorted(IO_RUNS))
+def test_read_deltas(tag, tmp_path):
+    from oracle import io as oio
+    from tests.golden import cases_io
+    gold = load("io")
+    in_dir, attr = io_inputs(tag, tmp_path)
+    tables = (gold["cosmo_z"], gold["cosmo_r_comov"], gold["cosmo_dist_m"])
+    data, num, z_min, z_max = oio.read_deltas(in_dir, tables=tables, delta_attributes=attr,
+                                              **dict(cases_io.READ_KW, **(IO_RUNS[tag] or {})))
+    flat = cases_io.flatten(data)
+    assert [num, z_min, z_max] == list(gold["%s_summary" % tag])
+    for k, v in flat.items():
+        want = gold["%s_%s" % (tag, k)]
+        if v.dtype.kind == "f" and k in ("weights", "delta"):
+            # NumPy's pairwise sums / power may differ between SIMD back-ends of two hosts
+            np.testing.assert_allclose(v, want, rtol=1e-12, atol=1e-14, err_msg=k)
+        else:
+            assert np.array_equal(v, want), k

@@ -182,3 +182,27 @@ def test_export_covariance_equals_live_reference(name):
     want_s = utils.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
     got_s = oexp.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
     assert np.array_equal(got_s, want_s)
+
+
+@pytest.mark.parametrize("which", ["bundled", "sdss", "desi", "blind"])
+def test_read_deltas_equals_live_reference(which, tmp_path):
+    """oracle/io.py against the live io.read_deltas (py/picca/io.py:383-512), bit for bit: the
+    reference's bundled Delta_LYA directory (936 forests) and the generated cases."""
+    from oracle import io as oio
+    from tests.golden import cases_io
+    from tests.refharness import load
+    _, _, io, constants, _ = load.reference_modules()
+    io.userprint = lambda *a, **k: None
+    cosmo = constants.Cosmo(Om=0.315, Or=0., Ok=0., wl=-1., blinding="none", verbose=False)
+    if which == "bundled":
+        in_dir, attr = DATA + "/test_delta/Delta_LYA/", DATA + "/test_delta/delta_attributes.fits.gz"
+    else:
+        in_dir, attr = cases_io.write_case(str(tmp_path), which)
+    want = io.read_deltas(in_dir, cosmo=cosmo, nproc=1, delta_attributes=attr, **cases_io.READ_KW)
+    tables = (cosmo.get_r_comov.x, cosmo.get_r_comov.y, cosmo.get_dist_m.y)
+    got = oio.read_deltas(in_dir.rstrip("/"), tables=tables, delta_attributes=attr,
+                          **cases_io.READ_KW)
+    assert got[1:] == want[1:]
+    a, b = cases_io.flatten(got[0]), cases_io.flatten(want[0])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k

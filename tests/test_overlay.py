@@ -87,3 +87,19 @@ def test_export_script_binds_b200_covariance(overlay_on):
     import numpy as np
     with pytest.raises(RuntimeError):
         script.compute_cov(np.ones((3, 4)), np.ones((3, 4)))
+
+
+def test_scripts_bind_b200_loader(overlay_on):
+    """picca_cf.py calls io.read_deltas (picca_cf.py:387-405): through the overlay that is the
+    B200 loader, the rest of picca.io is the reference's own code; without a CUDA device it
+    raises instead of falling back."""
+    cf_script = importlib.import_module("picca.bin.picca_cf")
+    import picca.io
+    assert cf_script.io is picca.io
+    assert picca.io.__file__.startswith(shims.REFERENCE_PY)
+    assert picca.io.read_deltas is not picca.io.reference_read_deltas
+    assert callable(picca.io.read_objects)
+    with pytest.raises(RuntimeError):
+        picca.io.read_deltas(shims.REFERENCE_PY + "/picca/tests/data/test_delta/Delta_LYA/",
+                             16, 1215.67, 2.9, 2.25, None, delta_attributes=shims.REFERENCE_PY +
+                             "/picca/tests/data/test_delta/delta_attributes.fits.gz")
