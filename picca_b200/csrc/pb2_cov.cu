@@ -64,7 +64,7 @@ __device__ __forceinline__ void cv_mbar_wait(unsigned bar, unsigned parity)
 
 // ---- column statistics (utils.py:113-116): one thread per bin, the sub-samples added in order
 // like NumPy's axis-0 reduction (bit-equal means and weight sums).  The loads of 16 sub-samples are
-// issued together, only the additions are sequential.
+// issued together and one batch ahead, only the additions are sequential.
 #define CV_BATCH 16
 __global__ void pb2_cov_colstats(int n_s, int nb, const double *__restrict__ xi,
                                  const double *__restrict__ we, double *__restrict__ mean_xi,
@@ -74,18 +74,31 @@ __global__ void pb2_cov_colstats(int n_s, int nb, const double *__restrict__ xi,
     if (i >= nb) return;
     double sx = 0., sw = 0.;
     int s = 0;
-    for (; s + CV_BATCH <= n_s; s += CV_BATCH) {
-        double x[CV_BATCH], w[CV_BATCH];
+    // software pipeline: the loads of batch k+1 are in flight while batch k is added
+    double x[CV_BATCH], w[CV_BATCH], xn[CV_BATCH], wn[CV_BATCH];
+    const int n_full = n_s / CV_BATCH;
+    if (n_full > 0) {
 #pragma unroll
         for (int k = 0; k < CV_BATCH; ++k) {
-            x[k] = __ldg(xi + (size_t)(s + k) * nb + i);
-            w[k] = __ldg(we + (size_t)(s + k) * nb + i);
+            x[k] = __ldg(xi + (size_t)k * nb + i);
+            w[k] = __ldg(we + (size_t)k * nb + i);
+        }
+    }
+    for (int b = 0; b < n_full; ++b, s += CV_BATCH) {
+        if (b + 1 < n_full) {
+#pragma unroll
+            for (int k = 0; k < CV_BATCH; ++k) {
+                xn[k] = __ldg(xi + (size_t)(s + CV_BATCH + k) * nb + i);
+                wn[k] = __ldg(we + (size_t)(s + CV_BATCH + k) * nb + i);
+            }
         }
 #pragma unroll
         for (int k = 0; k < CV_BATCH; ++k) {
             sx = add_rn(sx, mul_rn(x[k], w[k]));  // one rounded product per term, no FMA
             sw = add_rn(sw, w[k]);
         }
+#pragma unroll
+        for (int k = 0; k < CV_BATCH; ++k) x[k] = xn[k], w[k] = wn[k];
     }
     for (; s < n_s; ++s) {
         const double w = we[(size_t)s * nb + i];

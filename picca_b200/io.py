@@ -18,8 +18,8 @@ the CUDA library or a device the call raises.
 Parity: the table interpolation follows scipy's ``interp1d`` operation by operation, so r_comov
 and dist_m are bit-equal to the reference's GIVEN the same z; ``10**x`` on the device (``exp10``)
 can differ from NumPy's power in the last ulp, so by default z, r_comov and dist_m agree with the
-reference within 2 ulp.  ``PICCA_B200_HOST_POW=1`` (parity mode, used by the golden tests)
-evaluates ``10**log_lambda / lambda_abs - 1`` with NumPy on the host instead; then z, r_comov and
+reference within 4 ulp (16 ulp for files that store LAMBDA, whose log10 is taken on the device
+too).  ``PICCA_B200_HOST_POW=1`` (parity mode, used by the golden tests) evaluates ``10**log_lambda / lambda_abs - 1`` with NumPy on the host instead; then z, r_comov and
 dist_m are bit-equal.  Weights and projected deltas are within 1e-13 relative either way (``pow``
 and re-associated sums).  Not implemented: ``rebin_factor`` and the ImageHDU flavour
 (``Delta.from_image``) -- both raise NotImplementedError.
@@ -367,16 +367,19 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         tabs = (ctypes.c_int32(0), None, None, None)
         dist = (None, None)
     d_z_in = None
+    device_log10 = bool(wave_is_lambda.any())
     if os.environ.get("PICCA_B200_HOST_POW", "0") == "1":
         ll_host = d_ll.cpu().numpy()
-        if wave_is_lambda.any():
+        if device_log10:  # data.py:411-412 with NumPy's log10 as well
             ll_host = np.log10(ll_host)
+            d_ll.copy_(torch.from_numpy(ll_host))
+            device_log10 = False
         d_z_in = torch.from_numpy(10**ll_host / lambda_abs - 1.).to(dev)  # io.py:496, NumPy power
     _lib.check(eng.lib.pb2_delta_prepare(
         ctypes.c_int64(n_los), ctypes.c_void_p(d_offset.data_ptr()),
         ctypes.c_void_p(d_order.data_ptr()), ctypes.c_double(lambda_abs), ctypes.c_double(alpha),
         ctypes.c_double(z_ref), *tabs, ctypes.c_int32(0 if no_project else 1),
-        ctypes.c_int32(int(wave_is_lambda.any())),
+        ctypes.c_int32(int(device_log10)),
         ctypes.c_void_p(d_z_in.data_ptr()) if d_z_in is not None else None,
         ctypes.c_void_p(d_ll.data_ptr()), ctypes.c_void_p(d_delta.data_ptr()),
         ctypes.c_void_p(d_w.data_ptr()), ctypes.c_void_p(d_z.data_ptr()), *dist,

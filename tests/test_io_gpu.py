@@ -43,12 +43,12 @@ def ulp_distance(a, b):
     return np.abs(a.view(np.int64) - b.view(np.int64))
 
 
-def close_on_forest_scale(got, want, n_pix, rtol):
+def close_on_forest_scale(got, want, n_pix, rtol, atol=1e-300):
     edges = np.concatenate([[0], np.cumsum(n_pix)])
     for a, b in zip(edges[:-1], edges[1:]):
         if b > a:
             scale = np.abs(want[a:b]).max()
-            assert np.all(np.abs(got[a:b] - want[a:b]) <= rtol * scale + 1e-300)
+            assert np.all(np.abs(got[a:b] - want[a:b]) <= rtol * scale + atol)
 
 
 @pytest.mark.parametrize("host_pow", [True, False])
@@ -65,18 +65,22 @@ def test_read_deltas_matches_reference_golden(tag, host_pow, tmp_path, monkeypat
     g = lambda k: gold["%s_%s" % (tag, k)]
     assert num == int(g("summary")[0])
     for k in ("healpix", "los_id", "plate", "mjd", "fiberid", "n_pix", "order", "ra", "dec",
-              "z_qso", "log_lambda"):
+              "z_qso"):
         assert np.array_equal(flat[k], g(k)), k
+    # files that store LAMBDA: log10 is taken by the loader (data.py:411-412)
+    stores_lambda = cases_io.CASES.get(tag.split("_")[0], {}).get("wave") == "LAMBDA"
     if host_pow:
-        for k in ("z", "r_comov", "dist_m"):
+        for k in ("log_lambda", "z", "r_comov", "dist_m"):
             assert np.array_equal(flat[k], g(k)), k
         assert [z_min, z_max] == list(g("summary")[1:])
     else:
+        assert ulp_distance(flat["log_lambda"], g("log_lambda")).max() <= (2 if stores_lambda else 0)
         for k in ("z", "r_comov", "dist_m"):
-            assert ulp_distance(flat[k], g(k)).max() <= 4, k
-        np.testing.assert_allclose([z_min, z_max], g("summary")[1:], rtol=1e-15)
+            assert ulp_distance(flat[k], g(k)).max() <= (16 if stores_lambda else 4), k
+        np.testing.assert_allclose([z_min, z_max], g("summary")[1:], rtol=4e-15)
     close_on_forest_scale(flat["weights"], g("weights"), flat["n_pix"], 1e-12)
-    close_on_forest_scale(flat["delta"], g("delta"), flat["n_pix"], 1e-12)
+    # a projected delta is a difference of O(0.3) numbers: 1e-13 absolute where it cancels to ~0
+    close_on_forest_scale(flat["delta"], g("delta"), flat["n_pix"], 1e-12, atol=1e-13)
 
 
 def test_loader_feeds_the_pair_kernels_like_the_reference_loader(tmp_path, monkeypatch):
