@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 12
+#define PB2_ABI_VERSION 13
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -228,6 +228,13 @@ int64_t pb2_cov_scratch_bytes(int64_t n_samples, int32_t nb);
 int32_t pb2_cov_subsample(int64_t n_samples, int32_t nb, const double *d_xi, const double *d_weights,
                           double *d_cov, double *d_mean_xi, double *d_sum_weights, void *d_scratch,
                           int64_t scratch_bytes, void *stream);
+/* utils.compute_cov_boot (py/picca/utils.py:131-150; picca_export.py --num-boot-cov): d_idx
+ * [n_boot][n_samples] int32 = the host-drawn `default_rng(seed).choice(nhpx, size=nhpx)` of every
+ * realisation (the reference's RNG stream); output d_cov [nb][nb] = np.cov of the bootstrap means. */
+int64_t pb2_cov_boot_scratch_bytes(int64_t n_samples, int32_t nb, int32_t n_boot);
+int32_t pb2_cov_boot(int64_t n_samples, int32_t nb, int32_t n_boot, const double *d_xi,
+                     const double *d_weights, const int32_t *d_idx, double *d_cov, void *d_scratch,
+                     int64_t scratch_bytes, void *stream);
 int32_t pb2_cov_smooth(int32_t nb, const double *d_cov, const double *d_r_par,
                        const double *d_r_trans, double delta_r_par, double delta_r_trans,
                        int32_t per_r_par, int32_t n_dp, int32_t n_dt, int32_t rp_lo, int32_t n_rp,

@@ -26,6 +26,20 @@ def compute_cov(xi, weights):
     return covariance
 
 
+def compute_cov_boot(xi, weights, nboots=10000, seed=121567):
+    """utils.py:143-150"""
+    xi = np.asarray(xi, dtype=np.float64)
+    weights = np.asarray(weights, dtype=np.float64)
+    nhpx, ndata = xi.shape
+    boot_xis = np.empty((nboots, ndata))
+    rnst = np.random.default_rng(seed)                        # :145
+    for i in range(nboots):
+        idx = rnst.choice(nhpx, size=nhpx)                    # :148
+        wei = weights[idx]
+        boot_xis[i] = np.sum(wei * xi[idx], axis=0) / wei.sum(0)   # :150
+    return np.cov(boot_xis, rowvar=False)
+
+
 def smooth_cov(xi, weights, r_par, r_trans, delta_r_trans=4.0, delta_r_par=4.0, covariance=None,
                per_r_par=False):
     """utils.py:182-248.  The reference's two Python loops over (index, index2 > index) are

@@ -124,30 +124,21 @@ __global__ void pb2_cov_build_m(int n_s, int nb, int ld, const double *__restric
     M[(size_t)s * ld + i] = v;
 }
 
-// ---- C = M^T M / (W W^T), upper-triangular tiles + mirror
-__global__ void __launch_bounds__(CV_THREADS)
-pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
-             const double *__restrict__ sum_w, double *__restrict__ cov)
+// ---- one 64x64 tile of A^T B: A is [ks][lda], B is [ks][ldb] (K-major, zero padded), K chunks of
+// 16 rows staged by TMA bulk copies into a 3-stage ring.  Thread (ty, tx) ends with
+// acc[a][b] = sum_k A[k][i0 + ty*8 + a] * B[k][j0 + (b>>1)*32 + tx*2 + (b&1)].
+__device__ __forceinline__ void cv_tile_atb(const double *__restrict__ gA, size_t lda,
+                                            const double *__restrict__ gB, size_t ldb, int n_chunks,
+                                            unsigned char *smem, unsigned long long *s_bar,
+                                            double (&acc)[8][4])
 {
-    extern __shared__ __align__(128) unsigned char cv_smem[];
-    __shared__ __align__(8) unsigned long long s_bar[CV_STAGES];
-    // linear CTA index -> (bi <= bj)
-    int t = blockIdx.x, bi = 0;
-    while (t >= n_tiles - bi) {
-        t -= n_tiles - bi;
-        ++bi;
-    }
-    const int bj = bi + t;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < CV_STAGES; ++s) cv_mbar_init(cv_saddr(&s_bar[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int n_chunks = ks / CV_KC;
-    const double *gA = M + (size_t)bi * CV_TILE;
-    const double *gB = M + (size_t)bj * CV_TILE;
-    const unsigned smem0 = cv_saddr(cv_smem);
+    const unsigned smem0 = cv_saddr(smem);
 
     auto issue = [&](int chunk) {  // one thread: 2 x 16 rows of 512 bytes
         const int st = chunk % CV_STAGES;
@@ -157,8 +148,8 @@ pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
         const size_t row0 = (size_t)chunk * CV_KC;
 #pragma unroll
         for (int k = 0; k < CV_KC; ++k) {
-            cv_bulk_g2s(dst + k * CV_TILE * 8, gA + (row0 + k) * ld, CV_TILE * 8, bar);
-            cv_bulk_g2s(dst + (CV_KC + k) * CV_TILE * 8, gB + (row0 + k) * ld, CV_TILE * 8, bar);
+            cv_bulk_g2s(dst + k * CV_TILE * 8, gA + (row0 + k) * lda, CV_TILE * 8, bar);
+            cv_bulk_g2s(dst + (CV_KC + k) * CV_TILE * 8, gB + (row0 + k) * ldb, CV_TILE * 8, bar);
         }
     };
     if (tid == 0)
@@ -167,7 +158,6 @@ pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
     // thread (ty, tx): rows ty*8 .. ty*8+7 of the A tile; columns tx*2, tx*2+1, 32+tx*2, 32+tx*2+1
     // of the B tile (16-byte stride between lanes: conflict-free LDS.128)
     const int ty = tid >> 4, tx = tid & 15;
-    double acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -176,7 +166,7 @@ pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
     for (int c = 0; c < n_chunks; ++c) {
         const int st = c % CV_STAGES;
         cv_mbar_wait(cv_saddr(&s_bar[st]), (unsigned)((c / CV_STAGES) & 1));
-        const double *As = reinterpret_cast<const double *>(cv_smem + st * CV_STAGE_BYTES);
+        const double *As = reinterpret_cast<const double *>(smem + st * CV_STAGE_BYTES);
         const double *Bs = As + CV_KC * CV_TILE;
 #pragma unroll
         for (int k = 0; k < CV_KC; ++k) {
@@ -198,24 +188,121 @@ pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
         __syncthreads();  // every thread is done with stage st: refill it
         if (tid == 0 && c + CV_STAGES < n_chunks) issue(c + CV_STAGES);
     }
+}
 
-    // epilogue: covariance[w] /= sum_weights_squared[w] (utils.py:123-126), tile + mirror
+// ---- C = M^T M, upper-triangular tiles + mirror.  sum_w != NULL: C[w] /= (W W^T)[w]
+// (utils.py:123-126); sum_w == NULL: C *= scale (np.cov's `c *= 1/(N-1)`).
+__global__ void __launch_bounds__(CV_THREADS)
+pb2_cov_syrk(int nb, int ld, int ks, int n_tiles, const double *__restrict__ M,
+             const double *__restrict__ sum_w, double scale, double *__restrict__ cov)
+{
+    extern __shared__ __align__(128) unsigned char cv_smem[];
+    __shared__ __align__(8) unsigned long long s_bar[CV_STAGES];
+    // linear CTA index -> (bi <= bj)
+    int t = blockIdx.x, bi = 0;
+    while (t >= n_tiles - bi) {
+        t -= n_tiles - bi;
+        ++bi;
+    }
+    const int bj = bi + t;
+    double acc[8][4];
+    cv_tile_atb(M + (size_t)bi * CV_TILE, ld, M + (size_t)bj * CV_TILE, ld, ks / CV_KC, cv_smem,
+                s_bar, acc);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int i = bi * CV_TILE + ty * 8 + a;
         if (i >= nb) continue;
-        const double wi = sum_w[i];
+        const double wi = sum_w ? sum_w[i] : 0.;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int j = bj * CV_TILE + (b >> 1) * 32 + tx * 2 + (b & 1);
             if (j >= nb) continue;
-            const double den = mul_rn(sum_w[j], wi);
             double v = acc[a][b];
-            if (den > 0.) v = div_rn(v, den);
+            if (sum_w) {
+                const double den = mul_rn(sum_w[j], wi);
+                if (den > 0.) v = div_rn(v, den);
+            } else {
+                v = mul_rn(v, scale);
+            }
             cov[(size_t)i * nb + j] = v;
             if (bi != bj) cov[(size_t)j * nb + i] = v;
         }
     }
+}
+
+// ---- bootstrap covariance (utils.compute_cov_boot, utils.py:131-150)
+// out[b][i] (leading dimension ldo) = sum_s A[s][b] B[s][i];  divide != 0: out = out_prev / that
+__global__ void __launch_bounds__(CV_THREADS)
+pb2_cov_gemm_atb(int m, int n, int lda, int ldb, int ldo, int ks, const double *__restrict__ A,
+                 const double *__restrict__ B, int divide, double *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char cv_smem[];
+    __shared__ __align__(8) unsigned long long s_bar[CV_STAGES];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    double acc[8][4];
+    cv_tile_atb(A + (size_t)bi * CV_TILE, lda, B + (size_t)bj * CV_TILE, ldb, ks / CV_KC, cv_smem,
+                s_bar, acc);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = bi * CV_TILE + ty * 8 + a;
+        if (i >= m) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = bj * CV_TILE + (b >> 1) * 32 + tx * 2 + (b & 1);
+            if (j >= n) continue;
+            double *dst = out + (size_t)i * ldo + j;
+            *dst = divide ? div_rn(*dst, acc[a][b]) : acc[a][b];
+        }
+    }
+}
+
+// multiplicity of sub-sample s in bootstrap realisation b: cnt[s][b] (leading dimension ldc)
+__global__ void pb2_cov_boot_counts(long long total, int n_s, int ldc, const int *__restrict__ idx,
+                                    double *__restrict__ cnt)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int b = (int)(t / n_s);
+    atomicAdd(cnt + (size_t)idx[t] * ldc + b, 1.0);
+}
+
+// P[s][i] = weights * xi, Wm[s][i] = weights, zero padded [ks][ld]
+__global__ void pb2_cov_boot_operands(int n_s, int nb, int ld, const double *__restrict__ xi,
+                                      const double *__restrict__ we, double *__restrict__ P,
+                                      double *__restrict__ Wm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= ld) return;
+    double p = 0., w = 0.;
+    if (i < nb && s < n_s) {
+        w = we[(size_t)s * nb + i];
+        p = mul_rn(w, xi[(size_t)s * nb + i]);
+    }
+    P[(size_t)s * ld + i] = p;
+    Wm[(size_t)s * ld + i] = w;
+}
+
+// np.cov: X -= X.mean over the realisations, in place (boot is [kb][ld], rows >= n_boot are zero).
+// Block = 32 bins x 16 row groups; row group y sums rows y, y+16, ...
+__global__ void pb2_cov_boot_center(int n_boot, int nb, int ld, double *__restrict__ boot)
+{
+    __shared__ double part[16][33];
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const int y = threadIdx.y;
+    double acc = 0.;
+    if (i < nb)
+        for (int b = y; b < n_boot; b += 16) acc += boot[(size_t)b * ld + i];
+    part[y][threadIdx.x] = acc;
+    __syncthreads();
+    double tot = 0.;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tot += part[k][threadIdx.x];
+    const double mean = tot / (double)n_boot;
+    if (i < nb)
+        for (int b = y; b < n_boot; b += 16) boot[(size_t)b * ld + i] -= mean;
 }
 
 // ---- smooth_cov (utils.py:185-247)
@@ -330,9 +417,78 @@ int32_t pb2_cov_subsample(int64_t n_samples, int32_t nb, const double *d_xi, con
     const int smem = CV_STAGES * CV_STAGE_BYTES;
     PB2_CUDA(cudaFuncSetAttribute(pb2_cov_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pb2_cov_syrk<<<n_tiles * (n_tiles + 1) / 2, CV_THREADS, smem, s>>>(nb, ld, ks, n_tiles, M,
-                                                                      d_sum_weights, d_cov);
+                                                                      d_sum_weights, 1., d_cov);
     pb2_count_launch(1);
     rc = pb2_check_launch("pb2_cov_syrk");
+    pb2_timing_end(s);
+    return rc;
+}
+
+static inline int64_t cv_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+int64_t pb2_cov_boot_scratch_bytes(int64_t n_samples, int32_t nb, int32_t n_boot)
+{
+    const int64_t ld = cv_up(nb, CV_TILE), ks = cv_up(n_samples > 0 ? n_samples : 1, CV_KC);
+    const int64_t lc = cv_up(n_boot, CV_TILE), kb = cv_up(n_boot > 0 ? n_boot : 1, CV_KC);
+    // counts [ks][lc] + P [ks][ld] + W [ks][ld] + boot_xis [max(kb, lc)][ld]
+    return 8 * (ks * lc + 2 * ks * ld + (kb > lc ? kb : lc) * ld);
+}
+
+/* utils.compute_cov_boot (py/picca/utils.py:131-150): d_idx [n_boot][n_samples] int32 holds the
+ * host-drawn `rng.choice(nhpx, size=nhpx)` of every realisation (the reference's RNG stream);
+ * boot_xis[b] = sum_k w[idx_k] xi[idx_k] / sum_k w[idx_k] as two A^T B contractions with the
+ * multiplicity matrix, then np.cov(boot_xis, rowvar=False). */
+int32_t pb2_cov_boot(int64_t n_samples, int32_t nb, int32_t n_boot, const double *d_xi,
+                     const double *d_weights, const int32_t *d_idx, double *d_cov, void *d_scratch,
+                     int64_t scratch_bytes, void *stream)
+{
+    if (!d_xi || !d_weights || !d_idx || !d_cov || !d_scratch) {
+        pb2_set_error("pb2_cov_boot: null pointer argument");
+        return PB2_EINVAL;
+    }
+    if (nb <= 0 || n_samples <= 0 || n_samples > 0x7fffffff || n_boot < 2) {
+        pb2_set_error("pb2_cov_boot: bad sizes (n_samples %lld, nb %d, n_boot %d)",
+                      (long long)n_samples, nb, n_boot);
+        return PB2_EINVAL;
+    }
+    if (scratch_bytes < pb2_cov_boot_scratch_bytes(n_samples, nb, n_boot)) {
+        pb2_set_error("pb2_cov_boot: scratch too small");
+        return PB2_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ld = (int)cv_up(nb, CV_TILE), ks = (int)cv_up(n_samples, CV_KC);
+    const int lc = (int)cv_up(n_boot, CV_TILE), kb = (int)cv_up(n_boot, CV_KC);
+    const int rows_boot = kb > lc ? kb : lc;
+    double *cnt = (double *)d_scratch;
+    double *P = cnt + (size_t)ks * lc;
+    double *Wm = P + (size_t)ks * ld;
+    double *boot = Wm + (size_t)ks * ld;
+    PB2_CUDA(cudaMemsetAsync(cnt, 0, (size_t)ks * lc * 8, s));
+    PB2_CUDA(cudaMemsetAsync(boot, 0, (size_t)rows_boot * ld * 8, s));
+    pb2_timing_begin(s);
+    const long long total = (long long)n_boot * n_samples;
+    pb2_cov_boot_counts<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, (int)n_samples, lc,
+                                                                        d_idx, cnt);
+    pb2_cov_boot_operands<<<dim3((ld + 255) / 256, ks), 256, 0, s>>>((int)n_samples, nb, ld, d_xi,
+                                                                    d_weights, P, Wm);
+    pb2_count_launch(2);
+    int32_t rc = pb2_check_launch("pb2_cov_boot_operands");
+    if (rc) return rc;
+    const int smem = CV_STAGES * CV_STAGE_BYTES;
+    PB2_CUDA(cudaFuncSetAttribute(pb2_cov_gemm_atb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PB2_CUDA(cudaFuncSetAttribute(pb2_cov_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(ld / CV_TILE, lc / CV_TILE);
+    pb2_cov_gemm_atb<<<grid, CV_THREADS, smem, s>>>(n_boot, nb, lc, ld, ld, ks, cnt, P, 0, boot);
+    pb2_cov_gemm_atb<<<grid, CV_THREADS, smem, s>>>(n_boot, nb, lc, ld, ld, ks, cnt, Wm, 1, boot);
+    pb2_cov_boot_center<<<(nb + 31) / 32, dim3(32, 16), 0, s>>>(n_boot, nb, ld, boot);
+    pb2_count_launch(3);
+    rc = pb2_check_launch("pb2_cov_boot_center");
+    if (rc) return rc;
+    const int n_tiles = ld / CV_TILE;
+    pb2_cov_syrk<<<n_tiles * (n_tiles + 1) / 2, CV_THREADS, smem, s>>>(
+        nb, ld, kb, n_tiles, boot, nullptr, 1. / (double)(n_boot - 1), d_cov);
+    pb2_count_launch(1);
+    rc = pb2_check_launch("pb2_cov_syrk(boot)");
     pb2_timing_end(s);
     return rc;
 }

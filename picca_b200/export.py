@@ -1,11 +1,12 @@
 """B200 path of the covariance step of ``picca_export.py``: the sub-sample covariance of the
 per-HEALPix correlation blocks and its smoothing.  Same names, arguments and return values as the
-reference's ``picca.utils.compute_cov`` (py/picca/utils.py:100-128) and ``picca.utils.smooth_cov``
-(py/picca/utils.py:153-249); ``picca_b200.overlay`` makes ``picca.utils`` resolve them here so the
-unmodified ``picca_export.py`` (:262-300) runs on top.
+reference's ``picca.utils.compute_cov`` (py/picca/utils.py:100-128), ``compute_cov_boot``
+(py/picca/utils.py:131-150) and ``picca.utils.smooth_cov`` (py/picca/utils.py:153-249);
+``picca_b200.overlay`` makes ``picca.utils`` resolve them here so the unmodified
+``picca_export.py`` (:262-300) runs on top.
 
 NumPy host arrays in, NumPy host arrays out (what the script holds); the arithmetic runs in
-``pb2_cov_subsample`` / ``pb2_cov_smooth`` (csrc/pb2_cov.cu) through the C ABI.  No CPU fallback.
+``pb2_cov_subsample`` / ``pb2_cov_boot`` / ``pb2_cov_smooth`` (csrc/pb2_cov.cu) through the C ABI.  No CPU fallback.
 """
 import ctypes
 import sys
@@ -61,6 +62,39 @@ def compute_cov(xi, weights):
     eng = get_engine()
     userprint("Computing cov...")
     cov, _, _ = compute_cov_device(eng, _dev(eng, xi), _dev(eng, weights))
+    return cov.cpu().numpy()
+
+
+def compute_cov_boot(xi, weights, nboots=10000, seed=121567):
+    """Computes the covariance matrix using the bootstrap technique (utils.py:131-150).
+
+    The resampling indices come from the reference's generator and call sequence
+    (``np.random.default_rng(seed)``, one ``choice(nhpx, size=nhpx)`` per realisation), so the
+    realisations are the reference's; the weighted means and ``np.cov`` run on the device.
+    """
+    xi = np.asarray(xi, dtype=np.float64)
+    weights = np.asarray(weights, dtype=np.float64)
+    if xi.ndim != 2 or xi.shape != weights.shape:
+        raise ValueError("compute_cov_boot: xi and weights must be 2-D arrays of the same shape")
+    nhpx, ndata = xi.shape
+    eng = get_engine()
+    torch = eng.torch
+    rnst = np.random.default_rng(seed)
+    idx = np.empty((nboots, nhpx), dtype=np.int32)
+    for i in range(nboots):
+        idx[i] = rnst.choice(nhpx, size=nhpx)
+    d_idx = torch.from_numpy(idx).to(eng.device)
+    d_xi, d_we = _dev(eng, xi), _dev(eng, weights)
+    cov = torch.empty((ndata, ndata), dtype=torch.float64, device=eng.device)
+    nbytes = int(eng.lib.pb2_cov_boot_scratch_bytes(ctypes.c_int64(nhpx), ctypes.c_int32(ndata),
+                                                    ctypes.c_int32(nboots)))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+    _lib.check(eng.lib.pb2_cov_boot(
+        ctypes.c_int64(nhpx), ctypes.c_int32(ndata), ctypes.c_int32(nboots),
+        ctypes.c_void_p(d_xi.data_ptr()), ctypes.c_void_p(d_we.data_ptr()),
+        ctypes.c_void_p(d_idx.data_ptr()), ctypes.c_void_p(cov.data_ptr()),
+        ctypes.c_void_p(scratch.data_ptr()), ctypes.c_int64(nbytes), eng.stream_ptr()),
+        "pb2_cov_boot")
     return cov.cpu().numpy()
 
 

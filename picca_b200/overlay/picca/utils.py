@@ -1,5 +1,5 @@
 """``picca.utils`` = the reference's module with the covariance step of ``picca_export.py``
-(``compute_cov``, ``smooth_cov``; py/picca/utils.py:100-128, :153-249) replaced by the B200 path.
+(``compute_cov``, ``compute_cov_boot``, ``smooth_cov``; py/picca/utils.py:100-150, :153-249) replaced by the B200 path.
 Everything else in the module is the reference's own code, executed from its file."""
 import importlib.util
 import os
@@ -24,4 +24,6 @@ import picca_b200.export as _impl  # noqa: E402
 _mod.reference_compute_cov = _mod.compute_cov
 _mod.reference_smooth_cov = _mod.smooth_cov
 _mod.compute_cov = _impl.compute_cov
+_mod.reference_compute_cov_boot = _mod.compute_cov_boot
+_mod.compute_cov_boot = _impl.compute_cov_boot
 _mod.smooth_cov = _impl.smooth_cov

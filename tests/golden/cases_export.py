@@ -1,6 +1,8 @@
 """Seeded inputs of the covariance golden vectors (shared by the generator and the tests)."""
 import numpy as np
 
+NBOOTS, BOOT_SEED = 70, 121567  # bootstrap realisations of the golden vectors (utils.py:131)
+
 CASES = {
     # name: sub-samples, np, nt, bin widths, options
     "small": dict(n_s=23, np_=6, nt=5, delta_r_par=4., delta_r_trans=4., seed=3),

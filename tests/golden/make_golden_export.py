@@ -30,6 +30,9 @@ def main():
         out["%s_smooth" % name] = utils.smooth_cov(
             xi, we, rp, rt, delta_r_trans=cfg["delta_r_trans"], delta_r_par=cfg["delta_r_par"],
             covariance=cov.copy(), per_r_par=cfg.get("per_r_par", False))
+        with np.errstate(all="ignore"):
+            out["%s_boot" % name] = utils.compute_cov_boot(xi, we, nboots=cases_export.NBOOTS,
+                                                           seed=cases_export.BOOT_SEED)
         print(name, cov.shape, float(np.trace(cov)))
     # the reference's own fixtures (picca_export.py --data cf.fits.gz, test_3_cor.py:443-456)
     cor = load.DATA + "/test_cor/"

@@ -45,6 +45,34 @@ def test_cov_and_smoothing_match_reference_golden(name):
     cov_close(smooth2, gold["%s_smooth" % name], rtol=1e-8)
 
 
+@pytest.mark.parametrize("name", sorted(cases_export.CASES))
+def test_bootstrap_covariance_matches_reference_golden(name):
+    """utils.compute_cov_boot (utils.py:131-150): same realisations (the reference's generator and
+    call sequence), means and np.cov on the device."""
+    from picca_b200 import export
+    gold = np.load(GOLD)
+    xi, we, _, _ = cases_export.inputs(cases_export.CASES[name])
+    got = export.compute_cov_boot(xi, we, nboots=cases_export.NBOOTS, seed=cases_export.BOOT_SEED)
+    want = gold["%s_boot" % name]
+    assert np.array_equal(np.isnan(got), np.isnan(want))  # empty bin: 0/0 in every realisation
+    ok = ~np.isnan(want)
+    cov_close(np.where(ok, got, 0.), np.where(ok, want, 0.))
+    assert np.array_equal(got[ok], got.T[ok])
+
+
+def test_bootstrap_covariance_production_shape():
+    """1392 sub-samples x 2500 bins, 2000 realisations, against the oracle on a column subset
+    (the oracle's per-realisation gather is what makes the reference slow)."""
+    from oracle import export as oexp
+    from picca_b200 import export
+    cfg = dict(n_s=1392, np_=50, nt=50, delta_r_par=4., delta_r_trans=4., seed=12)
+    xi, we, _, _ = cases_export.inputs(cfg)
+    got = export.compute_cov_boot(xi, we, nboots=2000, seed=5)
+    cols = np.arange(0, 2500, 41)
+    want = oexp.compute_cov_boot(xi[:, cols], we[:, cols], nboots=2000, seed=5)
+    cov_close(got[np.ix_(cols, cols)], want)
+
+
 def test_reference_fixture_exported_cf():
     """cf.fits.gz -> exported_cf.fits.gz CO column (the reference's own golden, rtol 1e-5)."""
     from picca_b200 import export

@@ -150,6 +150,13 @@ def test_export_covariance(name):
     _cov_close(smooth, gold["%s_smooth" % name], 1e-12)
     if name == "empty_bin":  # zero variance: the reference returns the covariance unsmoothed
         assert np.array_equal(smooth, gold["%s_cov" % name])
+    with np.errstate(all="ignore"):
+        boot = oexp.compute_cov_boot(xi, we, nboots=cases_export.NBOOTS,
+                                     seed=cases_export.BOOT_SEED)
+    want = gold["%s_boot" % name]
+    assert np.array_equal(np.isnan(boot), np.isnan(want))  # an empty bin: 0/0 in every realisation
+    ok = ~np.isnan(want)
+    _cov_close(np.where(ok, boot, 0.), np.where(ok, want, 0.), 1e-10)
 
 
 def test_export_covariance_reference_fixture():

@@ -182,6 +182,10 @@ def test_export_covariance_equals_live_reference(name):
     want_s = utils.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
     got_s = oexp.smooth_cov(xi, we, rp, rt, covariance=want.copy(), **kw)
     assert np.array_equal(got_s, want_s)
+    with np.errstate(all="ignore"):
+        want_b = utils.compute_cov_boot(xi, we, nboots=40, seed=7)
+        got_b = oexp.compute_cov_boot(xi, we, nboots=40, seed=7)
+    assert np.array_equal(got_b, want_b, equal_nan=True)
 
 
 @pytest.mark.parametrize("which", ["bundled", "sdss", "desi", "blind"])
