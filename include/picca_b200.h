@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 13
+#define PB2_ABI_VERSION 14
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -267,6 +267,18 @@ int32_t pb2_delta_unpack(int64_t n_los, const uint8_t *d_raw, const int64_t *d_r
                          const int32_t *d_row_bytes, const int32_t *d_col_off,
                          const int64_t *d_offset, double *d_log_lambda, double *d_delta,
                          double *d_weights, void *stream);
+/* ImageHDU flavour (Delta.from_image, py/picca/data.py:519-620): images [n_forest][n_lambda] of
+ * big-endian fp64 at byte offsets delta_off / weight_off of d_raw, the common wavelength grid at
+ * lambda_off; forest f is image row d_rows[f] and keeps the pixels with WEIGHT > 0.
+ * pb2_delta_image_count gives the kept pixels per forest; after an exclusive scan,
+ * pb2_delta_image_unpack compacts them into the CSR arrays. */
+int32_t pb2_delta_image_count(int64_t n_los, const uint8_t *d_raw, int64_t weight_off,
+                              int32_t n_lambda, const int32_t *d_rows, int32_t *d_count,
+                              void *stream);
+int32_t pb2_delta_image_unpack(int64_t n_los, const uint8_t *d_raw, int64_t lambda_off,
+                               int64_t delta_off, int64_t weight_off, int32_t n_lambda,
+                               const int32_t *d_rows, const int64_t *d_offset, double *d_log_lambda,
+                               double *d_delta, double *d_weights, void *stream);
 int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t *d_order,
                           double lambda_abs, double alpha, double z_ref, int32_t n_table,
                           const double *d_tab_z, const double *d_tab_r_comov,

@@ -1,6 +1,7 @@
 """Oracle restatement of the delta loader: ``io.read_deltas`` / ``io.read_delta_file`` /
 ``Delta.from_fitsio`` / ``Delta.project`` (reference py/picca/io.py:338-381, :383-512;
-py/picca/data.py:375-474, :622-655), BinTable flavour, NumPy + scipy on the CPU.
+py/picca/data.py:375-474, :519-620, :622-655), BinTable and ImageHDU flavours, NumPy + scipy on
+the CPU.
 TEST INFRASTRUCTURE ONLY -- the referee for picca_b200.io, never the product.
 
 Pinned bit for bit against the live reference on its bundled delta files and on the generated
@@ -44,10 +45,38 @@ def project(d):
     d.delta -= mean_delta + res
 
 
+def from_image(hdul, z_min_qso, z_max_qso, order):
+    """Delta.from_image, data.py:543-620 (non-Pk1D)"""
+    meta = hdul["METADATA"]
+    header = meta.read_header()
+    blinding = header["BLINDING"] if "BLINDING" in header else "none"
+    delta = hdul["DELTA" if blinding == "none" else "DELTA_BLIND"].read().astype(float)
+    if "LOGLAM" in hdul:
+        log_lambda = hdul["LOGLAM"][:].astype(float)
+    else:
+        log_lambda = np.log10(hdul["LAMBDA"][:].astype(float))
+    weights = hdul["WEIGHT"].read().astype(float)
+    keep = weights > 0                                         # :572
+    if "THING_ID" in meta.get_colnames():
+        ids = [meta[c][:] for c in ("THING_ID", "PLATE", "MJD", "FIBERID")]
+    else:
+        ids = [meta["LOS_ID"][:]] * 4
+    ra, dec, z_qso = meta["RA"][:], meta["DEC"][:], meta["Z"][:]
+    out = []
+    for f in range(len(z_qso)):
+        if z_qso[f] >= z_min_qso and z_qso[f] <= z_max_qso:   # :602, inclusive
+            w = keep[f]
+            out.append(Delta(ids[0][f], ra[f], dec[f], z_qso[f], ids[1][f], ids[2][f], ids[3][f],
+                             log_lambda[w], weights[f][w], delta[f][w], order))
+    return out
+
+
 def read_delta_file(filename, z_min_qso, z_max_qso, order):
     """io.py:354-360 + data.py:392-474 (non-Pk1D branch)"""
     out = []
     with minifits.FITS(filename) as hdul:
+        if "LAMBDA" in hdul:                                   # io.py:356
+            return from_image(hdul, z_min_qso, z_max_qso, order)
         for hdu in hdul[1:]:
             header = hdu.read_header()
             if not z_min_qso < header["Z"] < z_max_qso:

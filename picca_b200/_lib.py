@@ -116,10 +116,11 @@ EXPORTS = [
     "pb2_cov_scratch_bytes", "pb2_cov_subsample", "pb2_cov_smooth",
     "pb2_cov_boot_scratch_bytes", "pb2_cov_boot",
     "pb2_fits_scan", "pb2_fits_cards", "pb2_delta_unpack", "pb2_delta_prepare",
+    "pb2_delta_image_count", "pb2_delta_image_unpack",
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 def lib():

@@ -225,6 +225,57 @@ __global__ void pb2_delta_unpack_kernel(long long n_los, const uint8_t *__restri
     }
 }
 
+// ImageHDU flavour (Delta.from_image, data.py:519-620): one common wavelength grid of n_lambda
+// pixels and 2-D images [n_forest][n_lambda]; forest f is image row rows[f] and keeps the pixels
+// with WEIGHT > 0 (data.py:572, :604-611).  Pass 1 counts them, pass 2 compacts them (warp per
+// forest, ballot prefix) into the CSR arrays.
+__global__ void pb2_delta_image_count_kernel(long long n_los, const uint8_t *__restrict__ raw,
+                                             long long weight_off, int n_lambda,
+                                             const int *__restrict__ rows, int *__restrict__ count)
+{
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= n_los) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t *w = raw + weight_off + (long long)rows[f] * n_lambda * 8;
+    int n = 0;
+    for (int p0 = 0; p0 < n_lambda; p0 += 32) {
+        const int p = p0 + lane;
+        const bool keep = p < n_lambda && be64_to_double(w + 8ll * p) > 0.;
+        n += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == 0) count[f] = n;
+}
+
+__global__ void pb2_delta_image_fill_kernel(long long n_los, const uint8_t *__restrict__ raw,
+                                            long long lambda_off, long long delta_off,
+                                            long long weight_off, int n_lambda,
+                                            const int *__restrict__ rows,
+                                            const long long *__restrict__ offset,
+                                            double *__restrict__ log_lambda,
+                                            double *__restrict__ delta, double *__restrict__ weights)
+{
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= n_los) return;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)rows[f] * n_lambda * 8;
+    const uint8_t *w = raw + weight_off + row, *d = raw + delta_off + row, *l = raw + lambda_off;
+    long long out = offset[f];
+    for (int p0 = 0; p0 < n_lambda; p0 += 32) {
+        const int p = p0 + lane;
+        double wv = 0.;
+        if (p < n_lambda) wv = be64_to_double(w + 8ll * p);
+        const bool keep = p < n_lambda && wv > 0.;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const long long at = out + __popc(mask & ((1u << lane) - 1u));
+            weights[at] = wv;
+            delta[at] = be64_to_double(d + 8ll * p);
+            log_lambda[at] = be64_to_double(l + 8ll * p);
+        }
+        out += __popc(mask);
+    }
+}
+
 // --------------------------------------------------------------------------------- device: prepare
 struct DeltaPrep {
     double lambda_abs, alpha_m1, one_plus_z_ref;
@@ -364,6 +415,42 @@ int32_t pb2_delta_unpack(int64_t n_los, const uint8_t *d_raw, const int64_t *d_r
         d_log_lambda, d_delta, d_weights);
     pb2_count_launch(1);
     return pb2_check_launch("pb2_delta_unpack");
+}
+
+int32_t pb2_delta_image_count(int64_t n_los, const uint8_t *d_raw, int64_t weight_off,
+                              int32_t n_lambda, const int32_t *d_rows, int32_t *d_count,
+                              void *stream)
+{
+    if (n_los <= 0) return 0;
+    if (!d_raw || !d_rows || !d_count || n_lambda <= 0) {
+        pb2_set_error("pb2_delta_image_count: bad argument");
+        return PB2_EINVAL;
+    }
+    const int warps = 8;
+    pb2_delta_image_count_kernel<<<(unsigned)((n_los + warps - 1) / warps), warps * 32, 0,
+                                   (cudaStream_t)stream>>>(n_los, d_raw, weight_off, n_lambda, d_rows,
+                                                           d_count);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_delta_image_count");
+}
+
+int32_t pb2_delta_image_unpack(int64_t n_los, const uint8_t *d_raw, int64_t lambda_off,
+                               int64_t delta_off, int64_t weight_off, int32_t n_lambda,
+                               const int32_t *d_rows, const int64_t *d_offset, double *d_log_lambda,
+                               double *d_delta, double *d_weights, void *stream)
+{
+    if (n_los <= 0) return 0;
+    if (!d_raw || !d_rows || !d_offset || !d_log_lambda || !d_delta || !d_weights || n_lambda <= 0) {
+        pb2_set_error("pb2_delta_image_unpack: bad argument");
+        return PB2_EINVAL;
+    }
+    const int warps = 8;
+    pb2_delta_image_fill_kernel<<<(unsigned)((n_los + warps - 1) / warps), warps * 32, 0,
+                                  (cudaStream_t)stream>>>(
+        n_los, d_raw, lambda_off, delta_off, weight_off, n_lambda, d_rows,
+        (const long long *)d_offset, d_log_lambda, d_delta, d_weights);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_delta_image_unpack");
 }
 
 int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t *d_order,

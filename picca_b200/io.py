@@ -21,8 +21,10 @@ can differ from NumPy's power in the last ulp, so by default z, r_comov and dist
 reference within 4 ulp (16 ulp for files that store LAMBDA, whose log10 is taken on the device
 too).  ``PICCA_B200_HOST_POW=1`` (parity mode, used by the golden tests) evaluates ``10**log_lambda / lambda_abs - 1`` with NumPy on the host instead; then z, r_comov and
 dist_m are bit-equal.  Weights and projected deltas are within 1e-13 relative either way (``pow``
-and re-associated sums).  Not implemented: ``rebin_factor`` and the ImageHDU flavour
-(``Delta.from_image``) -- both raise NotImplementedError.
+and re-associated sums).  Both on-disk flavours are read: one BinTable HDU per forest
+(``Delta.from_fitsio``) and the ImageHDU layout (``Delta.from_image``, data.py:519-620: common
+wavelength grid, METADATA table, 2-D images; ``pb2_delta_image_count`` / ``_unpack`` keep the
+pixels with WEIGHT > 0).  Not implemented: ``rebin_factor`` (raises NotImplementedError).
 """
 import ctypes
 import glob
@@ -75,10 +77,12 @@ def _scan(buf):
     return info[:n]
 
 
-def _cards(buf, header_off):
-    """Header cards _KEYS of the HDUs starting at ``header_off``: (kind, num, inum, strings)."""
+def _cards(buf, header_off, keys=None):
+    """Header cards ``keys`` (default _KEYS) of the HDUs starting at ``header_off``:
+    (kind, num, inum, strings)."""
     lib = _lib.lib()
-    n, nk = len(header_off), len(_KEYS)
+    key_bytes = _KEY_BYTES if keys is None else "".join(k.ljust(8) for k in keys).encode("ascii")
+    n, nk = len(header_off), len(_KEYS if keys is None else keys)
     kind = np.zeros((n, nk), dtype=np.int32)
     num = np.zeros((n, nk), dtype=np.float64)
     inum = np.zeros((n, nk), dtype=np.int64)
@@ -87,7 +91,7 @@ def _cards(buf, header_off):
     _lib.check(lib.pb2_fits_cards(
         buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size), ctypes.c_int64(n),
         header_off.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(nk),
-        ctypes.c_char_p(_KEY_BYTES), kind.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_char_p(key_bytes), kind.ctypes.data_as(ctypes.c_void_p),
         num.ctypes.data_as(ctypes.c_void_p), inum.ctypes.data_as(ctypes.c_void_p),
         strs.ctypes.data_as(ctypes.c_void_p)), "pb2_fits_cards")
     return kind, num, inum, strs
@@ -110,19 +114,117 @@ def _column_offsets(ttypes, tforms):
     return out, pos
 
 
-class _FileForests:
-    """What one delta file contributes: per kept forest the row geometry and the header values."""
+def _open_delta_file(path, z_min_qso, z_max_qso):
+    """One delta file -> _FileForests (BinTable flavour) or _ImageForests (ImageHDU flavour);
+    io.py:354-360: an extension called LAMBDA selects Delta.from_image."""
+    buf = _file_bytes(path)
+    info = _scan(buf)
+    kind, num, inum, strs = _cards(buf, info[:, 0])
+    names = [s.decode("ascii", "replace") for s in strs[:, _K["EXTNAME"]]]
+    if "LAMBDA" in names:
+        return _ImageForests(path, buf, info, names, z_min_qso, z_max_qso)
+    return _FileForests(path, buf, info, kind, num, inum, strs, z_min_qso, z_max_qso)
 
-    def __init__(self, path, z_min_qso, z_max_qso):
+
+class _ImageForests:
+    """ImageHDU flavour (Delta.from_image, data.py:519-620): a common wavelength grid, a METADATA
+    table and 2-D DELTA / WEIGHT images; a forest keeps its pixels with WEIGHT > 0."""
+    is_image = True
+
+    def __init__(self, path, buf, info, names, z_min_qso, z_max_qso):
+        self.path, self.buf = path, buf
+        hdu = {name: k for k, name in reversed(list(enumerate(names))) if name}
+        if "METADATA" not in hdu:
+            raise KeyError("METADATA")
+        meta = hdu["METADATA"]
+        n_col = int(info[meta, 7])
+        keys = ["BLINDING"] + ["TTYPE%d" % k for k in range(1, n_col + 1)] + \
+            ["TFORM%d" % k for k in range(1, n_col + 1)]
+        _, _, _, strs = _cards(buf, info[meta:meta + 1, 0], keys)
+        dec = [x.decode("ascii", "replace") for x in strs[0]]
+        blinding = dec[0] if dec[0] else "none"                       # data.py:546-554
+        delta_name = "DELTA" if blinding == "none" else "DELTA_BLIND"
+        cols, width = _column_offsets(dec[1:1 + n_col], dec[1 + n_col:1 + 2 * n_col])
+        if width != info[meta, 5]:
+            raise OSError("picca_b200.io: METADATA row width mismatch in %s" % path)
+        n_forest = int(info[meta, 6])
+        table = np.frombuffer(buf, dtype=np.uint8, count=n_forest * width,
+                              offset=int(info[meta, 1])).reshape(n_forest, width)
+
+        def column(name):
+            off, letter, rep = cols[name]
+            dt = {"D": ">f8", "E": ">f4", "K": ">i8", "J": ">i4", "I": ">i2", "B": "u1"}[letter]
+            nbytes = np.dtype(dt).itemsize
+            return np.ascontiguousarray(table[:, off:off + nbytes]).view(dt).reshape(n_forest)
+
+        if "LOGLAM" in hdu:                                            # data.py:558-563
+            wave, self.wave_flag = hdu["LOGLAM"], False
+        else:
+            wave, self.wave_flag = hdu["LAMBDA"], True
+        for name in (delta_name, "WEIGHT"):
+            if name not in hdu:
+                raise KeyError(name)
+        d, w = hdu[delta_name], hdu["WEIGHT"]
+        self.n_lambda = int(info[wave, 5])
+        for k in (d, w):
+            if info[k, 3] != -64 or info[k, 5] != self.n_lambda or info[k, 6] != n_forest:
+                raise NotImplementedError("picca_b200.io: image HDUs must be fp64 "
+                                          "[n_forest][n_lambda]; file %s" % path)
+        if info[wave, 3] != -64:
+            raise NotImplementedError("picca_b200.io: the wavelength grid must be fp64")
+        self.lambda_off, self.delta_off, self.weight_off = (int(info[k, 1]) for k in (wave, d, w))
+        if "THING_ID" in cols:                                         # data.py:575-586
+            los_id, plate, mjd, fiberid = (column(c) for c in ("THING_ID", "PLATE", "MJD",
+                                                               "FIBERID"))
+        elif "LOS_ID" in cols:
+            los_id = plate = mjd = fiberid = column("LOS_ID")
+        else:
+            raise Exception("Could not find THING_ID or LOS_ID")
+        z = column("Z").astype(np.float64)
+        keep = np.nonzero((z >= z_min_qso) & (z <= z_max_qso))[0]     # data.py:602, inclusive
+        self.rows = keep.astype(np.int32)
+        self.n = len(keep)
+        self.ra = column("RA").astype(np.float64)[keep]
+        self.dec = column("DEC").astype(np.float64)[keep]
+        self.z_qso = z[keep]
+        self.los_id, self.plate = los_id.astype(np.int64)[keep], plate.astype(np.int64)[keep]
+        self.mjd, self.fiberid = mjd.astype(np.int64)[keep], fiberid.astype(np.int64)[keep]
+        self.wave_is_lambda = np.full(self.n, self.wave_flag, dtype=bool)
+        self.n_pix = None  # known after the device count (count_pixels)
+        self.d_raw = None
+
+    def count_pixels(self, eng):
+        """upload the file and count the WEIGHT > 0 pixels of every kept forest"""
+        torch = eng.torch
+        self.d_raw = torch.from_numpy(np.array(self.buf, copy=True)).to(eng.device)
+        self.d_rows = torch.from_numpy(self.rows).to(eng.device)
+        count = torch.zeros(max(self.n, 1), dtype=torch.int32, device=eng.device)
+        _lib.check(eng.lib.pb2_delta_image_count(
+            ctypes.c_int64(self.n), ctypes.c_void_p(self.d_raw.data_ptr()),
+            ctypes.c_int64(self.weight_off), ctypes.c_int32(self.n_lambda),
+            ctypes.c_void_p(self.d_rows.data_ptr()), ctypes.c_void_p(count.data_ptr()),
+            eng.stream_ptr()), "pb2_delta_image_count")
+        self.n_pix = count[:self.n].cpu().numpy().astype(np.int64)
+        self.buf = None
+
+    def unpack(self, eng, n_take, d_offset_ptr, d_ll, d_delta, d_w):
+        _lib.check(eng.lib.pb2_delta_image_unpack(
+            ctypes.c_int64(n_take), ctypes.c_void_p(self.d_raw.data_ptr()),
+            ctypes.c_int64(self.lambda_off), ctypes.c_int64(self.delta_off),
+            ctypes.c_int64(self.weight_off), ctypes.c_int32(self.n_lambda),
+            ctypes.c_void_p(self.d_rows.data_ptr()), ctypes.c_void_p(d_offset_ptr),
+            ctypes.c_void_p(d_ll.data_ptr()), ctypes.c_void_p(d_delta.data_ptr()),
+            ctypes.c_void_p(d_w.data_ptr()), eng.stream_ptr()), "pb2_delta_image_unpack")
+        eng.torch.cuda.current_stream().synchronize()
+        self.d_raw = self.d_rows = None
+
+
+class _FileForests:
+    """BinTable flavour: per kept forest the row geometry and the header values."""
+    is_image = False
+
+    def __init__(self, path, buf, info, kind, num, inum, strs, z_min_qso, z_max_qso):
         self.path = path
-        buf = _file_bytes(path)
-        info = _scan(buf)
-        kind, num, inum, strs = _cards(buf, info[:, 0])
-        names = [s.decode("ascii", "replace") for s in strs[:, _K["EXTNAME"]]]
-        if "LAMBDA" in names:  # io.py:356: `'LAMBDA' in hdul` selects Delta.from_image
-            raise NotImplementedError(
-                "picca_b200.io: ImageHDU delta files (Delta.from_image, data.py:519-620) are not "
-                "implemented; file %s" % path)
         hdus = np.arange(1, len(info))  # hdul[1:]
         z = num[hdus, _K["Z"]]
         if np.any(kind[hdus, _K["Z"]] != 1):
@@ -271,7 +373,10 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     torch = eng.torch
     workers = nproc if nproc else (os.cpu_count() or 1)
     with ThreadPoolExecutor(max_workers=max(1, min(workers, 32))) as pool:
-        parts = list(pool.map(lambda f: _FileForests(f, z_min_qso, z_max_qso), files))
+        parts = list(pool.map(lambda f: _open_delta_file(f, z_min_qso, z_max_qso), files))
+    for p in parts:  # ImageHDU files: the pixel counts come from the device
+        if p.is_image:
+            p.count_pixels(eng)
 
     # truncate like io.py:467-480: files are consumed in order until max_num_spec is exceeded
     if max_num_spec is not None:
@@ -300,6 +405,8 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     if not no_project and order is None:
         raise RuntimeError("Trying to project but order is not defined for the deltas. "
                            "Check previous warning to solve this issue")  # data.py:628-633
+    if np.any(n_pix == 0):  # the reference's `z.min()` of an empty forest (io.py:497)
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
     offset = np.zeros(n_los + 1, dtype=np.int64)
     np.cumsum(n_pix, out=offset[1:])
     total_pix = int(offset[-1])
@@ -340,6 +447,14 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     for p in parts:
         if done >= n_los:
             break
+        if p.is_image:
+            flush(batch, first)
+            first, batch, batch_bytes = min(done, n_los), [], 0
+            p.unpack(eng, min(p.n, n_los - first), d_offset.data_ptr() + 8 * first, d_ll, d_delta,
+                     d_w)
+            done += p.n
+            first = min(done, n_los)
+            continue
         batch.append(p)
         batch_bytes += p.buf.size
         done += p.n
@@ -349,6 +464,8 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     flush(batch, first)
     for p in parts:
         p.buf = None
+        if p.is_image:
+            p.d_raw = p.d_rows = None
 
     # ---- z, distances, weight evolution, projection (io.py:493-507)
     d_z, d_range = f64(total_pix), f64(2 * n_los)
@@ -395,9 +512,8 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     if d_rc is not None:
         h["r_comov"], h["dist_m"] = d_rc.cpu().numpy(), d_dm.cpu().numpy()
     z_range = d_range.cpu().numpy().reshape(n_los, 2)
-    filled = n_pix > 0
-    z_min = float(z_range[filled, 0].min())
-    z_max = max(0., float(z_range[filled, 1].max()))  # io.py:493: z_max starts at 0
+    z_min = float(z_range[:, 0].min())
+    z_max = max(0., float(z_range[:, 1].max()))  # io.py:493: z_max starts at 0
     healpixs = ang2pix_ring(nside, np.pi / 2. - dec, ra)  # io.py:486-488
     data = {}
     for f in range(n_los):

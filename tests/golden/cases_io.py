@@ -72,6 +72,70 @@ def write_case(root, name):
     return in_dir, attr
 
 
+def _image_hdu(name, arr):
+    arr = np.asarray(arr, dtype=np.float64)
+    cards = [("XTENSION", "IMAGE"), ("BITPIX", -64), ("NAXIS", arr.ndim)]
+    cards += [("NAXIS%d" % (k + 1), n) for k, n in enumerate(arr.shape[::-1])]
+    cards += [("PCOUNT", 0), ("GCOUNT", 1), ("EXTNAME", name)]
+    raw = arr.astype(">f8").tobytes()
+    return minifits._cards_to_bytes(cards) + raw + b"\0" * ((-len(raw)) % minifits.BLOCK)
+
+
+IMAGE_CASES = {
+    "image": dict(seed=31, files=[30, 11], wave="LAMBDA", order=1),
+    # (an ImageHDU file with a LOGLAM grid is not reachable through io.read_delta_file: the
+    # flavour test is `'LAMBDA' in hdul`, io.py:356)
+    "imageblind": dict(seed=32, files=[17], wave="LAMBDA", order=0, blinding="desi_y3"),
+}
+
+
+def write_image_case(root, name):
+    """ImageHDU flavour: LAMBDA/LOGLAM grid, METADATA table, DELTA (or
+    DELTA_BLIND), WEIGHT, CONT images.  Returns (in_dir, delta_attributes path)."""
+    import gzip
+    cfg = IMAGE_CASES[name]
+    rng = np.random.default_rng(cfg["seed"])
+    in_dir = os.path.join(root, name, "Delta")
+    os.makedirs(in_dir, exist_ok=True)
+    n_lambda = 300
+    lam = 3600. + 0.8 * np.arange(n_lambda) * 4
+    los = 2000 * cfg["seed"]
+    for k, n_forest in enumerate(cfg["files"]):
+        z_qso = rng.uniform(2.0, 3.4, n_forest)
+        z_qso[::9] = 11.  # outside the default quasar redshift cut (data.py:602, inclusive)
+        delta = rng.normal(0., 0.3, (n_forest, n_lambda))
+        weight = rng.uniform(0.2, 3., (n_forest, n_lambda))
+        for f in range(n_forest):  # a forest covers part of the grid; zeros / negatives elsewhere
+            a = int(rng.integers(0, n_lambda - 40))
+            b = int(rng.integers(a + 1, n_lambda))
+            weight[f, :a] = 0.
+            weight[f, b:] = -1.
+            weight[f, rng.random(n_lambda) < 0.04] = 0.
+        ids = 39627000000000000 + los + np.arange(n_forest)
+        los += n_forest
+        out = bytearray(minifits._cards_to_bytes([("SIMPLE", True), ("BITPIX", 8), ("NAXIS", 0),
+                                                  ("EXTEND", True)]))
+        out += _image_hdu(cfg["wave"], lam if cfg["wave"] == "LAMBDA" else np.log10(lam))
+        head = [{"name": "BLINDING", "value": cfg.get("blinding", "none")}]
+        out += minifits._table_bytes(
+            [ids, rng.uniform(0.1, 0.2, n_forest), rng.uniform(-0.02, 0.08, n_forest), z_qso,
+             rng.uniform(1., 5., n_forest), ids, np.full(n_forest, 20210101), np.arange(n_forest),
+             np.full(n_forest, 80000 + k)],
+            ["LOS_ID", "RA", "DEC", "Z", "MEANSNR", "TARGETID", "NIGHT", "PETAL", "TILE"], None,
+            head, "METADATA")
+        out += _image_hdu("DELTA_BLIND" if "blinding" in cfg else "DELTA", delta)
+        out += _image_hdu("WEIGHT", weight)
+        out += _image_hdu("CONT", np.ones((n_forest, n_lambda)))
+        with gzip.open(os.path.join(in_dir, "delta-%d.fits.gz" % (200 + k)), "wb") as fh:
+            fh.write(bytes(out))
+    attr = os.path.join(root, name, "delta_attributes.fits.gz")
+    out = minifits.FITS(attr, "rw", clobber=True)
+    out.write([np.arange(2.)], names=["X"], header=[{"name": "FITORDER", "value": cfg["order"]}],
+              extname="FIT_METADATA")
+    out.close()
+    return in_dir, attr
+
+
 def flatten(data):
     """Concatenate a read_deltas dict in a canonical order (healpix, then list order)."""
     out = {k: [] for k in ("healpix", "los_id", "ra", "dec", "z_qso", "plate", "mjd", "fiberid",

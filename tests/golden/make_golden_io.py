@@ -40,7 +40,12 @@ def main():
     fx = os.path.join(HERE, "fixtures")
     run("fixture", os.path.join(fx, "delta-272.fits.gz"),
         os.path.join(fx, "delta_attributes.fits.gz"))
+    run("imagefixture", os.path.join(fx, "image-delta-50.fits.gz"),
+        os.path.join(fx, "delta_attributes.fits.gz"))
     with tempfile.TemporaryDirectory() as tmp:
+        for name in cases_io.IMAGE_CASES:
+            in_dir, attr = cases_io.write_image_case(tmp, name)
+            run(name, in_dir, attr)
         for name in cases_io.CASES:
             in_dir, attr = cases_io.write_case(tmp, name)
             run(name, in_dir, attr)

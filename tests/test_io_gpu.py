@@ -16,7 +16,7 @@ from tests.golden import cases_io
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RUNS = {"fixture": None, "sdss": {}, "desi": {}, "blind": {},
+RUNS = {"fixture": None, "imagefixture": None, "image": {}, "imageblind": {}, "sdss": {}, "desi": {}, "blind": {},
         "sdss_noproject": dict(no_project=True), "sdss_max30": dict(max_num_spec=30),
         "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0)}
 
@@ -32,9 +32,14 @@ class TableCosmo:
 
 
 def inputs(tag, tmp_path):
+    fx = os.path.join(GOLD, "fixtures")
     if tag == "fixture":
-        fx = os.path.join(GOLD, "fixtures")
         return os.path.join(fx, "delta-272.fits.gz"), os.path.join(fx, "delta_attributes.fits.gz")
+    if tag == "imagefixture":
+        return (os.path.join(fx, "image-delta-50.fits.gz"),
+                os.path.join(fx, "delta_attributes.fits.gz"))
+    if tag in cases_io.IMAGE_CASES:
+        return cases_io.write_image_case(str(tmp_path), tag)
     return cases_io.write_case(str(tmp_path), tag.split("_")[0])
 
 
@@ -68,7 +73,8 @@ def test_read_deltas_matches_reference_golden(tag, host_pow, tmp_path, monkeypat
               "z_qso"):
         assert np.array_equal(flat[k], g(k)), k
     # files that store LAMBDA: log10 is taken by the loader (data.py:411-412)
-    stores_lambda = cases_io.CASES.get(tag.split("_")[0], {}).get("wave") == "LAMBDA"
+    stores_lambda = (cases_io.CASES.get(tag.split("_")[0], {}).get("wave") == "LAMBDA" or
+                     tag.startswith("image"))
     if host_pow:
         for k in ("log_lambda", "z", "r_comov", "dist_m"):
             assert np.array_equal(flat[k], g(k)), k

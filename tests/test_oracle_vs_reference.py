@@ -188,7 +188,8 @@ def test_export_covariance_equals_live_reference(name):
     assert np.array_equal(got_b, want_b, equal_nan=True)
 
 
-@pytest.mark.parametrize("which", ["bundled", "sdss", "desi", "blind"])
+@pytest.mark.parametrize("which", ["bundled", "bundled_image", "image", "imageblind", "sdss", "desi",
+                                   "blind"])
 def test_read_deltas_equals_live_reference(which, tmp_path):
     """oracle/io.py against the live io.read_deltas (py/picca/io.py:383-512), bit for bit: the
     reference's bundled Delta_LYA directory (936 forests) and the generated cases."""
@@ -200,6 +201,11 @@ def test_read_deltas_equals_live_reference(which, tmp_path):
     cosmo = constants.Cosmo(Om=0.315, Or=0., Ok=0., wl=-1., blinding="none", verbose=False)
     if which == "bundled":
         in_dir, attr = DATA + "/test_delta/Delta_LYA/", DATA + "/test_delta/delta_attributes.fits.gz"
+    elif which == "bundled_image":
+        in_dir = DATA + "/test_delta/Delta_LYA_image/"
+        attr = DATA + "/test_delta/delta_attributes.fits.gz"
+    elif which in cases_io.IMAGE_CASES:
+        in_dir, attr = cases_io.write_image_case(str(tmp_path), which)
     else:
         in_dir, attr = cases_io.write_case(str(tmp_path), which)
     want = io.read_deltas(in_dir, cosmo=cosmo, nproc=1, delta_attributes=attr, **cases_io.READ_KW)
