@@ -85,8 +85,9 @@ def test_read_deltas_matches_reference_golden(tag, host_pow, tmp_path, monkeypat
             assert ulp_distance(flat[k], g(k)).max() <= (16 if stores_lambda else 4), k
         np.testing.assert_allclose([z_min, z_max], g("summary")[1:], rtol=4e-15)
     close_on_forest_scale(flat["weights"], g("weights"), flat["n_pix"], 1e-12)
-    # a projected delta is a difference of O(0.3) numbers: 1e-13 absolute where it cancels to ~0
-    close_on_forest_scale(flat["delta"], g("delta"), flat["n_pix"], 1e-12, atol=1e-13)
+    # a projected delta is a difference of O(1) numbers (and a 3-pixel linear fit is a cancelling
+    # sum): 1e-12 absolute on the scale of the unprojected deltas
+    close_on_forest_scale(flat["delta"], g("delta"), flat["n_pix"], 1e-12, atol=1e-12)
 
 
 def test_loader_feeds_the_pair_kernels_like_the_reference_loader(tmp_path, monkeypatch):
