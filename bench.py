@@ -307,6 +307,7 @@ def run_cuda(args):
             if world > 1:
                 f1_of_pair = prs.nb_f1.cpu().numpy()
                 keep = pdist.shard_keep_mask(keep, row_of_f1[f1_of_pair], row_owner, rank)
+            dm_counts["pairs"], dm_counts["keep"] = prs, keep
             return pdist.dmat_sharded(eng, dev_cat, dev_cat, dparams, prs, keep, world=world)
 
         dmat_step(dev)
@@ -337,12 +338,22 @@ def run_cuda(args):
             return r_
         dm_e2e_ms, _ = timed(dmat_e2e, args.dmat_steps)
         used = dm_counts["npused"]
+        # pixel pairs the matrix was built from: the binned pairs of this rank's kept forest pairs
+        # (one launch of the xi kernel over that sub-list, outside the timed region)
+        sub = dm_counts["pairs"].subset(dm_counts["keep"])
+        cnt = eng.xi(dev, dev, dparams, sub, torch.zeros(sub.n_f1, dtype=torch.int32,
+                                                         device=eng.device), 1)
+        dm_pix = cnt[:, 5, :].view(torch.int64).sum().reshape(1).clone()
+        if world > 1:
+            dist.all_reduce(dm_pix)
+        dm_pix = int(dm_pix.item())
         dmat_info = {
             "metric": "used forest pairs/sec (distortion matrix, --rej %.2f)" % DMAT_REJECT,
             "value": used / (dm_ms / args.dmat_steps * 1e-3), "unit": "forest pairs/s",
             "steps": args.dmat_steps, "ms_per_step": dm_ms / args.dmat_steps,
             "kernel_ms": float(np.mean(dm_kernel_ms)), "gpu_launches": int(dm_launches),
-            "NPALL": dm_counts["npall"], "NPUSED": used,
+            "NPALL": dm_counts["npall"], "NPUSED": used, "pixel_pairs_per_step": dm_pix,
+            "pixel_pairs_per_s": dm_pix / (dm_ms / args.dmat_steps * 1e-3),
             "dmat_shape": [int(dm_res[1].shape[0]), int(dm_res[1].shape[1])],
             "sum_dmat": float(dm_res[1].sum().item()),
             "sum_weights_dmat": float(dm_res[0].sum().item()),

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 14
+#define PB2_ABI_VERSION 15
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -210,6 +210,21 @@ int32_t pb2_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const p
                        const pb2_pairs *pairs, double *d_weights_dmat, double *d_dmat,
                        double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
                        double *d_weight_eff, void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* ---- metal distortion matrix, forest x forest: replaces the pair loop of
+ * cf.compute_metal_dmat (py/picca/cf.py:890-1232) for one (absorber of forest 1, absorber of
+ * forest 2) pass; the caller runs the swapped pass too when cf.py:1089-1091 asks for it.
+ * d_z*, d_rc*, d_dm*, d_pw*: per pixel of the catalogue, the redshift / r_comov / dist_m the pixel
+ * has for that absorber (cf.py:944-946, :976-978) and (1+z)^(alpha_abs-1); evol_den =
+ * (1+z_ref)^(alpha_abs1+alpha_abs2-2) (cf.py:1033-1037).  pairs->nb_keep = the --rej mask.
+ * Outputs are accumulated into, as pb2_dmat_auto. */
+int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                            const pb2_pairs *pairs, const double *d_z1, const double *d_rc1,
+                            const double *d_dm1, const double *d_pw1, const double *d_z2,
+                            const double *d_rc2, const double *d_dm2, const double *d_pw2,
+                            double evol_den, double *d_weights_dmat, double *d_dmat,
+                            double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                            double *d_weight_eff, void *stream);
 
 /* ---- sub-sample covariance of the per-HEALPix blocks (the consumer of the WE/DA columns the
  * pair kernels produce).

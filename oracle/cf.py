@@ -2,7 +2,8 @@
 functions, same return tuples, computed on the CPU by the C restatement.
 TEST INFRASTRUCTURE ONLY -- the referee for picca_b200.cf, never the product.
 
-Restates: fill_neighs (cf.py:82-135), compute_xi (cf.py:138-247), compute_dmat (cf.py:390-517).
+Restates: fill_neighs (cf.py:82-135), compute_xi (cf.py:138-247), compute_dmat (cf.py:390-517),
+compute_metal_dmat (cf.py:890-1232).
 """
 import sys
 
@@ -125,3 +126,94 @@ def compute_dmat(healpixs):
     dmat = dmat.reshape(nb, nbm)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
+
+
+# rest wavelengths of the transitions the tests use (reference constants.py:243-300); the live
+# reference's table is used by the pinning tests
+absorber_igm = {"LYA": 1215.67, "SiIII(1207)": 1206.500, "SiII(1190)": 1190.4158,
+                "SiII(1193)": 1193.2897, "SiII(1260)": 1260.4221, "CIV(eff)": 1549.06}
+
+
+def _metal_side(delta, name):
+    """cf.py:941-960 (and :973-992, :1092-1125 with the roles swapped): the pixels of one forest
+    that are consistent with the quasar redshift for absorber ``name``."""
+    z_abs = 10**delta.log_lambda / absorber_igm[name] - 1
+    r_comov_abs = cosmo.get_r_comov(z_abs)
+    dist_m_abs = cosmo.get_dist_m(z_abs)
+    w = z_abs < delta.z_qso
+    return (delta.r_comov[w], delta.dist_m[w], delta.weights[w], r_comov_abs[w], dist_m_abs[w],
+            z_abs[w])
+
+
+def _metal_pass(delta1, delta2, name1, name2, ang, same_half_plate, out):
+    """One (absorber of forest 1, absorber of forest 2) pass: cf.py:994-1087, repeated with the
+    absorbers swapped at cf.py:1126-1217."""
+    weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = out
+    r_comov1, dist_m1, weights1, r_comov1_abs, dist_m1_abs, z1_abs = _metal_side(delta1, name1)
+    r_comov2, dist_m2, weights2, r_comov2_abs, dist_m2_abs, z2_abs = _metal_side(delta2, name2)
+    r_par = (r_comov1[:, None] - r_comov2) * np.cos(ang / 2)
+    if not x_correlation:
+        r_par = abs(r_par)
+    r_trans = (dist_m1[:, None] + dist_m2) * np.sin(ang / 2)
+    weights12 = weights1[:, None] * weights2
+    bins_r_par = np.floor((r_par - r_par_min) / (r_par_max - r_par_min) *
+                          num_bins_r_par).astype(int)
+    bins_r_trans = (r_trans / r_trans_max * num_bins_r_trans).astype(int)
+    if remove_same_half_plate_close_pairs and same_half_plate:
+        weights12[abs(r_par) < (r_par_max - r_par_min) / num_bins_r_par] = 0.0
+    bins = bins_r_trans + num_bins_r_trans * bins_r_par
+    w = (bins_r_par < num_bins_r_par) & (bins_r_trans < num_bins_r_trans) & (bins_r_par >= 0)
+    rebin = np.bincount(bins[w], weights=weights12[w])
+    weights_dmat[:len(rebin)] += rebin
+
+    r_par_m = (r_comov1_abs[:, None] - r_comov2_abs) * np.cos(ang / 2)
+    if not x_correlation:
+        r_par_m = abs(r_par_m)
+    r_trans_m = (dist_m1_abs[:, None] + dist_m2_abs) * np.sin(ang / 2)
+    z_weight_evol = ((1 + z1_abs[:, None])**(alpha_abs[name1] - 1) *
+                     (1 + z2_abs)**(alpha_abs[name2] - 1) /
+                     (1 + z_ref)**(alpha_abs[name1] + alpha_abs[name2] - 2))
+    model_bins_r_par = np.floor((r_par_m - r_par_min) / (r_par_max - r_par_min) *
+                                num_model_bins_r_par).astype(int)
+    model_bins_r_trans = (r_trans_m / r_trans_max * num_model_bins_r_trans).astype(int)
+    model_bins = model_bins_r_trans + num_model_bins_r_trans * model_bins_r_par
+    w &= ((model_bins_r_par < num_model_bins_r_par) &
+          (model_bins_r_trans < num_model_bins_r_trans) & (model_bins_r_par >= 0))
+    nbm = num_model_bins_r_par * num_model_bins_r_trans
+    for target, index, values in (
+            (dmat, model_bins[w] + nbm * bins[w], weights12[w] * z_weight_evol[w]),
+            (r_par_eff, model_bins[w], r_par_m[w] * weights12[w] * z_weight_evol[w]),
+            (r_trans_eff, model_bins[w], r_trans_m[w] * weights12[w] * z_weight_evol[w]),
+            (z_eff, model_bins[w],
+             (z1_abs[:, None] + z2_abs)[w] / 2 * weights12[w] * z_weight_evol[w]),
+            (weight_eff, model_bins[w], weights12[w] * z_weight_evol[w])):
+        rebin = np.bincount(index, weights=values)
+        target[:len(rebin)] += rebin
+
+
+def compute_metal_dmat(healpixs, abs_igm1="LYA", abs_igm2="SiIII(1207)"):
+    """cf.py:890-1232."""
+    nb = num_bins_r_par * num_bins_r_trans
+    nbm = num_model_bins_r_par * num_model_bins_r_trans
+    out = (np.zeros(nb), np.zeros(nb * nbm), np.zeros(nbm), np.zeros(nbm), np.zeros(nbm),
+           np.zeros(nbm))
+    num_pairs = 0
+    num_pairs_used = 0
+    for healpix in healpixs:
+        for delta1 in data[healpix]:
+            _host.progress(_THIS)
+            w = np.random.rand(len(delta1.neighbours)) > reject  # cf.py:943
+            num_pairs += len(delta1.neighbours)
+            num_pairs_used += w.sum()
+            for delta2 in [d for d, keep in zip(delta1.neighbours, w) if keep]:
+                shp = _host.same_half_plate(delta1, delta2) \
+                    if remove_same_half_plate_close_pairs else False
+                ang = _host.angle_between_one(delta1, delta2)
+                _metal_pass(delta1, delta2, abs_igm1, abs_igm2, ang, shp, out)
+                if ((not x_correlation) and (abs_igm1 != abs_igm2)) or \
+                        (x_correlation and (lambda_abs == lambda_abs2)):  # cf.py:1089-1091
+                    _metal_pass(delta1, delta2, abs_igm2, abs_igm1, ang, shp, out)
+            setattr(delta1, "neighbours", None)
+    weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = out
+    return (weights_dmat, dmat.reshape(nb, nbm), r_par_eff, r_trans_eff, z_eff, weight_eff,
+            num_pairs, num_pairs_used)

@@ -7,6 +7,7 @@ Same module globals (reference py/picca/cf.py:28-79), same functions, same retur
     compute_dmat(healpixs) -> 8-tuple             cf.py:390-517
     compute_xi_forest_pairs_fast(...)             cf.py:250-387  (in-place accumulate)
     compute_dmat_forest_pairs_fast(...)           cf.py:520-887  (in-place accumulate)
+    compute_metal_dmat(healpixs, abs_igm1, abs_igm2) -> 8-tuple   cf.py:890-1232
 
 so that picca_cf.py / picca_dmat.py run unchanged once this module is importable as ``picca.cf``
 (see ``picca_b200.overlay`` and INTEGRATION.md).  All arithmetic runs in the CUDA kernels of
@@ -81,6 +82,13 @@ get_variance_1d = {}
 xi_1d = {}
 max_diagram = None
 xi_wick = {}
+
+# rest wavelengths (Angstrom) of the transitions compute_metal_dmat is usually run with; the
+# reference's full table (``picca.constants.ABSORBER_IGM``) is used when it is importable, and
+# entries can be added here (same names)
+absorber_igm = {"LYA": 1215.67, "LYB": 1025.72, "SiIII(1207)": 1206.500,
+                "SiII(1190)": 1190.4158, "SiII(1193)": 1193.2897, "SiII(1260)": 1260.4221,
+                "CIV(eff)": 1549.06}
 
 _THIS = sys.modules[__name__]
 _STORE = _corr.NeighbourStore()
@@ -290,3 +298,81 @@ def compute_dmat(healpixs):
     _STORE.drop(healpixs)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
+
+
+def _absorber_wavelength(name):
+    if name in absorber_igm:
+        return absorber_igm[name]
+    try:
+        from picca import constants  # the reference's table, when installed / overlaid
+        return constants.ABSORBER_IGM[name]
+    except ImportError:
+        raise KeyError(name)
+
+
+def _metal_arrays(eng, host, name):
+    """Per pixel of a packed catalogue, for absorber ``name``: the redshift the pixel would have
+    (cf.py:944), its distances on the fiducial cosmology (cf.py:945-946) and the evolution factor
+    (1+z)**(alpha_abs-1) (cf.py:1033-1035), evaluated on the host with NumPy / the caller's
+    cosmology exactly as the reference does, then placed in HBM."""
+    z_abs = 10**host.arrays["log_lambda"] / _absorber_wavelength(name) - 1
+    arrays = (z_abs, np.asarray(cosmo.get_r_comov(z_abs), dtype=np.float64),
+              np.asarray(cosmo.get_dist_m(z_abs), dtype=np.float64),
+              (1 + z_abs)**(alpha_abs[name] - 1))
+    return tuple(eng.torch.from_numpy(np.ascontiguousarray(a)).to(eng.device) for a in arrays)
+
+
+def compute_metal_dmat(healpixs, abs_igm1="LYA", abs_igm2="SiIII(1207)"):
+    """Metal distortion matrix of the forests of ``healpixs`` (cf.py:890-1232): data bins from
+    the Lyman-alpha distances, model bins from the distances of the (abs_igm1, abs_igm2)
+    absorptions.  Same --rej draw, same 8-tuple of un-normalised sums as the reference."""
+    import ctypes
+    from . import _lib
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    _check_half_plate(host1, host2)
+    params = params_from_module(_THIS)
+    pairs = _pairs_for(healpixs)
+    f1_index = pairs.f1_index.cpu().numpy()
+    offset = pairs.host_offset()
+    keep = np.random.rand(int(offset[-1])) > reject  # cf.py:944, one draw per forest in order
+    num_pairs = int(offset[-1])
+    num_pairs_used = int(keep.sum())
+    pairs.nb_keep = eng.torch.from_numpy(keep.astype(np.uint8)).to(eng.device)
+
+    torch = eng.torch
+    nb = params.num_bins_r_par * params.num_bins_r_trans
+    nbm = params.num_model_bins_r_par * params.num_model_bins_r_trans
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=eng.device)
+    weights_dmat, dmat = zeros(nb), zeros(nb, nbm)
+    r_par_eff, r_trans_eff, z_eff, weight_eff = zeros(nbm), zeros(nbm), zeros(nbm), zeros(nbm)
+    cache = {}
+
+    def arrays(host, name):
+        key = (id(host), name)
+        if key not in cache:
+            cache[key] = _metal_arrays(eng, host, name)
+        return cache[key]
+
+    passes = [(abs_igm1, abs_igm2)]
+    if ((not x_correlation) and (abs_igm1 != abs_igm2)) or \
+            (x_correlation and (lambda_abs == lambda_abs2)):  # cf.py:1089-1091
+        passes.append((abs_igm2, abs_igm1))
+    ps = pairs.struct()
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    for name1, name2 in passes:
+        m1, m2 = arrays(host1, name1), arrays(host2, name2)
+        den = (1 + z_ref)**(alpha_abs[abs_igm1] + alpha_abs[abs_igm2] - 2)  # cf.py:1036, :1168
+        _lib.check(eng.lib.pb2_metal_dmat_auto(
+            ctypes.byref(dev1.struct), ctypes.byref(dev2.struct), ctypes.byref(params),
+            ctypes.byref(ps), ptr(m1[0]), ptr(m1[1]), ptr(m1[2]), ptr(m1[3]), ptr(m2[0]),
+            ptr(m2[1]), ptr(m2[2]), ptr(m2[3]), ctypes.c_double(den), ptr(weights_dmat),
+            ptr(dmat), ptr(r_par_eff), ptr(r_trans_eff), ptr(z_eff), ptr(weight_eff),
+            eng.stream_ptr()), "pb2_metal_dmat_auto")
+    res = tuple(t.cpu().numpy() for t in (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff,
+                                          weight_eff))
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for f1 in f1_index:
+        setattr(host1.objs[f1], "neighbours", None)  # cf.py:1219
+    _STORE.drop(healpixs)
+    return res + (num_pairs, num_pairs_used)

@@ -1,0 +1,154 @@
+// Metal distortion matrix, forest x forest: replaces the pair loop of
+// cf.compute_metal_dmat (reference py/picca/cf.py:890-1232).
+//
+// For every kept forest pair and every pixel pair whose pixels are consistent with the quasar
+// redshift (z_abs < z_qso, cf.py:953-960, :985-992) the reference computes a DATA bin from the
+// Lyman-alpha distances (cf.py:995-1013) and a MODEL bin from the distances the pixels would have
+// if the absorption came from the metal transitions (cf.py:1021-1055), then scatters
+// weights12 * z_weight_evol into dmat[data bin][model bin] and four effective-coordinate sums
+// into the model bin -- NumPy bincounts per forest pair.  Here: one warp per kept forest pair
+// (claimed from a device-wide counter), lane = column, rows in turn; the column window of a row
+// comes from binary searches on the sorted distances (a superset of the pairs whose data bin is
+// valid: outside it nothing is added anywhere); every bin is evaluated with the reference's
+// IEEE operations in its order (floor for r_par bins, truncation for r_trans bins), so the bins
+// are bit-exact; the sums are native red.global.add.f64 in any order (1e-9 tolerance).
+// HBM/L2-atomic bound: six reductions per contributing pixel pair.
+#include "pb2_common.cuh"
+
+struct MetalArgs {
+    const double *z1, *rc1, *dm1, *pw1;  // per pixel of catalogue 1: absorber of forest 1
+    const double *z2, *rc2, *dm2, *pw2;  // per pixel of catalogue 2: absorber of forest 2
+    double evol_den;                     // (1 + z_ref)^(alpha_abs1 + alpha_abs2 - 2)
+};
+
+__device__ __forceinline__ int mt_lower(const double *__restrict__ a, int n, double v)
+{
+    int lo = 0, hi = n;  // first index with a[idx] >= v
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+pb2_metal_dmat_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, MetalArgs A,
+                      double *__restrict__ weights_dmat, double *__restrict__ dmat,
+                      double *__restrict__ r_par_eff, double *__restrict__ r_trans_eff,
+                      double *__restrict__ z_eff, double *__restrict__ weight_eff,
+                      unsigned long long *__restrict__ work_ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const int np_i = P.num_bins_r_par, nt_i = P.num_bins_r_trans;
+    const int npm = P.num_model_bins_r_par, ntm = P.num_model_bins_r_trans;
+    const long long nbm = (long long)npm * ntm;
+    const double span = sub_rn(P.r_par_max, P.r_par_min);
+    const double close_cut = div_rn(span, (double)np_i);
+    const bool windows = c1.sorted && c2.sorted;
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(work_ctr, 1ull);
+        const long long e = (long long)__shfl_sync(0xffffffffu, u, 0);
+        if (e >= pr.n_pairs) break;
+        if (pr.nb_keep && !pr.nb_keep[e]) continue;
+        const int f1 = pr.f1_index[pr.nb_f1[e]];
+        const int f2 = pr.nb_f2[e];
+        const long long a1 = c1.offset[f1], a2 = c2.offset[f2];
+        const int n1 = (int)(c1.offset[f1 + 1] - a1), n2 = (int)(c2.offset[f2 + 1] - a2);
+        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        const double zq1 = c1.z_qso[f1], zq2 = c2.z_qso[f2];
+        const bool same_hp = P.remove_same_half_plate_close_pairs &&
+                             pb2_same_half_plate(c1, c2, f1, f2);
+        const double *__restrict__ rc2 = c2.r_comov + a2;
+        // conservative column window of a row: |r_comov1 - r_comov2| * cos < reach
+        const double reach = (fmax(fabs(P.r_par_max), fabs(P.r_par_min)) / ch) * (1. + 1e-9) + 1e-9;
+        for (int i = 0; i < n1; ++i) {
+            const double z1 = A.z1[a1 + i];
+            if (!(z1 < zq1)) continue;  // w = z1_abs1 < delta1.z_qso (cf.py:953)
+            const double r1 = c1.r_comov[a1 + i], d1 = c1.dist_m[a1 + i], w1 = c1.weights[a1 + i];
+            const double r1m = A.rc1[a1 + i], d1m = A.dm1[a1 + i], p1 = A.pw1[a1 + i];
+            int j0 = 0, j1 = n2;
+            if (windows) {
+                j0 = mt_lower(rc2, n2, r1 - reach);
+                j1 = mt_lower(rc2, n2, r1 + reach);
+            }
+            for (int j = j0 + lane; j < j1; j += 32) {
+                const double z2 = A.z2[a2 + j];
+                if (!(z2 < zq2)) continue;  // cf.py:985
+                double r_par = mul_rn(sub_rn(r1, rc2[j]), ch);  // cf.py:995-999
+                if (!P.x_correlation) r_par = fabs(r_par);
+                const double r_trans = mul_rn(add_rn(d1, c2.dist_m[a2 + j]), sh);
+                double w12 = mul_rn(w1, c2.weights[a2 + j]);
+                const double bp = floor(mul_rn(div_rn(sub_rn(r_par, P.r_par_min), span), (double)np_i));
+                const double btf = mul_rn(div_rn(r_trans, P.r_trans_max), (double)nt_i);
+                if (!(bp >= 0. && bp < (double)np_i && btf < (double)nt_i)) continue;  // cf.py:1016-1020
+                const int bin = (int)btf + nt_i * (int)bp;  // .astype(int) truncates (cf.py:1006)
+                if (same_hp && fabs(r_par) < close_cut) w12 = 0.;  // cf.py:1010-1013
+                if (w12 != 0.) atomicAdd(weights_dmat + bin, w12);  // cf.py:1021-1022
+                double r_par_m = mul_rn(sub_rn(r1m, A.rc2[a2 + j]), ch);  // cf.py:1024-1032
+                if (!P.x_correlation) r_par_m = fabs(r_par_m);
+                const double r_trans_m = mul_rn(add_rn(d1m, A.dm2[a2 + j]), sh);
+                const double mbp = floor(mul_rn(div_rn(sub_rn(r_par_m, P.r_par_min), span), (double)npm));
+                const double mbtf = mul_rn(div_rn(r_trans_m, P.r_trans_max), (double)ntm);
+                if (!(mbp >= 0. && mbp < (double)npm && mbtf < (double)ntm)) continue;  // cf.py:1051-1055
+                if (w12 == 0.) continue;
+                const int mbin = (int)mbtf + ntm * (int)mbp;
+                // z_weight_evol (cf.py:1033-1037): (a * b) / c
+                const double zwe = div_rn(mul_rn(p1, A.pw2[a2 + j]), A.evol_den);
+                const double wz = mul_rn(w12, zwe);
+                atomicAdd(dmat + (long long)bin * nbm + mbin, wz);                    // cf.py:1056-1063
+                atomicAdd(r_par_eff + mbin, mul_rn(mul_rn(r_par_m, w12), zwe));       // cf.py:1064-1068
+                atomicAdd(r_trans_eff + mbin, mul_rn(mul_rn(r_trans_m, w12), zwe));   // cf.py:1069-1073
+                atomicAdd(z_eff + mbin,
+                          mul_rn(mul_rn(div_rn(add_rn(z1, z2), 2.), w12), zwe));      // cf.py:1074-1083
+                atomicAdd(weight_eff + mbin, wz);                                     // cf.py:1084-1087
+            }
+        }
+    }
+}
+
+extern "C" {
+
+int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                            const pb2_pairs *pairs, const double *d_z1, const double *d_rc1,
+                            const double *d_dm1, const double *d_pw1, const double *d_z2,
+                            const double *d_rc2, const double *d_dm2, const double *d_pw2,
+                            double evol_den, double *d_weights_dmat, double *d_dmat,
+                            double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
+                            double *d_weight_eff, void *stream)
+{
+    if (!cat1 || !cat2 || !par || !pairs || !d_z1 || !d_rc1 || !d_dm1 || !d_pw1 || !d_z2 || !d_rc2 ||
+        !d_dm2 || !d_pw2 || !d_weights_dmat || !d_dmat || !d_r_par_eff || !d_r_trans_eff ||
+        !d_z_eff || !d_weight_eff) {
+        pb2_set_error("pb2_metal_dmat_auto: null pointer argument");
+        return PB2_EINVAL;
+    }
+    if (par->rmu_binning || par->ang_correlation) {
+        pb2_set_error("pb2_metal_dmat_auto: the reference has no rmu / angular metal matrix");
+        return PB2_ECONFIG;
+    }
+    if (pairs->n_pairs <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    static unsigned long long *d_ctr[64] = {nullptr};
+    int dev = 0, sms = 0;
+    PB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    PB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!d_ctr[dev]) PB2_CUDA(cudaMalloc((void **)&d_ctr[dev], sizeof(unsigned long long)));
+    PB2_CUDA(cudaMemsetAsync(d_ctr[dev], 0, sizeof(unsigned long long), s));
+    MetalArgs A;
+    A.z1 = d_z1, A.rc1 = d_rc1, A.dm1 = d_dm1, A.pw1 = d_pw1;
+    A.z2 = d_z2, A.rc2 = d_rc2, A.dm2 = d_dm2, A.pw2 = d_pw2;
+    A.evol_den = evol_den;
+    pb2_timing_begin(s);
+    pb2_metal_dmat_kernel<<<sms * 8, 256, 0, s>>>(*cat1, *cat2, *par, *pairs, A, d_weights_dmat,
+                                                  d_dmat, d_r_par_eff, d_r_trans_eff, d_z_eff,
+                                                  d_weight_eff, d_ctr[dev]);
+    pb2_count_launch(1);
+    int32_t rc = pb2_check_launch("pb2_metal_dmat_kernel");
+    pb2_timing_end(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -62,6 +62,22 @@ class PairList:
         s.nb_keep = self.nb_keep.data_ptr() if self.nb_keep is not None else None
         return s
 
+    def subset(self, keep):
+        """The sub-list of the forest pairs flagged in ``keep`` (bool array / tensor over the
+        pairs), same lines of sight: what ``np.array(neighbours)[w]`` selects in cf.py:444-447."""
+        import torch
+        dev = self.nb_f2.device
+        keep = torch.as_tensor(np.asarray(keep, dtype=bool) if not torch.is_tensor(keep) else keep,
+                               device=dev).to(torch.bool)
+        counts = torch.zeros(self.n_f1, dtype=torch.int64, device=dev)
+        counts.index_add_(0, self.nb_f1[keep].to(torch.int64),
+                          torch.ones(int(keep.sum().item()), dtype=torch.int64, device=dev))
+        offset = torch.zeros(self.n_f1 + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, dim=0, out=offset[1:])
+        return PairList(self.engine, self.f1_index, offset, self.nb_f1[keep].contiguous(),
+                        self.nb_f2[keep].contiguous(), self.nb_ang[keep].contiguous(),
+                        self.nb_cos[keep].contiguous(), self.nb_sin[keep].contiguous())
+
     def host_offset(self):
         if self._host_offset is None:
             self._host_offset = self.nb_offset.cpu().numpy()

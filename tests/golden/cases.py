@@ -28,6 +28,19 @@ DMAT_CASES = {
                   num_model_bins_r_par=30, second=True),
 }
 
+ALPHA_ABS = {"LYA": 2.9, "SiIII(1207)": 1., "SiII(1190)": 1., "CIV(eff)": 1.}
+# (abs_igm1, abs_igm2) + module configuration of cf.compute_metal_dmat (cf.py:890-1232)
+METAL_CASES = {
+    "lya_si3": dict(R60, reject=0.9, pair=("LYA", "SiIII(1207)")),          # both passes
+    "si2_si2": dict(R60, reject=0.9, pair=("SiII(1190)", "SiII(1190)")),    # z_abs < z_qso filter
+    "si3_si2_coef2": dict(R60, reject=0.9, pair=("SiIII(1207)", "SiII(1190)"),
+                          num_model_bins_r_par=30, num_model_bins_r_trans=30),
+    "civ_far": dict(R60, reject=0.9, pair=("LYA", "CIV(eff)")),  # model bins all out of range
+    "cross": dict(R60, reject=0.9, pair=("LYA", "SiII(1190)"), x_correlation=True, r_par_min=-60.,
+                  num_bins_r_par=30, num_model_bins_r_par=30, second=True,
+                  remove_same_half_plate_close_pairs=True, lambda_abs="LYA", lambda_abs2="LYA"),
+}
+
 XCF_BASE = dict(r_par_max=60., r_par_min=-60., r_trans_max=60., num_bins_r_par=30,
                 num_bins_r_trans=15, num_model_bins_r_par=30, num_model_bins_r_trans=15,
                 alpha_obj=1.44)

@@ -104,6 +104,33 @@ def run_dmat(out):
         print("dmat", name, "pairs", res[6], "used", res[7])
 
 
+def run_metal(out):
+    for name, cfg in cases.METAL_CASES.items():
+        cf, _, _, _, _ = load.reference_modules()
+        cf.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        second = cfg.pop("second", False)
+        pair = cfg.pop("pair")
+        data, num, z_min, cosmo = cases.forests()
+        rdata = load.to_reference_deltas(data)
+        over = dict(cfg, alpha_abs=dict(cases.ALPHA_ABS), cosmo=cosmo)
+        z_min2 = None
+        if second:
+            data2, num2, z_min2, _ = cases.forests(second=True)
+            over["data2"] = load.to_reference_deltas(data2)
+            over["num_data2"] = num2
+        helpers.configure(cf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+        for k, v in over.items():
+            setattr(cf, k, v)
+        hps = sorted(rdata)
+        cf.fill_neighs(hps)
+        np.random.seed(hps[0])  # picca_metal_dmat.py:48
+        res = cf.compute_metal_dmat(hps, abs_igm1=pair[0], abs_igm2=pair[1])
+        for key, val in pack8(res).items():
+            out["metal_%s_%s" % (name, key)] = np.asarray(val)
+        print("metal", name, "pairs", res[6], "used", res[7], "sum", res[1].sum())
+
+
 def run_xcf(out):
     for name, cfg in cases.XCF_CASES.items():
         _, xcf, _, _, _ = load.reference_modules()
@@ -148,7 +175,12 @@ def run_xdmat(out):
 
 
 def main():
-    for tag, fn in (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat)):
+    todo = (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat),
+            ("metal", run_metal))
+    only = sys.argv[1:]
+    for tag, fn in todo:
+        if only and tag not in only:
+            continue
         out = {"host": np.array([platform.processor() + " numpy " + np.__version__])}
         fn(out)
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)

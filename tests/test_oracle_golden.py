@@ -211,3 +211,31 @@ def test_read_deltas(tag, tmp_path):
             np.testing.assert_allclose(v, want, rtol=1e-12, atol=1e-14, err_msg=k)
         else:
             assert np.array_equal(v, want), k
+
+
+# ---- metal distortion matrix (oracle compute_metal_dmat against the live reference's outputs)
+def setup_metal(mod, cfg):
+    cfg = dict(cfg)
+    second = cfg.pop("second", False)
+    pair = cfg.pop("pair")
+    data, num, z_min, cosmo = cases.forests()
+    over, z_min2 = dict(cfg, alpha_abs=dict(cases.ALPHA_ABS), cosmo=cosmo), None
+    if second:
+        data2, num2, z_min2, _ = cases.forests(second=True)
+        over["data2"], over["num_data2"] = data2, num2
+    helpers.configure(mod, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+    for k, v in over.items():
+        setattr(mod, k, v)
+    return data, pair
+
+
+@pytest.mark.parametrize("name", sorted(cases.METAL_CASES))
+def test_metal_dmat(name):
+    from oracle import cf as ocf
+    gold = load("metal")
+    data, pair = setup_metal(ocf, cases.METAL_CASES[name])
+    hps = sorted(data)
+    ocf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    res = ocf.compute_metal_dmat(hps, abs_igm1=pair[0], abs_igm2=pair[1])
+    check8(res, gold, "metal_%s_" % name, rtol=1e-12)

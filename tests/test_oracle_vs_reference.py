@@ -85,6 +85,39 @@ def test_dmat_bit_exact_on_bundled_fixtures(fixture_data, evol):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("abs1,abs2,cross", [("LYA", "SiIII(1207)", False),
+                                             ("SiIII(1207)", "SiIII(1207)", False),
+                                             ("LYA", "SiII(1190)", True)])
+def test_metal_dmat_bit_exact_on_bundled_fixtures(fixture_data, abs1, abs2, cross):
+    """oracle compute_metal_dmat against the live cf.compute_metal_dmat (cf.py:890-1232) with the
+    flags of test_3_cor.py:351-381 (auto) and :526-560 (cross: --in-dir2, --unfold-cf,
+    --remove-same-half-plate-close-pairs)."""
+    from tests.refharness import load
+    from oracle import cf as ocf
+    cf, _, _, _, utils = load.reference_modules()
+    cf.userprint = lambda *a, **k: None
+    hps = sorted(fixture_data[0])
+    over = dict(alpha_abs={"LYA": 2.9, "SiIII(1207)": 1., "SiII(1190)": 1.},
+                cosmo=fixture_data[3])
+    if cross:
+        over.update(data2=fixture_data[0], num_data2=fixture_data[1], x_correlation=True,
+                    r_par_min=-60., num_bins_r_par=30, num_model_bins_r_par=30,
+                    remove_same_half_plate_close_pairs=True, lambda_abs="LYA", lambda_abs2="LYA")
+    results = []
+    for mod in (cf, ocf):
+        _setup(mod, fixture_data, utils, load, **over)
+        for k, v in over.items():
+            setattr(mod, k, v)
+        mod.fill_neighs(hps)
+        np.random.seed(hps[0])
+        results.append(mod.compute_metal_dmat(hps, abs_igm1=abs1, abs_igm2=abs2))
+    want, got = results
+    assert (want[6], want[7]) == (got[6], got[7]) and want[7] > 50
+    assert want[1].sum() > 0
+    for a, b in zip(want[:6], got[:6]):
+        assert np.array_equal(a, b)
+
+
 def test_xcf_and_xdmat_bit_exact_on_bundled_fixtures(fixture_data):
     from tests.refharness import load
     from oracle import xcf as oxcf
