@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 15
+#define PB2_ABI_VERSION 16
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -225,6 +225,14 @@ int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, co
                             double evol_den, double *d_weights_dmat, double *d_dmat,
                             double *d_r_par_eff, double *d_r_trans_eff, double *d_z_eff,
                             double *d_weight_eff, void *stream);
+
+/* forest x object: replaces the pair loop of xcf.compute_metal_dmat (py/picca/xcf.py:677-835);
+ * d_pw1 = ((1+z_abs)/(1+z_ref))^(alpha_abs-1) per forest pixel (xcf.py:769-771). */
+int32_t pb2_metal_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                             const pb2_pairs *pairs, const double *d_z1, const double *d_rc1,
+                             const double *d_dm1, const double *d_pw1, double *d_weights_dmat,
+                             double *d_dmat, double *d_r_par_eff, double *d_r_trans_eff,
+                             double *d_z_eff, double *d_weight_eff, void *stream);
 
 /* ---- sub-sample covariance of the per-HEALPix blocks (the consumer of the WE/DA columns the
  * pair kernels produce).

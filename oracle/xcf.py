@@ -153,3 +153,68 @@ def compute_dmat(healpixs):
     dmat = dmat.reshape(nb, nbm)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
+
+
+# rest wavelengths of the transitions the tests use (reference constants.py:243-300)
+absorber_igm = {"LYA": 1215.67, "SiIII(1207)": 1206.500, "SiII(1190)": 1190.4158,
+                "SiII(1193)": 1193.2897, "SiII(1260)": 1260.4221, "CIV(eff)": 1549.06}
+
+
+def compute_metal_dmat(healpixs, abs_igm="SiII(1526)"):
+    """xcf.py:677-835."""
+    nb = num_bins_r_par * num_bins_r_trans
+    nbm = num_model_bins_r_par * num_model_bins_r_trans
+    dmat = np.zeros(nb * nbm)
+    weights_dmat = np.zeros(nb)
+    r_par_eff, r_trans_eff, z_eff, weight_eff = (np.zeros(nbm) for _ in range(4))
+    num_pairs = 0
+    num_pairs_used = 0
+    for healpix in healpixs:
+        for delta1 in data[healpix]:
+            _host.progress(_THIS)
+            z1_abs1 = 10**delta1.log_lambda / absorber_igm[abs_igm] - 1        # :729
+            r_comov1_abs1 = cosmo.get_r_comov(z1_abs1)
+            dist_m1_abs1 = cosmo.get_dist_m(z1_abs1)
+            w = z1_abs1 < delta1.z_qso                                         # :735
+            r_comov1, dist_m1, weights1 = delta1.r_comov[w], delta1.dist_m[w], delta1.weights[w]
+            z1_abs1, r_comov1_abs1, dist_m1_abs1 = z1_abs1[w], r_comov1_abs1[w], dist_m1_abs1[w]
+            if r_comov1.size == 0:                                             # :741-742
+                continue
+            w = np.random.rand(len(delta1.neighbours)) > reject               # :744
+            num_pairs += len(delta1.neighbours)
+            num_pairs_used += w.sum()
+            for obj2 in [o for o, keep in zip(delta1.neighbours, w) if keep]:
+                ang = _host.angle_between_one(delta1, obj2)
+                r_par = (r_comov1 - obj2.r_comov) * np.cos(ang / 2)           # :755-757
+                r_trans = (dist_m1 + obj2.dist_m) * np.sin(ang / 2)
+                weights12 = weights1 * obj2.weights
+                w = (r_par > r_par_min) & (r_par < r_par_max) & (r_trans < r_trans_max)
+                bins_r_par = ((r_par - r_par_min) / (r_par_max - r_par_min) *
+                              num_bins_r_par).astype(int)
+                bins_r_trans = (r_trans / r_trans_max * num_bins_r_trans).astype(int)
+                bins = bins_r_trans + num_bins_r_trans * bins_r_par
+                rebin = np.bincount(bins[w], weights=weights12[w])
+                weights_dmat[:len(rebin)] += rebin
+                r_par_abs = (r_comov1_abs1 - obj2.r_comov) * np.cos(ang / 2)  # :767-768
+                r_trans_abs = (dist_m1_abs1 + obj2.dist_m) * np.sin(ang / 2)
+                z_weight_evol = ((1.0 + z1_abs1) / (1.0 + z_ref))**(alpha_abs[abs_igm] - 1.0)
+                model_bins_r_par = ((r_par_abs - r_par_min) / (r_par_max - r_par_min) *
+                                    num_model_bins_r_par).astype(int)
+                model_bins_r_trans = (r_trans_abs / r_trans_max *
+                                      num_model_bins_r_trans).astype(int)
+                model_bins = model_bins_r_trans + num_model_bins_r_trans * model_bins_r_par
+                w &= (r_par_abs > r_par_min) & (r_par_abs < r_par_max) & \
+                    (r_trans_abs < r_trans_max)                                 # :785-789
+                for target, index, values in (
+                        (dmat, model_bins[w] + nbm * bins[w], weights12[w] * z_weight_evol[w]),
+                        (r_par_eff, model_bins[w], r_par_abs[w] * weights12[w] * z_weight_evol[w]),
+                        (r_trans_eff, model_bins[w],
+                         r_trans_abs[w] * weights12[w] * z_weight_evol[w]),
+                        (z_eff, model_bins[w],
+                         (z1_abs1 + obj2.z_qso)[w] / 2 * weights12[w] * z_weight_evol[w]),
+                        (weight_eff, model_bins[w], weights12[w] * z_weight_evol[w])):
+                    rebin = np.bincount(index, weights=values)
+                    target[:len(rebin)] += rebin
+            setattr(delta1, "neighbours", None)
+    return (weights_dmat, dmat.reshape(nb, nbm), r_par_eff, r_trans_eff, z_eff, weight_eff,
+            num_pairs, num_pairs_used)

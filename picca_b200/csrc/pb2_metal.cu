@@ -1,5 +1,6 @@
-// Metal distortion matrix, forest x forest: replaces the pair loop of
-// cf.compute_metal_dmat (reference py/picca/cf.py:890-1232).
+// Metal distortion matrices: replace the pair loops of
+// cf.compute_metal_dmat (reference py/picca/cf.py:890-1232, forest x forest, below) and
+// xcf.compute_metal_dmat (py/picca/xcf.py:677-835, forest x object, further down).
 //
 // For every kept forest pair and every pixel pair whose pixels are consistent with the quasar
 // redshift (z_abs < z_qso, cf.py:953-960, :985-992) the reference computes a DATA bin from the
@@ -108,7 +109,97 @@ pb2_metal_dmat_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr
     }
 }
 
+// ---- forest x object (xcf.compute_metal_dmat, reference py/picca/xcf.py:677-835): one warp per
+// kept (forest, object) pair, lane = forest pixel.  Differences from the auto version, all the
+// reference's: the range tests are on the separations themselves (r_par > min, r_par < max,
+// r_trans < max, xcf.py:759 and :785-789), both bin indices are truncations (xcf.py:760-763,
+// :773-781), the evolution factor is the forest pixel's alone (xcf.py:769-771).
+__global__ void __launch_bounds__(256)
+pb2_metal_dmat_cross_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
+                            const double *__restrict__ mz1, const double *__restrict__ mrc1,
+                            const double *__restrict__ mdm1, const double *__restrict__ mpw1,
+                            double *__restrict__ weights_dmat, double *__restrict__ dmat,
+                            double *__restrict__ r_par_eff, double *__restrict__ r_trans_eff,
+                            double *__restrict__ z_eff, double *__restrict__ weight_eff)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int np_i = P.num_bins_r_par, nt_i = P.num_bins_r_trans;
+    const int npm = P.num_model_bins_r_par, ntm = P.num_model_bins_r_trans;
+    const long long nbm = (long long)npm * ntm;
+    const double span = sub_rn(P.r_par_max, P.r_par_min);
+    for (long long e = warp; e < pr.n_pairs; e += n_warps) {
+        if (pr.nb_keep && !pr.nb_keep[e]) continue;
+        const int f1 = pr.f1_index[pr.nb_f1[e]];
+        const int q = pr.nb_f2[e];
+        const long long a1 = c1.offset[f1];
+        const int n1 = (int)(c1.offset[f1 + 1] - a1);
+        const double ch = pr.nb_cos[e], sh = pr.nb_sin[e];
+        const double zq1 = c1.z_qso[f1];
+        const long long aq = c2.offset[q];
+        const double r2 = c2.r_comov[aq], d2 = c2.dist_m[aq], w2 = c2.weights[aq], z2 = c2.z_qso[q];
+        for (int i = lane; i < n1; i += 32) {
+            const double z1 = mz1[a1 + i];
+            if (!(z1 < zq1)) continue;  // xcf.py:735
+            const double r_par = mul_rn(sub_rn(c1.r_comov[a1 + i], r2), ch);  // xcf.py:755-757
+            const double r_trans = mul_rn(add_rn(c1.dist_m[a1 + i], d2), sh);
+            const double w12 = mul_rn(c1.weights[a1 + i], w2);
+            if (!(r_par > P.r_par_min && r_par < P.r_par_max && r_trans < P.r_trans_max)) continue;
+            const int bp = (int)mul_rn(div_rn(sub_rn(r_par, P.r_par_min), span), (double)np_i);
+            const int bt = (int)mul_rn(div_rn(r_trans, P.r_trans_max), (double)nt_i);
+            if (bp >= np_i || bt >= nt_i) continue;  // rounding onto the upper edge: no such bin
+            const int bin = bt + nt_i * bp;
+            if (w12 != 0.) atomicAdd(weights_dmat + bin, w12);  // xcf.py:764-765
+            const double r_par_m = mul_rn(sub_rn(mrc1[a1 + i], r2), ch);  // xcf.py:767-768
+            const double r_trans_m = mul_rn(add_rn(mdm1[a1 + i], d2), sh);
+            if (!(r_par_m > P.r_par_min && r_par_m < P.r_par_max && r_trans_m < P.r_trans_max))
+                continue;  // xcf.py:785-789
+            const int mbp = (int)mul_rn(div_rn(sub_rn(r_par_m, P.r_par_min), span), (double)npm);
+            const int mbt = (int)mul_rn(div_rn(r_trans_m, P.r_trans_max), (double)ntm);
+            if (mbp >= npm || mbt >= ntm || w12 == 0.) continue;
+            const int mbin = mbt + ntm * mbp;
+            const double zwe = mpw1[a1 + i];
+            const double wz = mul_rn(w12, zwe);
+            atomicAdd(dmat + (long long)bin * nbm + mbin, wz);                               // :791-798
+            atomicAdd(r_par_eff + mbin, mul_rn(mul_rn(r_par_m, w12), zwe));                  // :800-804
+            atomicAdd(r_trans_eff + mbin, mul_rn(mul_rn(r_trans_m, w12), zwe));              // :805-809
+            atomicAdd(z_eff + mbin, mul_rn(mul_rn(div_rn(add_rn(z1, z2), 2.), w12), zwe));   // :810-814
+            atomicAdd(weight_eff + mbin, wz);                                                // :815-818
+        }
+    }
+}
+
 extern "C" {
+
+int32_t pb2_metal_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                             const pb2_pairs *pairs, const double *d_z1, const double *d_rc1,
+                             const double *d_dm1, const double *d_pw1, double *d_weights_dmat,
+                             double *d_dmat, double *d_r_par_eff, double *d_r_trans_eff,
+                             double *d_z_eff, double *d_weight_eff, void *stream)
+{
+    if (!cat1 || !objs || !par || !pairs || !d_z1 || !d_rc1 || !d_dm1 || !d_pw1 || !d_weights_dmat ||
+        !d_dmat || !d_r_par_eff || !d_r_trans_eff || !d_z_eff || !d_weight_eff) {
+        pb2_set_error("pb2_metal_dmat_cross: null pointer argument");
+        return PB2_EINVAL;
+    }
+    if (par->rmu_binning || par->ang_correlation) {
+        pb2_set_error("pb2_metal_dmat_cross: the reference has no rmu / angular metal matrix");
+        return PB2_ECONFIG;
+    }
+    if (pairs->n_pairs <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long blocks = (pairs->n_pairs + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pb2_timing_begin(s);
+    pb2_metal_dmat_cross_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+        *cat1, *objs, *par, *pairs, d_z1, d_rc1, d_dm1, d_pw1, d_weights_dmat, d_dmat, d_r_par_eff,
+        d_r_trans_eff, d_z_eff, d_weight_eff);
+    pb2_count_launch(1);
+    int32_t rc = pb2_check_launch("pb2_metal_dmat_cross_kernel");
+    pb2_timing_end(s);
+    return rc;
+}
 
 int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
                             const pb2_pairs *pairs, const double *d_z1, const double *d_rc1,

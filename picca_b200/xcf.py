@@ -254,3 +254,63 @@ def compute_dmat(healpixs):
     _STORE.drop(healpixs)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
+
+
+def compute_metal_dmat(healpixs, abs_igm="SiII(1526)"):
+    """Metal distortion matrix of the cross-correlation (xcf.py:677-835): data bins from the
+    Lyman-alpha distances of the forest pixels, model bins from the distances they would have if
+    the absorption came from ``abs_igm``.  Forests without a pixel consistent with the quasar
+    redshift are skipped BEFORE the --rej draw (xcf.py:741-742): they consume no random numbers
+    and are not counted.  Returns the reference's 8-tuple of un-normalised sums."""
+    import ctypes
+    from . import _lib
+    from .cf import _absorber_wavelength
+    healpixs = list(healpixs)
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    pairs = _pairs_for(healpixs)
+    f1_index = pairs.f1_index.cpu().numpy()
+    offset = pairs.host_offset()
+    # per pixel: xcf.py:729-731 and :769-771, evaluated on the host like the reference
+    z_abs = 10**host1.arrays["log_lambda"] / _absorber_wavelength(abs_igm) - 1
+    r_comov_abs = np.asarray(cosmo.get_r_comov(z_abs), dtype=np.float64)
+    dist_m_abs = np.asarray(cosmo.get_dist_m(z_abs), dtype=np.float64)
+    evol = ((1.0 + z_abs) / (1.0 + z_ref))**(alpha_abs[abs_igm] - 1.0)
+    # forests with at least one pixel with z_abs < z_qso (xcf.py:735-742)
+    pix_off = host1.arrays["offset"]
+    valid_pix = z_abs < np.repeat(host1.arrays["z_qso"], np.diff(pix_off))
+    n_valid = np.add.reduceat(np.append(valid_pix.astype(np.int64), 0), pix_off[:-1])
+    n_valid = np.where(np.diff(pix_off) > 0, n_valid, 0)
+    drawn = n_valid[f1_index] > 0
+    lengths = np.diff(offset)
+    keep = np.zeros(int(offset[-1]), dtype=bool)
+    draw = np.random.rand(int(lengths[drawn].sum())) > reject  # xcf.py:744, drawn forests only
+    pair_drawn = np.repeat(drawn, lengths)
+    keep[pair_drawn] = draw
+    num_pairs = int(lengths[drawn].sum())
+    num_pairs_used = int(keep.sum())
+    pairs.nb_keep = eng.torch.from_numpy(keep.astype(np.uint8)).to(eng.device)
+
+    torch = eng.torch
+    nb = params.num_bins_r_par * params.num_bins_r_trans
+    nbm = params.num_model_bins_r_par * params.num_model_bins_r_trans
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=eng.device)
+    weights_dmat, dmat = zeros(nb), zeros(nb, nbm)
+    r_par_eff, r_trans_eff, z_eff, weight_eff = zeros(nbm), zeros(nbm), zeros(nbm), zeros(nbm)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(eng.device)
+    m = [up(a) for a in (z_abs, r_comov_abs, dist_m_abs, evol)]
+    ps = pairs.struct()
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(eng.lib.pb2_metal_dmat_cross(
+        ctypes.byref(dev1.struct), ctypes.byref(dev2.struct), ctypes.byref(params),
+        ctypes.byref(ps), ptr(m[0]), ptr(m[1]), ptr(m[2]), ptr(m[3]), ptr(weights_dmat),
+        ptr(dmat), ptr(r_par_eff), ptr(r_trans_eff), ptr(z_eff), ptr(weight_eff),
+        eng.stream_ptr()), "pb2_metal_dmat_cross")
+    res = tuple(t.cpu().numpy() for t in (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff,
+                                          weight_eff))
+    _corr.bump_progress(_THIS, pairs.n_f1, userprint)
+    for k, f1 in enumerate(f1_index):
+        if drawn[k]:
+            setattr(host1.objs[f1], "neighbours", None)  # xcf.py:819 (skipped forests keep theirs)
+    _STORE.drop(healpixs)
+    return res + (num_pairs, num_pairs_used)

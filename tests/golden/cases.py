@@ -28,7 +28,11 @@ DMAT_CASES = {
                   num_model_bins_r_par=30, second=True),
 }
 
-ALPHA_ABS = {"LYA": 2.9, "SiIII(1207)": 1., "SiII(1190)": 1., "CIV(eff)": 1.}
+ALPHA_ABS = {"LYA": 2.9, "SiIII(1207)": 1., "SiII(1190)": 1., "CIV(eff)": 1., "TEST(1045)": 1.7}
+# a made-up transition just redward of the blue end of the synthetic forests: only ~20 % of the
+# forests have a pixel with z_abs < z_qso, the others are skipped before the --rej draw
+# (xcf.py:741-742)
+EXTRA_ABSORBERS = {"TEST(1045)": 1045.05}
 # (abs_igm1, abs_igm2) + module configuration of cf.compute_metal_dmat (cf.py:890-1232)
 METAL_CASES = {
     "lya_si3": dict(R60, reject=0.9, pair=("LYA", "SiIII(1207)")),          # both passes
@@ -49,6 +53,12 @@ XCF_CASES = {
     "zcuts": dict(XCF_BASE, z_min_pairs=2.0, z_max_pairs=2.6),
     "zerr": dict(XCF_BASE, zerr_cut_deg=0.5, zerr_cut_kms=40000.),
     "rmu": dict(XCF_BASE, rmu_binning=True, r_par_min=-1., r_par_max=1.),
+}
+XMETAL_CASES = {
+    "si2": dict(XCF_BASE, reject=0.8, abs_igm="SiII(1190)"),
+    "si3_coef2": dict(XCF_BASE, reject=0.8, abs_igm="SiIII(1207)", num_model_bins_r_par=60,
+                      num_model_bins_r_trans=30),
+    "edge_skip": dict(XCF_BASE, reject=0.5, abs_igm="TEST(1045)"),
 }
 XDMAT_CASES = {
     "default": dict(XCF_BASE, reject=0.8),

@@ -156,6 +156,32 @@ def run_xcf(out):
         print("xcf", name, "pairs", int(np.stack(rows)[:, 5].view(np.int64).sum()))
 
 
+def run_xmetal(out):
+    for name, cfg in cases.XMETAL_CASES.items():
+        _, xcf, _, constants, _ = load.reference_modules()
+        constants.ABSORBER_IGM.update(cases.EXTRA_ABSORBERS)
+        xcf.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        abs_igm = cfg.pop("abs_igm")
+        data, num, z_min, cosmo = cases.forests()
+        objs, z_min2 = cases.quasars(cosmo)
+        rdata, robjs = load.to_reference_deltas(data), load.to_reference_qsos(objs)
+        over = dict(cfg, alpha_abs=dict(cases.ALPHA_ABS), cosmo=cosmo)
+        helpers.configure(xcf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2),
+                          objs=robjs, **over)
+        for k, v in over.items():
+            setattr(xcf, k, v)
+        hps = sorted(rdata)
+        xcf.fill_neighs(hps)
+        np.random.seed(hps[0])
+        res = xcf.compute_metal_dmat(hps, abs_igm=abs_igm)
+        for key, val in pack8(res).items():
+            out["xmetal_%s_%s" % (name, key)] = np.asarray(val)
+        kept = sum(d.neighbours is not None for hp in hps for d in rdata[hp])
+        out["xmetal_%s_skipped" % name] = np.array([kept])
+        print("xmetal", name, "pairs", res[6], "used", res[7], "sum", res[1].sum(), "skipped", kept)
+
+
 def run_xdmat(out):
     for name, cfg in cases.XDMAT_CASES.items():
         _, xcf, _, _, _ = load.reference_modules()
@@ -176,7 +202,7 @@ def run_xdmat(out):
 
 def main():
     todo = (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat),
-            ("metal", run_metal))
+            ("metal", run_metal), ("xmetal", run_xmetal))
     only = sys.argv[1:]
     for tag, fn in todo:
         if only and tag not in only:

@@ -89,3 +89,28 @@ def test_metal_dmat_production_binning_matches_oracle():
     assert np.array_equal(got[1] != 0, want[1] != 0)
     for a, b in zip(got[:6], want[:6]):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12 * np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", sorted(cases.XMETAL_CASES))
+def test_xcf_metal_dmat_matches_reference_golden(name):
+    """xcf.compute_metal_dmat (xcf.py:677-835) incl. the forests skipped before the --rej draw."""
+    from picca_b200 import cf, xcf
+    gold = np.load(os.path.join(GOLD, "golden_xmetal.npz"))
+    cfg = dict(cases.XMETAL_CASES[name])
+    abs_igm = cfg.pop("abs_igm")
+    cf.absorber_igm.update(cases.EXTRA_ABSORBERS)
+    data, num, z_min, cosmo = cases.forests()
+    objs, z_min2 = cases.quasars(cosmo)
+    over = dict(cfg, alpha_abs=dict(cases.ALPHA_ABS), cosmo=cosmo)
+    helpers.configure(xcf, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), objs=objs,
+                      **over)
+    for k, v in over.items():
+        setattr(xcf, k, v)
+    hps = sorted(data)
+    xcf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    res = xcf.compute_metal_dmat(hps, abs_igm=abs_igm)
+    check8(res, gold, "xmetal_%s_" % name)
+    assert np.array_equal(res[1] != 0, gold["xmetal_%s_dmat" % name] != 0)
+    kept = sum(d.neighbours is not None for hp in hps for d in data[hp])
+    assert kept == int(gold["xmetal_%s_skipped" % name][0])  # xcf.py:741-742

@@ -239,3 +239,31 @@ def test_metal_dmat(name):
     np.random.seed(hps[0])
     res = ocf.compute_metal_dmat(hps, abs_igm1=pair[0], abs_igm2=pair[1])
     check8(res, gold, "metal_%s_" % name, rtol=1e-12)
+
+
+def setup_xmetal(mod, cfg, absorbers):
+    cfg = dict(cfg)
+    abs_igm = cfg.pop("abs_igm")
+    absorbers.update(cases.EXTRA_ABSORBERS)
+    data, num, z_min, cosmo = cases.forests()
+    objs, z_min2 = cases.quasars(cosmo)
+    over = dict(cfg, alpha_abs=dict(cases.ALPHA_ABS), cosmo=cosmo)
+    helpers.configure(mod, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), objs=objs,
+                      **over)
+    for k, v in over.items():
+        setattr(mod, k, v)
+    return data, abs_igm
+
+
+@pytest.mark.parametrize("name", sorted(cases.XMETAL_CASES))
+def test_xmetal_dmat(name):
+    from oracle import xcf as oxcf
+    gold = load("xmetal")
+    data, abs_igm = setup_xmetal(oxcf, cases.XMETAL_CASES[name], oxcf.absorber_igm)
+    hps = sorted(data)
+    oxcf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    res = oxcf.compute_metal_dmat(hps, abs_igm=abs_igm)
+    check8(res, gold, "xmetal_%s_" % name, rtol=1e-12)
+    kept = sum(d.neighbours is not None for hp in hps for d in data[hp])
+    assert kept == int(gold["xmetal_%s_skipped" % name][0])  # xcf.py:741-742

@@ -118,6 +118,32 @@ def test_metal_dmat_bit_exact_on_bundled_fixtures(fixture_data, abs1, abs2, cros
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("abs_igm", ["SiIII(1207)", "SiII(1190)"])
+def test_xcf_metal_dmat_bit_exact_on_bundled_fixtures(fixture_data, abs_igm):
+    """oracle xcf.compute_metal_dmat against the live one (xcf.py:677-835)."""
+    from tests.refharness import load
+    from oracle import xcf as oxcf
+    _, xcf, _, _, utils = load.reference_modules()
+    xcf.userprint = lambda *a, **k: None
+    hps = sorted(fixture_data[0])
+    over = dict(r_par_min=-60., num_bins_r_par=30, num_model_bins_r_par=30, alpha_obj=1.,
+                reject=0.9, alpha_abs={"LYA": 2.9, "SiIII(1207)": 1., "SiII(1190)": 1.},
+                cosmo=fixture_data[3])
+    results = []
+    for mod in (xcf, oxcf):
+        _setup(mod, fixture_data, utils, load, cross_obj=True, **over)
+        for k, v in over.items():
+            setattr(mod, k, v)
+        mod.fill_neighs(hps)
+        np.random.seed(hps[0])
+        results.append(mod.compute_metal_dmat(hps, abs_igm=abs_igm))
+    want, got = results
+    assert (want[6], want[7]) == (got[6], got[7]) and want[7] > 50
+    assert want[1].sum() > 0
+    for a, b in zip(want[:6], got[:6]):
+        assert np.array_equal(a, b)
+
+
 def test_xcf_and_xdmat_bit_exact_on_bundled_fixtures(fixture_data):
     from tests.refharness import load
     from oracle import xcf as oxcf
