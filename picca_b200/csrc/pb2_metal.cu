@@ -12,8 +12,9 @@
 // comes from binary searches on the sorted distances (a superset of the pairs whose data bin is
 // valid: outside it nothing is added anywhere); every bin is evaluated with the reference's
 // IEEE operations in its order (floor for r_par bins, truncation for r_trans bins), so the bins
-// are bit-exact; the sums are native red.global.add.f64 in any order (1e-9 tolerance).
-// HBM/L2-atomic bound: six reductions per contributing pixel pair.
+// are bit-exact; the sums are native red.global.add.f64 in any order (1e-9 tolerance), aggregated
+// over runs of neighbouring columns with equal bins by a segmented warp scan.
+// L2-reduction bound: six reductions per run of contributing pixel pairs.
 #include "pb2_common.cuh"
 
 struct MetalArgs {
@@ -31,6 +32,17 @@ __device__ __forceinline__ int mt_lower(const double *__restrict__ a, int n, dou
         else hi = mid;
     }
     return lo;
+}
+
+// inclusive sum over the lanes [start, lane] of the caller's run
+__device__ __forceinline__ double mt_seg_sum(double v, int start, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane - d >= start) v += t;
+    }
+    return v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -74,46 +86,85 @@ pb2_metal_dmat_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr
                 j0 = mt_lower(rc2, n2, r1 - reach);
                 j1 = mt_lower(rc2, n2, r1 + reach);
             }
-            for (int j = j0 + lane; j < j1; j += 32) {
-                const double z2 = A.z2[a2 + j];
-                if (!(z2 < zq2)) continue;  // cf.py:985
-                double r_par = mul_rn(sub_rn(r1, rc2[j]), ch);  // cf.py:995-999
-                if (!P.x_correlation) r_par = fabs(r_par);
-                const double r_trans = mul_rn(add_rn(d1, c2.dist_m[a2 + j]), sh);
-                double w12 = mul_rn(w1, c2.weights[a2 + j]);
-                const double bp = floor(mul_rn(div_rn(sub_rn(r_par, P.r_par_min), span), (double)np_i));
-                const double btf = mul_rn(div_rn(r_trans, P.r_trans_max), (double)nt_i);
-                if (!(bp >= 0. && bp < (double)np_i && btf < (double)nt_i)) continue;  // cf.py:1016-1020
-                const int bin = (int)btf + nt_i * (int)bp;  // .astype(int) truncates (cf.py:1006)
-                if (same_hp && fabs(r_par) < close_cut) w12 = 0.;  // cf.py:1010-1013
-                if (w12 != 0.) atomicAdd(weights_dmat + bin, w12);  // cf.py:1021-1022
-                double r_par_m = mul_rn(sub_rn(r1m, A.rc2[a2 + j]), ch);  // cf.py:1024-1032
-                if (!P.x_correlation) r_par_m = fabs(r_par_m);
-                const double r_trans_m = mul_rn(add_rn(d1m, A.dm2[a2 + j]), sh);
-                const double mbp = floor(mul_rn(div_rn(sub_rn(r_par_m, P.r_par_min), span), (double)npm));
-                const double mbtf = mul_rn(div_rn(r_trans_m, P.r_trans_max), (double)ntm);
-                if (!(mbp >= 0. && mbp < (double)npm && mbtf < (double)ntm)) continue;  // cf.py:1051-1055
-                if (w12 == 0.) continue;
-                const int mbin = (int)mbtf + ntm * (int)mbp;
-                // z_weight_evol (cf.py:1033-1037): (a * b) / c
-                const double zwe = div_rn(mul_rn(p1, A.pw2[a2 + j]), A.evol_den);
-                const double wz = mul_rn(w12, zwe);
-                atomicAdd(dmat + (long long)bin * nbm + mbin, wz);                    // cf.py:1056-1063
-                atomicAdd(r_par_eff + mbin, mul_rn(mul_rn(r_par_m, w12), zwe));       // cf.py:1064-1068
-                atomicAdd(r_trans_eff + mbin, mul_rn(mul_rn(r_trans_m, w12), zwe));   // cf.py:1069-1073
-                atomicAdd(z_eff + mbin,
-                          mul_rn(mul_rn(div_rn(add_rn(z1, z2), 2.), w12), zwe));      // cf.py:1074-1083
-                atomicAdd(weight_eff + mbin, wz);                                     // cf.py:1084-1087
+            // 32 consecutive columns per step, all lanes in step (the shuffles below need the whole
+            // warp).  Neighbouring columns mostly share their bins (r_par moves ~0.5 Mpc/h per
+            // pixel), so the reductions are aggregated over runs of equal keys first: a segmented
+            // warp scan, then ONE red.global.add per run and sum instead of one per pixel pair.
+            for (int jb = j0; jb < j1; jb += 32) {
+                const int j = jb + lane;
+                bool dvalid = false, mvalid = false;
+                int bin = 0, mbin = 0;
+                double w12 = 0., wz = 0., s_rp = 0., s_rt = 0., s_z = 0.;
+                if (j < j1) {
+                    const double z2 = A.z2[a2 + j];
+                    if (z2 < zq2) {  // cf.py:985
+                        double r_par = mul_rn(sub_rn(r1, rc2[j]), ch);  // cf.py:995-999
+                        if (!P.x_correlation) r_par = fabs(r_par);
+                        const double r_trans = mul_rn(add_rn(d1, c2.dist_m[a2 + j]), sh);
+                        w12 = mul_rn(w1, c2.weights[a2 + j]);
+                        const double bp =
+                            floor(mul_rn(div_rn(sub_rn(r_par, P.r_par_min), span), (double)np_i));
+                        const double btf = mul_rn(div_rn(r_trans, P.r_trans_max), (double)nt_i);
+                        if (bp >= 0. && bp < (double)np_i && btf < (double)nt_i) {  // cf.py:1016-1020
+                            bin = (int)btf + nt_i * (int)bp;  // .astype(int) truncates (cf.py:1006)
+                            if (same_hp && fabs(r_par) < close_cut) w12 = 0.;  // cf.py:1010-1013
+                            dvalid = w12 != 0.;  // adding a zero weight changes nothing
+                            double r_par_m = mul_rn(sub_rn(r1m, A.rc2[a2 + j]), ch);  // cf.py:1024-1032
+                            if (!P.x_correlation) r_par_m = fabs(r_par_m);
+                            const double r_trans_m = mul_rn(add_rn(d1m, A.dm2[a2 + j]), sh);
+                            const double mbp = floor(
+                                mul_rn(div_rn(sub_rn(r_par_m, P.r_par_min), span), (double)npm));
+                            const double mbtf = mul_rn(div_rn(r_trans_m, P.r_trans_max), (double)ntm);
+                            if (dvalid && mbp >= 0. && mbp < (double)npm && mbtf < (double)ntm) {
+                                mvalid = true;  // cf.py:1051-1055
+                                mbin = (int)mbtf + ntm * (int)mbp;
+                                // z_weight_evol (cf.py:1033-1037): (a * b) / c
+                                const double zwe = div_rn(mul_rn(p1, A.pw2[a2 + j]), A.evol_den);
+                                wz = mul_rn(w12, zwe);                                   // cf.py:1056-1063
+                                s_rp = mul_rn(mul_rn(r_par_m, w12), zwe);                // cf.py:1064-1068
+                                s_rt = mul_rn(mul_rn(r_trans_m, w12), zwe);              // cf.py:1069-1073
+                                s_z = mul_rn(mul_rn(div_rn(add_rn(z1, z2), 2.), w12), zwe);  // :1074-1083
+                            }
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, dvalid)) continue;
+                // ---- data-bin runs: weights_dmat (cf.py:1021-1022)
+                {
+                    const int key = dvalid ? bin : -1;
+                    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+                    const unsigned heads =
+                        __ballot_sync(0xffffffffu, lane == 0 || prev != key || key < 0);
+                    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                    const double tot = mt_seg_sum(dvalid ? w12 : 0., start, lane);
+                    if (dvalid && (lane == 31 || ((heads >> (lane + 1)) & 1u)))
+                        atomicAdd(weights_dmat + bin, tot);
+                }
+                if (!__any_sync(0xffffffffu, mvalid)) continue;
+                // ---- (data bin, model bin) runs: dmat and the four model-bin sums
+                {
+                    const long long key = mvalid ? (long long)bin * nbm + mbin : -1;
+                    const long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+                    const unsigned heads =
+                        __ballot_sync(0xffffffffu, lane == 0 || prev != key || key < 0);
+                    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                    const double t_wz = mt_seg_sum(wz, start, lane);
+                    const double t_rp = mt_seg_sum(s_rp, start, lane);
+                    const double t_rt = mt_seg_sum(s_rt, start, lane);
+                    const double t_z = mt_seg_sum(s_z, start, lane);
+                    if (mvalid && (lane == 31 || ((heads >> (lane + 1)) & 1u))) {
+                        atomicAdd(dmat + key, t_wz);
+                        atomicAdd(r_par_eff + mbin, t_rp);
+                        atomicAdd(r_trans_eff + mbin, t_rt);
+                        atomicAdd(z_eff + mbin, t_z);
+                        atomicAdd(weight_eff + mbin, t_wz);  // cf.py:1084-1087
+                    }
+                }
             }
         }
     }
 }
 
-// ---- forest x object (xcf.compute_metal_dmat, reference py/picca/xcf.py:677-835): one warp per
-// kept (forest, object) pair, lane = forest pixel.  Differences from the auto version, all the
-// reference's: the range tests are on the separations themselves (r_par > min, r_par < max,
-// r_trans < max, xcf.py:759 and :785-789), both bin indices are truncations (xcf.py:760-763,
-// :773-781), the evolution factor is the forest pixel's alone (xcf.py:769-771).
 __global__ void __launch_bounds__(256)
 pb2_metal_dmat_cross_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                             const double *__restrict__ mz1, const double *__restrict__ mrc1,

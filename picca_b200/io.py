@@ -370,6 +370,9 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     order = find_order(in_dir, delta_attributes)
 
     eng = get_engine()  # raises without a device: no CPU fallback
+    import time
+    marks = [("start", time.perf_counter())]
+    mark = lambda name: marks.append((name, time.perf_counter()))
     torch = eng.torch
     workers = nproc if nproc else (os.cpu_count() or 1)
     with ThreadPoolExecutor(max_workers=max(1, min(workers, 32))) as pool:
@@ -378,6 +381,7 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         if p.is_image:
             p.count_pixels(eng)
 
+    mark("read + gunzip + header scan (host, %d threads)" % max(1, min(workers, 32)))
     # truncate like io.py:467-480: files are consumed in order until max_num_spec is exceeded
     if max_num_spec is not None:
         kept, total = [], 0
@@ -467,6 +471,7 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         if p.is_image:
             p.d_raw = p.d_rows = None
 
+    mark("pinned staging + H2D + unpack kernels")
     # ---- z, distances, weight evolution, projection (io.py:493-507)
     d_z, d_range = f64(total_pix), f64(2 * n_los)
     d_status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -506,6 +511,8 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         raise ValueError("A value in x_new is outside the interpolation range of the cosmology "
                          "table (scipy interp1d bounds error in the reference)")
 
+    eng.torch.cuda.synchronize()
+    mark("prepare kernel")
     # ---- back to the reference's data model: dict[healpix] -> list[Delta] of array views
     h = {name: t.cpu().numpy() for name, t in (("log_lambda", d_ll), ("delta", d_delta),
                                                ("weights", d_w), ("z", d_z))}
@@ -525,5 +532,9 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         if d_rc is not None:
             d.r_comov, d.dist_m = h["r_comov"][a:b], h["dist_m"][a:b]
         data.setdefault(int(healpixs[f]), []).append(d)
+    mark("D2H + Delta objects")
+    if os.environ.get("PICCA_B200_IO_TIMING", "0") == "1":
+        for (_, t0), (name, t1) in zip(marks[:-1], marks[1:]):
+            userprint("picca_b200.io: %-52s %.3f s" % (name, t1 - t0))
     userprint("\n")
     return data, n_los, z_min, z_max

@@ -52,6 +52,9 @@ eng = get_engine()
 kw = dict(nside=32, lambda_abs=synth.LYA, alpha=2.9, z_ref=2.25, cosmo=cosmo,
           delta_attributes=attr)
 for rep in range(3):
+    os.environ["PICCA_B200_IO_TIMING"] = "1" if rep == 2 else "0"
+    if rep == 2:
+        io.userprint = lambda *a, **k: print(*a, **k) if a and str(a[0]).startswith("picca_b200.io") else None
     launches = eng.launch_count()
     t0 = time.perf_counter()
     data, num, z_min, z_max = io.read_deltas(in_dir, **kw)
