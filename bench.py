@@ -33,6 +33,10 @@ WORKLOADS = {
     "c2_20k": dict(n_forest=20000, seed=20260102, nside=32, ra_deg=(0., 53.6),
                    dec_deg=(0., 18.)),
     "c2_5k": dict(n_forest=5000, seed=20260102, nside=32, ra_deg=(0., 26.8), dec_deg=(0., 9.)),
+    # one eighth of BASELINE.json configs[4] / SURVEY.md 8d C5 (1M forests over ~14 000 deg^2,
+    # ~71 per deg^2): the share one GPU of an 8-GPU box holds, at the full surface density
+    "c5_eighth": dict(n_forest=125000, seed=20260105, nside=32, ra_deg=(0., 60.),
+                      dec_deg=(0., 30.8)),
 }
 CF_CFG = dict(num_bins_r_par=50, num_bins_r_trans=50, r_par_max=200., r_par_min=0.,
               r_trans_max=200., nside=32)
@@ -279,9 +283,11 @@ def run_cuda(args):
         if o is not None:
             result_host[:o.shape[0]].copy_(o, non_blocking=True)
         return o
-    for _ in range(1):
+    if args.no_e2e:
+        e2e_ms = total_ms
+    else:
         step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
+        e2e_ms, _ = timed(step_e2e, args.steps)
 
     # ---- distortion-matrix leg (BASELINE config 4: --rej 0.99 on the same sample, one reference
     # chunk seeded with the first HEALPix pixel as picca_dmat.py --nproc 1 does, :36,:471-485)
@@ -447,6 +453,8 @@ def main():
     ap.add_argument("--cpu-healpix", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dmat", action="store_true", help="skip the distortion-matrix leg")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="probe runs only: skip the host-buffer arm (e2e repeats `value`)")
     ap.add_argument("--dmat-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
