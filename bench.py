@@ -318,6 +318,7 @@ def run_cuda(args):
 
         dmat_step(dev)
         eng.lib.pb2_set_timing(1)
+        eng.collect_dmat_stats = True
         dm_kernel_ms = []
 
         def dmat_resident():
@@ -328,6 +329,8 @@ def run_cuda(args):
         dm_ms, dm_res = timed(dmat_resident, args.dmat_steps)
         dm_launches = eng.launch_count() - dl0
         eng.lib.pb2_set_timing(0)
+        eng.collect_dmat_stats = False
+        dm_stats = dict(eng.last_dmat_stats or {})
         dm_nbytes = int(sum(t.numel() * 8 for t in dm_res))
         dm_host = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in dm_res]
 
@@ -366,6 +369,17 @@ def run_cuda(args):
             "e2e": {"value": used / (dm_e2e_ms / args.dmat_steps * 1e-3),
                     "unit": "forest pairs/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": dm_nbytes},
+            # the FP64 work of the reference algorithm AS WRITTEN (N_sel (15 U + 4) +
+            # 40 N_inrange per used forest pair, cf.py:623-887) over this rank's kernel time; the
+            # kernels contract per data bin instead and execute far fewer
+            # operations, so this can exceed the machine's peak: it measures the algebra, the
+            # used-forest-pair rate above measures the kernel
+            "as_written": {"ops_per_step_this_rank": dm_stats.get("as_written_ops"),
+                           "ops_per_s": (dm_stats.get("as_written_ops", 0.) /
+                                         (float(np.mean(dm_kernel_ms)) * 1e-3)),
+                           "unique_model_bins_per_used_pair":
+                               dm_stats.get("sum_unique_model_bins", 0.) / max(1, used // world),
+                           "fp64_peak_ops_per_s": eng.fp64_peak(8192)[0]},
             "parallelism": "kept forest pairs sharded by owning HEALPix row x%d, "
                            "NCCL all-reduce(SUM) of dmat + 5 vectors" % world if world > 1 else
                            "one GPU, one reference chunk",

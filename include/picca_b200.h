@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 16
+#define PB2_ABI_VERSION 17
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -309,6 +309,12 @@ int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t 
                           const double *d_z_in, double *d_log_lambda, double *d_delta,
                           double *d_weights, double *d_z, double *d_r_comov, double *d_dist_m,
                           double *d_z_range, int32_t *d_status, void *stream);
+
+/* measurement: statistics of the last pb2_dmat_auto call that used d_scratch -- out3[0] the FP64
+ * ops the reference algorithm would execute as written (N_sel (15 U + 4) +
+ * 40 N_inrange per used forest pair, cf.py:623-887), out3[1] the sum of U, out3[2] the in-range
+ * pixel pairs.  Synchronises the stream. */
+int32_t pb2_dmat_stats(const void *d_scratch, double *out3, void *stream);
 
 /* ---- measurement helpers
  * pb2_fp64_peak: dependent-free DFMA microbenchmark; returns achieved FP64 op/s (1 DFMA = 1 op,

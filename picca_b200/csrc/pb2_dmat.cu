@@ -218,6 +218,9 @@ __device__ __forceinline__ void col_window(const pb2_params &P, bool windows, do
 struct DmatWork {
     long long *kept;            // kept pair indices
     unsigned long long *count;  // [0] number of kept pairs, [1] claim counter
+    double *stats;              // [0] as-written FP64 ops of the reference algorithm (SURVEY 8d:
+                                // N_sel (15 U + 4) + 40 N_inrange per forest pair), [1] sum of U,
+                                // [2] in-range pixel pairs -- measurement only
     char *cta_base;             // per-CTA scratch
     long long cta_stride;
     int rows_max;               // 2*max_pix1 + 2*max_pix2 + 4
@@ -393,6 +396,11 @@ pb2_dmat_auto_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr,
                     if (kidx[x] == 0) { kidx[x] = u; klist[u++] = x; }
                 }
             s_U = u;
+            if (W.stats) {
+                atomicAdd(W.stats, (double)s_cnt[0] * (15. * u + 4.) + 40. * (double)s_cnt[1]);
+                atomicAdd(W.stats + 1, (double)u);
+                atomicAdd(W.stats + 2, (double)s_cnt[1]);
+            }
             u = 0;
             for (int t = 0; t < P.num_bins_r_trans; t++)
                 for (int q = 0; q < P.num_bins_r_par; q++) {
@@ -935,6 +943,7 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
     DmatWork W;
     char *p = (char *)d_scratch;
     W.count = (unsigned long long *)p;
+    W.stats = cross ? nullptr : (double *)(p + 64);  // inside the 256-byte header, zeroed below
     W.cta_base = p + 256;
     W.cta_stride = cross ? (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg))
                          : auto_cta_bytes(cat1, cat2, par);
@@ -1005,6 +1014,22 @@ int32_t pb2_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const p
 {
     return dmat_launch(cat1, objs, par, pairs, d_weights_dmat, d_dmat, d_r_par_eff, d_r_trans_eff,
                        d_z_eff, d_weight_eff, d_scratch, scratch_bytes, stream, true);
+}
+
+/* measurement: the statistics the last pb2_dmat_auto call on this scratch buffer accumulated --
+ * out[0] as-written FP64 ops of the reference algorithm, out[1] sum over used forest pairs of the
+ * unique model bins U, out[2] in-range pixel pairs.  Synchronises the stream. */
+int32_t pb2_dmat_stats(const void *d_scratch, double *out3, void *stream)
+{
+    if (!d_scratch || !out3) {
+        pb2_set_error("pb2_dmat_stats: null pointer argument");
+        return PB2_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PB2_CUDA(cudaMemcpyAsync(out3, (const char *)d_scratch + 64, 3 * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+    PB2_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 
 }  // extern "C"

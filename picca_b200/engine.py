@@ -110,6 +110,9 @@ class Engine:
         self._cats = {}
 
     # ------------------------------------------------------------------ memory
+    collect_dmat_stats = False   # bench.py: read pb2_dmat_stats after every dmat launch
+    last_dmat_stats = None
+
     def stream_ptr(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -205,6 +208,12 @@ class Engine:
                       ctypes.c_void_p(weight_eff.data_ptr()), ctypes.c_void_p(scratch.data_ptr()),
                       ctypes.c_int64(nbytes), self.stream_ptr()),
                    "pb2_dmat_cross" if cross_obj else "pb2_dmat_auto")
+        if not cross_obj and self.collect_dmat_stats:
+            out3 = (ctypes.c_double * 3)()
+            _lib.check(self.lib.pb2_dmat_stats(ctypes.c_void_p(scratch.data_ptr()), out3,
+                                               self.stream_ptr()), "pb2_dmat_stats")
+            self.last_dmat_stats = {"as_written_ops": out3[0], "sum_unique_model_bins": out3[1],
+                                    "in_range_pixel_pairs": out3[2]}
         return weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff
 
     # ------------------------------------------------------------------ measurement
