@@ -356,6 +356,13 @@ def run_cuda(args):
         if world > 1:
             dist.all_reduce(dm_pix)
         dm_pix = int(dm_pix.item())
+        dm_peak = eng.fp64_peak(8192)[0]
+        dm_ops_s = dm_stats.get("as_written_ops", 0.) / (float(np.mean(dm_kernel_ms)) * 1e-3)
+        dm_as_written = {"ops_per_step_this_rank": dm_stats.get("as_written_ops"),
+                         "ops_per_s": dm_ops_s, "fp64_peak_ops_per_s": dm_peak,
+                         "frac_of_fp64_peak": dm_ops_s / dm_peak,
+                         "unique_model_bins_per_used_pair":
+                             dm_stats.get("sum_unique_model_bins", 0.) / max(1, used // world)}
         dmat_info = {
             "metric": "used forest pairs/sec (distortion matrix, --rej %.2f)" % DMAT_REJECT,
             "value": used / (dm_ms / args.dmat_steps * 1e-3), "unit": "forest pairs/s",
@@ -374,12 +381,7 @@ def run_cuda(args):
             # kernels contract per data bin instead and execute far fewer
             # operations, so this can exceed the machine's peak: it measures the algebra, the
             # used-forest-pair rate above measures the kernel
-            "as_written": {"ops_per_step_this_rank": dm_stats.get("as_written_ops"),
-                           "ops_per_s": (dm_stats.get("as_written_ops", 0.) /
-                                         (float(np.mean(dm_kernel_ms)) * 1e-3)),
-                           "unique_model_bins_per_used_pair":
-                               dm_stats.get("sum_unique_model_bins", 0.) / max(1, used // world),
-                           "fp64_peak_ops_per_s": eng.fp64_peak(8192)[0]},
+            "as_written": dm_as_written,
             "parallelism": "kept forest pairs sharded by owning HEALPix row x%d, "
                            "NCCL all-reduce(SUM) of dmat + 5 vectors" % world if world > 1 else
                            "one GPU, one reference chunk",
