@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 17
+#define PB2_ABI_VERSION 18
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -233,6 +233,16 @@ int32_t pb2_metal_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, c
                              const double *d_dm1, const double *d_pw1, double *d_weights_dmat,
                              double *d_dmat, double *d_r_par_eff, double *d_r_trans_eff,
                              double *d_z_eff, double *d_weight_eff, void *stream);
+
+/* ---- object x object pair counting: replaces the pair loop of
+ * co.compute_xi / co.compute_xi_forest_pairs (py/picca/co.py:77-132, :135-202).  pairs = the
+ * neighbour list of pb2_neigh_* in mode 1 (co.py:43-69); the mean-redshift cut of co.py:70-74 is
+ * applied per pair when has_z_cut; take_abs = `not x_correlation or type_corr in (DR, RD)`
+ * (co.py:172).  d_out [n_rows][5][np*nt]: weight, r_par*w, r_trans*w, z*w sums and int64 counts. */
+int32_t pb2_co_pairs(const pb2_catalog *objs1, const pb2_catalog *objs2, const pb2_params *par,
+                     const pb2_pairs *pairs, int32_t take_abs, int32_t has_z_cut, double z_cut_min,
+                     double z_cut_max, const int32_t *d_out_row, int64_t n_rows, double *d_out,
+                     void *stream);
 
 /* ---- sub-sample covariance of the per-HEALPix blocks (the consumer of the WE/DA columns the
  * pair kernels produce).

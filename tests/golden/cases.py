@@ -60,6 +60,15 @@ XMETAL_CASES = {
                       num_model_bins_r_trans=30),
     "edge_skip": dict(XCF_BASE, reject=0.5, abs_igm="TEST(1045)"),
 }
+CO_BASE = dict(r_par_max=80., r_par_min=0., r_trans_max=80., num_bins_r_par=20,
+               num_bins_r_trans=20, z_cut_min=0., z_cut_max=10.)
+CO_CASES = {
+    "dd": dict(CO_BASE, type_corr="DD"),
+    "zcut": dict(CO_BASE, type_corr="DD", z_cut_min=2.2, z_cut_max=2.8),
+    "xdd": dict(CO_BASE, type_corr="xDD", x_correlation=True, r_par_min=-80., num_bins_r_par=40,
+                second=True),
+    "dr": dict(CO_BASE, type_corr="DR", x_correlation=True, second=True),  # abs although crossed
+}
 XDMAT_CASES = {
     "default": dict(XCF_BASE, reject=0.8),
     "noevol": dict(XCF_BASE, reject=0.8, redshift_evolution_in_distortion_matrix=False),
@@ -91,6 +100,12 @@ def dmat_forests(second=False):
 def quasars(cosmo):
     return synth.make_quasars(400, seed=31, nside=16, ra_deg=(10., 16.), dec_deg=(5., 11.),
                               z_range=(1.9, 3.2), cosmo=cosmo)
+
+
+def quasars2(cosmo):
+    """second object catalogue of the crossed co cases (other seed, other ids)"""
+    return synth.make_quasars(300, seed=37, nside=16, ra_deg=(10., 16.), dec_deg=(5., 11.),
+                              z_range=(1.9, 3.2), cosmo=cosmo, id_offset=2 * 10**7)
 
 
 def ang_max_for(cosmo, cfg, z_min, z_min2=None):

@@ -182,6 +182,44 @@ def run_xmetal(out):
         print("xmetal", name, "pairs", res[6], "used", res[7], "sum", res[1].sum(), "skipped", kept)
 
 
+def run_co(out):
+    from picca_b200 import synth
+    for name, cfg in cases.CO_CASES.items():
+        assert shims_install()
+        import picca.co
+        import importlib
+        co = importlib.reload(picca.co)
+        co.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        second = cfg.pop("second", False)
+        cosmo = synth.FlatLCDM()
+        objs, z_min = cases.quasars(cosmo)
+        robjs = load.to_reference_qsos(objs)
+        for k, v in cfg.items():
+            setattr(co, k, v)
+        co.objs, co.objs2, z_min2 = robjs, None, None
+        if second:
+            objs2, z_min2 = cases.quasars2(cosmo)
+            co.objs2 = load.to_reference_qsos(objs2)
+        co.ang_max = cases.ang_max_for(cosmo, cfg, z_min, z_min2)
+        co.nside = 16
+        co.num_data = sum(len(v) for v in robjs.values())
+        co.lock, co.counter = load.DummyLock(), load.DummyCounter()
+        rows = []
+        for hp in sorted(robjs):
+            co.fill_neighs([hp])
+            res = co.compute_xi([hp])
+            rows.append(np.stack([np.asarray(r, dtype=np.float64) for r in res[:4]] +
+                                 [np.asarray(res[4], dtype=np.int64).view(np.float64)]))
+        out["co_%s" % name] = np.stack(rows)
+        print("co", name, "pairs", int(np.stack(rows)[:, 4].view(np.int64).sum()))
+
+
+def shims_install():
+    from tests.refharness import shims
+    return shims.install()
+
+
 def run_xdmat(out):
     for name, cfg in cases.XDMAT_CASES.items():
         _, xcf, _, _, _ = load.reference_modules()
@@ -202,7 +240,7 @@ def run_xdmat(out):
 
 def main():
     todo = (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat),
-            ("metal", run_metal), ("xmetal", run_xmetal))
+            ("metal", run_metal), ("xmetal", run_xmetal), ("co", run_co))
     only = sys.argv[1:]
     for tag, fn in todo:
         if only and tag not in only:

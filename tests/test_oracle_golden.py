@@ -267,3 +267,39 @@ def test_xmetal_dmat(name):
     check8(res, gold, "xmetal_%s_" % name, rtol=1e-12)
     kept = sum(d.neighbours is not None for hp in hps for d in data[hp])
     assert kept == int(gold["xmetal_%s_skipped" % name][0])  # xcf.py:741-742
+
+
+# ---- object x object correlation (oracle/co.py against the live reference's outputs)
+def setup_co(mod, cfg):
+    from picca_b200 import synth
+    cfg = dict(cfg)
+    second = cfg.pop("second", False)
+    cosmo = synth.FlatLCDM()
+    objs, z_min = cases.quasars(cosmo)
+    for k, v in dict(dict(x_correlation=False), **cfg).items():
+        setattr(mod, k, v)
+    mod.objs, mod.objs2, z_min2 = objs, None, None
+    if second:
+        mod.objs2, z_min2 = cases.quasars2(cosmo)
+    mod.ang_max = cases.ang_max_for(cosmo, cfg, z_min, z_min2)
+    mod.nside = 16
+    mod.num_data = sum(len(v) for v in objs.values())
+    mod.lock, mod.counter = helpers.DummyLock(), helpers.DummyCounter()
+    return objs
+
+
+@pytest.mark.parametrize("name", sorted(cases.CO_CASES))
+def test_co(name):
+    from oracle import co as oco
+    gold = load("co")["co_%s" % name]
+    objs = setup_co(oco, cases.CO_CASES[name])
+    rows = []
+    for hp in sorted(objs):
+        oco.fill_neighs([hp])
+        res = oco.compute_xi([hp])
+        rows.append(np.stack([np.asarray(r, dtype=np.float64) for r in res[:4]] +
+                             [np.asarray(res[4], dtype=np.int64).view(np.float64)]))
+    rows = np.stack(rows)
+    assert np.array_equal(rows[:, 4].view(np.int64), gold[:, 4].view(np.int64))
+    for k in range(4):
+        np.testing.assert_allclose(rows[:, k], gold[:, k], rtol=1e-12, atol=1e-300)

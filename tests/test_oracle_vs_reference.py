@@ -275,3 +275,36 @@ def test_read_deltas_equals_live_reference(which, tmp_path):
     a, b = cases_io.flatten(got[0]), cases_io.flatten(want[0])
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("type_corr,x_corr", [("DD", False), ("xDD", True), ("DR", True)])
+def test_co_bit_exact_on_bundled_catalogue(fixture_data, type_corr, x_corr):
+    """oracle/co.py against the live picca.co (co.py:35-202) on the reference's bundled quasar
+    catalogue (cat.fits, 1000 objects), the binning of test_3_cor.py:1084-1139."""
+    import importlib
+    from oracle import co as oco
+    from tests.refharness import load
+    _, _, _, _, utils = load.reference_modules()
+    import picca.co
+    co = importlib.reload(picca.co)
+    co.userprint = lambda *a, **k: None
+    cosmo, objs, z_min2 = fixture_data[3], fixture_data[4], fixture_data[5]
+    cfg = dict(r_par_min=-80. if type_corr == "xDD" else 0., r_par_max=80., r_trans_max=80.,
+               num_bins_r_par=40 if type_corr == "xDD" else 20, num_bins_r_trans=20, nside=16,
+               type_corr=type_corr, x_correlation=x_corr, z_cut_min=0., z_cut_max=10.,
+               objs=objs, objs2=objs if x_corr else None,
+               ang_max=utils.compute_ang_max(cosmo, 80., z_min2, z_min2),
+               num_data=sum(len(v) for v in objs.values()))
+    total = 0
+    for hp in sorted(objs)[:6]:
+        res = []
+        for mod in (co, oco):
+            for k, v in cfg.items():
+                setattr(mod, k, v)
+            mod.lock, mod.counter = load.DummyLock(), load.DummyCounter()
+            mod.fill_neighs([hp])
+            res.append(mod.compute_xi([hp]))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+        total += int(res[0][4].sum())
+    assert total > 100

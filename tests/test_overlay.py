@@ -103,3 +103,16 @@ def test_scripts_bind_b200_loader(overlay_on):
         picca.io.read_deltas(shims.REFERENCE_PY + "/picca/tests/data/test_delta/Delta_LYA/",
                              16, 1215.67, 2.9, 2.25, None, delta_attributes=shims.REFERENCE_PY +
                              "/picca/tests/data/test_delta/delta_attributes.fits.gz")
+
+
+def test_co_script_binds_b200_module(overlay_on):
+    import picca_b200.co
+    script = importlib.import_module("picca.bin.picca_co")
+    assert script.co is picca_b200.co
+    import ast
+    tree = ast.parse(open(shims.REFERENCE_PY + "/picca/co.py").read())
+    for node in tree.body:
+        if isinstance(node, ast.Assign):
+            for tgt in node.targets:
+                assert hasattr(picca_b200.co, tgt.id), tgt.id
+    assert callable(picca_b200.co.fill_neighs) and callable(picca_b200.co.compute_xi)
