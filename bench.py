@@ -33,6 +33,10 @@ WORKLOADS = {
     "c2_20k": dict(n_forest=20000, seed=20260102, nside=32, ra_deg=(0., 53.6),
                    dec_deg=(0., 18.)),
     "c2_5k": dict(n_forest=5000, seed=20260102, nside=32, ra_deg=(0., 26.8), dec_deg=(0., 9.)),
+    # BASELINE.json configs[2] / SURVEY.md 8d C3: 300k forests over ~14 000 deg^2 (with 500k quasars
+    # on the same footprint, scripts/perf_c3_xcf.py)
+    "c3_300k": dict(n_forest=300000, seed=20260103, nside=32, ra_deg=(0., 360.),
+                    dec_deg=(0., 42.8)),
     # one eighth of BASELINE.json configs[4] / SURVEY.md 8d C5 (1M forests over ~14 000 deg^2,
     # ~71 per deg^2): the share one GPU of an 8-GPU box holds, at the full surface density
     "c5_eighth": dict(n_forest=125000, seed=20260105, nside=32, ra_deg=(0., 60.),
