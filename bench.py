@@ -8,8 +8,8 @@ pairs per second, auto-correlation, synthetic 100k-forest DR16-like sample, nsid
 A step is one pass of the hot path over the workload: device neighbour search (fill_neighs) +
 pair kernel (compute_xi) + normalisation, per-HEALPix blocks produced for every pixel.  `value`
 is timed with the packed catalogue already resident in HBM; `e2e` repeats the steps through the
-host-buffer entry (pinned host catalogue -> H2D -> kernels -> D2H of the blocks), copies inside
-the timed region.  N > 1: HEALPix pixels are LPT-partitioned over the ranks (strong scaling),
+host-buffer entry (pinned host catalogue -> H2D -> record packing + kernels -> D2H of the blocks),
+copies inside the timed region.  N > 1: HEALPix pixels are LPT-partitioned over the ranks (strong scaling),
 blocks gathered to rank 0 inside the timed region, time = max over ranks.
 """
 import argparse
@@ -278,11 +278,8 @@ def run_cuda(args):
     result_host = torch.empty((n_rows if world == 1 else len(hps), 6, nb), dtype=torch.float64).pin_memory()
 
     def step_e2e():
-        fresh = catalog.DeviceCatalog.__new__(catalog.DeviceCatalog)
-        fresh.host, fresh.device, fresh.tensors = host, eng.device, {}
-        for k, v in pinned.items():
-            fresh.tensors[k] = v.to(eng.device, non_blocking=True)
-        fresh.struct = catalog.build_struct(host, fresh.tensors)
+        fresh = catalog.DeviceCatalog.from_tensors(
+            host, eng.device, {k: v.to(eng.device, non_blocking=True) for k, v in pinned.items()})
         o = one_step(fresh)
         if o is not None:
             result_host[:o.shape[0]].copy_(o, non_blocking=True)
@@ -339,11 +336,9 @@ def run_cuda(args):
         dm_host = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in dm_res]
 
         def dmat_e2e():
-            fresh = catalog.DeviceCatalog.__new__(catalog.DeviceCatalog)
-            fresh.host, fresh.device, fresh.tensors = host, eng.device, {}
-            for k, v in pinned.items():
-                fresh.tensors[k] = v.to(eng.device, non_blocking=True)
-            fresh.struct = catalog.build_struct(host, fresh.tensors)
+            fresh = catalog.DeviceCatalog.from_tensors(
+                host, eng.device,
+                {k: v.to(eng.device, non_blocking=True) for k, v in pinned.items()})
             r_ = dmat_step(fresh)
             if rank == 0:
                 for h_, t_ in zip(dm_host, r_):
@@ -435,7 +430,7 @@ def run_cuda(args):
             "config": {"workload": args.workload, "forests": host.n_los, "pixels": host.n_pix,
                        "healpix": len(hps), "np": 50, "nt": 50, "rp_max": 200., "rt_max": 200.,
                        "nside": 32, "binned_pairs_per_step": pairs,
-                       "l2_policy": "inputs (%.2f GB) larger than L2" % (host.nbytes() / 1e9),
+                       "l2_policy": "inputs (%.2f GB in HBM) larger than L2" % (dev.device_bytes() / 1e9),
                        "parallelism": "healpix LPT shards x%d, gather to rank 0" % world},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(result_host.numel() * 8)},

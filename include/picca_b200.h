@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 18
+#define PB2_ABI_VERSION 19
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -187,6 +187,11 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
 int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
                      const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                      double *d_out, int32_t variant, void *stream);
+
+/* Write the packed record copies of the diagonal-lane xi kernel (cat->dg_rec: dg_total records,
+ * cat->il_rec: PB2_DIAG_LANES * il_total records; layout above) from the SoA arrays of the
+ * catalogue on the device.  cat->dg_offset / dg_count / il_offset / il_total describe the layout. */
+int32_t pb2_pack_diag(const pb2_catalog *cat, int64_t dg_total, void *stream);
 
 /* Fill the prefix records of a delta catalogue: d_px_rec holds 6 * (n_pix + n_los) doubles (see
  * pb2_catalog.px_rec); the caller then stores the pointer in the catalogue it passes on. */

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 
 _PIXEL_FIELDS = ("r_comov", "dist_m", "z", "weights", "delta_w", "z_w", "log_lambda")
-_DIAG_FIELDS = ("dg_offset", "dg_count", "dg_rec", "il_offset", "il_rec")
+_DIAG_FIELDS = ("dg_offset", "dg_count", "dg_rec", "il_offset", "il_rec")  # dg_rec / il_rec: device
 DIAG_DUMMY_COL = 1e300   # distance of the dummy pixels around a line of sight (interleaved copy)
 DIAG_DUMMY_ROW = 1e299   # ... and after it in the natural-order copy
 _LOS_F64 = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso")
@@ -34,7 +34,8 @@ class HostCatalog:
         self.max_pix = 0
         self.ids_are_int = True
         self.is_object = False
-        self.il_total = 0         # diagonal-lane copies (see _pack_diag_copies)
+        self.il_total = 0         # diagonal-lane copies (see _diag_metadata)
+        self.dg_total = 0
         self.dg_lanes = 0
         self.dg_max_pix = 0
         self.dg_ok = 0
@@ -69,8 +70,43 @@ def diag_layout():
     return lanes, 34 * lanes, 8, 32
 
 
-def _pack_diag_copies(cat, offset):
-    """Packed copies for the diagonal-lane xi kernel (layout: include/picca_b200.h, pb2_catalog).
+def _diag_metadata(cat, offset):
+    """Geometry of the packed copies the diagonal-lane xi kernel reads (layout:
+    include/picca_b200.h, pb2_catalog): per-forest counts of non-zero-weight pixels, record
+    offsets of the natural-order and of the interleaved copy, totals, and the flags the launcher
+    checks.  The records themselves are written on the device (``pb2_pack_diag``)."""
+    A = cat.arrays
+    lanes, pad, row_pad, chunk = diag_layout()
+    n = cat.n_los
+    keep = A["weights"] != 0
+    if n:
+        first_pix = offset[:-1]
+        count = np.add.reduceat(np.append(keep.astype(np.int64), 0), first_pix)
+        count = np.where(np.diff(offset) > 0, count, 0).astype(np.int64)
+    else:
+        count = np.zeros(0, np.int64)
+    first = np.zeros(n + 1, dtype=np.int64)
+    first[1:] = np.cumsum(count)
+    A["dg_offset"] = np.ascontiguousarray(first[:-1] + row_pad * np.arange(n, dtype=np.int64))
+    A["dg_count"] = count.astype(np.int32)
+    cat.dg_total = int(first[-1]) + row_pad * n + chunk
+    per_plane = (count + lanes - 1) // lanes + 2 * pad // lanes
+    il_offset = np.zeros(n + 1, dtype=np.int64)
+    il_offset[1:] = np.cumsum(per_plane)
+    A["il_offset"] = np.ascontiguousarray(il_offset[:-1])
+    cat.il_total = int(il_offset[-1]) + chunk + 64
+    cat.dg_lanes = lanes
+    cat.dg_max_pix = int(count.max()) if n else 0
+    fields = ("r_comov", "dist_m", "weights", "delta_w", "z")
+    finite = all(bool(np.all(np.isfinite(A[name][keep]))) for name in fields)
+    cat.dg_ok = int(finite)
+    cat.dg_reach = float(max(np.abs(A["r_comov"][keep]).max(), np.abs(A["dist_m"][keep]).max())) \
+        if keep.any() and finite else 0.0
+
+
+def diag_records_host(cat):
+    """NumPy statement of what ``pb2_pack_diag`` writes -- the layout specification the tests
+    check the device packer against (never used on the product path).  Returns (dg_rec, il_rec).
 
     Zero-weight pixels are dropped (the reference never counts them, cf.py:318,331).  A pixel is
     a record of six doubles (r_comov, dist_m, weights, delta*weights, z/2, 0).  Natural order with
@@ -80,46 +116,24 @@ def _pack_diag_copies(cat, offset):
     A = cat.arrays
     lanes, pad, row_pad, chunk = diag_layout()
     n = cat.n_los
+    offset = A["offset"]
     keep = A["weights"] != 0
-    lengths = np.diff(offset)
-    los_all = np.repeat(np.arange(n, dtype=np.int64), lengths)
-    count = np.bincount(los_all[keep], minlength=n).astype(np.int64) if n else np.zeros(0, np.int64)
-    los = los_all[keep]
+    los = np.repeat(np.arange(n, dtype=np.int64), np.diff(offset))[keep]
     rec = np.zeros((len(los), 6), dtype=np.float64)
     rec[:, 0], rec[:, 1] = A["r_comov"][keep], A["dist_m"][keep]
     rec[:, 2], rec[:, 3] = A["weights"][keep], A["delta_w"][keep]
     rec[:, 4] = 0.5 * A["z"][keep]
     first = np.zeros(n + 1, dtype=np.int64)
-    first[1:] = np.cumsum(count)
+    first[1:] = np.cumsum(A["dg_count"].astype(np.int64))
     rank = np.arange(len(los), dtype=np.int64) - first[:-1][los]   # pixel index inside its forest
-
-    # natural order
-    dg_offset = first[:-1] + row_pad * np.arange(n, dtype=np.int64)
-    total = int(first[-1]) + row_pad * n + chunk
-    dg_rec = np.zeros((total, 6), dtype=np.float64)
+    dg_rec = np.zeros((cat.dg_total, 6), dtype=np.float64)
     dg_rec[:, 0] = dg_rec[:, 1] = DIAG_DUMMY_ROW
-    dg_rec[dg_offset[los] + rank] = rec
-    A["dg_offset"] = np.ascontiguousarray(dg_offset)
-    A["dg_count"] = count.astype(np.int32)
-    A["dg_rec"] = dg_rec.reshape(-1)
-
-    # interleaved by `lanes`
-    per_plane = (count + lanes - 1) // lanes + 2 * pad // lanes
-    il_offset = np.zeros(n + 1, dtype=np.int64)
-    il_offset[1:] = np.cumsum(per_plane)
-    il_total = int(il_offset[-1]) + chunk + 64
+    dg_rec[A["dg_offset"][los] + rank] = rec
     jp = rank + pad
-    il_rec = np.zeros((lanes * il_total, 6), dtype=np.float64)
+    il_rec = np.zeros((lanes * cat.il_total, 6), dtype=np.float64)
     il_rec[:, 0] = il_rec[:, 1] = DIAG_DUMMY_COL
-    il_rec[(jp % lanes) * il_total + il_offset[:-1][los] + jp // lanes] = rec
-    A["il_offset"] = np.ascontiguousarray(il_offset[:-1])
-    A["il_rec"] = il_rec.reshape(-1)
-    cat.il_total = il_total
-    cat.dg_lanes = lanes
-    cat.dg_max_pix = int(count.max()) if n else 0
-    finite = bool(np.all(np.isfinite(rec)))
-    cat.dg_ok = int(finite)
-    cat.dg_reach = float(np.abs(rec[:, :2]).max()) if len(rec) and finite else 0.0
+    il_rec[(jp % lanes) * cat.il_total + A["il_offset"][los] + jp // lanes] = rec
+    return dg_rec.reshape(-1), il_rec.reshape(-1)
 
 
 def pack(data, is_object=False, ang_correlation=False):
@@ -212,7 +226,7 @@ def pack(data, is_object=False, ang_correlation=False):
     cat.max_pix = int(lengths.max()) if n else 0
 
     if not is_object:
-        _pack_diag_copies(cat, offset)
+        _diag_metadata(cat, offset)
 
     # sortedness inside each forest (enables the column windows of the pair kernel)
     cat.sorted = 1
@@ -249,26 +263,50 @@ class DeviceCatalog:
 
     def __init__(self, host, device, pin=False):
         import torch
-        self.host = host
-        self.device = device
-        self.tensors = {}
-        self.h2d_bytes = 0
+        tensors, self.h2d_bytes = {}, 0
         for name, arr in host.arrays.items():
             t = torch.from_numpy(arr)
             if pin:
                 t = t.pin_memory()
-            self.tensors[name] = t.to(device, non_blocking=pin)
+            tensors[name] = t.to(device, non_blocking=pin)
             self.h2d_bytes += arr.nbytes
-        self.struct = build_struct(host, self.tensors)
+        self._finish(host, device, tensors)
+
+    @classmethod
+    def from_tensors(cls, host, device, tensors):
+        """A catalogue whose SoA arrays are already on the device (e.g. copied from pinned host
+        buffers by the caller); the derived copies are built here."""
+        self = cls.__new__(cls)
+        self.h2d_bytes = 0
+        self._finish(host, device, dict(tensors))
+        return self
+
+    def _finish(self, host, device, tensors):
+        """Derived device-side structures: the packed record copies of the diagonal-lane xi
+        kernel (pb2_pack_diag) and the per-forest prefix sums of the forest x object kernel
+        (pb2_build_prefix) -- both pure data movement over the SoA, done in HBM."""
+        import ctypes
+        import torch
+        self.host, self.device, self.tensors = host, device, tensors
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         if not host.is_object and host.n_los:
+            tensors["dg_rec"] = torch.empty(6 * host.dg_total, dtype=torch.float64, device=device)
+            tensors["il_rec"] = torch.empty(6 * host.dg_lanes * host.il_total, dtype=torch.float64,
+                                            device=device)
+        self.struct = build_struct(host, tensors)
+        if not host.is_object and host.n_los:
+            _lib.check(_lib.lib().pb2_pack_diag(
+                ctypes.byref(self.struct), ctypes.c_int64(host.dg_total), stream), "pb2_pack_diag")
             # per-forest prefix sums for the forest x object kernel, built on the device
-            import ctypes
-            self.tensors["px_rec"] = torch.empty(6 * (host.n_pix + host.n_los), dtype=torch.float64,
-                                                 device=device)
+            tensors["px_rec"] = torch.empty(6 * (host.n_pix + host.n_los), dtype=torch.float64,
+                                            device=device)
             _lib.check(_lib.lib().pb2_build_prefix(
-                ctypes.byref(self.struct), ctypes.c_void_p(self.tensors["px_rec"].data_ptr()),
-                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "pb2_build_prefix")
-            self.struct.px_rec = self.tensors["px_rec"].data_ptr()
+                ctypes.byref(self.struct), ctypes.c_void_p(tensors["px_rec"].data_ptr()), stream),
+                "pb2_build_prefix")
+            self.struct.px_rec = tensors["px_rec"].data_ptr()
+
+    def device_bytes(self):
+        return int(sum(t.numel() * t.element_size() for t in self.tensors.values()))
 
 
 def build_struct(host, tensors):

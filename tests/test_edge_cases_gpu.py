@@ -153,3 +153,24 @@ def test_pairs_exactly_on_bin_edges():
     total = run_both(data, len(forests), ang_max, num_bins_r_par=50, num_bins_r_trans=50,
                      r_par_max=200., r_trans_max=200.)
     assert total > 10**4
+
+
+def test_device_packed_copies_equal_the_numpy_specification():
+    """pb2_pack_diag (records written in HBM from the SoA) against catalog.diag_records_host, bit
+    for bit, on a sample with zero-weight pixels, ragged and tiny forests."""
+    from picca_b200 import catalog
+    from picca_b200.engine import get_engine
+    data, num, z_min, _, cosmo = helpers.small_sample(n=260, seed=3, max_pix=150)
+    rng = np.random.default_rng(1)
+    flat = [d for hp in sorted(data) for d in data[hp]]
+    for k in (0, 5, 77):
+        flat[k].weights = flat[k].weights.copy()
+        flat[k].weights[rng.random(len(flat[k].weights)) < 0.4] = 0.
+    flat[9].weights = np.zeros_like(flat[9].weights)  # a forest that disappears entirely
+    host = catalog.pack(data)
+    eng = get_engine()
+    dev = eng.device_catalog(host, cache=False)
+    want_dg, want_il = catalog.diag_records_host(host)
+    assert np.array_equal(dev.tensors["dg_rec"].cpu().numpy(), want_dg)
+    assert np.array_equal(dev.tensors["il_rec"].cpu().numpy(), want_il)
+    assert host.arrays["dg_count"][9] == 0

@@ -123,8 +123,9 @@ def test_diag_copies_layout(sample):
     assert cat.dg_lanes == lanes and cat.dg_ok == 1
     A = cat.arrays
     flat = [x for hp in sorted(data) for x in data[hp]]
-    rec = A["dg_rec"].reshape(-1, 6)
-    il = A["il_rec"].reshape(lanes, cat.il_total, 6)
+    dg_rec, il_rec = catalog.diag_records_host(cat)  # the specification of pb2_pack_diag
+    rec = dg_rec.reshape(-1, 6)
+    il = il_rec.reshape(lanes, cat.il_total, 6)
     assert A["dg_count"][0] == int((d.weights != 0).sum()) < len(d.weights) - 1
     assert cat.dg_max_pix == int(A["dg_count"].max())
     seen = np.zeros(il.shape[:2], dtype=bool)
