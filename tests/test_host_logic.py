@@ -166,3 +166,28 @@ def test_diag_copies_flag_non_finite(sample):
     d.z[1] = np.inf
     data[hp0][0] = d
     assert catalog.pack(data).dg_ok == 0
+
+
+def test_pair_list_subset_matches_numpy_selection():
+    """PairList.subset (what np.array(neighbours)[w] selects, cf.py:444-447): CSR offsets and the
+    per-pair arrays of the kept pairs, on CPU tensors."""
+    import torch
+    from picca_b200.engine import PairList
+    counts = np.array([3, 0, 4, 1, 2])
+    offset = np.concatenate([[0], np.cumsum(counts)])
+    n = int(offset[-1])
+    rng = np.random.default_rng(0)
+    f1 = np.repeat(np.arange(len(counts)), counts).astype(np.int32)
+    f2 = rng.integers(0, 50, n).astype(np.int32)
+    ang = rng.random(n)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    pairs = PairList(None, t(np.arange(len(counts), dtype=np.int32)), t(offset), t(f1), t(f2),
+                     t(ang), t(np.cos(ang / 2)), t(np.sin(ang / 2)))
+    keep = rng.random(n) > 0.5
+    sub = pairs.subset(keep)
+    assert sub.n_f1 == pairs.n_f1 and sub.n_pairs == int(keep.sum())
+    want_counts = np.array([keep[a:b].sum() for a, b in zip(offset[:-1], offset[1:])])
+    assert np.array_equal(np.diff(sub.nb_offset.numpy()), want_counts)
+    assert np.array_equal(sub.nb_f2.numpy(), f2[keep])
+    assert np.array_equal(sub.nb_f1.numpy(), f1[keep])
+    assert np.array_equal(sub.nb_ang.numpy(), ang[keep])
