@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 19
+#define PB2_ABI_VERSION 20
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -317,6 +317,22 @@ int32_t pb2_delta_image_unpack(int64_t n_los, const uint8_t *d_raw, int64_t lamb
                                int64_t delta_off, int64_t weight_off, int32_t n_lambda,
                                const int32_t *d_rows, const int64_t *d_offset, double *d_log_lambda,
                                double *d_delta, double *d_weights, void *stream);
+/* Delta.rebin (py/picca/data.py:657-686; read_deltas' rebin_factor, io.py:362-378).
+ * pb2_fits_hierarch: one long keyword of the ESO HIERARCH convention (WAVE_SOLUTION, DELTA_LAMBDA)
+ * from the header at header_off.  pb2_delta_wave: wave = 10^log_lambda per pixel (log10 first
+ * when the file stores LAMBDA).  pb2_delta_rebin: d_new_offset == NULL -> d_count[f] = surviving
+ * bins of forest f; else the bins are written at d_new_offset[f] (mid-point wavelength, weighted
+ * mean delta, weight sum).  d_dwave[f] = DELTA_LAMBDA of the forest's file.  *d_status = 2 if a
+ * forest's wavelengths are not ascending. */
+int32_t pb2_fits_hierarch(const uint8_t *buf, int64_t len, int64_t header_off, const char *key,
+                          int32_t *kind, double *num, char *str24);
+int32_t pb2_delta_wave(int64_t n_pix, int32_t wave_is_lambda, double *d_log_lambda, double *d_wave,
+                       void *stream);
+int32_t pb2_delta_rebin(int64_t n_los, const int64_t *d_offset, const double *d_wave,
+                        const double *d_delta, const double *d_weights, const double *d_dwave,
+                        int32_t factor, int32_t *d_count, int32_t *d_status,
+                        const int64_t *d_new_offset, double *d_new_wave, double *d_new_delta,
+                        double *d_new_weights, void *stream);
 int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t *d_order,
                           double lambda_abs, double alpha, double z_ref, int32_t n_table,
                           const double *d_tab_z, const double *d_tab_r_comov,

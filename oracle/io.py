@@ -71,12 +71,38 @@ def from_image(hdul, z_min_qso, z_max_qso, order):
     return out
 
 
-def read_delta_file(filename, z_min_qso, z_max_qso, order):
-    """io.py:354-360 + data.py:392-474 (non-Pk1D branch)"""
+def rebin(d, factor, dwave):
+    """Delta.rebin, data.py:666-686"""
+    wave = 10**np.array(d.log_lambda)
+    start = wave.min() - dwave / 2
+    num_bins = np.ceil(((wave[-1] - wave[0]) / dwave + 1) / factor)
+    edges = np.arange(num_bins) * dwave * factor + start
+    new_indx = np.searchsorted(edges, wave)
+    binned_delta = np.bincount(new_indx, weights=d.delta * d.weights,
+                               minlength=edges.size + 1)[1:-1]
+    binned_weight = np.bincount(new_indx, weights=d.weights, minlength=edges.size + 1)[1:-1]
+    mask = binned_weight != 0
+    binned_delta[mask] /= binned_weight[mask]
+    new_wave = (edges[1:] + edges[:-1]) / 2
+    d.log_lambda = np.log10(new_wave[mask])
+    d.delta = binned_delta[mask]
+    d.weights = binned_weight[mask]
+
+
+def read_delta_file(filename, z_min_qso, z_max_qso, order, rebin_factor=None):
+    """io.py:354-380 + data.py:392-474 (non-Pk1D branch)"""
     out = []
     with minifits.FITS(filename) as hdul:
+        if rebin_factor is not None:                           # io.py:362-373
+            head = hdul["LAMBDA" if "LAMBDA" in hdul else 1].read_header()
+            if head["WAVE_SOLUTION"] != "lin":
+                raise ValueError("Delta rebinning only implemented for linear lambda bins")
+            dwave = head["DELTA_LAMBDA"]
         if "LAMBDA" in hdul:                                   # io.py:356
-            return from_image(hdul, z_min_qso, z_max_qso, order)
+            out = from_image(hdul, z_min_qso, z_max_qso, order)
+            for d in out if rebin_factor is not None else ():
+                rebin(d, rebin_factor, dwave)
+            return out
         for hdu in hdul[1:]:
             header = hdu.read_header()
             if not z_min_qso < header["Z"] < z_max_qso:
@@ -94,11 +120,14 @@ def read_delta_file(filename, z_min_qso, z_max_qso, order):
                 ids = (header["LOS_ID"],) * 4
             out.append(Delta(ids[0], header["RA"], header["DEC"], header["Z"], ids[1], ids[2],
                              ids[3], log_lambda, weights, delta, order))
+    for d in out if rebin_factor is not None else ():
+        rebin(d, rebin_factor, dwave)
     return out
 
 
 def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, tables, max_num_spec=None,
-                no_project=False, z_min_qso=0, z_max_qso=10, delta_attributes=None):
+                no_project=False, z_min_qso=0, z_max_qso=10, delta_attributes=None,
+                rebin_factor=None):
     """io.py:448-512.  ``tables`` = (z, r_comov, dist_m) of the cosmology; the distances are
     evaluated with scipy's interp1d like constants.py:211-229."""
     if in_dir.endswith(".fits.gz") or in_dir.endswith(".fits"):
@@ -108,7 +137,7 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, tables, max_num_spec=No
     order = find_order(delta_attributes)
     deltas = []
     for f in files:
-        deltas += read_delta_file(f, z_min_qso, z_max_qso, order)
+        deltas += read_delta_file(f, z_min_qso, z_max_qso, order, rebin_factor)
         if max_num_spec is not None and len(deltas) > max_num_spec:
             break
     if max_num_spec is not None:

@@ -117,10 +117,11 @@ EXPORTS = [
     "pb2_cov_boot_scratch_bytes", "pb2_cov_boot",
     "pb2_fits_scan", "pb2_fits_cards", "pb2_delta_unpack", "pb2_delta_prepare",
     "pb2_delta_image_count", "pb2_delta_image_unpack",
+    "pb2_fits_hierarch", "pb2_delta_wave", "pb2_delta_rebin",
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 
 def lib():

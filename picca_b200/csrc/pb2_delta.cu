@@ -182,6 +182,64 @@ int32_t pb2_fits_cards(const uint8_t *buf, int64_t len, int64_t n_hdu, const int
     return 0;
 }
 
+/* One long keyword in the ESO HIERARCH convention ("HIERARCH WAVE_SOLUTION = 'lin'", what fitsio
+ * writes for keywords longer than 8 characters) of the header starting at header_off.
+ * *kind = 0 missing / 1 number / 2 string; *num = numeric value; str24 = string value. */
+int32_t pb2_fits_hierarch(const uint8_t *buf, int64_t len, int64_t header_off, const char *key,
+                          int32_t *kind, double *num, char *str24)
+{
+    *kind = 0;
+    *num = 0.;
+    memset(str24, 0, 24);
+    const size_t klen = strlen(key);
+    int64_t pos = header_off;
+    for (;;) {
+        if (pos + FITS_BLOCK > len) {
+            pb2_set_error("pb2_fits_hierarch: header runs past the end of the file");
+            return PB2_EINVAL;
+        }
+        for (int c = 0; c < FITS_BLOCK / FITS_CARD; ++c) {
+            const uint8_t *card = buf + pos + c * FITS_CARD;
+            if (fits_key_is(card, "END     ")) return 0;
+            if (memcmp(card, "HIERARCH", 8) != 0) continue;
+            int p = 8;
+            while (p < FITS_CARD && card[p] == ' ') ++p;
+            if (p + (int)klen >= FITS_CARD || memcmp(card + p, key, klen) != 0) continue;
+            p += (int)klen;
+            while (p < FITS_CARD && card[p] == ' ') ++p;
+            if (p >= FITS_CARD || card[p] != '=') continue;
+            ++p;
+            while (p < FITS_CARD && card[p] == ' ') ++p;
+            if (p >= FITS_CARD) return 0;
+            if (card[p] == '\'') {
+                int o = 0;
+                ++p;
+                while (p < FITS_CARD && card[p] != '\'') {
+                    if (o < 23) str24[o++] = (char)card[p];
+                    ++p;
+                }
+                while (o > 0 && str24[o - 1] == ' ') str24[--o] = 0;
+                *kind = 2;
+            } else {
+                char tmp[72];
+                int o = 0;
+                while (p < FITS_CARD && card[p] != ' ' && card[p] != '/' && o < 70) {
+                    char ch = (char)card[p++];
+                    if (ch == 'D' || ch == 'd') ch = 'E';
+                    tmp[o++] = ch;
+                }
+                tmp[o] = 0;
+                if (o) {
+                    *kind = 1;
+                    *num = strtod(tmp, nullptr);
+                }
+            }
+            return 0;
+        }
+        pos += FITS_BLOCK;
+    }
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------- device: unpack
@@ -274,6 +332,114 @@ __global__ void pb2_delta_image_fill_kernel(long long n_los, const uint8_t *__re
         }
         out += __popc(mask);
     }
+}
+
+// ---------------------------------------------------------------------------------- device: rebin
+// Delta.rebin (data.py:657-686): the pixels of a forest are summed into bins of `factor` original
+// pixels: wave = 10**log_lambda; start = wave.min() - dwave/2; num_bins = ceil(((wave[-1] -
+// wave[0])/dwave + 1)/factor); edges[k] = k*dwave*factor + start; a pixel goes to bin
+// searchsorted(edges, wave) (left); bins 1 .. num_bins-1 with a non-zero weight sum survive, at the
+// mid-points of their edges.  One warp per forest, lane = output bin; the pixels of a bin are a
+// contiguous range of the (ascending) wavelengths, found by binary search and added in order --
+// the association of np.bincount, so the sums are bit-equal.  Pass 1 (fill == false) counts the
+// surviving bins, pass 2 compacts them (ballot prefix) into the new CSR arrays.
+__device__ __forceinline__ double rb_edge(int k, double dwave, double factor, double start)
+{
+    // np.arange(num_bins) * dwave * factor + start: left to right
+    return add_rn(mul_rn(mul_rn((double)k, dwave), factor), start);
+}
+
+// first pixel with wave > v
+__device__ __forceinline__ int rb_upper(const double *__restrict__ w, int n, double v)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (w[mid] <= v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool FILL>
+__global__ void pb2_delta_rebin_kernel(long long n_los, const long long *__restrict__ offset,
+                                       const double *__restrict__ wave,
+                                       const double *__restrict__ delta,
+                                       const double *__restrict__ weights,
+                                       const double *__restrict__ dwave_of, int factor_i,
+                                       int *__restrict__ count, int *__restrict__ status,
+                                       const long long *__restrict__ new_offset,
+                                       double *__restrict__ new_wave, double *__restrict__ new_delta,
+                                       double *__restrict__ new_weights)
+{
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= n_los) return;
+    const int lane = threadIdx.x & 31;
+    const long long a = offset[f];
+    const int n = (int)(offset[f + 1] - a);
+    if (n == 0) {
+        if (!FILL && lane == 0) count[f] = 0;
+        return;
+    }
+    const double *__restrict__ w = wave + a;
+    const double dwave = dwave_of[f], factor = (double)factor_i;
+    // wave.min() and the ascending order the bin ranges rely on
+    double wmin = 1e300;
+    bool sorted = true;
+    for (int p = lane; p < n; p += 32) {
+        wmin = fmin(wmin, w[p]);
+        if (p > 0 && w[p] < w[p - 1]) sorted = false;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, m));
+    if (!__all_sync(0xffffffffu, sorted)) {
+        if (lane == 0) atomicExch(status, 2);
+        if (!FILL && lane == 0) count[f] = 0;
+        return;
+    }
+    const double start = sub_rn(wmin, div_rn(dwave, 2.));
+    const int num_bins = (int)ceil(div_rn(add_rn(div_rn(sub_rn(w[n - 1], w[0]), dwave), 1.), factor));
+    int kept = 0;
+    long long out = FILL ? new_offset[f] : 0;
+    for (int k0 = 1; k0 < num_bins; k0 += 32) {  // [1:-1] of the bincount: bins 1 .. num_bins-1
+        const int k = k0 + lane;
+        double sw = 0., sdw = 0., lo_e = 0., hi_e = 0.;
+        if (k < num_bins) {
+            lo_e = rb_edge(k - 1, dwave, factor, start);
+            hi_e = rb_edge(k, dwave, factor, start);
+            const int p_lo = rb_upper(w, n, lo_e), p_hi = rb_upper(w, n, hi_e);
+            for (int p = p_lo; p < p_hi; ++p) {  // edges[k-1] < wave <= edges[k]
+                const double wp = weights[a + p];
+                sdw = add_rn(sdw, mul_rn(delta[a + p], wp));
+                sw = add_rn(sw, wp);
+            }
+        }
+        const bool keep = k < num_bins && sw != 0.;  // mask = binned_weight != 0
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (FILL && keep) {
+            const long long at = out + __popc(mask & ((1u << lane) - 1u));
+            new_wave[at] = div_rn(add_rn(hi_e, lo_e), 2.);  // (edges[1:] + edges[:-1]) / 2
+            new_delta[at] = div_rn(sdw, sw);
+            new_weights[at] = sw;
+        }
+        out += __popc(mask);
+        kept += __popc(mask);
+    }
+    if (!FILL && lane == 0) count[f] = kept;
+}
+
+// wave = 10**log_lambda (log_lambda = log10(lambda) first when the file stores LAMBDA)
+__global__ void pb2_delta_wave_kernel(long long n_pix, int wave_is_lambda,
+                                      double *__restrict__ log_lambda, double *__restrict__ wave)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    double ll = log_lambda[p];
+    if (wave_is_lambda) {
+        ll = log10(ll);
+        log_lambda[p] = ll;
+    }
+    wave[p] = exp10(ll);
 }
 
 // --------------------------------------------------------------------------------- device: prepare
@@ -451,6 +617,47 @@ int32_t pb2_delta_image_unpack(int64_t n_los, const uint8_t *d_raw, int64_t lamb
         (const long long *)d_offset, d_log_lambda, d_delta, d_weights);
     pb2_count_launch(1);
     return pb2_check_launch("pb2_delta_image_unpack");
+}
+
+int32_t pb2_delta_wave(int64_t n_pix, int32_t wave_is_lambda, double *d_log_lambda, double *d_wave,
+                       void *stream)
+{
+    if (n_pix <= 0) return 0;
+    if (!d_log_lambda || !d_wave) {
+        pb2_set_error("pb2_delta_wave: null pointer argument");
+        return PB2_EINVAL;
+    }
+    pb2_delta_wave_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n_pix, wave_is_lambda, d_log_lambda, d_wave);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_delta_wave");
+}
+
+int32_t pb2_delta_rebin(int64_t n_los, const int64_t *d_offset, const double *d_wave,
+                        const double *d_delta, const double *d_weights, const double *d_dwave,
+                        int32_t factor, int32_t *d_count, int32_t *d_status,
+                        const int64_t *d_new_offset, double *d_new_wave, double *d_new_delta,
+                        double *d_new_weights, void *stream)
+{
+    if (n_los <= 0) return 0;
+    if (!d_offset || !d_wave || !d_delta || !d_weights || !d_dwave || !d_status || factor < 1 ||
+        (!d_new_offset && !d_count) ||
+        (d_new_offset && (!d_new_wave || !d_new_delta || !d_new_weights))) {
+        pb2_set_error("pb2_delta_rebin: bad argument");
+        return PB2_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((n_los + 7) / 8);
+    if (!d_new_offset)
+        pb2_delta_rebin_kernel<false><<<blocks, 256, 0, s>>>(
+            n_los, (const long long *)d_offset, d_wave, d_delta, d_weights, d_dwave, factor, d_count,
+            d_status, nullptr, nullptr, nullptr, nullptr);
+    else
+        pb2_delta_rebin_kernel<true><<<blocks, 256, 0, s>>>(
+            n_los, (const long long *)d_offset, d_wave, d_delta, d_weights, d_dwave, factor, nullptr,
+            d_status, (const long long *)d_new_offset, d_new_wave, d_new_delta, d_new_weights);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_delta_rebin");
 }
 
 int32_t pb2_delta_prepare(int64_t n_los, const int64_t *d_offset, const int32_t *d_order,

@@ -24,7 +24,8 @@ dist_m are bit-equal.  Weights and projected deltas are within 1e-13 relative ei
 and re-associated sums).  Both on-disk flavours are read: one BinTable HDU per forest
 (``Delta.from_fitsio``) and the ImageHDU layout (``Delta.from_image``, data.py:519-620: common
 wavelength grid, METADATA table, 2-D images; ``pb2_delta_image_count`` / ``_unpack`` keep the
-pixels with WEIGHT > 0).  Not implemented: ``rebin_factor`` (raises NotImplementedError).
+pixels with WEIGHT > 0).  ``rebin_factor`` (``Delta.rebin``, data.py:657-686) runs on the device
+too (``pb2_delta_rebin``: bin sums in np.bincount's order, bit-equal given the same wavelengths).
 """
 import ctypes
 import glob
@@ -114,16 +115,42 @@ def _column_offsets(ttypes, tforms):
     return out, pos
 
 
-def _open_delta_file(path, z_min_qso, z_max_qso):
+def _hierarch(buf, header_off, key):
+    """Value of a long (HIERARCH) keyword of one header, or KeyError like fitsio's header."""
+    lib = _lib.lib()
+    kind, num = ctypes.c_int32(0), ctypes.c_double(0.)
+    text = ctypes.create_string_buffer(24)
+    _lib.check(lib.pb2_fits_hierarch(
+        buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size), ctypes.c_int64(header_off),
+        ctypes.c_char_p(key.encode("ascii")), ctypes.byref(kind), ctypes.byref(num), text),
+        "pb2_fits_hierarch")
+    if kind.value == 0:
+        raise KeyError(key)
+    return num.value if kind.value == 1 else text.value.decode("ascii", "replace")
+
+
+def _open_delta_file(path, z_min_qso, z_max_qso, rebin=False):
     """One delta file -> _FileForests (BinTable flavour) or _ImageForests (ImageHDU flavour);
-    io.py:354-360: an extension called LAMBDA selects Delta.from_image."""
+    io.py:354-360: an extension called LAMBDA selects Delta.from_image.  With ``rebin`` the
+    wavelength solution of the file is read like io.py:362-373 (header of the LAMBDA extension,
+    else of HDU 1)."""
     buf = _file_bytes(path)
     info = _scan(buf)
     kind, num, inum, strs = _cards(buf, info[:, 0])
     names = [s.decode("ascii", "replace") for s in strs[:, _K["EXTNAME"]]]
-    if "LAMBDA" in names:
-        return _ImageForests(path, buf, info, names, z_min_qso, z_max_qso)
-    return _FileForests(path, buf, info, kind, num, inum, strs, z_min_qso, z_max_qso)
+    image = "LAMBDA" in names
+    dwave = None
+    if rebin:
+        card = names.index("LAMBDA") if image else 1
+        if _hierarch(buf, int(info[card, 0]), "WAVE_SOLUTION") != 'lin':
+            raise ValueError('Delta rebinning only implemented for linear lambda bins')
+        dwave = float(_hierarch(buf, int(info[card, 0]), "DELTA_LAMBDA"))
+    if image:
+        part = _ImageForests(path, buf, info, names, z_min_qso, z_max_qso)
+    else:
+        part = _FileForests(path, buf, info, kind, num, inum, strs, z_min_qso, z_max_qso)
+    part.dwave = dwave
+    return part
 
 
 class _ImageForests:
@@ -358,8 +385,6 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         RuntimeError: projecting without a continuum order (data.py:628-633); CUDA errors
         ValueError: a redshift outside the cosmology table (scipy interp1d bounds error)
     """
-    if rebin_factor is not None:
-        raise NotImplementedError("picca_b200.io.read_deltas: rebin_factor is not implemented")
     in_dir = os.path.expandvars(in_dir)
     if len(in_dir) > 8 and in_dir[-8:] == '.fits.gz':
         files = sorted(glob.glob(in_dir))
@@ -376,7 +401,8 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     torch = eng.torch
     workers = nproc if nproc else (os.cpu_count() or 1)
     with ThreadPoolExecutor(max_workers=max(1, min(workers, 32))) as pool:
-        parts = list(pool.map(lambda f: _open_delta_file(f, z_min_qso, z_max_qso), files))
+        parts = list(pool.map(lambda f: _open_delta_file(f, z_min_qso, z_max_qso,
+                                                         rebin=rebin_factor is not None), files))
     for p in parts:  # ImageHDU files: the pixel counts come from the device
         if p.is_image:
             p.count_pixels(eng)
@@ -472,6 +498,62 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
             p.d_raw = p.d_rows = None
 
     mark("pinned staging + H2D + unpack kernels")
+    device_log10 = bool(wave_is_lambda.any())
+    host_pow = os.environ.get("PICCA_B200_HOST_POW", "0") == "1"
+
+    def host_log_lambda():
+        """parity mode: log_lambda (log10 taken with NumPy when the array holds wavelengths)"""
+        ll = d_ll.cpu().numpy()
+        if device_log10:
+            ll = np.log10(ll)
+            d_ll.copy_(torch.from_numpy(ll))
+        return ll
+
+    # ---- Delta.rebin (data.py:657-686, io.py:362-378)
+    if rebin_factor is not None:
+        userprint(f"Rebinning deltas by a factor of {rebin_factor}\n")
+        d_dwave = torch.from_numpy(np.concatenate(
+            [np.full(p.n, p.dwave, dtype=np.float64) for p in parts])[:n_los].copy()).to(dev)
+        d_wave = f64(total_pix)
+        if host_pow:
+            d_wave.copy_(torch.from_numpy(10**host_log_lambda()))  # data.py:666, NumPy power
+        else:
+            _lib.check(eng.lib.pb2_delta_wave(
+                ctypes.c_int64(total_pix), ctypes.c_int32(int(device_log10)),
+                ctypes.c_void_p(d_ll.data_ptr()), ctypes.c_void_p(d_wave.data_ptr()),
+                eng.stream_ptr()), "pb2_delta_wave")
+        d_count = torch.zeros(n_los, dtype=torch.int32, device=dev)
+        d_rstat = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def rebin_pass(new_offset, outs):
+            _lib.check(eng.lib.pb2_delta_rebin(
+                ctypes.c_int64(n_los), ctypes.c_void_p(d_offset.data_ptr()),
+                ctypes.c_void_p(d_wave.data_ptr()), ctypes.c_void_p(d_delta.data_ptr()),
+                ctypes.c_void_p(d_w.data_ptr()), ctypes.c_void_p(d_dwave.data_ptr()),
+                ctypes.c_int32(int(rebin_factor)), ctypes.c_void_p(d_count.data_ptr()),
+                ctypes.c_void_p(d_rstat.data_ptr()),
+                ctypes.c_void_p(new_offset.data_ptr()) if new_offset is not None else None,
+                *[ctypes.c_void_p(t.data_ptr()) if t is not None else None for t in outs],
+                eng.stream_ptr()), "pb2_delta_rebin")
+
+        rebin_pass(None, (None, None, None))
+        if int(d_rstat.item()) == 2:
+            raise NotImplementedError("picca_b200.io: rebinning needs ascending wavelengths in "
+                                      "every forest")
+        n_pix = d_count.cpu().numpy().astype(np.int64)
+        if np.any(n_pix == 0):  # the reference's `z.min()` of an emptied forest (io.py:497)
+            raise ValueError("zero-size array to reduction operation minimum which has no "
+                             "identity")
+        offset = np.zeros(n_los + 1, dtype=np.int64)
+        np.cumsum(n_pix, out=offset[1:])
+        total_pix = int(offset[-1])
+        d_new_offset = torch.from_numpy(offset).to(dev)
+        new_ll, new_delta, new_w = f64(total_pix), f64(total_pix), f64(total_pix)
+        rebin_pass(d_new_offset, (new_ll, new_delta, new_w))
+        # the rebinned forests hold WAVELENGTHS until log10 is taken below (data.py:684)
+        d_ll, d_delta, d_w, d_offset = new_ll, new_delta, new_w, d_new_offset
+        device_log10 = True
+        mark("rebin kernels")
     # ---- z, distances, weight evolution, projection (io.py:493-507)
     d_z, d_range = f64(total_pix), f64(2 * n_los)
     d_status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -489,13 +571,9 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         tabs = (ctypes.c_int32(0), None, None, None)
         dist = (None, None)
     d_z_in = None
-    device_log10 = bool(wave_is_lambda.any())
-    if os.environ.get("PICCA_B200_HOST_POW", "0") == "1":
-        ll_host = d_ll.cpu().numpy()
-        if device_log10:  # data.py:411-412 with NumPy's log10 as well
-            ll_host = np.log10(ll_host)
-            d_ll.copy_(torch.from_numpy(ll_host))
-            device_log10 = False
+    if host_pow:
+        ll_host = host_log_lambda()
+        device_log10 = False
         d_z_in = torch.from_numpy(10**ll_host / lambda_abs - 1.).to(dev)  # io.py:496, NumPy power
     _lib.check(eng.lib.pb2_delta_prepare(
         ctypes.c_int64(n_los), ctypes.c_void_p(d_offset.data_ptr()),

@@ -1,8 +1,8 @@
 """``picca.io`` = the reference's module with ``read_deltas`` (py/picca/io.py:383-512) replaced
 by the B200 delta loader.  Everything else in the module (read_objects, read_drq, read_blinding,
 ...) is the reference's own code, executed from its file.  Inputs the B200 loader does not
-implement (``rebin_factor``) are handed to the reference's own
-``read_deltas`` with a notice; ``PICCA_B200_IO=0`` keeps the reference loader for everything."""
+implement (it raises NotImplementedError: e.g. non-fp64 columns, unsorted wavelengths under
+``rebin_factor``) are handed to the reference's own ``read_deltas`` with a notice; ``PICCA_B200_IO=0`` keeps the reference loader for everything."""
 import importlib.util
 import os
 import sys

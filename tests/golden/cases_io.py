@@ -17,6 +17,10 @@ CASES = {
     "sdss": dict(seed=21, files=[40, 7, 25], ids="THING_ID", wave="LOGLAM", order=1),
     "desi": dict(seed=22, files=[33, 12], ids="LOS_ID", wave="LAMBDA", order=0),
     "blind": dict(seed=23, files=[9], ids="LOS_ID", wave="LOGLAM", order=1, blinding="desi_m2"),
+    # for rebin_factor: no single-pixel and no all-zero-weight forests (rebinning empties them and
+    # the reference then fails on the empty arrays, io.py:493-497)
+    "lin": dict(seed=24, files=[20, 9], ids="THING_ID", wave="LOGLAM", order=1, min_pix=12,
+                keep_weights=True),
 }
 
 
@@ -36,13 +40,14 @@ def write_case(root, name):
             z_qso = float(rng.uniform(2.0, 3.5))
             if f % 13 == 5:
                 z_qso = 10.5  # outside the default quasar redshift cut (io.py:359-360)
-            n = int(rng.integers(1, 260)) if f % 7 else 1  # single-pixel forests too
+            lo = cfg.get("min_pix", 1)
+            n = int(rng.integers(lo, 260)) if f % 7 else lo  # single-pixel forests too
             lam0 = 1040. * (1. + min(z_qso, 3.5)) + rng.uniform(0, 0.8)
             lam = lam0 + 0.8 * np.arange(n)
             delta = rng.normal(0., 0.3, n)
             weight = rng.uniform(0.2, 3., n)
             weight[rng.random(n) < 0.05] = 0.
-            if f % 11 == 3:
+            if f % 11 == 3 and not cfg.get("keep_weights"):
                 weight[:] = 0.  # project() returns early (data.py:636-640)
             cont = rng.uniform(0.5, 2., n)
             wave = np.log10(lam) if cfg["wave"] == "LOGLAM" else lam
@@ -57,12 +62,19 @@ def write_case(root, name):
             else:
                 head += [{"name": "LOS_ID", "value": 39627000000000000 + los}]
             head.append({"name": "ORDER", "value": cfg["order"]})
+            head += [{"name": k, "value": v} for k, v in WAVE_CARDS]
             names = [cfg["wave"], "DELTA", "WEIGHT", "CONT"]
             if "blinding" in cfg:
                 head.append({"name": "BLINDING", "value": cfg["blinding"]})
                 names[1] = "DELTA_BLIND"
             out.write([wave, delta, weight, cont], names=names, header=head, extname=str(los))
         out.close()
+        import gzip
+        path = os.path.join(in_dir, "delta-%d.fits.gz" % (100 + k))
+        with gzip.open(path, "rb") as fh:
+            raw = fh.read()
+        with gzip.open(path, "wb") as fh:
+            fh.write(_hierarch(raw))
     attr = os.path.join(root, name, "delta_attributes.fits.gz")
     out = minifits.FITS(attr, "rw", clobber=True)
     out.write([np.arange(3.)], names=["LOGLAM"], extname="STACK_DELTAS")
@@ -72,13 +84,30 @@ def write_case(root, name):
     return in_dir, attr
 
 
-def _image_hdu(name, arr):
+def _hierarch(raw):
+    """swap the placeholder cards HWAVESOL / HDLAMBDA for the HIERARCH cards fitsio writes for the
+    long keywords WAVE_SOLUTION / DELTA_LAMBDA (delta files of picca's delta extraction)"""
+    raw = bytes(raw)
+    for short, long in ((b"HWAVESOL", b"WAVE_SOLUTION"), (b"HDLAMBDA", b"DELTA_LAMBDA")):
+        pos = raw.find(short + b"= ")
+        while pos >= 0:
+            value = raw[pos + 10:pos + 80].strip()
+            card = (b"HIERARCH " + long + b" = " + value).ljust(80)
+            raw = raw[:pos] + card + raw[pos + 80:]
+            pos = raw.find(short + b"= ")
+    return raw
+
+
+WAVE_CARDS = [("HWAVESOL", "lin"), ("HDLAMBDA", 0.8)]
+
+
+def _image_hdu(name, arr, extra=()):
     arr = np.asarray(arr, dtype=np.float64)
     cards = [("XTENSION", "IMAGE"), ("BITPIX", -64), ("NAXIS", arr.ndim)]
     cards += [("NAXIS%d" % (k + 1), n) for k, n in enumerate(arr.shape[::-1])]
-    cards += [("PCOUNT", 0), ("GCOUNT", 1), ("EXTNAME", name)]
+    cards += [("PCOUNT", 0), ("GCOUNT", 1), ("EXTNAME", name)] + list(extra)
     raw = arr.astype(">f8").tobytes()
-    return minifits._cards_to_bytes(cards) + raw + b"\0" * ((-len(raw)) % minifits.BLOCK)
+    return _hierarch(minifits._cards_to_bytes(cards)) + raw + b"\0" * ((-len(raw)) % minifits.BLOCK)
 
 
 IMAGE_CASES = {
@@ -98,7 +127,7 @@ def write_image_case(root, name):
     in_dir = os.path.join(root, name, "Delta")
     os.makedirs(in_dir, exist_ok=True)
     n_lambda = 300
-    lam = 3600. + 0.8 * np.arange(n_lambda) * 4
+    lam = 3600. + 0.8 * np.arange(n_lambda)
     los = 2000 * cfg["seed"]
     for k, n_forest in enumerate(cfg["files"]):
         z_qso = rng.uniform(2.0, 3.4, n_forest)
@@ -107,7 +136,7 @@ def write_image_case(root, name):
         weight = rng.uniform(0.2, 3., (n_forest, n_lambda))
         for f in range(n_forest):  # a forest covers part of the grid; zeros / negatives elsewhere
             a = int(rng.integers(0, n_lambda - 40))
-            b = int(rng.integers(a + 1, n_lambda))
+            b = int(rng.integers(a + 12, n_lambda))
             weight[f, :a] = 0.
             weight[f, b:] = -1.
             weight[f, rng.random(n_lambda) < 0.04] = 0.
@@ -115,7 +144,8 @@ def write_image_case(root, name):
         los += n_forest
         out = bytearray(minifits._cards_to_bytes([("SIMPLE", True), ("BITPIX", 8), ("NAXIS", 0),
                                                   ("EXTEND", True)]))
-        out += _image_hdu(cfg["wave"], lam if cfg["wave"] == "LAMBDA" else np.log10(lam))
+        out += _image_hdu(cfg["wave"], lam if cfg["wave"] == "LAMBDA" else np.log10(lam),
+                          extra=WAVE_CARDS)
         head = [{"name": "BLINDING", "value": cfg.get("blinding", "none")}]
         out += minifits._table_bytes(
             [ids, rng.uniform(0.1, 0.2, n_forest), rng.uniform(-0.02, 0.08, n_forest), z_qso,

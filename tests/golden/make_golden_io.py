@@ -42,6 +42,8 @@ def main():
         os.path.join(fx, "delta_attributes.fits.gz"))
     run("imagefixture", os.path.join(fx, "image-delta-50.fits.gz"),
         os.path.join(fx, "delta_attributes.fits.gz"))
+    run("imagefixture_rebin3", os.path.join(fx, "image-delta-50.fits.gz"),
+        os.path.join(fx, "delta_attributes.fits.gz"), rebin_factor=3)
     with tempfile.TemporaryDirectory() as tmp:
         for name in cases_io.IMAGE_CASES:
             in_dir, attr = cases_io.write_image_case(tmp, name)
@@ -53,6 +55,10 @@ def main():
         run("sdss_noproject", in_dir, attr, no_project=True)
         run("sdss_max30", in_dir, attr, max_num_spec=30)
         run("sdss_zcut", in_dir, attr, z_min_qso=2.4, z_max_qso=3.0)
+        in_dir, attr = cases_io.write_case(tmp, "lin")
+        run("lin_rebin2", in_dir, attr, rebin_factor=2)
+        in_dir, attr = cases_io.write_image_case(tmp, "image")
+        run("image_rebin3", in_dir, attr, rebin_factor=3)
     np.savez_compressed(os.path.join(HERE, "golden_io.npz"), **out)
 
 

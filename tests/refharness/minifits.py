@@ -71,6 +71,11 @@ def _read_header(buf, pos):
                 break
             if card[8:10] == "= ":
                 header[key] = _parse_value(card[10:])
+            elif key == "HIERARCH" and "=" in card:
+                # ESO HIERARCH convention for keywords longer than 8 characters (what fitsio
+                # writes for WAVE_SOLUTION / DELTA_LAMBDA in the delta files)
+                long_key, value = card[8:].split("=", 1)
+                header[long_key.strip()] = _parse_value(value)
         if done:
             break
     return header, pos

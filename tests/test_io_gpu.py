@@ -18,7 +18,9 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RUNS = {"fixture": None, "imagefixture": None, "image": {}, "imageblind": {}, "sdss": {}, "desi": {}, "blind": {},
         "sdss_noproject": dict(no_project=True), "sdss_max30": dict(max_num_spec=30),
-        "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0)}
+        "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0),
+        "lin_rebin2": dict(rebin_factor=2), "image_rebin3": dict(rebin_factor=3),
+        "imagefixture_rebin3": dict(rebin_factor=3)}
 
 
 class TableCosmo:
@@ -35,11 +37,11 @@ def inputs(tag, tmp_path):
     fx = os.path.join(GOLD, "fixtures")
     if tag == "fixture":
         return os.path.join(fx, "delta-272.fits.gz"), os.path.join(fx, "delta_attributes.fits.gz")
-    if tag == "imagefixture":
+    if tag.startswith("imagefixture"):
         return (os.path.join(fx, "image-delta-50.fits.gz"),
                 os.path.join(fx, "delta_attributes.fits.gz"))
-    if tag in cases_io.IMAGE_CASES:
-        return cases_io.write_image_case(str(tmp_path), tag)
+    if tag.split("_")[0] in cases_io.IMAGE_CASES:
+        return cases_io.write_image_case(str(tmp_path), tag.split("_")[0])
     return cases_io.write_case(str(tmp_path), tag.split("_")[0])
 
 
@@ -80,9 +82,13 @@ def test_read_deltas_matches_reference_golden(tag, host_pow, tmp_path, monkeypat
             assert np.array_equal(flat[k], g(k)), k
         assert [z_min, z_max] == list(g("summary")[1:])
     else:
-        assert ulp_distance(flat["log_lambda"], g("log_lambda")).max() <= (2 if stores_lambda else 0)
+        # rebinned forests: exp10 -> bin mid-points -> log10 all on the device
+        rebinned = "rebin" in tag
+        ll_ulp = 4 if rebinned else (2 if stores_lambda else 0)
+        assert ulp_distance(flat["log_lambda"], g("log_lambda")).max() <= ll_ulp
         for k in ("z", "r_comov", "dist_m"):
-            assert ulp_distance(flat[k], g(k)).max() <= (16 if stores_lambda else 4), k
+            assert ulp_distance(flat[k], g(k)).max() <= (32 if rebinned else
+                                                         16 if stores_lambda else 4), k
         np.testing.assert_allclose([z_min, z_max], g("summary")[1:], rtol=4e-15)
     close_on_forest_scale(flat["weights"], g("weights"), flat["n_pix"], 1e-12)
     # a projected delta is a difference of O(1) numbers (and a 3-pixel linear fit is a cancelling
@@ -123,8 +129,13 @@ def test_error_behaviour(tmp_path):
     gold = np.load(os.path.join(GOLD, "golden_io.npz"))
     cosmo = TableCosmo(gold)
     in_dir, attr = cases_io.write_case(str(tmp_path), "desi")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # rebinning empties the single-pixel forests of this case
         io.read_deltas(in_dir, cosmo=cosmo, delta_attributes=attr, rebin_factor=2,
+                       **cases_io.READ_KW)
+    fx = os.path.join(GOLD, "fixtures")
+    with pytest.raises(KeyError):  # no WAVE_SOLUTION card in the bundled BinTable file (io.py:368)
+        io.read_deltas(os.path.join(fx, "delta-272.fits.gz"), cosmo=cosmo, rebin_factor=2,
+                       delta_attributes=os.path.join(fx, "delta_attributes.fits.gz"),
                        **cases_io.READ_KW)
     with pytest.raises(AssertionError):  # io.py:489-490: nothing passes the quasar redshift cut
         io.read_deltas(in_dir, cosmo=cosmo, delta_attributes=attr, z_min_qso=8., z_max_qso=9.,

@@ -177,7 +177,9 @@ def test_export_covariance_reference_fixture():
 # ---- delta loader (oracle/io.py against the live reference's io.read_deltas outputs)
 IO_RUNS = {"fixture": None, "imagefixture": None, "image": {}, "imageblind": {}, "sdss": {}, "desi": {}, "blind": {},
            "sdss_noproject": dict(no_project=True), "sdss_max30": dict(max_num_spec=30),
-           "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0)}
+           "sdss_zcut": dict(z_min_qso=2.4, z_max_qso=3.0),
+        "lin_rebin2": dict(rebin_factor=2), "image_rebin3": dict(rebin_factor=3),
+        "imagefixture_rebin3": dict(rebin_factor=3)}
 
 
 def io_inputs(tag, tmp_path):
@@ -185,11 +187,11 @@ def io_inputs(tag, tmp_path):
     fx = os.path.join(GOLD, "fixtures")
     if tag == "fixture":
         return os.path.join(fx, "delta-272.fits.gz"), os.path.join(fx, "delta_attributes.fits.gz")
-    if tag == "imagefixture":
+    if tag.startswith("imagefixture"):
         return (os.path.join(fx, "image-delta-50.fits.gz"),
                 os.path.join(fx, "delta_attributes.fits.gz"))
-    if tag in cases_io.IMAGE_CASES:
-        return cases_io.write_image_case(str(tmp_path), tag)
+    if tag.split("_")[0] in cases_io.IMAGE_CASES:
+        return cases_io.write_image_case(str(tmp_path), tag.split("_")[0])
     return cases_io.write_case(str(tmp_path), tag.split("_")[0])
 
 

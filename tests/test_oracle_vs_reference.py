@@ -247,8 +247,8 @@ def test_export_covariance_equals_live_reference(name):
     assert np.array_equal(got_b, want_b, equal_nan=True)
 
 
-@pytest.mark.parametrize("which", ["bundled", "bundled_image", "image", "imageblind", "sdss", "desi",
-                                   "blind"])
+@pytest.mark.parametrize("which", ["bundled", "bundled_image", "bundled_image_rebin3", "image",
+                                   "imageblind", "sdss", "desi", "blind", "lin_rebin2"])
 def test_read_deltas_equals_live_reference(which, tmp_path):
     """oracle/io.py against the live io.read_deltas (py/picca/io.py:383-512), bit for bit: the
     reference's bundled Delta_LYA directory (936 forests) and the generated cases."""
@@ -260,17 +260,19 @@ def test_read_deltas_equals_live_reference(which, tmp_path):
     cosmo = constants.Cosmo(Om=0.315, Or=0., Ok=0., wl=-1., blinding="none", verbose=False)
     if which == "bundled":
         in_dir, attr = DATA + "/test_delta/Delta_LYA/", DATA + "/test_delta/delta_attributes.fits.gz"
-    elif which == "bundled_image":
+    elif which.startswith("bundled_image"):
         in_dir = DATA + "/test_delta/Delta_LYA_image/"
         attr = DATA + "/test_delta/delta_attributes.fits.gz"
     elif which in cases_io.IMAGE_CASES:
         in_dir, attr = cases_io.write_image_case(str(tmp_path), which)
     else:
-        in_dir, attr = cases_io.write_case(str(tmp_path), which)
-    want = io.read_deltas(in_dir, cosmo=cosmo, nproc=1, delta_attributes=attr, **cases_io.READ_KW)
+        in_dir, attr = cases_io.write_case(str(tmp_path), which.split("_")[0])
+    kw = dict(cases_io.READ_KW)
+    if "rebin" in which:  # io.py:362-378, data.py:657-686 (test_3_cor.py:288-316 uses 3)
+        kw["rebin_factor"] = int(which[-1])
+    want = io.read_deltas(in_dir, cosmo=cosmo, nproc=1, delta_attributes=attr, **kw)
     tables = (cosmo.get_r_comov.x, cosmo.get_r_comov.y, cosmo.get_dist_m.y)
-    got = oio.read_deltas(in_dir.rstrip("/"), tables=tables, delta_attributes=attr,
-                          **cases_io.READ_KW)
+    got = oio.read_deltas(in_dir.rstrip("/"), tables=tables, delta_attributes=attr, **kw)
     assert got[1:] == want[1:]
     a, b = cases_io.flatten(got[0]), cases_io.flatten(want[0])
     for k in a:
