@@ -25,7 +25,9 @@ and re-associated sums).  Both on-disk flavours are read: one BinTable HDU per f
 (``Delta.from_fitsio``) and the ImageHDU layout (``Delta.from_image``, data.py:519-620: common
 wavelength grid, METADATA table, 2-D images; ``pb2_delta_image_count`` / ``_unpack`` keep the
 pixels with WEIGHT > 0).  ``rebin_factor`` (``Delta.rebin``, data.py:657-686) runs on the device
-too (``pb2_delta_rebin``: bin sums in np.bincount's order, bit-equal given the same wavelengths).
+too (``pb2_delta_rebin``: bin sums in np.bincount's order, bit-equal given the same wavelengths;
+the wavelengths ``10**log_lambda`` of that step are always NumPy's, because the reference's bin
+count is decided by their last ulp).
 """
 import ctypes
 import glob
@@ -515,8 +517,13 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
         d_dwave = torch.from_numpy(np.concatenate(
             [np.full(p.n, p.dwave, dtype=np.float64) for p in parts])[:n_los].copy()).to(dev)
         d_wave = f64(total_pix)
-        if host_pow:
-            d_wave.copy_(torch.from_numpy(10**host_log_lambda()))  # data.py:666, NumPy power
+        if host_pow or os.environ.get("PICCA_B200_REBIN_DEVICE_WAVE", "0") != "1":
+            # data.py:666 with NumPy's power, always: the reference's bin count
+            # ceil(((wave[-1] - wave[0]) / dwave + 1) / factor) sits exactly on an integer whenever
+            # the forest length + 1 is a multiple of the factor, so one ulp in `wave` decides
+            # whether a trailing bin exists; taking the reference's own power keeps its answer
+            d_wave.copy_(torch.from_numpy(10**host_log_lambda()))
+            device_log10 = False  # d_ll now holds log10 values
         else:
             _lib.check(eng.lib.pb2_delta_wave(
                 ctypes.c_int64(total_pix), ctypes.c_int32(int(device_log10)),
