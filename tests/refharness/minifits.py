@@ -297,6 +297,12 @@ def _table_bytes(data, names, units, header, extname):
             base, code = ">i8", "K"
         elif col.dtype.kind == "b":
             base, code = "S1", "L"
+        elif col.dtype.kind in "SU":  # fixed-width strings: nA (picca_metal_dmat.py's ABS_IGM)
+            col = col.astype("S")
+            cols[len(fields)] = col
+            fields.append((name, col.dtype))
+            tforms.append("%dA" % col.dtype.itemsize)
+            continue
         else:
             raise TypeError(col.dtype)
         fields.append((name, base, shape) if shape else (name, base))

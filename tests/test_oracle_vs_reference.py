@@ -186,7 +186,7 @@ def _compare_fits(path_got, path_want):
     assert len(got) == len(want)
     for h in range(1, len(want)):
         tg, tw = got[h].read(), want[h].read()
-        assert tg.dtype.names == tw.dtype.names
+        assert sorted(tg.dtype.names) == sorted(tw.dtype.names)  # test_helpers.py:77-81: by name
         for name in tw.dtype.names:
             if not np.array_equal(tg[name], tw[name]):
                 assert np.allclose(tg[name], tw[name], rtol=1e-5, atol=1e-8), (h, name)
@@ -310,3 +310,109 @@ def test_co_bit_exact_on_bundled_catalogue(fixture_data, type_corr, x_corr):
             assert np.array_equal(a, b)
         total += int(res[0][4].sum())
     assert total > 100
+
+
+# ---- the rows of SURVEY 8f: the reference's unmodified scripts on the oracle doubles against the
+# reference's own golden FITS (exact command lines of test_3_cor.py)
+def test_metal_dmat_script_on_oracle_matches_golden_fits(tmp_path):
+    """picca_metal_dmat.py (test_3_cor.py:351-381) driving oracle.cf.compute_metal_dmat."""
+    import importlib
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin.picca_metal_dmat")
+    ocf = importlib.reload(importlib.import_module("oracle.cf"))
+    saved = mod.cf
+    mod.cf = ocf
+    out = str(tmp_path / "metal_dmat.fits.gz")
+    try:
+        mod.main((COMMON + " --rp-min +0.0 --np 15 --rej 0.99 --abs-igm SiIII(1207) --out "
+                  + out).split())
+    finally:
+        mod.cf = saved
+    _compare_fits(out, DATA + "/test_cor/metal_dmat.fits.gz")
+
+
+def test_metal_xdmat_script_on_oracle_matches_golden_fits(tmp_path):
+    """picca_metal_xdmat.py (test_3_cor.py:700-730) driving oracle.xcf.compute_metal_dmat."""
+    import importlib
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin.picca_metal_xdmat")
+    oxcf = importlib.reload(importlib.import_module("oracle.xcf"))
+    saved = mod.xcf
+    mod.xcf = oxcf
+    out = str(tmp_path / "metal_xdmat.fits.gz")
+    try:
+        mod.main((COMMON + " --rp-min -60.0 --np 30 --rej 0.99 --z-evol-obj 1. --abs-igm SiIII(1207)"
+                  " --drq " + DATA + "/test_delta/cat.fits --out " + out).split())
+    finally:
+        mod.xcf = saved
+    _compare_fits(out, DATA + "/test_cor/metal_xdmat.fits.gz")
+
+
+def test_co_script_on_oracle_matches_golden_fits(tmp_path):
+    """picca_co.py --type-corr DD (test_3_cor.py:1084-1095) driving oracle.co."""
+    import importlib
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin.picca_co")
+    oco = importlib.reload(importlib.import_module("oracle.co"))
+    saved = mod.co
+    mod.co = oco
+    out = str(tmp_path / "co_DD.fits.gz")
+    try:
+        mod.main(("--drq " + DATA + "/test_delta/cat.fits --out " + out + " --rp-min 0. --rp-max +60.0"
+                  " --rt-max +60.0 --np 15 --nt 15 --nproc 1 --type-corr DD").split())
+    finally:
+        mod.co = saved
+    _compare_fits(out, DATA + "/test_cor/co_DD.fits.gz")
+
+
+def test_export_script_on_oracle_matches_golden_fits(tmp_path):
+    """picca_export.py (test_3_cor.py:443-456) with the oracle's compute_cov / smooth_cov."""
+    import importlib
+    from oracle import export as oexp
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin.picca_export")
+    saved = mod.compute_cov, mod.smooth_cov
+    mod.compute_cov, mod.smooth_cov = oexp.compute_cov, oexp.smooth_cov
+    out = str(tmp_path / "exported_cf.fits.gz")
+    try:
+        mod.main(("--data " + DATA + "/test_cor/cf.fits.gz --dmat " + DATA +
+                  "/test_cor/dmat.fits.gz --out " + out).split())
+    finally:
+        mod.compute_cov, mod.smooth_cov = saved
+    _compare_fits(out, DATA + "/test_cor/exported_cf.fits.gz")
+
+
+@pytest.mark.parametrize("flags,golden", [("", "cf_image"), (" --rebin-factor 3", "cf_image_rebinned")])
+def test_cf_script_on_oracle_loader_matches_golden_fits(tmp_path, flags, golden):
+    """picca_cf.py on the ImageHDU deltas (test_3_cor.py:259-316) with BOTH the oracle loader
+    (oracle.io.read_deltas in place of io.read_deltas) and the oracle cf."""
+    import importlib
+    from oracle import io as oio
+    from tests.refharness import load
+    load.reference_modules()
+    mod = importlib.import_module("picca.bin.picca_cf")
+    ocf = importlib.reload(importlib.import_module("oracle.cf"))
+
+    def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=None,
+                    no_project=False, nproc=None, rebin_factor=None, z_min_qso=0, z_max_qso=10,
+                    delta_attributes=None):
+        tables = (cosmo.get_r_comov.x, cosmo.get_r_comov.y, cosmo.get_dist_m.y)
+        return oio.read_deltas(in_dir.rstrip("/"), nside, lambda_abs, alpha, z_ref, tables,
+                               max_num_spec=max_num_spec, no_project=no_project,
+                               z_min_qso=z_min_qso, z_max_qso=z_max_qso,
+                               delta_attributes=delta_attributes, rebin_factor=rebin_factor)
+
+    saved_cf, saved_rd = mod.cf, mod.io.read_deltas
+    mod.cf, mod.io.read_deltas = ocf, read_deltas
+    out = str(tmp_path / (golden + ".fits.gz"))
+    try:
+        mod.main((" --rp-max +60.0 --rt-max +60.0 --nt 15 --nproc 1 --rp-min +0.0 --np 15"
+                  " --in-attributes " + DATA + "/test_delta/delta_attributes.fits.gz --in-dir " +
+                  DATA + "/test_delta/Delta_LYA_image/" + flags + " --out " + out).split())
+    finally:
+        mod.cf, mod.io.read_deltas = saved_cf, saved_rd
+    _compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz")
