@@ -191,3 +191,22 @@ def test_pair_list_subset_matches_numpy_selection():
     assert np.array_equal(sub.nb_f2.numpy(), f2[keep])
     assert np.array_equal(sub.nb_f1.numpy(), f1[keep])
     assert np.array_equal(sub.nb_ang.numpy(), ang[keep])
+
+
+def test_smooth_cov_key_extents_cover_every_key():
+    """export._smooth_extents sizes the device key table of pb2_cov_smooth: every key the
+    reference's loops form (utils.py:203-211) must fall inside, for cf- and xcf-like binnings."""
+    from picca_b200 import export
+    from tests.golden import cases_export
+    for name, cfg in cases_export.CASES.items():
+        _, _, rp, rt = cases_export.inputs(cfg)
+        for per_r_par in (False, True):
+            n_dp, n_dt, rp_lo, n_rp = export._smooth_extents(rp, rt, cfg["delta_r_par"],
+                                                             cfg["delta_r_trans"], per_r_par)
+            i, j = np.triu_indices(len(rp), 1)
+            k_dp = np.rint(np.abs(rp[j] - rp[i]) / cfg["delta_r_par"]).astype(int)
+            k_dt = np.rint(np.abs(rt[i] - rt[j]) / cfg["delta_r_trans"]).astype(int)
+            assert k_dp.max() < n_dp and k_dt.max() < n_dt, name
+            if per_r_par:
+                k_rp = np.trunc(rp[i] / cfg["delta_r_par"]).astype(int) - rp_lo
+                assert k_rp.min() >= 0 and k_rp.max() < n_rp, name
