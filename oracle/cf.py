@@ -3,7 +3,9 @@ functions, same return tuples, computed on the CPU by the C restatement.
 TEST INFRASTRUCTURE ONLY -- the referee for picca_b200.cf, never the product.
 
 Restates: fill_neighs (cf.py:82-135), compute_xi (cf.py:138-247), compute_dmat (cf.py:390-517),
-compute_metal_dmat (cf.py:890-1232).
+compute_metal_dmat (cf.py:890-1232), compute_wick_terms for max_diagram <= 3 with
+compute_wickT123_pairs (cf.py:1326-1494, :1497-1626; prepared for the next round: no CUDA
+counterpart yet).
 """
 import sys
 
@@ -217,3 +219,88 @@ def compute_metal_dmat(healpixs, abs_igm1="LYA", abs_igm2="SiIII(1207)"):
     weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = out
     return (weights_dmat, dmat.reshape(nb, nbm), r_par_eff, r_trans_eff, z_eff, weight_eff,
             num_pairs, num_pairs_used)
+
+
+# ---- Wick expansion, terms T1-T3 (cf.py:1326-1626).  Globals as the reference: the script fills
+# get_variance_1d / xi_1d per delta.fname and sets max_diagram (picca_wick.py:336, :393-416).
+get_variance_1d = {}
+xi_1d = {}
+max_diagram = None
+
+
+def _weighted_xi_1d(delta):
+    """cf.py:1413-1421"""
+    variance_1d = get_variance_1d[delta.fname](delta.log_lambda)
+    weights = delta.weights
+    return ((weights * weights[:, None]) *
+            xi_1d[delta.fname](abs(delta.log_lambda - delta.log_lambda[:, None])) *
+            np.sqrt(variance_1d * variance_1d[:, None]))
+
+
+def compute_wickT123_pairs(r_comov1, r_comov2, ang, weights1, weights2, z1, z2, weighted_xi_1d_1,
+                           weighted_xi_1d_2, weights_wick, num_pairs_wick, t1, t2, t3):
+    """cf.py:1553-1626.  The selected pixel pairs are enumerated in the reference's order (ind2
+    outer, ind1 inner, :1562-1596); its double loop over ordered pairs of selected pixel pairs
+    (:1598-1624) is restated with the (index1 < index2) list in row-major order and np.add.at
+    (sequential, unbuffered), each product added to [p1, p2] then [p2, p1] as the reference does."""
+    n1, n2 = len(r_comov1), len(r_comov2)
+    z_weight_evol1 = ((1 + z1) / (1 + z_ref))**(alpha - 1)
+    z_weight_evol2 = ((1 + z2) / (1 + z_ref))**(alpha2 - 1)
+    ind2, ind1 = [a.reshape(-1) for a in np.meshgrid(np.arange(n2), np.arange(n1), indexing="ij")]
+    r_par = (r_comov1[ind1] - r_comov2[ind2]) * np.cos(ang / 2)
+    if not x_correlation:
+        r_par = abs(r_par)
+    r_trans = (r_comov1[ind1] + r_comov2[ind2]) * np.sin(ang / 2)   # r_comov, not dist_m (:1567)
+    sel = (r_par < r_par_max) & (r_trans < r_trans_max) & (r_par >= r_par_min)
+    if sel.sum() == 0:
+        return
+    i, j, r_par, r_trans = ind1[sel], ind2[sel], r_par[sel], r_trans[sel]
+    bins_forest = ((r_trans / r_trans_max * num_bins_r_trans).astype(np.int64) + num_bins_r_trans *
+                   ((r_par - r_par_min) / (r_par_max - r_par_min) * num_bins_r_par).astype(np.int64))
+    weights12 = weights1[i] * weights2[j]
+    weight1, weight2 = weights1[i], weights2[j]
+    z_weight_evol = z_weight_evol1[i] * z_weight_evol2[j]
+    np.add.at(weights_wick, bins_forest, weights12)                       # :1602
+    np.add.at(num_pairs_wick, bins_forest, 1)
+    np.add.at(t1, (bins_forest, bins_forest), weights12 * z_weight_evol)  # :1604
+    a, b = np.triu_indices(len(i), 1)                                     # index1 < index2
+    p1, p2 = bins_forest[a], bins_forest[b]
+    same_i, same_j = i[a] == i[b], (j[a] == j[b]) & (i[a] != i[b])
+    other = ~same_i & ~same_j
+    prod = np.where(same_i, weighted_xi_1d_2[j[a], j[b]] * weight1[a] * z_weight_evol1[i[a]],
+                    weighted_xi_1d_1[i[a], i[b]] * weight2[b] * z_weight_evol2[j[a]])   # :1610-1617
+    prod3 = weighted_xi_1d_1[i[a], i[b]] * weighted_xi_1d_2[j[a], j[b]]                # :1619-1621
+    for target, mask, values in ((t2, ~other, prod), (t3, other, prod3)):
+        rows = np.stack([p1[mask], p2[mask]], axis=1).reshape(-1)   # [p1, p2] then [p2, p1]
+        cols = np.stack([p2[mask], p1[mask]], axis=1).reshape(-1)
+        np.add.at(target, (rows, cols), np.repeat(values[mask], 2))
+
+
+def compute_wick_terms(healpixs):
+    """cf.py:1326-1494 for max_diagram <= 3 (T4-T6 stay zero)."""
+    if max_diagram is not None and max_diagram > 3:
+        raise NotImplementedError("oracle: Wick diagrams T4-T6 are not restated")
+    nb = num_bins_r_par * num_bins_r_trans
+    t1, t2, t3, t4, t5, t6 = (np.zeros((nb, nb)) for _ in range(6))
+    weights_wick = np.zeros(nb)
+    num_pairs_wick = np.zeros(nb, dtype=np.int64)
+    num_pairs = 0
+    num_pairs_used = 0
+    for healpix in healpixs:
+        w = np.random.rand(len(data[healpix])) > reject      # :1378, one number per FOREST
+        num_pairs += len(data[healpix])
+        num_pairs_used += w.sum()
+        if w.sum() == 0:
+            continue
+        for delta1 in [delta for index, delta in enumerate(data[healpix]) if w[index]]:
+            _host.progress(_THIS)
+            if len(delta1.neighbours) == 0:
+                continue
+            weighted_xi_1d_1 = _weighted_xi_1d(delta1)
+            for delta2 in delta1.neighbours:
+                ang12 = _host.angle_between_one(delta1, delta2)
+                compute_wickT123_pairs(delta1.r_comov, delta2.r_comov, ang12, delta1.weights,
+                                       delta2.weights, delta1.z, delta2.z, weighted_xi_1d_1,
+                                       _weighted_xi_1d(delta2), weights_wick, num_pairs_wick,
+                                       t1, t2, t3)
+    return weights_wick, num_pairs_wick, num_pairs, num_pairs_used, t1, t2, t3, t4, t5, t6

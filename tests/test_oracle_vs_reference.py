@@ -416,3 +416,39 @@ def test_cf_script_on_oracle_loader_matches_golden_fits(tmp_path, flags, golden)
     finally:
         mod.cf, mod.io.read_deltas = saved_cf, saved_rd
     _compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz")
+
+
+def test_wick_t123_on_bundled_fixtures(fixture_data):
+    """oracle compute_wick_terms (max_diagram 3) against the live cf.compute_wick_terms /
+    compute_wickT123_pairs (cf.py:1326-1626) on a few HEALPix pixels of the bundled forests, with
+    analytic stand-ins for the 1-D products the script interpolates (picca_wick.py:393-416).
+    Groundwork for the Wick row; there is no CUDA counterpart yet."""
+    from tests.refharness import load
+    from oracle import cf as ocf
+    cf, _, _, _, utils = load.reference_modules()
+    cf.userprint = lambda *a, **k: None
+    hps = sorted(fixture_data[0])[:3]
+    over = dict(r_par_max=20., r_trans_max=20., num_bins_r_par=5, num_bins_r_trans=5, reject=0.9,
+                max_diagram=3,
+                get_variance_1d={"D1": lambda ll: 0.05 + 0.01 * (ll - 3.55)},
+                xi_1d={"D1": lambda dll: np.exp(-dll / 2e-3)})
+    results = []
+    for mod in (cf, ocf):
+        _setup(mod, fixture_data, utils, load, **over)
+        for k, v in over.items():
+            setattr(mod, k, v)
+        for hp in fixture_data[0]:
+            for d in fixture_data[0][hp]:
+                d.fname = "D1"  # picca_wick.py:371
+        mod.fill_neighs(hps)
+        np.random.seed(hps[0])
+        results.append(mod.compute_wick_terms(hps))
+    want, got = results
+    assert (want[2], want[3]) == (got[2], got[3]) and want[3] > 0
+    assert want[1].sum() > 0 and np.array_equal(want[1], got[1])
+    assert np.array_equal(want[0], got[0])
+    # the evolution factors are powers taken inside Numba (libm) there and by NumPy here: last ulp
+    for k in (4, 5, 6):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-13, atol=1e-13 * np.abs(want[k]).max())
+        assert np.array_equal(got[k] != 0, want[k] != 0)
+    assert np.abs(want[5]).sum() > 0 and np.abs(want[6]).sum() > 0
