@@ -49,20 +49,26 @@ class NeighbourStore:
     def __init__(self):
         self.by_healpix = {}
 
-    def put(self, healpixs, pairs, ranges):
+    def put(self, healpixs, pairs, ranges, cats=()):
+        """``cats``: the packed catalogues the list was built from (kept alive with it)."""
         for hp in healpixs:
-            self.by_healpix[hp] = (pairs, ranges[hp])
+            self.by_healpix[hp] = (pairs, ranges[hp], tuple(cats))
 
-    def take(self, healpixs):
-        """Return (pairs, None) when ``healpixs`` is exactly one stored batch, else a merged
-        PairList built from the stored per-healpix pieces."""
+    def take(self, healpixs, cats=()):
+        """The stored PairList when ``healpixs`` is exactly one stored batch built from the
+        catalogues ``cats``; None when it has to be rebuilt (stored in other batches, or built
+        from a catalogue that has been re-packed since)."""
         missing = [hp for hp in healpixs if hp not in self.by_healpix]
         if missing:
             raise RuntimeError("picca_b200: compute called before fill_neighs for healpix %r"
                                % (missing[:5],))
+        for hp in healpixs:
+            have = self.by_healpix[hp][2]
+            if len(have) != len(cats) or any(a is not b for a, b in zip(have, cats)):
+                return None
         first = self.by_healpix[healpixs[0]][0]
         same = all(self.by_healpix[hp][0] is first for hp in healpixs)
-        covered = sum(r[1] - r[0] for _, r in (self.by_healpix[hp] for hp in healpixs))
+        covered = sum(e[1][1] - e[1][0] for e in (self.by_healpix[hp] for hp in healpixs))
         in_order = same and all(
             self.by_healpix[a][1][1] == self.by_healpix[b][1][0]
             for a, b in zip(healpixs[:-1], healpixs[1:]))
@@ -136,4 +142,8 @@ def bump_progress(mod, n_forests, userprint):
 def engine_and_catalog(data, is_object=False, ang_correlation=False):
     eng = get_engine()
     host = _catalog.cached_pack(data, is_object=is_object, ang_correlation=ang_correlation)
+    if id(host) not in eng._cats:  # a (re-)packed catalogue: release device copies of stale ones
+        live = {id(hit[1]) for hit in _catalog._HOST_CACHE.values()}
+        for key in [k for k in eng._cats if k not in live]:
+            del eng._cats[key]
     return eng, host, eng.device_catalog(host)

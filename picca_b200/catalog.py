@@ -33,6 +33,7 @@ class HostCatalog:
         self.sorted = 1
         self.max_pix = 0
         self.ids_are_int = True
+        self.thingid_remapped = False
         self.is_object = False
         self.il_total = 0         # diagonal-lane copies (see _diag_metadata)
         self.dg_total = 0
@@ -166,10 +167,12 @@ def pack(data, is_object=False, ang_correlation=False):
     A["z_qso"] = np.array([o.z_qso for o in objs], dtype=np.float64).reshape(n)
     A["thingid"], ok_t = _as_int64([o.thingid for o in objs])
     if not ok_t:
-        # non-integer ids: map equal ids to equal integers (only equality is ever used)
-        table = {}
-        A["thingid"] = np.array([table.setdefault(o.thingid, len(table)) for o in objs],
+        # non-integer ids: map equal ids to equal integers (only equality is ever used).  The
+        # table is process-wide: the neighbour search compares ids ACROSS catalogues (data vs
+        # data2, forests vs objects), so equal ids must map to equal integers in all of them
+        A["thingid"] = np.array([_ID_TABLE.setdefault(o.thingid, len(_ID_TABLE)) for o in objs],
                                 dtype=np.int64)
+    cat.thingid_remapped = not ok_t
     A["plate"], ok_p = _as_int64([o.plate for o in objs])
     A["fiberid"], ok_f = _as_int64([o.fiberid for o in objs])
     cat.ids_are_int = bool(ok_p and ok_f)
@@ -332,15 +335,35 @@ def build_struct(host, tensors):
 
 
 _HOST_CACHE = {}
+_ID_TABLE = {}  # non-integer line-of-sight id -> integer, shared by every catalogue of the process
+
+
+def _fingerprint(data):
+    """Cheap identity of a catalogue dict: which list objects it holds per HEALPix pixel and how
+    long they are.  Replacing or resizing a per-pixel list (re-reading, shuffling, trimming)
+    changes it; in-place edits of the arrays of a forest do not -- call ``invalidate`` then."""
+    return tuple((hp, id(v), len(v)) for hp, v in data.items())
+
+
+def invalidate(data=None):
+    """Forget the packed copy of ``data`` (or of everything): the next cf / xcf call packs and
+    uploads again.  Needed after in-place changes of weights / deltas / distances, which the
+    fingerprint cannot see."""
+    if data is None:
+        _HOST_CACHE.clear()
+        return
+    for key in [k for k in _HOST_CACHE if k[0] == id(data)]:
+        del _HOST_CACHE[key]
 
 
 def cached_pack(data, is_object=False, ang_correlation=False):
-    """Pack once per (dict object, flavour); the scripts keep the same dict for a whole run."""
+    """Pack once per (dict object, flavour, fingerprint); the scripts keep the same dict for a
+    whole run.  The mixed-id catalogues of one process share ``_ID_TABLE``."""
     key = (id(data), is_object, bool(ang_correlation))
-    n_now = sum(len(v) for v in data.values())
+    mark = _fingerprint(data)
     hit = _HOST_CACHE.get(key)
-    if hit is not None and hit[0] is data and hit[1].n_los == n_now:
+    if hit is not None and hit[0] is data and hit[2] == mark:
         return hit[1]
     cat = pack(data, is_object=is_object, ang_correlation=ang_correlation)
-    _HOST_CACHE[key] = (data, cat)
+    _HOST_CACHE[key] = (data, cat, mark)
     return cat

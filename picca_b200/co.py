@@ -73,7 +73,7 @@ def fill_neighs(healpixs):
     pairs = eng.neighbours(dev1, dev2, params, MODE_CROSS, index)
     if _corr.HOST_ANGLES:
         _corr.apply_host_angles(pairs, host1, host2)
-    _STORE.put(healpixs, pairs, ranges)
+    _STORE.put(healpixs, pairs, ranges, (host1, host2))
     for k, f1 in enumerate(index):
         host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
 
@@ -85,10 +85,10 @@ def compute_xi(healpixs):
     healpixs = list(healpixs)
     eng, host1, dev1, host2, dev2 = _catalogs()
     params = params_from_module(_THIS)
-    pairs = _STORE.take(healpixs)
+    pairs = _STORE.take(healpixs, (host1, host2))
     if pairs is None:
         fill_neighs(healpixs)
-        pairs = _STORE.take(healpixs)
+        pairs = _STORE.take(healpixs, (host1, host2))
     torch = eng.torch
     nb = params.num_bins_r_par * params.num_bins_r_trans
     out = torch.zeros((1, 5, nb), dtype=torch.float64, device=eng.device)

@@ -272,13 +272,14 @@ int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, co
     }
     if (pairs->n_pairs <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    static unsigned long long *d_ctr[64] = {nullptr};
+    // the work counter lives for this call only, allocated in stream order: concurrent calls on
+    // other streams / threads / devices each get their own
+    unsigned long long *d_ctr = nullptr;
     int dev = 0, sms = 0;
     PB2_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) dev = 0;
     PB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (!d_ctr[dev]) PB2_CUDA(cudaMalloc((void **)&d_ctr[dev], sizeof(unsigned long long)));
-    PB2_CUDA(cudaMemsetAsync(d_ctr[dev], 0, sizeof(unsigned long long), s));
+    PB2_CUDA(cudaMallocAsync((void **)&d_ctr, sizeof(unsigned long long), s));
+    PB2_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned long long), s));
     MetalArgs A;
     A.z1 = d_z1, A.rc1 = d_rc1, A.dm1 = d_dm1, A.pw1 = d_pw1;
     A.z2 = d_z2, A.rc2 = d_rc2, A.dm2 = d_dm2, A.pw2 = d_pw2;
@@ -286,10 +287,11 @@ int32_t pb2_metal_dmat_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, co
     pb2_timing_begin(s);
     pb2_metal_dmat_kernel<<<sms * 8, 256, 0, s>>>(*cat1, *cat2, *par, *pairs, A, d_weights_dmat,
                                                   d_dmat, d_r_par_eff, d_r_trans_eff, d_z_eff,
-                                                  d_weight_eff, d_ctr[dev]);
+                                                  d_weight_eff, d_ctr);
     pb2_count_launch(1);
     int32_t rc = pb2_check_launch("pb2_metal_dmat_kernel");
     pb2_timing_end(s);
+    cudaFreeAsync(d_ctr, s);
     return rc;
 }
 

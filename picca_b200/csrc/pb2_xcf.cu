@@ -411,21 +411,20 @@ int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2
     const size_t chunk_smem = (size_t)64 * (cat1->max_pix + 1);
     if (variant == 0 && F.fast && cat1->px_rec && !par->has_z_min_pairs && !par->has_z_max_pairs &&
         chunk_smem <= 100 * 1024) {
-        // forest-claim counter: one per device, reset on the stream before every launch
-        static unsigned long long *d_ctr[64] = {nullptr};
-        int dev = 0;
-        PB2_CUDA(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64) dev = 0;
-        if (!d_ctr[dev]) PB2_CUDA(cudaMalloc((void **)&d_ctr[dev], sizeof(unsigned long long)));
-        PB2_CUDA(cudaMemsetAsync(d_ctr[dev], 0, sizeof(unsigned long long), s));
+        // forest-claim counter: allocated in stream order for this call only (concurrent calls
+        // on other streams / threads each get their own)
+        unsigned long long *d_ctr = nullptr;
+        PB2_CUDA(cudaMallocAsync((void **)&d_ctr, sizeof(unsigned long long), s));
+        PB2_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned long long), s));
         PB2_CUDA(cudaFuncSetAttribute(pb2_xi_cross_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)chunk_smem));
         long long ctas = pairs->n_f1 < 148 * 4 ? pairs->n_f1 : 148 * 4;
         pb2_xi_cross_chunk<<<(unsigned)ctas, 256, chunk_smem, s>>>(*cat1, *objs, *par, *pairs, F,
-                                                                   d_out_row, d_out, d_ctr[dev]);
+                                                                   d_out_row, d_out, d_ctr);
         pb2_count_launch(1);
         int32_t rc2 = pb2_check_launch("pb2_xi_cross_chunk");
         pb2_timing_end(s);
+        cudaFreeAsync(d_ctr, s);
         return rc2;
     }
     if (F.fast)

@@ -109,3 +109,118 @@ def dmat_sharded(eng, dev1, dev2, params, pairs, keep_local, group=None, world=1
     if world > 1:
         allreduce_dmat(res, group=group)
     return res
+
+
+class Shard:
+    """This rank's share of the HEALPix rows of catalogue 1 (LPT over estimated pair work,
+    identical on every rank) and the index arrays its kernels need."""
+
+    def __init__(self, eng, host1, host2, ang_max, world, rank):
+        torch = eng.torch
+        self.world, self.rank = world, rank
+        self.n_rows_total = len(host1.healpixs)
+        self.work = estimate_work(host1, host2, ang_max)
+        self.parts = lpt_partition(self.work, world)
+        self.mine = self.parts[rank]
+        hp_first = host1.arrays["hp_first"]
+        parts = [np.arange(hp_first[k], hp_first[k + 1], dtype=np.int32) for k in self.mine]
+        self.f1_index = np.concatenate(parts) if parts else np.zeros(0, np.int32)
+        self.rows = np.concatenate([np.full(len(p), k, np.int32) for k, p in enumerate(parts)]) \
+            if parts else np.zeros(0, np.int32)
+        self.row_owner = np.zeros(self.n_rows_total, dtype=np.int64)
+        for r, part in enumerate(self.parts):
+            self.row_owner[part] = r
+        self.d_f1 = torch.as_tensor(self.f1_index, device=eng.device)
+        self.d_rows = torch.as_tensor(self.rows, device=eng.device)
+        # every line of sight of catalogue 1, catalogue order (the --rej stream order)
+        self.d_all_f1 = torch.arange(host1.n_los, dtype=torch.int32, device=eng.device)
+        owner_of_f1 = np.repeat(self.row_owner, np.diff(hp_first))
+        self.d_f1_is_mine = torch.as_tensor(owner_of_f1 == rank, device=eng.device)
+
+
+def xi_sharded(eng, dev1, dev2, params, shard, mode, cross_obj=False, gather=True):
+    """compute_xi of every HEALPix row, each rank doing its LPT share (neighbour search + pair
+    kernel + per-row normalisation); rows gathered to rank 0 ([n_rows_total, 6, nb]; None on the
+    other ranks).  No collective on the data path: rows are independent (picca_cf.py:454-473)."""
+    pairs = eng.neighbours(dev1, dev2, params, mode, shard.d_f1)
+    out = eng.xi(dev1, dev2, params, pairs, shard.d_rows, len(shard.mine), cross_obj=cross_obj,
+                 normalise=True)
+    if shard.world > 1 and gather:
+        return gather_rows(out, shard.mine, shard.n_rows_total)
+    return out
+
+
+def dmat_chunk_sharded(eng, dev1, dev2, params, shard, mode, reject, seed, cross_obj=False,
+                       segments=8, group=None):
+    """Distortion matrix of ONE reference chunk (all HEALPix rows of catalogue 1, seeded with
+    ``seed`` = its first pixel as picca_dmat.py:36 does), the kept forest pairs sharded over the
+    ranks by owning HEALPix row.
+
+    The --rej draw is a property of the chunk: one legacy MT19937 stream, ``len(neighbours)``
+    numbers per forest in catalogue order (cf.py:444, xcf.py:379), so every rank needs the
+    neighbour COUNT of every forest (count-only pass, replicated: milliseconds) but the neighbour
+    LISTS of its own forests only.  The stream is drawn on the host in ``segments`` pieces while
+    the device works on the previous piece: piece k of the mask is uploaded, this rank's forest
+    pairs inside it are selected on the device and the kernels run on them, accumulating into
+    the same matrices; ONE all-reduce(SUM) of a flat buffer (matrix + five vectors) follows.
+
+    Returns ([weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff] device tensors,
+    NPALL, NPUSED)."""
+    torch = eng.torch
+    dev = eng.device
+    # ---- 1. neighbour counts of every forest of the chunk -> stream offsets
+    count_all = eng.neighbour_counts(dev1, dev2, params, mode, shard.d_all_f1)
+    off_all = torch.zeros(count_all.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(count_all, dim=0, out=off_all[1:])
+    h_off_all = off_all.cpu().numpy()                     # 0.8 MB per 100k forests
+    npall = int(h_off_all[-1])
+    # ---- 2. neighbour lists of this rank's forests
+    pairs = eng.neighbours(dev1, dev2, params, mode, shard.d_f1)
+    # stream position of each of my pairs: start of its forest's draw + rank inside the forest
+    f1_cat = shard.d_f1.to(torch.int64)[pairs.nb_f1.to(torch.int64)]
+    pos = off_all[f1_cat] + (torch.arange(pairs.n_pairs, dtype=torch.int64, device=dev) -
+                             pairs.nb_offset[pairs.nb_f1.to(torch.int64)])
+    # ---- 3. segments of the stream, cut at forest boundaries
+    n_los = count_all.numel()
+    cuts = np.unique(np.linspace(0, n_los, max(1, segments) + 1).astype(np.int64))
+    state = np.random.RandomState(seed)
+    outs = eng.dmat_outputs(params)
+    keep_dev = torch.zeros(max(pairs.n_pairs, 1), dtype=torch.uint8, device=dev)
+    npused = npall_cross = 0
+    my_f1 = shard.f1_index.astype(np.int64)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s0, s1 = int(h_off_all[a]), int(h_off_all[b])
+        if s1 == s0:
+            continue
+        mask = state.rand(s1 - s0) > reject             # host MT19937, reference stream
+        npused += int(mask.sum())
+        if cross_obj:
+            # xcf.py:379-383: a forest whose draw keeps nothing is skipped BEFORE it is counted
+            starts = h_off_all[a:b] - s0
+            has = h_off_all[a + 1:b + 1] > h_off_all[a:b]
+            kept_any = np.zeros(b - a, dtype=bool)
+            if has.any():
+                kept_any[has] = np.add.reduceat(mask.astype(np.int64), starts[has]) > 0
+            npall_cross += int((h_off_all[a + 1:b + 1] - h_off_all[a:b])[kept_any].sum())
+        lo, hi = np.searchsorted(my_f1, [a, b])           # my forests inside this segment
+        if hi == lo:
+            continue
+        p0 = int(pairs.host_offset()[lo])
+        p1 = int(pairs.host_offset()[hi])
+        if p1 == p0:
+            continue
+        d_mask = torch.from_numpy(mask.view(np.uint8)).to(dev, non_blocking=True)
+        keep_dev.zero_()
+        keep_dev[p0:p1] = d_mask[pos[p0:p1] - s0]
+        pairs.nb_keep = keep_dev
+        eng.dmat(dev1, dev2, params, pairs, cross_obj=cross_obj, out=outs)
+    # ---- 4. one collective over a flat buffer
+    if shard.world > 1:
+        import torch.distributed as dist
+        flat = torch.cat([t.reshape(-1) for t in outs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        k = 0
+        for t in outs:
+            t.copy_(flat[k:k + t.numel()].view_as(t))
+            k += t.numel()
+    return list(outs), (npall_cross if cross_obj else npall), npused

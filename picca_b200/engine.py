@@ -129,6 +129,23 @@ class Engine:
         self._cats.clear()
 
     # ------------------------------------------------------------------ neighbours
+    def neighbour_counts(self, cat1, cat2, params, mode, f1_index):
+        """``len(delta.neighbours)`` of every listed line of sight (int32 device tensor) without
+        building the lists: what the --rej draw of a chunk needs from the forests of other
+        ranks."""
+        torch = self.torch
+        if not torch.is_tensor(f1_index):
+            f1_index = torch.as_tensor(np.ascontiguousarray(f1_index, dtype=np.int32),
+                                       device=self.device)
+        n_f1 = int(f1_index.numel())
+        count = torch.empty(n_f1, dtype=torch.int32, device=self.device)
+        if n_f1:
+            _lib.check(self.lib.pb2_neigh_count(
+                ctypes.byref(cat1.struct), ctypes.byref(cat2.struct), ctypes.byref(params),
+                ctypes.c_int32(mode), ctypes.c_int64(n_f1), ctypes.c_void_p(f1_index.data_ptr()),
+                ctypes.c_void_p(count.data_ptr()), self.stream_ptr()), "pb2_neigh_count")
+        return count
+
     def neighbours(self, cat1, cat2, params, mode, f1_index):
         """cf.fill_neighs / xcf.fill_neighs on the device for the lines of sight ``f1_index``
         (int32 tensor on the device or array-like)."""
@@ -137,11 +154,7 @@ class Engine:
             f1_index = torch.as_tensor(np.ascontiguousarray(f1_index, dtype=np.int32),
                                        device=self.device)
         n_f1 = int(f1_index.numel())
-        count = torch.empty(n_f1, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.pb2_neigh_count(
-            ctypes.byref(cat1.struct), ctypes.byref(cat2.struct), ctypes.byref(params),
-            ctypes.c_int32(mode), ctypes.c_int64(n_f1), ctypes.c_void_p(f1_index.data_ptr()),
-            ctypes.c_void_p(count.data_ptr()), self.stream_ptr()), "pb2_neigh_count")
+        count = self.neighbour_counts(cat1, cat2, params, mode, f1_index)
         nb_offset = torch.zeros(n_f1 + 1, dtype=torch.int64, device=self.device)
         torch.cumsum(count, dim=0, out=nb_offset[1:])
         n_pairs = int(nb_offset[-1].item()) if n_f1 else 0
@@ -186,15 +199,22 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ distortion matrix
-    def dmat(self, cat1, cat2, params, pairs, cross_obj=False):
-        """Accumulate the distortion matrix over the kept pairs.  Returns device tensors
-        (weights_dmat[nb], dmat[nb, nbm], r_par_eff, r_trans_eff, z_eff, weight_eff [nbm])."""
+    def dmat_outputs(self, params):
+        """Zeroed accumulators (weights_dmat[nb], dmat[nb, nbm], r_par_eff, r_trans_eff, z_eff,
+        weight_eff [nbm]) on the device."""
         torch = self.torch
         nb = params.num_bins_r_par * params.num_bins_r_trans
         nbm = params.num_model_bins_r_par * params.num_model_bins_r_trans
         z = lambda *s: torch.zeros(s, dtype=torch.float64, device=self.device)
-        weights_dmat, dmat = z(nb), z(nb, nbm)
-        r_par_eff, r_trans_eff, z_eff, weight_eff = z(nbm), z(nbm), z(nbm), z(nbm)
+        return z(nb), z(nb, nbm), z(nbm), z(nbm), z(nbm), z(nbm)
+
+    def dmat(self, cat1, cat2, params, pairs, cross_obj=False, out=None):
+        """Accumulate the distortion matrix over the kept pairs into ``out`` (default: fresh
+        zeroed accumulators).  Returns device tensors (weights_dmat[nb], dmat[nb, nbm],
+        r_par_eff, r_trans_eff, z_eff, weight_eff [nbm])."""
+        torch = self.torch
+        weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = \
+            out if out is not None else self.dmat_outputs(params)
         nbytes = int(self.lib.pb2_dmat_scratch_bytes(
             ctypes.byref(cat1.struct), ctypes.byref(cat2.struct), ctypes.byref(params),
             ctypes.c_int32(int(cross_obj)))) + 8 * pairs.n_pairs + 256

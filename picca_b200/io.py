@@ -376,17 +376,90 @@ def _cosmo_tables(cosmo):
             np.ascontiguousarray(f_m.y, dtype=np.float64))
 
 
+class TableCosmo:
+    """The distance tables of a cosmology object, detached from it (picklable): what the
+    isolated loader process receives instead of the caller's ``Cosmo``."""
+
+    def __init__(self, cosmo):
+        self._tables = _cosmo_tables(cosmo)
+
+    def table(self):
+        return self._tables
+
+
 def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=None,
                 no_project=False, nproc=None, rebin_factor=None, z_min_qso=0, z_max_qso=10,
-                delta_attributes=None):
+                delta_attributes=None, isolate=None):
     """Reads deltas and computes their redshifts, distances, evolved weights and projection
     (io.py:383-512).  Same arguments; returns ``(data, num_data, z_min, z_max)``.
+
+    ``isolate`` (default: env ``PICCA_B200_IO_ISOLATE`` == "1"): run the device part in a
+    short-lived child process (``python -m picca_b200._io_worker``) and take the SoA back through
+    /dev/shm, so that THIS process never initialises CUDA.  The reference's scripts call
+    ``read_deltas`` in the parent and only then fork their worker pool (picca_cf.py:387 then
+    :455); a CUDA context cannot be used across a fork, so under the overlay the loader is
+    isolated by default.
 
     Raises:
         AssertionError: if no healpix numbers are found (io.py:489-490)
         RuntimeError: projecting without a continuum order (data.py:628-633); CUDA errors
         ValueError: a redshift outside the cosmology table (scipy interp1d bounds error)
     """
+    if isolate is None:
+        isolate = os.environ.get("PICCA_B200_IO_ISOLATE", "0") == "1"
+    kwds = dict(max_num_spec=max_num_spec, no_project=no_project, nproc=nproc,
+                rebin_factor=rebin_factor, z_min_qso=z_min_qso, z_max_qso=z_max_qso,
+                delta_attributes=delta_attributes)
+    if isolate:
+        soa = _read_soa_isolated(in_dir, nside, lambda_abs, alpha, z_ref,
+                                 None if cosmo is None else TableCosmo(cosmo), **kwds)
+    else:
+        soa = read_deltas_soa(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, **kwds)
+    return soa_to_objects(soa)
+
+
+def _read_soa_isolated(*args, **kwds):
+    """``read_deltas_soa`` in a child process; arrays come back as .npy files in /dev/shm."""
+    import pickle
+    import shutil
+    import subprocess
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="pb2_loader_", dir=base)
+    try:
+        with open(os.path.join(tmp, "args.pkl"), "wb") as f:
+            pickle.dump((args, kwds), f)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        res = subprocess.run([sys.executable, "-m", "picca_b200._io_worker", tmp], env=env)
+        meta_path = os.path.join(tmp, "meta.pkl")
+        if not os.path.exists(meta_path):
+            raise RuntimeError("picca_b200.io: the loader process died (exit code %d)"
+                               % res.returncode)
+        with open(meta_path, "rb") as f:
+            meta = pickle.load(f)
+        if "error" in meta:
+            kind, msg = meta["error"]
+            exc = {"AssertionError": AssertionError, "ValueError": ValueError,
+                   "NotImplementedError": NotImplementedError, "OSError": OSError,
+                   "TypeError": TypeError}.get(kind, RuntimeError)
+            raise exc(msg)
+        soa = dict(meta["scalars"])
+        for name in meta["arrays"]:
+            soa[name] = np.load(os.path.join(tmp, name + ".npy"))
+        return soa
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def read_deltas_soa(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=None,
+                    no_project=False, nproc=None, rebin_factor=None, z_min_qso=0, z_max_qso=10,
+                    delta_attributes=None):
+    """The loader proper: the forests of ``in_dir`` as ONE structure of host arrays (CSR
+    ``offset`` + per-pixel ``log_lambda, delta, weights, z, r_comov, dist_m`` + per-forest
+    metadata + ``healpix``), in file order.  ``read_deltas`` wraps it into the reference's data
+    model; ``picca_b200.catalog.pack_soa`` packs it for the pair kernels without that detour."""
     in_dir = os.path.expandvars(in_dir)
     if len(in_dir) > 8 and in_dir[-8:] == '.fits.gz':
         files = sorted(glob.glob(in_dir))
@@ -607,19 +680,45 @@ def read_deltas(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec=Non
     z_min = float(z_range[:, 0].min())
     z_max = max(0., float(z_range[:, 1].max()))  # io.py:493: z_max starts at 0
     healpixs = ang2pix_ring(nside, np.pi / 2. - dec, ra)  # io.py:486-488
-    data = {}
-    for f in range(n_los):
-        a, b = offset[f], offset[f + 1]
-        d = Delta(int(los_id[f]), float(ra[f]), float(dec[f]), float(z_qso[f]), int(plate[f]),
-                  int(mjd[f]), int(fiberid[f]), h["log_lambda"][a:b], h["weights"][a:b],
-                  h["delta"][a:b], order)
-        d.z = h["z"][a:b]
-        if d_rc is not None:
-            d.r_comov, d.dist_m = h["r_comov"][a:b], h["dist_m"][a:b]
-        data.setdefault(int(healpixs[f]), []).append(d)
-    mark("D2H + Delta objects")
+    mark("D2H")
     if os.environ.get("PICCA_B200_IO_TIMING", "0") == "1":
         for (_, t0), (name, t1) in zip(marks[:-1], marks[1:]):
             userprint("picca_b200.io: %-52s %.3f s" % (name, t1 - t0))
+    soa = dict(h)
+    soa.update(offset=offset, ra=ra, dec=dec, z_qso=z_qso, los_id=los_id, plate=plate, mjd=mjd,
+               fiberid=fiberid, healpix=np.asarray(healpixs, dtype=np.int64), n_los=int(n_los),
+               z_min=z_min, z_max=z_max, order=order)
+    return soa
+
+
+SOA_ARRAYS = ("log_lambda", "delta", "weights", "z", "r_comov", "dist_m", "offset", "ra", "dec",
+              "z_qso", "los_id", "plate", "mjd", "fiberid", "healpix")
+
+
+def soa_to_objects(soa):
+    """The reference's data model from the loader's SoA: ``dict[healpix] -> list[Delta]`` whose
+    array attributes are views into the SoA (io.py:485-512 builds the same dict per forest).
+    The SoA is remembered in ``SOA_OF`` under ``id(data)`` so that ``catalog.cached_pack`` can
+    pack straight from it (after checking that the objects still are those views) instead of
+    gathering 100 000 Python objects again."""
+    offset, order = soa["offset"], soa["order"]
+    has_dist = "r_comov" in soa
+    data = {}
+    los_id, ra, dec, z_qso = soa["los_id"], soa["ra"], soa["dec"], soa["z_qso"]
+    plate, mjd, fiberid, healpixs = soa["plate"], soa["mjd"], soa["fiberid"], soa["healpix"]
+    for f in range(soa["n_los"]):
+        a, b = offset[f], offset[f + 1]
+        d = Delta(int(los_id[f]), float(ra[f]), float(dec[f]), float(z_qso[f]), int(plate[f]),
+                  int(mjd[f]), int(fiberid[f]), soa["log_lambda"][a:b], soa["weights"][a:b],
+                  soa["delta"][a:b], order)
+        d.z = soa["z"][a:b]
+        if has_dist:
+            d.r_comov, d.dist_m = soa["r_comov"][a:b], soa["dist_m"][a:b]
+        data.setdefault(int(healpixs[f]), []).append(d)
     userprint("\n")
-    return data, n_los, z_min, z_max
+    SOA_OF.clear()  # one catalogue at a time is remembered (a run holds one or two)
+    SOA_OF[id(data)] = (data, soa)
+    return data, soa["n_los"], soa["z_min"], soa["z_max"]
+
+
+SOA_OF = {}

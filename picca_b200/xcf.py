@@ -94,16 +94,17 @@ def fill_neighs(healpixs):
     pairs = eng.neighbours(dev1, dev2, params, MODE_XCF, index)
     if _corr.HOST_ANGLES:
         _corr.apply_host_angles(pairs, host1, host2)
-    _STORE.put(healpixs, pairs, ranges)
+    _STORE.put(healpixs, pairs, ranges, (host1, host2))
     for k, f1 in enumerate(index):
         host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
 
 
 def _pairs_for(healpixs):
-    pairs = _STORE.take(healpixs)
-    if pairs is None:
+    _, host1, _, host2, _ = _catalogs()
+    pairs = _STORE.take(healpixs, (host1, host2))
+    if pairs is None:  # stored in different batches or for a re-packed catalogue: rebuild
         fill_neighs(healpixs)
-        pairs = _STORE.take(healpixs)
+        pairs = _STORE.take(healpixs, (host1, host2))
     return pairs
 
 

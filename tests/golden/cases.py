@@ -2,20 +2,33 @@
 tests run) + the module configuration.  ``make_golden.py`` runs the LIVE reference on them and
 stores its outputs in ``golden_*.npz``; the tests replay the same cases on the oracle (CPU) and on
 the CUDA path (GPU)."""
+import numpy as np
+
 from picca_b200 import synth
 from tests import helpers
 
 R60 = dict(r_par_max=60., r_trans_max=60., num_bins_r_par=15, num_bins_r_trans=15,
            num_model_bins_r_par=15, num_model_bins_r_trans=15)
 
+# angular correlation: "r_par" = wavelength ratio, "r_trans" = angle (rad), ang_max = r_trans_max
+ANGL = dict(ang_correlation=True, r_par_min=1., r_par_max=1.1, r_trans_max=0.02,
+            num_bins_r_par=20, num_bins_r_trans=10)
+
 CF_CASES = {
     "default": dict(R60),
     "half_plate": dict(R60, remove_same_half_plate_close_pairs=True),
+    # the synthetic forests have one plate each: `plates` deals them onto 7 shared plates so that
+    # the same-half-plate rule (cf.py:171-183, :378-380) actually removes pairs
+    "half_plate_shared": dict(R60, remove_same_half_plate_close_pairs=True, plates=True),
     "zcuts": dict(R60, z_min_pairs=2.0, z_max_pairs=2.6),
     "zerr": dict(R60, zerr_cut_deg=0.5, zerr_cut_kms=40000.),
     "rmu": dict(R60, rmu_binning=True, r_par_min=0., r_par_max=1.),
     "prod": dict(r_par_max=200., r_trans_max=200., num_bins_r_par=50, num_bins_r_trans=50),
     "cross": dict(R60, x_correlation=True, r_par_min=-60., num_bins_r_par=30, second=True),
+    # picca_cf_angl.py (:212-222): wavelength ratio x angle, cf.py:186-208, :350-354
+    "angl": dict(ANGL),
+    "angl_half_plate": dict(ANGL, remove_same_half_plate_close_pairs=True, plates=True),
+    "angl_cross": dict(ANGL, x_correlation=True, r_par_min=0.92, r_par_max=1.08, second=True),
 }
 
 DMAT_CASES = {
@@ -53,6 +66,9 @@ XCF_CASES = {
     "zcuts": dict(XCF_BASE, z_min_pairs=2.0, z_max_pairs=2.6),
     "zerr": dict(XCF_BASE, zerr_cut_deg=0.5, zerr_cut_kms=40000.),
     "rmu": dict(XCF_BASE, rmu_binning=True, r_par_min=-1., r_par_max=1.),
+    # picca_xcf_angl.py (:268-276): xcf.py:161-182, :293-295 (no r_par pre-filter, :117)
+    "angl": dict(ANGL, r_par_min=0.9, alpha_obj=1.44),
+    "angl_zcuts": dict(ANGL, r_par_min=0.9, alpha_obj=1.44, z_min_pairs=2.0, z_max_pairs=2.6),
 }
 XMETAL_CASES = {
     "si2": dict(XCF_BASE, reject=0.8, abs_igm="SiII(1190)"),
@@ -76,14 +92,25 @@ XDMAT_CASES = {
 }
 
 
-def forests(second=False):
+def share_plates(data):
+    """Deal the forests onto 7 plates / 1000 fibres (deterministic in the thingid)."""
+    for forests_ in data.values():
+        for d in forests_:
+            d.plate = 1 + int(d.thingid) % 7
+            d.fiberid = 1 + (int(d.thingid) * 131) % 1000
+    return data
+
+
+def forests(second=False, plates=False):
     """(data, num_data, z_min, cosmo); ``second`` gives the independent second sample used by the
-    delta x delta cross-correlation cases."""
+    delta x delta cross-correlation cases; ``plates``: see ``share_plates``."""
     if second:
         data, num, z_min, _, cosmo = helpers.small_sample(n=200, seed=23, max_pix=100,
                                                           id_offset=5000)
     else:
         data, num, z_min, _, cosmo = helpers.small_sample(n=300, seed=11, max_pix=120)
+    if plates:
+        share_plates(data)
     return data, num, z_min, cosmo
 
 
@@ -98,8 +125,12 @@ def dmat_forests(second=False):
 
 
 def quasars(cosmo):
-    return synth.make_quasars(400, seed=31, nside=16, ra_deg=(10., 16.), dec_deg=(5., 11.),
-                              z_range=(1.9, 3.2), cosmo=cosmo)
+    objs, z_min = synth.make_quasars(400, seed=31, nside=16, ra_deg=(10., 16.), dec_deg=(5., 11.),
+                                     z_range=(1.9, 3.2), cosmo=cosmo)
+    for qsos in objs.values():  # picca_xcf_angl.py: observed Lyman-alpha wavelength of the object
+        for q in qsos:
+            q.log_lambda = np.log10((1. + q.z_qso) * synth.LYA)
+    return objs, z_min
 
 
 def quasars2(cosmo):
@@ -109,4 +140,6 @@ def quasars2(cosmo):
 
 
 def ang_max_for(cosmo, cfg, z_min, z_min2=None):
+    if cfg.get("ang_correlation"):  # picca_cf_angl.py:214,222: ang_max IS r_trans_max
+        return cfg["r_trans_max"]
     return synth.compute_ang_max(cosmo, cfg["r_trans_max"], z_min, z_min2)

@@ -49,12 +49,13 @@ def run_cf(out):
         cf.userprint = lambda *a, **k: None
         cfg = dict(cfg)
         second = cfg.pop("second", False)
-        data, num, z_min, cosmo = cases.forests()
+        plates = cfg.pop("plates", False)
+        data, num, z_min, cosmo = cases.forests(plates=plates)
         rdata = load.to_reference_deltas(data)
         over = dict(cfg)
         z_min2 = None
         if second:
-            data2, num2, z_min2, _ = cases.forests(second=True)
+            data2, num2, z_min2, _ = cases.forests(second=True, plates=plates)
             over["data2"] = load.to_reference_deltas(data2)
             over["num_data2"] = num2
         helpers.configure(cf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)

@@ -6,7 +6,7 @@ import warnings
 
 from . import shims
 
-DATA = "/root/reference/py/picca/tests/data"
+DATA = shims.REFERENCE_DATA
 
 
 def reference_modules():
@@ -86,5 +86,6 @@ def to_reference_qsos(objs):
         for q in qsos:
             r = QSO(q.thingid, q.ra, q.dec, q.z_qso, q.plate, q.mjd, q.fiberid)
             r.weights, r.r_comov, r.dist_m = q.weights, q.r_comov, q.dist_m
+            r.log_lambda = q.log_lambda
             out[hp].append(r)
     return out

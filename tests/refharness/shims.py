@@ -16,11 +16,31 @@ import numpy as np
 
 from . import minifits
 
-REFERENCE_PY = "/root/reference/py"
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _locate():
+    """The reference tree: /root/reference in the build container, else the unmodified copy that
+    ``scripts/stage_reference.py`` installed under the git-ignored ``baseline/_ref`` (it travels
+    to the GPU box with the gpurun snapshot).  Returns (python path entry, test-data dir)."""
+    if os.environ.get("PICCA_B200_FORCE_STAGED_REF", "0") != "1" and \
+            os.path.isdir("/root/reference/py/picca"):
+        return "/root/reference/py", "/root/reference/py/picca/tests/data"
+    staged = os.path.join(_ROOT, "baseline", "_ref")
+    if os.path.isfile(os.path.join(staged, "picca", "cf.py")):
+        return staged, os.path.join(staged, "picca", "tests", "data")
+    return None, None
+
+
+REFERENCE_PY, REFERENCE_DATA = _locate()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_PY, "picca"))
+    return REFERENCE_PY is not None
+
+
+def in_build_container():
+    return REFERENCE_PY == "/root/reference/py"
 
 
 # ----------------------------------------------------------------------------- HEALPix (RING)

@@ -174,3 +174,34 @@ def test_device_packed_copies_equal_the_numpy_specification():
     assert np.array_equal(dev.tensors["dg_rec"].cpu().numpy(), want_dg)
     assert np.array_equal(dev.tensors["il_rec"].cpu().numpy(), want_il)
     assert host.arrays["dg_count"][9] == 0
+
+
+def test_string_ids_across_two_catalogues(base):
+    """delta x delta cross-correlation whose thingids are strings: a forest must still be
+    excluded from pairing with ITS OWN copy in the other catalogue (cf.py:109-112), which needs
+    one id -> integer mapping shared by both packed catalogues."""
+    data, num, ang_max = base
+    data2 = {hp: [copy.copy(d) for d in v] for hp, v in data.items()}
+    for cat in (data, data2):
+        for v in cat.values():
+            for d in v:
+                d.thingid = "tid-%s" % d.thingid
+    hp0 = sorted(data2)[0]
+    data2[hp0] = list(reversed(data2[hp0]))   # other insertion order than `data`
+    from oracle import cf as ocf
+    from picca_b200 import cf
+    over = dict(data2=data2, num_data2=num, x_correlation=True, r_par_min=-60., num_bins_r_par=30)
+    total = 0
+    for mod in (ocf, cf):
+        helpers.configure(mod, data, num, ang_max, **over)
+    for hp in sorted(data):
+        ocf.fill_neighs([hp])
+        want_n = [[d2.thingid for d2 in d.neighbours] for d in data[hp]]
+        want = ocf.compute_xi([hp])
+        cf.fill_neighs([hp])
+        assert [[d2.thingid for d2 in d.neighbours] for d in data[hp]] == want_n
+        assert all(d.thingid not in ids for d, ids in zip(data[hp], want_n))
+        helpers.assert_xi_close(cf.compute_xi([hp]), want, tag="hp %d" % hp)
+        total += int(want[5].sum())
+    assert total > 0
+    cf.data2 = ocf.data2 = None

@@ -30,10 +30,11 @@ def test_cf_matches_reference_golden(name, host_angles, monkeypatch):
     gold = np.load(os.path.join(GOLD, "golden_cf.npz"))
     cfg = dict(cases.CF_CASES[name])
     second = cfg.pop("second", False)
-    data, num, z_min, cosmo = cases.forests()
+    plates = cfg.pop("plates", False)
+    data, num, z_min, cosmo = cases.forests(plates=plates)
     over, z_min2 = dict(cfg), None
     if second:
-        data2, num2, z_min2, _ = cases.forests(second=True)
+        data2, num2, z_min2, _ = cases.forests(second=True, plates=plates)
         over["data2"], over["num_data2"] = data2, num2
     helpers.configure(cf, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
     want = gold["cf_%s" % name]

@@ -210,3 +210,47 @@ def test_smooth_cov_key_extents_cover_every_key():
             if per_r_par:
                 k_rp = np.trunc(rp[i] / cfg["delta_r_par"]).astype(int) - rp_lo
                 assert k_rp.min() >= 0 and k_rp.max() < n_rp, name
+
+
+def test_string_ids_share_one_mapping_across_catalogues():
+    """Non-integer line-of-sight ids (combined re-observations) are mapped to integers through
+    ONE process-wide table: the neighbour kernel compares ``thingid`` ACROSS catalogues (data vs
+    data2, forests vs objects; cf.py:109-112, xcf.py:95-97), so equal ids must get equal
+    integers in both and different ids different ones."""
+    import copy
+    from picca_b200 import catalog
+    data, _, _, _, _ = helpers.small_sample(n=40, seed=3, max_pix=20)
+    data2 = {hp: [copy.copy(d) for d in v] for hp, v in data.items()}
+    for v in data.values():
+        for d in v:
+            d.thingid = "obj-%d" % d.thingid
+    for k, v in enumerate(data2.values()):
+        for d in reversed(v):      # other order, and one foreign id per pixel
+            d.thingid = "obj-%d" % d.thingid
+        v[0].thingid = "foreign-%d" % k
+    c1, c2 = catalog.pack(data), catalog.pack(data2)
+    assert c1.thingid_remapped and c2.thingid_remapped
+    ids1 = {o.thingid: int(t) for o, t in zip(c1.objs, c1.arrays["thingid"])}
+    ids2 = {o.thingid: int(t) for o, t in zip(c2.objs, c2.arrays["thingid"])}
+    for name, t in ids2.items():
+        if name in ids1:
+            assert ids1[name] == t
+        else:
+            assert t not in ids1.values()
+    assert len(set(ids1.values())) == len(ids1)
+
+
+def test_cached_pack_sees_replaced_lists_and_invalidate():
+    from picca_b200 import catalog
+    data, _, _, _, _ = helpers.small_sample(n=30, seed=4, max_pix=20)
+    a = catalog.cached_pack(data)
+    assert catalog.cached_pack(data) is a
+    hp = sorted(data)[0]
+    data[hp] = list(reversed(data[hp]))          # same length, other list object
+    b = catalog.cached_pack(data)
+    assert b is not a and b.objs[0] is data[hp][0]
+    data[hp][0].weights = data[hp][0].weights * 2.  # in-place style edit: invisible ...
+    assert catalog.cached_pack(data) is b
+    catalog.invalidate(data)                         # ... until the caller says so
+    c = catalog.cached_pack(data)
+    assert c is not b

@@ -1,0 +1,70 @@
+"""GPU, >= 2 devices: the sharded paths (HEALPix rows LPT-partitioned over the ranks, blocks
+gathered over NCCL; distortion matrix of one reference chunk with the kept forest pairs sharded
+and ONE all-reduce) equal the single-GPU plugin calls -- num_pairs / NPALL / NPUSED exactly, sums
+to 1e-11.  Skipped on a one-GPU box (run with ``gpurun --gpus 2``)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_xi_and_dmat_equal_single_gpu(world):
+    if _n_devices() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "multi-gpu ok" in res.stdout
+
+
+def test_one_rank_shard_equals_plugin_call():
+    """world = 1 through the same sharded entry points (no process group): the segmented --rej
+    draw and the accumulate-into launches reproduce cf.compute_dmat."""
+    import numpy as np
+    from picca_b200 import catalog, cf, dist as pdist
+    from picca_b200.engine import MODE_AUTO, get_engine
+    from picca_b200.params import params_from_module
+    from tests import helpers
+    from tests.golden import cases
+    eng = get_engine()
+    cfg = dict(cases.DMAT_CASES["default"], reject=0.7)
+    data, num, z_min, cosmo = cases.dmat_forests()
+    ang_max = cases.ang_max_for(cosmo, cfg, z_min)
+    helpers.configure(cf, data, num, ang_max, **cfg)
+    host = catalog.cached_pack(data)
+    dev = eng.device_catalog(host)
+    params = params_from_module(cf)
+    shard = pdist.Shard(eng, host, host, ang_max, 1, 0)
+    hps = host.healpixs
+    res, npall, npused = pdist.dmat_chunk_sharded(eng, dev, dev, params, shard, MODE_AUTO,
+                                                  cf.reject, hps[0], segments=4)
+    cf.fill_neighs(hps)
+    np.random.seed(hps[0])
+    one = cf.compute_dmat(hps)
+    assert (npall, npused) == (one[6], one[7])
+    for a, b in zip(res, one[:6]):
+        a = a.cpu().numpy()
+        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300)
+    full = pdist.xi_sharded(eng, dev, dev, params, shard, MODE_AUTO).cpu().numpy()
+    cf.fill_neighs(hps)
+    want = cf.compute_xi_batch(hps)
+    assert np.array_equal(full[:, 5].view(np.int64), want[:, 5].view(np.int64))

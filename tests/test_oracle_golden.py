@@ -35,11 +35,16 @@ def check_rows(rows, gold, rtol):
 def setup_cf(mod, cfg, dmat=False):
     cfg = dict(cfg)
     second = cfg.pop("second", False)
+    plates = cfg.pop("plates", False)
     src = cases.dmat_forests if dmat else cases.forests
     data, num, z_min, cosmo = src()
+    if plates:
+        cases.share_plates(data)
     over, z_min2 = dict(cfg), None
     if second:
         data2, num2, z_min2, _ = src(second=True)
+        if plates:
+            cases.share_plates(data2)
         over["data2"], over["num_data2"] = data2, num2
     helpers.configure(mod, data, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
     return data

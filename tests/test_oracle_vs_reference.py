@@ -11,7 +11,7 @@ from tests.refharness import shims
 pytestmark = [pytest.mark.reference,
               pytest.mark.skipif(not shims.reference_available(), reason="needs /root/reference")]
 
-DATA = "/root/reference/py/picca/tests/data"
+DATA = shims.REFERENCE_DATA
 
 
 @pytest.fixture(scope="module")
@@ -206,6 +206,28 @@ COMMON = (" --rp-max +60.0 --rt-max +60.0 --nt 15 --nproc 1 --in-attributes " + 
      " --no-redshift-evolution --drq " + DATA + "/test_delta/cat.fits", "xdmat"),
 ])
 def test_unmodified_script_on_oracle_matches_golden_fits(tmp_path, script, double, flags, golden):
+    _script_on_oracle(tmp_path, script, double, COMMON + flags, golden)
+
+
+ANGL = (" --nproc 1 --in-attributes " + DATA + "/test_delta/delta_attributes.fits.gz --in-dir " +
+        DATA + "/test_delta/Delta_LYA/")
+
+
+@pytest.mark.parametrize("script,double,flags,golden", [
+    # test_3_cor.py:206-227: wavelength-ratio x angle binning, cosmo=None deltas
+    ("picca_cf_angl", "cf", "", "cf_angl"),
+    # test_3_cor.py:611-634
+    ("picca_xcf_angl", "xcf", " --z-evol-obj 1. --drq " + DATA + "/test_delta/cat.fits",
+     "xcf_angl"),
+])
+def test_unmodified_angular_script_on_oracle_matches_golden_fits(tmp_path, script, double, flags,
+                                                                 golden):
+    """``ang_correlation`` branch (cf.py:186-208, :350-354; xcf.py:161-182, :293-295) against the
+    reference's own golden files cf_angl.fits.gz / xcf_angl.fits.gz."""
+    _script_on_oracle(tmp_path, script, double, ANGL + flags, golden)
+
+
+def _script_on_oracle(tmp_path, script, double, flags, golden):
     import importlib
     from tests.refharness import load
     load.reference_modules()
@@ -215,7 +237,7 @@ def test_unmodified_script_on_oracle_matches_golden_fits(tmp_path, script, doubl
     setattr(mod, double, oracle_mod)  # the script now drives the oracle double of picca.cf/xcf
     out = str(tmp_path / (golden + ".fits.gz"))
     try:
-        mod.main((COMMON + flags + " --out " + out).split())
+        mod.main((flags + " --out " + out).split())
     finally:
         setattr(mod, double, saved)
     _compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz")

@@ -100,9 +100,9 @@ def test_scripts_bind_b200_loader(overlay_on):
     assert picca.io.read_deltas is not picca.io.reference_read_deltas
     assert callable(picca.io.read_objects)
     with pytest.raises(RuntimeError):
-        picca.io.read_deltas(shims.REFERENCE_PY + "/picca/tests/data/test_delta/Delta_LYA/",
-                             16, 1215.67, 2.9, 2.25, None, delta_attributes=shims.REFERENCE_PY +
-                             "/picca/tests/data/test_delta/delta_attributes.fits.gz")
+        picca.io.read_deltas(shims.REFERENCE_DATA + "/test_delta/Delta_LYA/",
+                             16, 1215.67, 2.9, 2.25, None, delta_attributes=shims.REFERENCE_DATA +
+                             "/test_delta/delta_attributes.fits.gz")
 
 
 def test_co_script_binds_b200_module(overlay_on):
@@ -116,3 +116,24 @@ def test_co_script_binds_b200_module(overlay_on):
             for tgt in node.targets:
                 assert hasattr(picca_b200.co, tgt.id), tgt.id
     assert callable(picca_b200.co.fill_neighs) and callable(picca_b200.co.compute_xi)
+
+
+def test_loader_rejection_is_loud_unless_fallback_is_requested(overlay_on, monkeypatch):
+    """No silent CPU fallback on the delta loader: an input the B200 loader
+    rejects raises; only PICCA_B200_IO_FALLBACK=1 hands it to the reference's read_deltas."""
+    import picca.io
+    import picca_b200.io as impl
+
+    def reject(*args, **kwds):
+        raise NotImplementedError("picca_b200.io: mixed LOGLAM / LAMBDA delta files")
+    monkeypatch.setattr(impl, "read_deltas", reject)
+    called = []
+    monkeypatch.setattr(picca.io, "reference_read_deltas", lambda *a, **k: called.append(1) or 7)
+    monkeypatch.delenv("PICCA_B200_IO_FALLBACK", raising=False)
+    with pytest.raises(NotImplementedError):
+        picca.io.read_deltas("x", 16, 1215.67, 2.9, 2.25, None)
+    assert not called
+    monkeypatch.setenv("PICCA_B200_IO_FALLBACK", "1")
+    assert picca.io.read_deltas("x", 16, 1215.67, 2.9, 2.25, None) == 7 and called
+    monkeypatch.setenv("PICCA_B200_IO", "0")  # explicit opt-out of the B200 loader
+    assert picca.io.read_deltas("x", 16, 1215.67, 2.9, 2.25, None) == 7 and len(called) == 2
