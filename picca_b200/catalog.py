@@ -34,6 +34,7 @@ class HostCatalog:
         self.max_pix = 0
         self.ids_are_int = True
         self.thingid_remapped = False
+        self.from_soa = False     # packed straight from a registered SoA (forest.register_soa)
         self.is_object = False
         self.il_total = 0         # diagonal-lane copies (see _diag_metadata)
         self.dg_total = 0
@@ -80,12 +81,13 @@ def _diag_metadata(cat, offset):
     lanes, pad, row_pad, chunk = diag_layout()
     n = cat.n_los
     keep = A["weights"] != 0
-    if n:
-        first_pix = offset[:-1]
-        count = np.add.reduceat(np.append(keep.astype(np.int64), 0), first_pix)
-        count = np.where(np.diff(offset) > 0, count, 0).astype(np.int64)
+    if n and keep.size:
+        # non-zero-weight pixels per forest: prefix count sampled at the CSR offsets
+        csum = np.zeros(keep.size + 1, dtype=np.int64)
+        np.cumsum(keep, out=csum[1:], dtype=np.int64)
+        count = np.diff(csum[offset])
     else:
-        count = np.zeros(0, np.int64)
+        count = np.zeros(n, np.int64)
     first = np.zeros(n + 1, dtype=np.int64)
     first[1:] = np.cumsum(count)
     A["dg_offset"] = np.ascontiguousarray(first[:-1] + row_pad * np.arange(n, dtype=np.int64))
@@ -99,10 +101,22 @@ def _diag_metadata(cat, offset):
     cat.dg_lanes = lanes
     cat.dg_max_pix = int(count.max()) if n else 0
     fields = ("r_comov", "dist_m", "weights", "delta_w", "z")
-    finite = all(bool(np.all(np.isfinite(A[name][keep]))) for name in fields)
+    # a sum is finite iff every term is (no overflow at these magnitudes): one pass per field,
+    # the masked test only when a zero-weight pixel carries the non-finite value
+    finite = all(bool(np.isfinite(A[name].sum())) or bool(np.all(np.isfinite(A[name][keep])))
+                 for name in fields)
     cat.dg_ok = int(finite)
-    cat.dg_reach = float(max(np.abs(A["r_comov"][keep]).max(), np.abs(A["dist_m"][keep]).max())) \
-        if keep.any() and finite else 0.0
+    if keep.any() and finite:
+        if np.isfinite(A["r_comov"].sum()) and np.isfinite(A["dist_m"].sum()):
+            # over all pixels: an upper bound of the reach of the kept ones (conservative: the
+            # launcher only uses it to rule the low-word bin arithmetic out)
+            cat.dg_reach = float(max(-A["r_comov"].min(), A["r_comov"].max(),
+                                     -A["dist_m"].min(), A["dist_m"].max()))
+        else:
+            cat.dg_reach = float(max(np.abs(A["r_comov"][keep]).max(),
+                                     np.abs(A["dist_m"][keep]).max()))
+    else:
+        cat.dg_reach = 0.0
 
 
 def diag_records_host(cat):
@@ -194,27 +208,40 @@ def pack(data, is_object=False, ang_correlation=False):
         A["log_lambda"] = np.zeros(n, dtype=np.float64)
         A["order"] = np.zeros(n, dtype=np.int32)
     else:
-        npix = np.array([len(o.weights) for o in objs], dtype=np.int64)
-        offset = np.zeros(n + 1, dtype=np.int64)
-        offset[1:] = np.cumsum(npix)
+        from . import forest as _forest
+        soa = _forest.soa_of(data)
+        fields = ("log_lambda", "delta", "weights", "z") + \
+            (() if ang_correlation else ("r_comov", "dist_m"))
+        if soa is not None and n and all(k in soa for k in fields) and \
+                _forest.views_intact(objs, soa, fields):
+            # the producer (B200 loader, synthetic generator) built these forests as views into
+            # one array per field in catalogue order: pack without touching the objects' arrays
+            cat.from_soa = True
+            offset = np.ascontiguousarray(soa["offset"], dtype=np.int64)
+            cat_field = lambda name: soa[name]
+        else:
+            cat.from_soa = False
+            npix = np.array([len(o.weights) for o in objs], dtype=np.int64)
+            offset = np.zeros(n + 1, dtype=np.int64)
+            offset[1:] = np.cumsum(npix)
 
-        def cat_field(getter):
-            if n == 0:
-                return np.zeros(0, dtype=np.float64)
-            return np.ascontiguousarray(
-                np.concatenate([np.asarray(getter(o), dtype=np.float64) for o in objs]))
+            def cat_field(name):
+                if n == 0:
+                    return np.zeros(0, dtype=np.float64)
+                return np.ascontiguousarray(np.concatenate(
+                    [np.asarray(getattr(o, name), dtype=np.float64) for o in objs]))
 
-        weights = cat_field(lambda o: o.weights)
-        delta = cat_field(lambda o: o.delta)
-        log_lambda = cat_field(lambda o: o.log_lambda)
-        A["z"] = cat_field(lambda o: o.z)
+        weights = cat_field("weights")
+        delta = cat_field("delta")
+        log_lambda = cat_field("log_lambda")
+        A["z"] = cat_field("z")
         if ang_correlation:
             lam = 10.0**log_lambda
             A["r_comov"] = lam
             A["dist_m"] = lam.copy()
         else:
-            A["r_comov"] = cat_field(lambda o: o.r_comov)
-            A["dist_m"] = cat_field(lambda o: o.dist_m)
+            A["r_comov"] = cat_field("r_comov")
+            A["dist_m"] = cat_field("dist_m")
         A["weights"] = weights
         # delta*weights is the product the reference forms first (cf.py:367-368); zero-weight
         # pixels never contribute (cf.py:318, :331) so a NaN delta there must not leak
@@ -237,8 +264,8 @@ def pack(data, is_object=False, ang_correlation=False):
         inner = np.ones(cat.n_pix - 1, dtype=bool)
         inner[offset[1:-1][(offset[1:-1] > 0) & (offset[1:-1] < cat.n_pix)] - 1] = False
         for name in ("r_comov", "dist_m"):
-            d = np.diff(A[name])
-            if np.any((d < 0) & inner) or not np.all(np.isfinite(A[name])):
+            v = A[name]
+            if np.any((v[1:] < v[:-1]) & inner) or not np.isfinite(v.sum()):
                 cat.sorted = 0
 
     # bounding caps per HEALPix pixel

@@ -158,7 +158,7 @@ def compute_xi(healpixs):
     return weights, xi, r_par, r_trans, z, num_pairs
 
 
-def compute_xi_batch(healpixs, normalise=True):
+def compute_xi_batch(healpixs, normalise=True, to_host=True):
     """One launch for many HEALPix pixels: row k of the result is ``compute_xi([healpixs[k]])``.
     Returns an array [len(healpixs), 6, nb] (row 5 = int64 counts viewed as float64 slots) --
     what picca_cf.py stacks from its Pool.map (picca_cf.py:466-473)."""
@@ -171,7 +171,7 @@ def compute_xi_batch(healpixs, normalise=True):
                            for k, hp in enumerate(healpixs)]) if healpixs else np.zeros(0, np.int32)
     out = eng.xi(dev1, dev2, params, pairs, rows, len(healpixs), variant=_XI_VARIANT,
                  normalise=normalise)
-    host = out.cpu().numpy()
+    host = out.cpu().numpy() if to_host else out  # to_host=False: device tensor (multi-GPU gather)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
     for f1 in pairs.f1_index.cpu().numpy():
         setattr(host1.objs[f1], "neighbours", None)

@@ -112,6 +112,8 @@ class Engine:
     # ------------------------------------------------------------------ memory
     collect_dmat_stats = False   # bench.py: read pb2_dmat_stats after every dmat launch
     last_dmat_stats = None
+    sum_dmat_stats = None        # ... summed over the launches since it was last reset
+    dmat_kernel_ms_log = None    # bench.py: list that receives the kernel time of every launch
 
     def stream_ptr(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -234,6 +236,10 @@ class Engine:
                                                self.stream_ptr()), "pb2_dmat_stats")
             self.last_dmat_stats = {"as_written_ops": out3[0], "sum_unique_model_bins": out3[1],
                                     "in_range_pixel_pairs": out3[2]}
+            tot = self.sum_dmat_stats or {}
+            self.sum_dmat_stats = {k: tot.get(k, 0.) + v for k, v in self.last_dmat_stats.items()}
+        if self.dmat_kernel_ms_log is not None:
+            self.dmat_kernel_ms_log.append(float(self.lib.pb2_last_kernel_ms()))
         return weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff
 
     # ------------------------------------------------------------------ measurement

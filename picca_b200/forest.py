@@ -49,3 +49,60 @@ class Delta(QSO):
         self.r_comov = None
         self.dist_m = None
         self.neighbours = None
+
+
+# ---------------------------------------------------------------------------------------------
+# SoA registry: a producer that builds the forests of a ``data`` dict as VIEWS into one
+# contiguous array per field, forests back to back in catalogue order (ascending HEALPix, list
+# order), registers those arrays here; ``catalog.pack`` then packs straight from them instead of
+# concatenating 100 000 per-forest arrays again -- after checking, pointer by pointer, that the
+# objects still are those views (any re-bound attribute sends it back to the generic path).
+PIXEL_FIELDS = ("log_lambda", "delta", "weights", "z", "r_comov", "dist_m")
+_SOA_OF = {}
+
+
+def register_soa(data, soa):
+    """``soa``: dict with ``offset`` (int64[n_los + 1]) and the PIXEL_FIELDS arrays (float64,
+    C-contiguous, catalogue order).  One or two catalogues live in a run: older entries whose
+    dict has been garbage-collected are dropped."""
+    if len(_SOA_OF) > 8:
+        _SOA_OF.clear()
+    _SOA_OF[id(data)] = (data, soa)
+
+
+def soa_of(data):
+    hit = _SOA_OF.get(id(data))
+    return hit[1] if hit is not None and hit[0] is data else None
+
+
+def views_intact(objs, soa, fields):
+    """True when attribute ``name`` of object k is ``soa[name][offset[k]:offset[k+1]]`` for every
+    k and every name in ``fields``: a view of that very array (``.base``), of that length, and --
+    checked address by address on the ``weights`` field, whose forests are laid out like all the
+    others -- at that position."""
+    import numpy as np
+    offset = soa["offset"]
+    n = len(objs)
+    if n != len(offset) - 1:
+        return False
+    sizes = np.diff(offset)
+    try:
+        for name in fields:
+            base = soa[name]
+            if base.dtype != np.float64 or not base.flags.c_contiguous:
+                return False
+            root = base if base.base is None else base.base
+            for o in objs:
+                v = getattr(o, name)
+                if v.base is not base and v.base is not root:
+                    return False
+            lens = np.fromiter((getattr(o, name).size for o in objs), dtype=np.int64, count=n)
+            if not np.array_equal(lens, sizes):
+                return False
+        base = soa["weights"]
+        ptr0 = base.__array_interface__["data"][0]
+        got = np.fromiter((o.weights.__array_interface__["data"][0] for o in objs),
+                          dtype=np.int64, count=n)
+    except (AttributeError, TypeError):
+        return False
+    return bool(np.array_equal(got[sizes > 0], (ptr0 + 8 * offset[:-1])[sizes > 0]))

@@ -41,7 +41,7 @@ import numpy as np
 
 from . import _lib
 from .engine import get_engine
-from .forest import Delta
+from .forest import PIXEL_FIELDS, Delta, register_soa
 from .synth import ang2pix_ring
 
 _KEYS = (["EXTNAME", "RA", "DEC", "Z", "THING_ID", "PLATE", "MJD", "FIBERID", "LOS_ID",
@@ -671,15 +671,28 @@ def read_deltas_soa(in_dir, nside, lambda_abs, alpha, z_ref, cosmo, max_num_spec
 
     eng.torch.cuda.synchronize()
     mark("prepare kernel")
-    # ---- back to the reference's data model: dict[healpix] -> list[Delta] of array views
-    h = {name: t.cpu().numpy() for name, t in (("log_lambda", d_ll), ("delta", d_delta),
-                                               ("weights", d_w), ("z", d_z))}
+    # ---- catalogue order (ascending HEALPix, file order inside a pixel: the iteration order of
+    # fill_neighs, cf.py:91-122) before the copy back, so that catalog.pack can take the arrays
+    # as they are; the gather runs in HBM
+    healpixs = ang2pix_ring(nside, np.pi / 2. - dec, ra)  # io.py:486-488
+    perm = np.argsort(healpixs, kind="stable")
+    fields = [("log_lambda", d_ll), ("delta", d_delta), ("weights", d_w), ("z", d_z)]
     if d_rc is not None:
-        h["r_comov"], h["dist_m"] = d_rc.cpu().numpy(), d_dm.cpu().numpy()
+        fields += [("r_comov", d_rc), ("dist_m", d_dm)]
     z_range = d_range.cpu().numpy().reshape(n_los, 2)
+    if not np.array_equal(perm, np.arange(n_los)):
+        lengths = np.diff(offset)[perm]
+        new_offset = np.zeros(n_los + 1, dtype=np.int64)
+        np.cumsum(lengths, out=new_offset[1:])
+        d_shift = torch.from_numpy(np.repeat(offset[:-1][perm] - new_offset[:-1], lengths)).to(dev)
+        d_idx = d_shift + torch.arange(total_pix, dtype=torch.int64, device=dev)
+        fields = [(name, t.index_select(0, d_idx)) for name, t in fields]
+        offset = new_offset
+        ra, dec, z_qso, los_id, plate, mjd, fiberid, healpixs = (
+            v[perm] for v in (ra, dec, z_qso, los_id, plate, mjd, fiberid, healpixs))
+    h = {name: t.cpu().numpy() for name, t in fields}
     z_min = float(z_range[:, 0].min())
     z_max = max(0., float(z_range[:, 1].max()))  # io.py:493: z_max starts at 0
-    healpixs = ang2pix_ring(nside, np.pi / 2. - dec, ra)  # io.py:486-488
     mark("D2H")
     if os.environ.get("PICCA_B200_IO_TIMING", "0") == "1":
         for (_, t0), (name, t1) in zip(marks[:-1], marks[1:]):
@@ -698,9 +711,9 @@ SOA_ARRAYS = ("log_lambda", "delta", "weights", "z", "r_comov", "dist_m", "offse
 def soa_to_objects(soa):
     """The reference's data model from the loader's SoA: ``dict[healpix] -> list[Delta]`` whose
     array attributes are views into the SoA (io.py:485-512 builds the same dict per forest).
-    The SoA is remembered in ``SOA_OF`` under ``id(data)`` so that ``catalog.cached_pack`` can
-    pack straight from it (after checking that the objects still are those views) instead of
-    gathering 100 000 Python objects again."""
+    The SoA is in catalogue order and registered (``forest.register_soa``) so that
+    ``catalog.pack`` takes the arrays as they are (after checking that the objects still are
+    those views) instead of concatenating 100 000 per-forest arrays again."""
     offset, order = soa["offset"], soa["order"]
     has_dist = "r_comov" in soa
     data = {}
@@ -716,9 +729,5 @@ def soa_to_objects(soa):
             d.r_comov, d.dist_m = soa["r_comov"][a:b], soa["dist_m"][a:b]
         data.setdefault(int(healpixs[f]), []).append(d)
     userprint("\n")
-    SOA_OF.clear()  # one catalogue at a time is remembered (a run holds one or two)
-    SOA_OF[id(data)] = (data, soa)
+    register_soa(data, {k: soa[k] for k in ("offset",) + PIXEL_FIELDS if k in soa})
     return data, soa["n_los"], soa["z_min"], soa["z_max"]
-
-
-SOA_OF = {}

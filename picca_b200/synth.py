@@ -7,7 +7,7 @@ read or need the reference.
 """
 import numpy as np
 
-from .forest import Delta, QSO
+from .forest import PIXEL_FIELDS, Delta, QSO, register_soa
 
 LYA = 1215.67  # reference py/picca/constants.py ABSORBER_IGM["LYA"]
 SPEED_LIGHT = 299792.458
@@ -116,27 +116,45 @@ def make_forests(n_forest, seed=20260102, nside=32, ra_deg=(0., 120.), dec_deg=(
     if max_pix is not None:
         npix = np.minimum(npix, max_pix)
 
+    # the forests are written as views into one array per field, forests back to back in
+    # catalogue order (ascending HEALPix, generation order inside a pixel), like the B200 loader
+    # does, and registered for catalog.pack (forest.register_soa)
+    order_cat = np.argsort(healpix, kind="stable")
+    offset = np.zeros(n_forest + 1, dtype=np.int64)
+    np.cumsum(npix[order_cat], out=offset[1:])
+    start = np.empty(n_forest, dtype=np.int64)
+    start[order_cat] = offset[:-1]
+    soa = {name: np.empty(int(offset[-1]), dtype=np.float64) for name in PIXEL_FIELDS}
+    soa["offset"] = offset
     data = {}
     z_min, z_max = np.inf, 0.
     for f in range(n_forest):
         n = int(npix[f])
+        a = int(start[f])
         lam = lambda_min + dlambda * (k_lo[f] + np.arange(n))
-        log_lambda = np.log10(lam)
+        log_lambda = soa["log_lambda"][a:a + n]
+        log_lambda[:] = np.log10(lam)
         delta = rng.normal(0., 0.25, n)
         weights = rng.uniform(0.5, 2.0, n)
         weights[rng.random(n) < zero_weight_frac] = 0.
-        z = 10**log_lambda / LYA - 1.
-        weights = weights * ((1 + z) / (1 + z_ref))**(alpha - 1)  # io.py:503
-        delta = project(delta, weights, log_lambda, order)        # io.py:505-506
+        z = soa["z"][a:a + n]
+        z[:] = 10**log_lambda / LYA - 1.
+        w_view = soa["weights"][a:a + n]
+        w_view[:] = weights * ((1 + z) / (1 + z_ref))**(alpha - 1)  # io.py:503
+        d_view = soa["delta"][a:a + n]
+        d_view[:] = project(delta, w_view, log_lambda, order)        # io.py:505-506
         tid = id_offset + f + 1
         d = Delta(tid, float(ra[f]), float(dec[f]), float(z_qso[f]), tid, tid, tid, log_lambda,
-                  weights, delta, order)
+                  w_view, d_view, order)
         d.z = z
-        d.r_comov = cosmo.get_r_comov(z)
-        d.dist_m = cosmo.get_dist_m(z)
+        d.r_comov = soa["r_comov"][a:a + n]
+        d.r_comov[:] = cosmo.get_r_comov(z)
+        d.dist_m = soa["dist_m"][a:a + n]
+        d.dist_m[:] = cosmo.get_dist_m(z)
         z_min = min(z_min, z.min())
         z_max = max(z_max, z.max())
         data.setdefault(int(healpix[f]), []).append(d)
+    register_soa(data, soa)
     return data, n_forest, float(z_min), float(z_max), cosmo
 
 
