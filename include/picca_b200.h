@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 20
+#define PB2_ABI_VERSION 21
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -238,6 +238,37 @@ int32_t pb2_metal_dmat_cross(const pb2_catalog *cat1, const pb2_catalog *objs, c
                              const double *d_dm1, const double *d_pw1, double *d_weights_dmat,
                              double *d_dmat, double *d_r_par_eff, double *d_r_trans_eff,
                              double *d_z_eff, double *d_weight_eff, void *stream);
+
+/* ---- Wick expansion of the covariance.
+ * pb2_wick_auto replaces the forest-pair loop of cf.compute_wick_terms and
+ * cf.compute_wickT123_pairs (py/picca/cf.py:1326-1494, :1497-1626; diagrams T1-T3, i.e.
+ * max_diagram <= 3) over the forest pairs flagged in pairs->nb_keep (the caller's per-forest
+ * --rej draw, cf.py:1378).  d_var*: get_variance_1d(log_lambda) per pixel of the catalogue
+ * (cf.py:1412); d_ze*: ((1+z)/(1+z_ref))^(alpha-1) per pixel (cf.py:1556-1557); the 1-D
+ * correlation xi_1d (picca_wick.py:412-417: scipy interp1d, kind "nearest", extrapolating) comes
+ * as a table: n_x values d_xy and the n_x - 1 decision bounds d_xb between them.
+ * Outputs are accumulated into: weights_wick[nb], num_pairs_wick[nb] (int64), t1/t2/t3 [nb][nb].
+ * pb2_wick_cross: xcf.compute_wick_terms / compute_wickT1234_pairs (py/picca/xcf.py:838-1153,
+ * :1219-1351; T1-T4) over the forests flagged in d_keep_f1 [pairs->n_f1] with ALL their
+ * neighbouring objects; d_ze_obj: ((1+z_q)/(1+z_ref))^(alpha_obj-1) per object;
+ * max_neighbours: the longest neighbour list among the flagged forests.
+ * Scratch: pb2_wick_scratch_bytes(longest forest of catalogue 1, longest forest of catalogue 2
+ * or max_neighbours, cross). */
+int64_t pb2_wick_scratch_bytes(int64_t max_pix1, int64_t max_rows2, int32_t cross);
+int32_t pb2_wick_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                      const pb2_pairs *pairs, const double *d_var1, const double *d_ze1,
+                      const double *d_var2, const double *d_ze2, int32_t n_x1,
+                      const double *d_xb1, const double *d_xy1, int32_t n_x2,
+                      const double *d_xb2, const double *d_xy2, double *d_weights_wick,
+                      int64_t *d_num_pairs_wick, double *d_t1, double *d_t2, double *d_t3,
+                      void *d_scratch, int64_t scratch_bytes, void *stream);
+int32_t pb2_wick_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
+                       const pb2_pairs *pairs, const uint8_t *d_keep_f1, int64_t max_neighbours,
+                       const double *d_var1, const double *d_ze1, const double *d_ze_obj,
+                       int32_t n_x1, const double *d_xb1, const double *d_xy1,
+                       double *d_weights_wick, int64_t *d_num_pairs_wick, double *d_t1,
+                       double *d_t2, double *d_t3, double *d_t4, void *d_scratch,
+                       int64_t scratch_bytes, void *stream);
 
 /* ---- object x object pair counting: replaces the pair loop of
  * co.compute_xi / co.compute_xi_forest_pairs (py/picca/co.py:77-132, :135-202).  pairs = the

@@ -239,41 +239,21 @@ def _weighted_xi_1d(delta):
 
 def compute_wickT123_pairs(r_comov1, r_comov2, ang, weights1, weights2, z1, z2, weighted_xi_1d_1,
                            weighted_xi_1d_2, weights_wick, num_pairs_wick, t1, t2, t3):
-    """cf.py:1553-1626.  The selected pixel pairs are enumerated in the reference's order (ind2
-    outer, ind1 inner, :1562-1596); its double loop over ordered pairs of selected pixel pairs
-    (:1598-1624) is restated with the (index1 < index2) list in row-major order and np.add.at
-    (sequential, unbuffered), each product added to [p1, p2] then [p2, p1] as the reference does."""
-    n1, n2 = len(r_comov1), len(r_comov2)
-    z_weight_evol1 = ((1 + z1) / (1 + z_ref))**(alpha - 1)
-    z_weight_evol2 = ((1 + z2) / (1 + z_ref))**(alpha2 - 1)
-    ind2, ind1 = [a.reshape(-1) for a in np.meshgrid(np.arange(n2), np.arange(n1), indexing="ij")]
-    r_par = (r_comov1[ind1] - r_comov2[ind2]) * np.cos(ang / 2)
-    if not x_correlation:
-        r_par = abs(r_par)
-    r_trans = (r_comov1[ind1] + r_comov2[ind2]) * np.sin(ang / 2)   # r_comov, not dist_m (:1567)
-    sel = (r_par < r_par_max) & (r_trans < r_trans_max) & (r_par >= r_par_min)
-    if sel.sum() == 0:
-        return
-    i, j, r_par, r_trans = ind1[sel], ind2[sel], r_par[sel], r_trans[sel]
-    bins_forest = ((r_trans / r_trans_max * num_bins_r_trans).astype(np.int64) + num_bins_r_trans *
-                   ((r_par - r_par_min) / (r_par_max - r_par_min) * num_bins_r_par).astype(np.int64))
-    weights12 = weights1[i] * weights2[j]
-    weight1, weight2 = weights1[i], weights2[j]
-    z_weight_evol = z_weight_evol1[i] * z_weight_evol2[j]
-    np.add.at(weights_wick, bins_forest, weights12)                       # :1602
-    np.add.at(num_pairs_wick, bins_forest, 1)
-    np.add.at(t1, (bins_forest, bins_forest), weights12 * z_weight_evol)  # :1604
-    a, b = np.triu_indices(len(i), 1)                                     # index1 < index2
-    p1, p2 = bins_forest[a], bins_forest[b]
-    same_i, same_j = i[a] == i[b], (j[a] == j[b]) & (i[a] != i[b])
-    other = ~same_i & ~same_j
-    prod = np.where(same_i, weighted_xi_1d_2[j[a], j[b]] * weight1[a] * z_weight_evol1[i[a]],
-                    weighted_xi_1d_1[i[a], i[b]] * weight2[b] * z_weight_evol2[j[a]])   # :1610-1617
-    prod3 = weighted_xi_1d_1[i[a], i[b]] * weighted_xi_1d_2[j[a], j[b]]                # :1619-1621
-    for target, mask, values in ((t2, ~other, prod), (t3, other, prod3)):
-        rows = np.stack([p1[mask], p2[mask]], axis=1).reshape(-1)   # [p1, p2] then [p2, p1]
-        cols = np.stack([p2[mask], p1[mask]], axis=1).reshape(-1)
-        np.add.at(target, (rows, cols), np.repeat(values[mask], 2))
+    """cf.py:1497-1626: the C restatement ``orc_wick_t123_pair`` (statement by statement: the
+    selected pixel pairs in the reference's order, then its double loop over pairs of list
+    entries), accumulating in place like the Numba function."""
+    import ctypes
+    lib = _kernels.lib()
+    p = _kernels.params_from_module(_THIS)
+    f64, dp, lp = _kernels.f64, _kernels.dp, _kernels.lp
+    r1, r2, w1, w2, zz1, zz2 = (f64(a) for a in (r_comov1, r_comov2, weights1, weights2, z1, z2))
+    x1, x2 = f64(weighted_xi_1d_1), f64(weighted_xi_1d_2)
+    for arr in (weights_wick, num_pairs_wick, t1, t2, t3):
+        assert arr.flags.c_contiguous
+    lib.orc_wick_t123_pair(
+        ctypes.byref(p), ctypes.c_int64(len(r1)), dp(r1), ctypes.c_int64(len(r2)), dp(r2),
+        ctypes.c_double(float(ang)), dp(w1), dp(w2), dp(zz1), dp(zz2), dp(x1), dp(x2),
+        dp(weights_wick), lp(num_pairs_wick), dp(t1), dp(t2), dp(t3))
 
 
 def compute_wick_terms(healpixs):

@@ -10,6 +10,8 @@
  *   orc_xi_cross_forest <- reference py/picca/xcf.py:223-322  (compute_xi_forest_pairs_fast)
  *   orc_dmat_auto_pair  <- reference py/picca/cf.py:520-887   (compute_dmat_forest_pairs_fast)
  *   orc_dmat_cross_forest <- reference py/picca/xcf.py:427-674 (compute_dmat_forest_pairs_fast)
+ *   orc_wick_t123_pair  <- reference py/picca/cf.py:1497-1626  (compute_wickT123_pairs)
+ *   orc_wick_t1234_forest <- reference py/picca/xcf.py:1219-1351 (compute_wickT1234_pairs)
  *   orc_xi_auto_batch / orc_xi_cross_batch: the compute_xi loops (cf.py:138-247, xcf.py:126-220)
  *       over a CSR catalogue + neighbour list, one histogram row per HEALPix pixel, OpenMP over
  *       pixels -- the analogue of the reference's Pool.map over pixels (picca_cf.py:454-457).
@@ -729,6 +731,185 @@ void orc_xi_cross_batch(const orc_params *P, const int64_t *offset1, const doubl
     B.nb_offset = nb_offset; B.nb_index = nb_index; B.nb_ang = nb_ang; B.n_rows = n_rows;
     B.out = out; B.cross = 1;
     orc_batch_run(&B, n_f1, out_row, num_threads);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cf.compute_wickT123_pairs, cf.py:1497-1626 (statement by statement; z_weight_evol with libm
+ * pow as Numba's `**` lowers to).  weighted_xi_1d_1 is [n1][n1], weighted_xi_1d_2 [n2][n2]
+ * (cf.py:1413-1421, built by the caller with NumPy as the reference does); t1, t2, t3 [nb][nb].
+ * ---------------------------------------------------------------------------------------- */
+void orc_wick_t123_pair(const orc_params *P, int64_t num_pixels1, const double *r_comov1,
+                        int64_t num_pixels2, const double *r_comov2, double ang,
+                        const double *weights1, const double *weights2, const double *z1,
+                        const double *z2, const double *weighted_xi_1d_1,
+                        const double *weighted_xi_1d_2, double *weights_wick,
+                        int64_t *num_pairs_wick, double *t1, double *t2, double *t3)
+{
+    const double r_par_max = P->r_par_max, r_par_min = P->r_par_min, r_trans_max = P->r_trans_max;
+    const int num_bins_r_par = P->num_bins_r_par, num_bins_r_trans = P->num_bins_r_trans;
+    const int64_t nb = (int64_t)num_bins_r_par * num_bins_r_trans;
+    double *z_weight_evol1 = (double *)malloc(sizeof(double) * (size_t)(num_pixels1 + 1));
+    double *z_weight_evol2 = (double *)malloc(sizeof(double) * (size_t)(num_pixels2 + 1));
+    for (int64_t i = 0; i < num_pixels1; i++) /* cf.py:1556 */
+        z_weight_evol1[i] = pow((1 + z1[i]) / (1 + P->z_ref), P->alpha - 1);
+    for (int64_t j = 0; j < num_pixels2; j++) /* cf.py:1557 */
+        z_weight_evol2[j] = pow((1 + z2[j]) / (1 + P->z_ref), P->alpha2 - 1);
+    const double cos_half = cos(ang / 2), sin_half = sin(ang / 2);
+
+    int64_t wsum = 0; /* cf.py:1560-1572 */
+    for (int64_t ind2 = 0; ind2 < num_pixels2; ind2++)
+        for (int64_t ind1 = 0; ind1 < num_pixels1; ind1++) {
+            double r_par = (r_comov1[ind1] - r_comov2[ind2]) * cos_half;
+            if (!P->x_correlation) r_par = fabs(r_par);
+            double r_trans = (r_comov1[ind1] + r_comov2[ind2]) * sin_half;
+            if ((r_par < r_par_max) && (r_trans < r_trans_max) && (r_par >= r_par_min)) wsum += 1;
+        }
+    if (wsum == 0) { /* cf.py:1573-1574 */
+        free(z_weight_evol1);
+        free(z_weight_evol2);
+        return;
+    }
+    int64_t *bins = (int64_t *)malloc(sizeof(int64_t) * (size_t)wsum);
+    int64_t *bins_forest = (int64_t *)malloc(sizeof(int64_t) * (size_t)wsum);
+    double *weights12 = (double *)malloc(sizeof(double) * (size_t)wsum);
+    double *weight1 = (double *)malloc(sizeof(double) * (size_t)wsum);
+    double *weight2 = (double *)malloc(sizeof(double) * (size_t)wsum);
+    double *z_weight_evol = (double *)malloc(sizeof(double) * (size_t)wsum);
+    int64_t ind = 0; /* cf.py:1583-1596 */
+    for (int64_t ind2 = 0; ind2 < num_pixels2; ind2++)
+        for (int64_t ind1 = 0; ind1 < num_pixels1; ind1++) {
+            double r_par = (r_comov1[ind1] - r_comov2[ind2]) * cos_half;
+            if (!P->x_correlation) r_par = fabs(r_par);
+            double r_trans = (r_comov1[ind1] + r_comov2[ind2]) * sin_half;
+            if (!((r_par < r_par_max) && (r_trans < r_trans_max) && (r_par >= r_par_min))) continue;
+            bins[ind] = ind1 + num_pixels1 * ind2;
+            int64_t bin_r_par =
+                (int64_t)((r_par - r_par_min) / (r_par_max - r_par_min) * num_bins_r_par);
+            int64_t bin_r_trans = (int64_t)(r_trans / r_trans_max * num_bins_r_trans);
+            bins_forest[ind] = bin_r_trans + num_bins_r_trans * bin_r_par;
+            weights12[ind] = weights1[ind1] * weights2[ind2];
+            weight1[ind] = weights1[ind1];
+            weight2[ind] = weights2[ind2];
+            z_weight_evol[ind] = z_weight_evol1[ind1] * z_weight_evol2[ind2];
+            ind += 1;
+        }
+    for (int64_t index1 = 0; index1 < wsum; index1++) { /* cf.py:1598-1624 */
+        const int64_t p1 = bins_forest[index1];
+        const int64_t i1 = bins[index1] % num_pixels1;
+        const int64_t j1 = (bins[index1] - i1) / num_pixels1;
+        weights_wick[p1] += weights12[index1];
+        num_pairs_wick[p1] += 1;
+        t1[p1 * nb + p1] += weights12[index1] * z_weight_evol[index1];
+        for (int64_t index2 = index1 + 1; index2 < wsum; index2++) {
+            const int64_t p2 = bins_forest[index2];
+            const int64_t i2 = bins[index2] % num_pixels1;
+            const int64_t j2 = (bins[index2] - i2) / num_pixels1;
+            if (i1 == i2) {
+                const double prod =
+                    weighted_xi_1d_2[j1 * num_pixels2 + j2] * weight1[index1] * z_weight_evol1[i1];
+                t2[p1 * nb + p2] += prod;
+                t2[p2 * nb + p1] += prod;
+            } else if (j1 == j2) {
+                const double prod =
+                    weighted_xi_1d_1[i1 * num_pixels1 + i2] * weight2[index2] * z_weight_evol2[j1];
+                t2[p1 * nb + p2] += prod;
+                t2[p2 * nb + p1] += prod;
+            } else {
+                const double prod = weighted_xi_1d_1[i1 * num_pixels1 + i2] *
+                                    weighted_xi_1d_2[j1 * num_pixels2 + j2];
+                t3[p1 * nb + p2] += prod;
+                t3[p2 * nb + p1] += prod;
+            }
+        }
+    }
+    free(bins); free(bins_forest); free(weights12); free(weight1); free(weight2);
+    free(z_weight_evol); free(z_weight_evol1); free(z_weight_evol2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * xcf.compute_wickT1234_pairs, xcf.py:1219-1351: one forest against its neighbouring objects
+ * (ang, r_comov2, z2, weights2 are arrays over the objects).  t1..t4 [nb][nb].
+ * ---------------------------------------------------------------------------------------- */
+void orc_wick_t1234_forest(const orc_params *P, int64_t num_pixels1, const double *r_comov1,
+                           const double *z1, const double *weights1,
+                           const double *weighted_xi_1d_1, int64_t num_pixels2, const double *ang,
+                           const double *r_comov2, const double *z2, const double *weights2,
+                           double *weights_wick, int64_t *num_pairs_wick, double *t1, double *t2,
+                           double *t3, double *t4)
+{
+    const double r_par_max = P->r_par_max, r_par_min = P->r_par_min, r_trans_max = P->r_trans_max;
+    const int num_bins_r_par = P->num_bins_r_par, num_bins_r_trans = P->num_bins_r_trans;
+    const int64_t nb = (int64_t)num_bins_r_par * num_bins_r_trans;
+    double *z_weight_evol1 = (double *)malloc(sizeof(double) * (size_t)(num_pixels1 + 1));
+    double *z_weight_evol2 = (double *)malloc(sizeof(double) * (size_t)(num_pixels2 + 1));
+    for (int64_t i = 0; i < num_pixels1; i++) /* xcf.py:1271 */
+        z_weight_evol1[i] = pow((1 + z1[i]) / (1 + P->z_ref), P->alpha - 1);
+    for (int64_t j = 0; j < num_pixels2; j++) /* xcf.py:1272: alpha_obj */
+        z_weight_evol2[j] = pow((1 + z2[j]) / (1 + P->z_ref), P->alpha2 - 1);
+
+    int64_t wsum = 0; /* xcf.py:1275-1286 */
+    for (int64_t ind2 = 0; ind2 < num_pixels2; ind2++)
+        for (int64_t ind1 = 0; ind1 < num_pixels1; ind1++) {
+            double r_par = (r_comov1[ind1] - r_comov2[ind2]) * cos(ang[ind2] / 2);
+            double r_trans = (r_comov1[ind1] + r_comov2[ind2]) * sin(ang[ind2] / 2);
+            if ((r_par < r_par_max) && (r_trans < r_trans_max) && (r_par >= r_par_min)) wsum += 1;
+        }
+    if (wsum == 0) {
+        free(z_weight_evol1);
+        free(z_weight_evol2);
+        return;
+    }
+    int64_t *bins_forest = (int64_t *)malloc(sizeof(int64_t) * (size_t)wsum);
+    double *weights12 = (double *)malloc(sizeof(double) * (size_t)wsum);
+    double *weight1 = (double *)malloc(sizeof(double) * (size_t)wsum);
+    int64_t *index_obj = (int64_t *)malloc(sizeof(int64_t) * (size_t)wsum);
+    int64_t *index_delta = (int64_t *)malloc(sizeof(int64_t) * (size_t)wsum);
+    int64_t ind = 0; /* xcf.py:1295-1311 */
+    for (int64_t ind2 = 0; ind2 < num_pixels2; ind2++)
+        for (int64_t ind1 = 0; ind1 < num_pixels1; ind1++) {
+            double r_par = (r_comov1[ind1] - r_comov2[ind2]) * cos(ang[ind2] / 2);
+            double r_trans = (r_comov1[ind1] + r_comov2[ind2]) * sin(ang[ind2] / 2);
+            if (!((r_par < r_par_max) && (r_trans < r_trans_max) && (r_par >= r_par_min))) continue;
+            int64_t bin_r_par =
+                (int64_t)((r_par - r_par_min) / (r_par_max - r_par_min) * num_bins_r_par);
+            int64_t bin_r_trans = (int64_t)(r_trans / r_trans_max * num_bins_r_trans);
+            bins_forest[ind] = bin_r_trans + num_bins_r_trans * bin_r_par;
+            weights12[ind] = weights1[ind1] * weights2[ind2];
+            weight1[ind] = weights1[ind1];
+            index_delta[ind] = ind1;
+            index_obj[ind] = ind2;
+            ind += 1;
+        }
+    for (int64_t index1 = 0; index1 < wsum; index1++) { /* xcf.py:1313-1342 */
+        const int64_t p1 = bins_forest[index1];
+        const int64_t i1 = index_delta[index1], j1 = index_obj[index1];
+        weights_wick[p1] += weights12[index1];
+        num_pairs_wick[p1] += 1;
+        t1[p1 * nb + p1] +=
+            weights12[index1] * weights12[index1] / weight1[index1] * z_weight_evol1[i1];
+        for (int64_t index2 = index1 + 1; index2 < wsum; index2++) {
+            const int64_t p2 = bins_forest[index2];
+            const int64_t i2 = index_delta[index2], j2 = index_obj[index2];
+            if (j1 == j2) {
+                const double prod = weighted_xi_1d_1[i1 * num_pixels1 + i2] *
+                                    (z_weight_evol2[j1] * z_weight_evol2[j1]);
+                t2[p1 * nb + p2] += prod;
+                t2[p2 * nb + p1] += prod;
+            } else if (i1 == i2) {
+                const double prod =
+                    weights12[index1] * weights12[index2] / weight1[index1] * z_weight_evol1[i1];
+                t3[p1 * nb + p2] += prod;
+                t3[p2 * nb + p1] += prod;
+            } else {
+                const double prod = weighted_xi_1d_1[i1 * num_pixels1 + i2] * z_weight_evol2[j1] *
+                                    z_weight_evol2[j2];
+                t4[p1 * nb + p2] += prod;
+                t4[p2 * nb + p1] += prod;
+            }
+        }
+    }
+    free(bins_forest); free(weights12); free(weight1); free(index_obj); free(index_delta);
+    free(z_weight_evol1); free(z_weight_evol2);
 }
 
 int32_t orc_sizeof_params(void) { return (int32_t)sizeof(orc_params); }

@@ -218,3 +218,66 @@ def compute_metal_dmat(healpixs, abs_igm="SiII(1526)"):
             setattr(delta1, "neighbours", None)
     return (weights_dmat, dmat.reshape(nb, nbm), r_par_eff, r_trans_eff, z_eff, weight_eff,
             num_pairs, num_pairs_used)
+
+
+# ---- Wick expansion, terms T1-T4 (xcf.py:838-1153, :1219-1351).  Globals as the reference: the
+# script fills get_variance_1d / xi_1d per delta.fname (picca_xwick.py:394-409).
+get_variance_1d = {}
+xi_1d = {}
+max_diagram = None
+xi_wick = None
+
+
+def compute_wickT1234_pairs(ang, r_comov1, r_comov2, z1, z2, weights1, weights2, weighted_xi_1d_1,
+                            weights_wick, num_pairs_wick, t1, t2, t3, t4):
+    """xcf.py:1219-1351: the C restatement ``orc_wick_t1234_forest``, accumulating in place."""
+    import ctypes
+    lib = _kernels.lib()
+    p = _kernels.params_from_module(_THIS, cross=True)
+    f64, dp, lp = _kernels.f64, _kernels.dp, _kernels.lp
+    a, r1, r2, zz1, zz2, w1, w2 = (f64(v) for v in (ang, r_comov1, r_comov2, z1, z2, weights1,
+                                                    weights2))
+    x1 = f64(weighted_xi_1d_1)
+    for arr in (weights_wick, num_pairs_wick, t1, t2, t3, t4):
+        assert arr.flags.c_contiguous
+    lib.orc_wick_t1234_forest(
+        ctypes.byref(p), ctypes.c_int64(len(r1)), dp(r1), dp(zz1), dp(w1), dp(x1),
+        ctypes.c_int64(len(r2)), dp(a), dp(r2), dp(zz2), dp(w2), dp(weights_wick),
+        lp(num_pairs_wick), dp(t1), dp(t2), dp(t3), dp(t4))
+
+
+def compute_wick_terms(healpixs):
+    """xcf.py:838-1153 for the diagrams T1-T4 (``xi_wick is None or max_diagram <= 4``)."""
+    if xi_wick is not None and max_diagram is not None and max_diagram > 4:
+        raise NotImplementedError("oracle: Wick diagrams T5-T6 are not restated")
+    nb = num_bins_r_par * num_bins_r_trans
+    t1, t2, t3, t4, t5, t6 = (np.zeros((nb, nb)) for _ in range(6))
+    weights_wick = np.zeros(nb)
+    num_pairs_wick = np.zeros(nb, dtype=np.int64)
+    num_pairs = 0
+    num_pairs_used = 0
+    for healpix in healpixs:
+        num_pairs += len(data[healpix])
+        w = np.random.rand(len(data[healpix])) > reject      # xcf.py:889
+        num_pairs_used += w.sum()
+        if w.sum() == 0:
+            continue
+        for delta1 in [delta for index, delta in enumerate(data[healpix]) if w[index]]:
+            _host.progress(_THIS)
+            if delta1.neighbours.size == 0:
+                continue
+            variance_1d = get_variance_1d[delta1.fname](delta1.log_lambda)
+            weights1 = delta1.weights
+            weighted_xi_1d_1 = ((weights1 * weights1[:, None]) *
+                                xi_1d[delta1.fname](abs(delta1.log_lambda -
+                                                        delta1.log_lambda[:, None])) *
+                                np.sqrt(variance_1d * variance_1d[:, None]))   # xcf.py:907-914
+            neighbours = delta1.neighbours
+            ang12 = np.array([_host.angle_between_one(delta1, obj2) for obj2 in neighbours])
+            r_comov2 = np.array([obj2.r_comov for obj2 in neighbours])
+            z2 = np.array([obj2.z_qso for obj2 in neighbours])
+            weights2 = np.array([obj2.weights for obj2 in neighbours])
+            compute_wickT1234_pairs(ang12, delta1.r_comov, r_comov2, delta1.z, z2, weights1,
+                                    weights2, weighted_xi_1d_1, weights_wick, num_pairs_wick,
+                                    t1, t2, t3, t4)
+    return weights_wick, num_pairs_wick, num_pairs, num_pairs_used, t1, t2, t3, t4, t5, t6

@@ -113,7 +113,8 @@ EXPORTS = [
     "pb2_abi_version", "pb2_last_error", "pb2_sizeof_params", "pb2_sizeof_catalog",
     "pb2_sizeof_pairs", "pb2_diag_lanes", "pb2_neigh_count", "pb2_neigh_fill", "pb2_xi_auto", "pb2_xi_cross",
     "pb2_pack_diag", "pb2_build_prefix", "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross", "pb2_dmat_stats",
-    "pb2_metal_dmat_auto", "pb2_metal_dmat_cross", "pb2_co_pairs", "pb2_cov_scratch_bytes", "pb2_cov_subsample", "pb2_cov_smooth",
+    "pb2_metal_dmat_auto", "pb2_metal_dmat_cross", "pb2_wick_scratch_bytes", "pb2_wick_auto",
+    "pb2_wick_cross", "pb2_co_pairs", "pb2_cov_scratch_bytes", "pb2_cov_subsample", "pb2_cov_smooth",
     "pb2_cov_boot_scratch_bytes", "pb2_cov_boot",
     "pb2_fits_scan", "pb2_fits_cards", "pb2_delta_unpack", "pb2_delta_prepare",
     "pb2_delta_image_count", "pb2_delta_image_unpack",
@@ -121,7 +122,7 @@ EXPORTS = [
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 
 def lib():
@@ -141,6 +142,7 @@ def lib():
     handle.pb2_cov_scratch_bytes.restype = ctypes.c_int64
     handle.pb2_fits_scan.restype = ctypes.c_int64
     handle.pb2_cov_boot_scratch_bytes.restype = ctypes.c_int64
+    handle.pb2_wick_scratch_bytes.restype = ctypes.c_int64
     if handle.pb2_abi_version() != ABI_VERSION:
         raise RuntimeError("picca_b200: ABI mismatch, rebuild libpicca_b200.so")
     assert handle.pb2_sizeof_params() == ctypes.sizeof(Params)

@@ -301,6 +301,66 @@ def compute_dmat(healpixs):
             num_pairs_used)
 
 
+def compute_wick_terms(healpixs):
+    """Wick expansion of the covariance matrix, diagrams T1-T3 (cf.py:1326-1494 with
+    ``max_diagram <= 3``; compute_wickT123_pairs :1497-1626).  The per-forest --rej draw uses the
+    global legacy NumPy RNG in the reference's order (cf.py:1378: one number per forest of each
+    HEALPix pixel).  Returns (weights_wick, num_pairs_wick, num_pairs, num_pairs_used, t1..t6);
+    t4-t6 need ``max_diagram > 3`` (three-forest diagrams): not built -- NotImplementedError."""
+    import ctypes
+    from . import _lib, _wick
+    healpixs = list(healpixs)
+    if max_diagram is not None and max_diagram > 3:
+        raise NotImplementedError("picca_b200: Wick diagrams T4-T6 (max_diagram > 3) are not "
+                                  "implemented on the B200 path")
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS)
+    pairs = _pairs_for(healpixs)
+    torch = eng.torch
+    nb = params.num_bins_r_par * params.num_bins_r_trans
+    num_pairs = 0
+    num_pairs_used = 0
+    keep_forest = []
+    for healpix in healpixs:
+        w = np.random.rand(len(data[healpix])) > reject   # cf.py:1378
+        num_pairs += len(data[healpix])
+        num_pairs_used += int(w.sum())
+        keep_forest.append(w)
+    keep_forest = np.concatenate(keep_forest) if keep_forest else np.zeros(0, dtype=bool)
+    keep_dev = torch.from_numpy(keep_forest.astype(np.uint8)).to(eng.device)
+    pairs.nb_keep = keep_dev[pairs.nb_f1.to(torch.int64)].contiguous()   # pair kept iff its forest is
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=eng.device)
+    t1, t2, t3 = zeros(nb, nb), zeros(nb, nb), zeros(nb, nb)
+    weights_wick = zeros(nb)
+    num_pairs_wick = torch.zeros(nb, dtype=torch.int64, device=eng.device)
+    if pairs.n_pairs and keep_forest.any():
+        in1 = _wick.pixel_inputs(eng, host1, get_variance_1d, xi_1d, z_ref, alpha)
+        in2 = in1 if host2 is host1 else _wick.pixel_inputs(eng, host2, get_variance_1d, xi_1d,
+                                                            z_ref, alpha2)
+        if host2 is host1 and alpha2 is not None and alpha2 != alpha:  # cf.py:1557 uses alpha2
+            ze2 = torch.from_numpy(np.ascontiguousarray(
+                ((1 + host2.arrays["z"]) / (1 + z_ref))**(alpha2 - 1))).to(eng.device)
+            in2 = (in1[0], ze2) + in1[2:]
+        nbytes = int(eng.lib.pb2_wick_scratch_bytes(ctypes.c_int64(host1.max_pix),
+                                                    ctypes.c_int64(host2.max_pix),
+                                                    ctypes.c_int32(0)))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        ps = pairs.struct()
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(eng.lib.pb2_wick_auto(
+            ctypes.byref(dev1.struct), ctypes.byref(dev2.struct), ctypes.byref(params),
+            ctypes.byref(ps), ptr(in1[0]), ptr(in1[1]), ptr(in2[0]), ptr(in2[1]),
+            ctypes.c_int32(in1[4]), ptr(in1[2]), ptr(in1[3]), ctypes.c_int32(in2[4]), ptr(in2[2]),
+            ptr(in2[3]), ptr(weights_wick), ptr(num_pairs_wick), ptr(t1), ptr(t2), ptr(t3),
+            ptr(scratch), ctypes.c_int64(nbytes), eng.stream_ptr()), "pb2_wick_auto")
+    _corr.bump_progress(_THIS, int(keep_forest.sum()), userprint)
+    _STORE.drop(healpixs)
+    host_t = [t.cpu().numpy() for t in (t1, t2, t3)]
+    empty = lambda: np.zeros((nb, nb))
+    return (weights_wick.cpu().numpy(), num_pairs_wick.cpu().numpy(), num_pairs, num_pairs_used,
+            host_t[0], host_t[1], host_t[2], empty(), empty(), empty())
+
+
 def _absorber_wavelength(name):
     if name in absorber_igm:
         return absorber_igm[name]

@@ -257,6 +257,67 @@ def compute_dmat(healpixs):
             num_pairs_used)
 
 
+def compute_wick_terms(healpixs):
+    """Wick expansion of the covariance matrix of the cross-correlation, diagrams T1-T4
+    (xcf.py:838-941; compute_wickT1234_pairs :1219-1351).  The per-forest --rej draw uses the
+    global legacy NumPy RNG in the reference's order (xcf.py:888-890).  Returns (weights_wick,
+    num_pairs_wick, num_pairs, num_pairs_used, t1..t6); t5, t6 (``xi_wick`` given and
+    ``max_diagram > 4``: four-point diagrams over pairs of forests) are not built --
+    NotImplementedError."""
+    import ctypes
+    from . import _lib, _wick
+    healpixs = list(healpixs)
+    if xi_wick is not None and max_diagram is not None and max_diagram > 4:
+        raise NotImplementedError("picca_b200: Wick diagrams T5-T6 (max_diagram > 4) are not "
+                                  "implemented on the B200 path")
+    eng, host1, dev1, host2, dev2 = _catalogs()
+    params = params_from_module(_THIS, cross=True)
+    pairs = _pairs_for(healpixs)
+    torch = eng.torch
+    nb = params.num_bins_r_par * params.num_bins_r_trans
+    num_pairs = 0
+    num_pairs_used = 0
+    keep_forest = []
+    for healpix in healpixs:
+        num_pairs += len(data[healpix])
+        w = np.random.rand(len(data[healpix])) > reject   # xcf.py:889
+        num_pairs_used += int(w.sum())
+        keep_forest.append(w)
+    keep_forest = np.concatenate(keep_forest) if keep_forest else np.zeros(0, dtype=bool)
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=eng.device)
+    t1, t2, t3, t4 = zeros(nb, nb), zeros(nb, nb), zeros(nb, nb), zeros(nb, nb)
+    weights_wick = zeros(nb)
+    num_pairs_wick = torch.zeros(nb, dtype=torch.int64, device=eng.device)
+    counts = np.diff(pairs.host_offset())
+    if pairs.n_pairs and keep_forest.any() and counts[keep_forest].max(initial=0) > 0:
+        var1, ze1, xb1, xy1, n_x1 = _wick.pixel_inputs(eng, host1, get_variance_1d, xi_1d, z_ref,
+                                                       alpha)
+        ze_obj = torch.from_numpy(np.ascontiguousarray(
+            ((1 + host2.arrays["z_qso"]) / (1 + z_ref))**(alpha_obj - 1))).to(eng.device)
+        keep_dev = torch.from_numpy(keep_forest.astype(np.uint8)).to(eng.device)
+        max_nb = int(counts[keep_forest].max())
+        nbytes = int(eng.lib.pb2_wick_scratch_bytes(ctypes.c_int64(host1.max_pix),
+                                                    ctypes.c_int64(max_nb), ctypes.c_int32(1)))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=eng.device)
+        ps = pairs.struct()
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(eng.lib.pb2_wick_cross(
+            ctypes.byref(dev1.struct), ctypes.byref(dev2.struct), ctypes.byref(params),
+            ctypes.byref(ps), ptr(keep_dev), ctypes.c_int64(max_nb), ptr(var1), ptr(ze1),
+            ptr(ze_obj), ctypes.c_int32(n_x1), ptr(xb1), ptr(xy1), ptr(weights_wick),
+            ptr(num_pairs_wick), ptr(t1), ptr(t2), ptr(t3), ptr(t4), ptr(scratch),
+            ctypes.c_int64(nbytes), eng.stream_ptr()), "pb2_wick_cross")
+    _corr.bump_progress(_THIS, int(keep_forest.sum()), userprint)
+    _STORE.drop(healpixs)
+    host_t = [t.cpu().numpy() for t in (t1, t2, t3, t4)]
+    if np.isnan(np.diagonal(host_t[0])).any():
+        # weights12**2 / weight1 with a zero-weight pixel in range (xcf.py:1316): Numba raises
+        raise ZeroDivisionError("division by zero")
+    empty = lambda: np.zeros((nb, nb))
+    return (weights_wick.cpu().numpy(), num_pairs_wick.cpu().numpy(), num_pairs, num_pairs_used,
+            host_t[0], host_t[1], host_t[2], host_t[3], empty(), empty())
+
+
 def compute_metal_dmat(healpixs, abs_igm="SiII(1526)"):
     """Metal distortion matrix of the cross-correlation (xcf.py:677-835): data bins from the
     Lyman-alpha distances of the forest pixels, model bins from the distances they would have if

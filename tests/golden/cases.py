@@ -101,6 +101,39 @@ def share_plates(data):
     return data
 
 
+# Wick expansion (cf.compute_wick_terms T1-T3, xcf.compute_wick_terms T1-T4): per-forest --rej draw,
+# 1-D inputs as picca_wick.py builds them (scipy interp1d, nearest, extrapolating; :393-417)
+WICK_CASES = {
+    "default": dict(R60, reject=0.8, max_diagram=3),
+    "coarse_x": dict(R60, reject=0.7, max_diagram=3, x_correlation=True, r_par_min=-60.,
+                     num_bins_r_par=12, num_bins_r_trans=6, second=True, alpha2=1.7),
+}
+XWICK_CASES = {
+    "default": dict(XCF_BASE, reject=0.5, max_diagram=4),
+    "coarse": dict(XCF_BASE, reject=0.3, max_diagram=4, num_bins_r_par=10, num_bins_r_trans=5,
+                   alpha_obj=1.),
+}
+
+
+def wick_1d(fname):
+    """(get_variance_1d, xi_1d) interpolators of one delta sample (deterministic tables)."""
+    from scipy.interpolate import interp1d
+    shift = 0. if fname == "D1" else 0.013
+    ll = 3.55 + 5e-4 * np.arange(420)
+    var = 0.05 + 0.1 * (ll - 3.55) + 0.01 * np.sin(40. * ll) + shift
+    dll = 5e-4 * np.arange(260)
+    xi = np.exp(-dll / 3e-3) * np.cos(dll / (2e-3 + shift)) + 0.02
+    return (interp1d(ll, var, kind="nearest", fill_value="extrapolate"),
+            interp1d(dll, xi, kind="nearest", fill_value="extrapolate"))
+
+
+def set_fname(data, fname):
+    for forests_ in data.values():
+        for d in forests_:
+            d.fname = fname
+    return data
+
+
 def forests(second=False, plates=False):
     """(data, num_data, z_min, cosmo); ``second`` gives the independent second sample used by the
     delta x delta cross-correlation cases; ``plates``: see ``share_plates``."""
@@ -114,14 +147,21 @@ def forests(second=False, plates=False):
     return data, num, z_min, cosmo
 
 
-def dmat_forests(second=False):
+def dmat_forests(second=False, **kw):
     """smaller forests: the as-written reference dmat is O(N_pairs * U) per forest pair."""
     if second:
         data, num, z_min, _, cosmo = helpers.small_sample(n=80, seed=29, max_pix=60, side_deg=3.,
-                                                          id_offset=5000)
+                                                          id_offset=5000, **kw)
     else:
-        data, num, z_min, _, cosmo = helpers.small_sample(n=120, seed=17, max_pix=70, side_deg=3.)
+        data, num, z_min, _, cosmo = helpers.small_sample(n=120, seed=17, max_pix=70, side_deg=3.,
+                                                          **kw)
     return data, num, z_min, cosmo
+
+
+def xwick_forests():
+    """no zero-weight pixels: xcf.compute_wickT1234_pairs divides by the pixel weight
+    (xcf.py:1316, :1330) and Numba raises ZeroDivisionError on 0/0"""
+    return dmat_forests(zero_weight_frac=0.)
 
 
 def quasars(cosmo):

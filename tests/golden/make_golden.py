@@ -239,9 +239,72 @@ def run_xdmat(out):
         print("xdmat", name, "pairs", res[6], "used", res[7])
 
 
+def pack_wick(res, n_t):
+    out = dict(weights_wick=res[0], num_pairs_wick=np.asarray(res[1], dtype=np.int64),
+               counts=np.array([res[2], res[3]], dtype=np.int64))
+    for k in range(n_t):
+        out["t%d" % (k + 1)] = res[4 + k]
+    return out
+
+
+def run_wick(out):
+    for name, cfg in cases.WICK_CASES.items():
+        cf, _, _, _, _ = load.reference_modules()
+        cf.userprint = lambda *a, **k: None
+        cfg = dict(cfg)
+        second = cfg.pop("second", False)
+        data, num, z_min, cosmo = cases.dmat_forests()
+        rdata = cases.set_fname(load.to_reference_deltas(data), "D1")
+        var1, xi1 = cases.wick_1d("D1")
+        over = dict(cfg, get_variance_1d={"D1": var1}, xi_1d={"D1": xi1})
+        z_min2 = None
+        if second:
+            data2, num2, z_min2, _ = cases.dmat_forests(second=True)
+            over["data2"] = cases.set_fname(load.to_reference_deltas(data2), "D2")
+            over["num_data2"] = num2
+            var2, xi2 = cases.wick_1d("D2")
+            over["get_variance_1d"]["D2"], over["xi_1d"]["D2"] = var2, xi2
+        helpers.configure(cf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2), **over)
+        for k, v in over.items():
+            setattr(cf, k, v)
+        hps = sorted(rdata)
+        cf.fill_neighs(hps)
+        np.random.seed(hps[0])  # picca_wick.py:35
+        res = cf.compute_wick_terms(hps)
+        for key, val in pack_wick(res, 3).items():
+            out["wick_%s_%s" % (name, key)] = np.asarray(val)
+        print("wick", name, "forests", res[2], "used", res[3], "pairs", int(res[1].sum()),
+              "t3", np.abs(res[6]).sum())
+
+
+def run_xwick(out):
+    for name, cfg in cases.XWICK_CASES.items():
+        _, xcf, _, _, _ = load.reference_modules()
+        xcf.userprint = lambda *a, **k: None
+        data, num, z_min, cosmo = cases.xwick_forests()
+        objs, z_min2 = cases.quasars(cosmo)
+        rdata = cases.set_fname(load.to_reference_deltas(data), "D1")
+        robjs = load.to_reference_qsos(objs)
+        var1, xi1 = cases.wick_1d("D1")
+        over = dict(cfg, get_variance_1d={"D1": var1}, xi_1d={"D1": xi1}, xi_wick=None)
+        helpers.configure(xcf, rdata, num, cases.ang_max_for(cosmo, cfg, z_min, z_min2),
+                          objs=robjs, **over)
+        for k, v in over.items():
+            setattr(xcf, k, v)
+        hps = sorted(rdata)
+        xcf.fill_neighs(hps)
+        np.random.seed(hps[0])  # picca_xwick.py:36
+        res = xcf.compute_wick_terms(hps)
+        for key, val in pack_wick(res, 4).items():
+            out["xwick_%s_%s" % (name, key)] = np.asarray(val)
+        print("xwick", name, "forests", res[2], "used", res[3], "pairs", int(res[1].sum()),
+              "t4", np.abs(res[7]).sum())
+
+
 def main():
     todo = (("cf", run_cf), ("dmat", run_dmat), ("xcf", run_xcf), ("xdmat", run_xdmat),
-            ("metal", run_metal), ("xmetal", run_xmetal), ("co", run_co))
+            ("metal", run_metal), ("xmetal", run_xmetal), ("co", run_co), ("wick", run_wick),
+            ("xwick", run_xwick))
     only = sys.argv[1:]
     for tag, fn in todo:
         if only and tag not in only:

@@ -254,3 +254,21 @@ def test_cached_pack_sees_replaced_lists_and_invalidate():
     catalog.invalidate(data)                         # ... until the caller says so
     c = catalog.cached_pack(data)
     assert c is not b
+
+
+def test_nearest_table_equals_scipy_interp1d():
+    """The (bounds, values) table handed to the Wick kernels reproduces scipy's
+    interp1d(kind="nearest", fill_value="extrapolate") -- picca_wick.py:412-417 -- including points
+    exactly on a decision bound and beyond both ends."""
+    import pytest
+    from picca_b200 import _wick
+    from tests.golden import cases
+    _, xi = cases.wick_1d("D1")
+    bounds, values = _wick.nearest_table(xi)
+    x = np.abs(np.random.default_rng(0).normal(0., 0.05, 20000))
+    x[:bounds.size] = np.asarray(xi.x_bds)
+    x[-3:] = [0., 10., 1e-9]
+    idx = np.searchsorted(bounds, x, side="left").clip(0, values.size - 1)
+    assert np.array_equal(values[idx], xi(x))
+    with pytest.raises(NotImplementedError):
+        _wick.nearest_table(lambda v: v)

@@ -444,7 +444,7 @@ def test_wick_t123_on_bundled_fixtures(fixture_data):
     """oracle compute_wick_terms (max_diagram 3) against the live cf.compute_wick_terms /
     compute_wickT123_pairs (cf.py:1326-1626) on a few HEALPix pixels of the bundled forests, with
     analytic stand-ins for the 1-D products the script interpolates (picca_wick.py:393-416).
-    Groundwork for the Wick row; there is no CUDA counterpart yet."""
+    SURVEY 8f rank 4; the CUDA counterpart is pb2_wick.cu (tests/test_wick_gpu.py)."""
     from tests.refharness import load
     from oracle import cf as ocf
     cf, _, _, _, utils = load.reference_modules()
@@ -474,3 +474,54 @@ def test_wick_t123_on_bundled_fixtures(fixture_data):
         np.testing.assert_allclose(got[k], want[k], rtol=1e-13, atol=1e-13 * np.abs(want[k]).max())
         assert np.array_equal(got[k] != 0, want[k] != 0)
     assert np.abs(want[5]).sum() > 0 and np.abs(want[6]).sum() > 0
+
+
+def test_xwick_t1234_on_bundled_fixtures(fixture_data):
+    """oracle xcf.compute_wick_terms against the live xcf.compute_wick_terms /
+    compute_wickT1234_pairs (xcf.py:838-1351) on the bundled forests x quasars, with the kind of
+    interpolators picca_xwick.py builds (:394-409: interp1d, nearest, extrapolating)."""
+    from scipy.interpolate import interp1d
+    from tests.refharness import load
+    from oracle import xcf as oxcf
+    _, xcf, _, _, utils = load.reference_modules()
+    xcf.userprint = lambda *a, **k: None
+    hps = sorted(fixture_data[0])
+    ll = 3.55 + 3e-4 * np.arange(400)
+    over = dict(r_par_min=-60., num_bins_r_par=30, num_model_bins_r_par=30, alpha_obj=1.,
+                reject=0.5, max_diagram=4, xi_wick=None,
+                get_variance_1d={"D1": interp1d(ll, 0.05 + 0.1 * (ll - 3.55), kind="nearest",
+                                                fill_value="extrapolate")},
+                xi_1d={"D1": interp1d(ll - ll[0], np.exp(-(ll - ll[0]) / 2e-3), kind="nearest",
+                                      fill_value="extrapolate")})
+    results = []
+    for mod in (xcf, oxcf):
+        _setup(mod, fixture_data, utils, load, cross_obj=True, **over)
+        for k, v in over.items():
+            setattr(mod, k, v)
+        for hp in fixture_data[0]:
+            for d in fixture_data[0][hp]:
+                d.fname = "D1"  # picca_xwick.py:336
+        mod.fill_neighs(hps)
+        np.random.seed(hps[0])
+        results.append(mod.compute_wick_terms(hps))
+    want, got = results
+    assert (want[2], want[3]) == (got[2], got[3]) and want[3] > 100
+    assert want[1].sum() > 1000 and np.array_equal(want[1], got[1])
+    assert np.array_equal(want[0], got[0])
+    for k in (4, 5, 6, 7):
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-13, atol=1e-13 * np.abs(want[k]).max())
+        assert np.array_equal(got[k] != 0, want[k] != 0)
+        assert np.abs(want[k]).sum() > 0
+
+
+@pytest.mark.parametrize("script,double,flags,golden", [
+    # test_3_cor.py:413-445 / :759-793 (default --max-diagram: 3 for the auto-, 4 for the
+    # cross-correlation)
+    ("picca_wick", "cf", " --rp-min +0.0 --np 15 --rej 0.99 --cf1d " + DATA +
+     "/test_cor/cf1d.fits.gz", "wick"),
+    ("picca_xwick", "xcf", " --rp-min -60.0 --np 30 --rej 0.99 --z-evol-obj 1. --cf1d " + DATA +
+     "/test_cor/cf1d.fits.gz --drq " + DATA + "/test_delta/cat.fits", "xwick"),
+])
+def test_unmodified_wick_script_on_oracle_matches_golden_fits(tmp_path, script, double, flags,
+                                                              golden):
+    _script_on_oracle(tmp_path, script, double, COMMON + flags, golden)

@@ -84,6 +84,19 @@ def test_distortion_script_matches_reference_golden(tmp_path, script, flags, gol
     assert (hg["NPALL"], hg["NPUSED"]) == (hw["NPALL"], hw["NPUSED"])
 
 
+@pytest.mark.parametrize("script,flags,golden", [
+    # test_3_cor.py:413-445, :759-793 (default --max-diagram: T1-T3 / T1-T4)
+    ("picca_wick.py", COMMON + " --rp-min +0.0 --np 15 --rej 0.99 --nproc 1 --cf1d " + DATA +
+     "/test_cor/cf1d.fits.gz", "wick"),
+    ("picca_xwick.py", COMMON + " --rp-min -60.0 --np 30 --rej 0.99 --nproc 1 --z-evol-obj 1."
+     " --cf1d " + DATA + "/test_cor/cf1d.fits.gz" + DRQ, "xwick"),
+])
+def test_wick_script_matches_reference_golden(tmp_path, script, flags, golden):
+    out = str(tmp_path / (golden + ".fits.gz"))
+    run_script("b200", script, flags, out)
+    compare_fits(out, DATA + "/test_cor/" + golden + ".fits.gz", exact=("NB",))
+
+
 def test_dmat_script_fork_pool_matches_oracle_with_same_chunking(tmp_path):
     """--nproc 2: two forked workers, round-robin HEALPix chunks, one seed per chunk
     (picca_dmat.py:36, :471-501).  The result depends on --nproc, so the comparison is
