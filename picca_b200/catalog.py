@@ -210,7 +210,9 @@ def pack(data, is_object=False, ang_correlation=False):
     else:
         from . import forest as _forest
         soa = _forest.soa_of(data)
-        fields = ("log_lambda", "delta", "weights", "z") + \
+        # picca_wick.py:369-384 drops `delta` (and others) from every forest to save memory
+        has_delta = all(getattr(o, "delta", None) is not None for o in objs)
+        fields = ("log_lambda", "weights", "z") + (("delta",) if has_delta else ()) + \
             (() if ang_correlation else ("r_comov", "dist_m"))
         if soa is not None and n and all(k in soa for k in fields) and \
                 _forest.views_intact(objs, soa, fields):
@@ -232,7 +234,7 @@ def pack(data, is_object=False, ang_correlation=False):
                     [np.asarray(getattr(o, name), dtype=np.float64) for o in objs]))
 
         weights = cat_field("weights")
-        delta = cat_field("delta")
+        delta = cat_field("delta") if has_delta else np.zeros(int(offset[-1]), dtype=np.float64)
         log_lambda = cat_field("log_lambda")
         A["z"] = cat_field("z")
         if ang_correlation:
