@@ -25,211 +25,9 @@
 // All bins use the reference expression with true IEEE divisions (no fast path here: the sweeps
 // are <5 % of the work).  The sums are re-associated with respect to the reference, which stays
 // within 1e-9 (measured 2e-11 in the survey) but is not bit-exact; counts of pairs are exact.
-#include "pb2_common.cuh"
+#include <stdlib.h>
 
-#define DM_THREADS 256
-#define DM_TILE 64
-#define DM_KCH 32
-#define DM_CAP 512  // compact bins handled per chunk (padded to DM_TILE)
-#define DM_MAXCH 256  // K chunks of rows with a column range (more: no tile skipping)
-
-struct DmatGeom {
-    bool in;       // inside the model range (cf.py:667)
-    bool close;    // same-half-plate close pair (cf.py:669-671)
-    int A, B;      // data bin, model bin
-    double rp, rt;
-};
-
-// bin constants n / range * (1 -+ 2^-40) of the data and model grids, for the division-free proof
-// of a pixel pair's bins (same sandwich as the xi kernels: both round-down products against
-// 2^52 + 2^51 must agree, otherwise the reference expression below decides)
-struct DmatFast {
-    double kp_lo, kp_hi, kt_lo, kt_hi;  // data grid
-    double mp_lo, mp_hi, mt_lo, mt_hi;  // model grid
-    int same;                           // model grid == data grid (coefficient 1)
-};
-#define DM_MAGIC 6755399441055744.0  // 2^52 + 2^51
-
-// evaluation of one pixel pair for the distortion matrix (cf.py:660-700 / xcf.py:528-564): bins
-// proven by the sandwich, else the reference expression with IEEE divisions
-__device__ __forceinline__ DmatGeom dmat_pair(const pb2_params &P, const DmatFast &F, double rc1,
-                                              double dm1, double rc2, double dm2, double ch,
-                                              double sh, bool cross_obj, bool shp)
-{
-    DmatGeom g;
-    g.in = false;
-    g.close = false;
-    g.A = g.B = -1;
-    double r_par = mul_rn(sub_rn(rc1, rc2), ch);
-    double r_trans = mul_rn(add_rn(dm1, dm2), sh);
-    if (P.rmu_binning) {
-        r_trans = sqrt(add_rn(mul_rn(r_trans, r_trans), mul_rn(r_par, r_par)));
-        r_par = div_rn(r_par, r_trans);
-    }
-    if (!cross_obj && !P.x_correlation) r_par = fabs(r_par);
-    g.rp = r_par;
-    g.rt = r_trans;
-    if (r_par >= P.r_par_max || r_trans >= P.r_trans_max || r_par < P.r_par_min) return g;
-    const double span = sub_rn(P.r_par_max, P.r_par_min);
-    if (shp && fabs(r_par) < div_rn(span, (double)P.num_bins_r_par)) g.close = true;
-    {
-        const double x = sub_rn(r_par, P.r_par_min);
-        const int bpl = __double2loint(__fma_rd(x, F.kp_lo, DM_MAGIC));
-        const int bph = __double2loint(__fma_rd(x, F.kp_hi, DM_MAGIC));
-        const int btl = __double2loint(__fma_rd(r_trans, F.kt_lo, DM_MAGIC));
-        const int bth = __double2loint(__fma_rd(r_trans, F.kt_hi, DM_MAGIC));
-        int mpl = bpl, mph = bph, mtl = btl, mth = bth;
-        if (!F.same) {
-            mpl = __double2loint(__fma_rd(x, F.mp_lo, DM_MAGIC));
-            mph = __double2loint(__fma_rd(x, F.mp_hi, DM_MAGIC));
-            mtl = __double2loint(__fma_rd(r_trans, F.mt_lo, DM_MAGIC));
-            mth = __double2loint(__fma_rd(r_trans, F.mt_hi, DM_MAGIC));
-        }
-        if (bpl == bph && btl == bth && mpl == mph && mtl == mth &&
-            (unsigned)bpl < (unsigned)P.num_bins_r_par && (unsigned)btl < (unsigned)P.num_bins_r_trans &&
-            (unsigned)mpl < (unsigned)P.num_model_bins_r_par &&
-            (unsigned)mtl < (unsigned)P.num_model_bins_r_trans) {
-            g.in = true;
-            g.A = btl + P.num_bins_r_trans * bpl;
-            g.B = mtl + P.num_model_bins_r_trans * mpl;
-            return g;
-        }
-    }
-    const double fp = div_rn(sub_rn(r_par, P.r_par_min), span);
-    const double ft = div_rn(r_trans, P.r_trans_max);
-    const double bp = floor(mul_rn(fp, (double)P.num_bins_r_par));
-    const double bt = floor(mul_rn(ft, (double)P.num_bins_r_trans));
-    const double mp = floor(mul_rn(fp, (double)P.num_model_bins_r_par));
-    const double mt = floor(mul_rn(ft, (double)P.num_model_bins_r_trans));
-    const long long A = (long long)add_rn(bt, mul_rn((double)P.num_bins_r_trans, bp));
-    const long long B = (long long)add_rn(mt, mul_rn((double)P.num_model_bins_r_trans, mp));
-    const long long nb = (long long)P.num_bins_r_par * P.num_bins_r_trans;
-    const long long nbm = (long long)P.num_model_bins_r_par * P.num_model_bins_r_trans;
-    if (A < 0 || A >= nb || B < 0 || B >= nbm) return g;  // the reference would index out of bounds
-    g.in = true;
-    g.A = (int)A;
-    g.B = (int)B;
-    return g;
-}
-
-__device__ __forceinline__ int warp_max(int v)
-{
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
-    return v;
-}
-
-__device__ __forceinline__ double block_sum(double v, double *red)
-{
-    __syncthreads();
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.;
-    for (int w = 0; w < DM_THREADS / 32; w++) t += red[w];
-    return t;
-}
-
-// conservative column window of a row (sorted forests, standard binning); full range otherwise
-__device__ __forceinline__ void row_window(const pb2_params &P, bool windows, double rc_i,
-                                           double dm_i, const double *rc2, const double *dm2,
-                                           int n2, double ch, double sh, bool signed_rp, int &lo,
-                                           int &hi)
-{
-    lo = 0;
-    hi = n2;
-    if (!windows) return;
-    const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
-    const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
-    const double dmin = P.r_par_min * inv_c;
-    const double dlow = signed_rp ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
-    // rc2 > rc_i - dmax, rc2 < rc_i - dlow, dm2 < r_trans_max/sh - dm_i
-    int a = 0, b = n2;
-    const double v0 = rc_i - dmax;
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (rc2[m] <= v0) a = m + 1; else b = m;
-    }
-    lo = a;
-    a = lo;
-    b = n2;
-    const double v1 = rc_i - dlow;
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (rc2[m] < v1) a = m + 1; else b = m;
-    }
-    hi = a;
-    const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
-    if (isfinite(tsum)) {
-        a = lo;
-        b = hi;
-        const double v2 = tsum - dm_i;
-        while (a < b) {
-            const int m = (a + b) >> 1;
-            if (dm2[m] < v2) a = m + 1; else b = m;
-        }
-        hi = a;
-    }
-}
-
-// conservative row window of a column: rows i with rc1[i] - rc_j in [dlow, dmax] and
-// dm1[i] + dm_j below the r_trans limit (the mirror image of row_window)
-__device__ __forceinline__ void col_window(const pb2_params &P, bool windows, double rc_j,
-                                           double dm_j, const double *rc1, const double *dm1,
-                                           int n1, double ch, double sh, bool signed_rp, int &lo,
-                                           int &hi)
-{
-    lo = 0;
-    hi = n1;
-    if (!windows) return;
-    const double inv_c = 1.0 / ch, inv_s = 1.0 / sh;
-    const double dmax = P.r_par_max * inv_c * (1. + 1e-9) + 1e-9;
-    const double dmin = P.r_par_min * inv_c;
-    const double dlow = signed_rp ? (dmin - fabs(dmin) * 1e-9 - 1e-9) : -dmax;
-    // rc1 >= rc_j + dlow, rc1 <= rc_j + dmax, dm1 < r_trans_max/sh - dm_j
-    int a = 0, b = n1;
-    const double v0 = rc_j + dlow;
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (rc1[m] < v0) a = m + 1; else b = m;
-    }
-    lo = a;
-    b = n1;
-    const double v1 = rc_j + dmax;
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (rc1[m] <= v1) a = m + 1; else b = m;
-    }
-    hi = a;
-    const double tsum = P.r_trans_max * inv_s * (1. + 1e-9) + 1e-9;
-    if (isfinite(tsum)) {
-        a = lo;
-        b = hi;
-        const double v2 = tsum - dm_j;
-        while (a < b) {
-            const int m = (a + b) >> 1;
-            if (dm1[m] < v2) a = m + 1; else b = m;
-        }
-        hi = a;
-    }
-}
-
-struct DmatWork {
-    long long *kept;            // kept pair indices
-    unsigned long long *count;  // [0] number of kept pairs, [1] claim counter
-    double *stats;              // [0] as-written FP64 ops of the reference algorithm (SURVEY 8d:
-                                // N_sel (15 U + 4) + 40 N_inrange per forest pair), [1] sum of U,
-                                // [2] in-range pixel pairs -- measurement only
-    char *cta_base;             // per-CTA scratch
-    long long cta_stride;
-    int rows_max;               // 2*max_pix1 + 2*max_pix2 + 4
-    int cap;                    // DM_CAP
-    DmatFast fast;
-    // per pixel / per line of sight constants of cf.py:577-594, 680-685 (filled by dmat_prologue)
-    double *fz1, *dl1, *fz2, *dl2;  // ((1+z)/(1+z_ref))^(alpha-1), log_lambda - <log_lambda>_w
-    double2 *fs1, *fs2;             // (sum w, sum w dll^2) per line of sight
-};
+#include "pb2_dmat.cuh"
 
 __global__ void dmat_compact_kernel(pb2_pairs pr, DmatWork W)
 {
@@ -897,6 +695,27 @@ static long long auto_prologue_bytes(const pb2_catalog *c1, const pb2_catalog *c
 static const int DM_AUTO_BLOCKS = 148 * 2;
 static const int DM_CROSS_BLOCKS = 148 * 8;
 
+// pb2_dmat_run.cu: the product kernel of the auto / delta x delta distortion matrix
+long long pb2_dmat_run_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par);
+int pb2_dmat_run_blocks(void);
+int32_t pb2_launch_dmat_run(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_params *par,
+                            const pb2_pairs *pairs, const DmatWork &W, int blocks,
+                            double *d_weights_dmat, double *d_dmat, double *d_r_par_eff,
+                            double *d_r_trans_eff, double *d_z_eff, double *d_weight_eff,
+                            cudaStream_t s);
+
+// run-length / prefix-sum kernel unless the binning is r-mu (its sums do not factorise) or the
+// dense-scratch kernel is forced (PB2_DMAT_KERNEL=dense: A/B measurements and cross-checks)
+static bool use_run_kernel(const pb2_params *par)
+{
+    if (par->rmu_binning) return false;
+    const char *force = getenv("PB2_DMAT_KERNEL");
+    if (force && force[0] == 'd') return false;
+    const long long nb = (long long)par->num_bins_r_par * par->num_bins_r_trans;
+    const long long nbm = (long long)par->num_model_bins_r_par * par->num_model_bins_r_trans;
+    return nb < (1 << 24) && nbm < (1 << 24);   // run keys pack both bins in 24 bits each
+}
+
 extern "C" {
 
 int64_t pb2_dmat_scratch_bytes(const pb2_catalog *cat1, const pb2_catalog *cat2,
@@ -908,6 +727,9 @@ int64_t pb2_dmat_scratch_bytes(const pb2_catalog *cat1, const pb2_catalog *cat2,
     long long bytes = 256;
     if (cross)
         bytes += (long long)DM_CROSS_BLOCKS * (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg));
+    else if (use_run_kernel(par))
+        bytes += (long long)pb2_dmat_run_blocks() * pb2_dmat_run_cta_bytes(cat1, cat2, par) +
+                 auto_prologue_bytes(cat1, cat2);
     else
         bytes += (long long)DM_AUTO_BLOCKS * auto_cta_bytes(cat1, cat2, par) +
                  auto_prologue_bytes(cat1, cat2);
@@ -945,8 +767,11 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
     W.count = (unsigned long long *)p;
     W.stats = cross ? nullptr : (double *)(p + 64);  // inside the 256-byte header, zeroed below
     W.cta_base = p + 256;
+    const bool run_kernel = !cross && use_run_kernel(par);
+    const int auto_blocks = run_kernel ? pb2_dmat_run_blocks() : DM_AUTO_BLOCKS;
     W.cta_stride = cross ? (4ll * (cat1->max_pix + 1) * (long long)sizeof(XSeg))
-                         : auto_cta_bytes(cat1, cat2, par);
+                   : run_kernel ? pb2_dmat_run_cta_bytes(cat1, cat2, par)
+                                : auto_cta_bytes(cat1, cat2, par);
     W.kept = (long long *)(p + fixed);
     W.rows_max = cross ? (cat1->max_pix + 1) : (2 * cat1->max_pix + 2 * cat2->max_pix + 4);
     W.cap = DM_CAP;
@@ -967,7 +792,7 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
     pb2_timing_begin(s);
     if (!cross) {
         // prologue arrays sit between the per-CTA areas and the kept-pair list
-        char *q = p + 256 + (long long)DM_AUTO_BLOCKS * W.cta_stride;
+        char *q = p + 256 + (long long)auto_blocks * W.cta_stride;
         W.fs1 = (double2 *)q;
         W.fs2 = W.fs1 + cat1->n_los;
         W.fz1 = (double *)(W.fs2 + cat2->n_los);
@@ -987,13 +812,18 @@ static int32_t dmat_launch(const pb2_catalog *cat1, const pb2_catalog *cat2, con
         pb2_dmat_cross_kernel<<<DM_CROSS_BLOCKS, 128, 0, s>>>(*cat1, *cat2, *par, *pairs, W,
                                                              d_weights_dmat, d_dmat, d_r_par_eff,
                                                              d_r_trans_eff, d_z_eff, d_weight_eff);
-    else
+    else if (run_kernel) {
+        int32_t rc0 = pb2_launch_dmat_run(cat1, cat2, par, pairs, W, auto_blocks, d_weights_dmat,
+                                          d_dmat, d_r_par_eff, d_r_trans_eff, d_z_eff, d_weight_eff, s);
+        if (rc0) return rc0;
+    } else
         pb2_dmat_auto_kernel<<<DM_AUTO_BLOCKS, DM_THREADS, 0, s>>>(*cat1, *cat2, *par, *pairs, W,
                                                                   d_weights_dmat, d_dmat,
                                                                   d_r_par_eff, d_r_trans_eff,
                                                                   d_z_eff, d_weight_eff);
     pb2_count_launch(2);
-    int32_t rc = pb2_check_launch(cross ? "pb2_dmat_cross_kernel" : "pb2_dmat_auto_kernel");
+    int32_t rc = pb2_check_launch(cross ? "pb2_dmat_cross_kernel"
+                                  : run_kernel ? "pb2_dmat_auto_run_kernel" : "pb2_dmat_auto_kernel");
     pb2_timing_end(s);
     return rc;
 }

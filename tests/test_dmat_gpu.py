@@ -11,6 +11,17 @@ from tests import helpers
 from tests.golden import cases
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["run", "dense"], autouse=True)
+def dmat_kernel(request, monkeypatch):
+    """Every test runs on both auto-correlation kernels: the product one (run lengths + prefix
+    sums, register tile; pb2_dmat_run.cu) and the dense-scratch one kept for r-mu binning
+    (pb2_dmat.cu), selected per call through PB2_DMAT_KERNEL."""
+    monkeypatch.setenv("PB2_DMAT_KERNEL", request.param)
+    return request.param
+
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAMES = ("weights_dmat", "dmat", "r_par_eff", "r_trans_eff", "z_eff", "weight_eff")
 
@@ -131,3 +142,45 @@ def test_dmat_long_forests_without_tile_skipping():
     ang_max = synth.compute_ang_max(cosmo, 60., z_min)
     used = _dmat_vs_oracle(data, num, ang_max, reject=0.)
     assert used >= 3
+
+
+def test_dmat_same_half_plate_close_pairs_truncated_unique(dmat_kernel):
+    """with --remove-same-half-plate-close-pairs the reference's pass 0 does not count
+    the close pairs of a same-half-plate forest pair (cf.py:565-568) while pass 1 records the model
+    bin of EVERY in-range pair in an array sized by that count (cf.py:702-703), so np.unique
+    (cf.py:846-848) only sees the model bins of the first `count` in-range pairs.  The oracle
+    restates exactly that ("record only while in bounds"); the product kernel reproduces it."""
+    if dmat_kernel == "dense":
+        pytest.skip("the dense-scratch kernel (r-mu binning only) does not emulate Q8")
+    data, num, z_min, cosmo = cases.dmat_forests()
+    cases.share_plates(data)
+    cfg = dict(cases.DMAT_CASES["default"], reject=0.5, remove_same_half_plate_close_pairs=True)
+    # there are same-half-plate neighbours, and they share a wavelength grid: close pairs exist
+    plates = {}
+    for v in data.values():
+        for d in v:
+            plates.setdefault((d.plate, d.fiberid <= 500), []).append(d)
+    assert max(len(v) for v in plates.values()) > 5
+    used = _dmat_vs_oracle(data, num, cases.ang_max_for(cosmo, cfg, z_min), **cfg)
+    assert used > 100
+
+
+def test_dmat_no_selected_pair_and_two_pixel_forests(dmat_kernel):
+    """z-pair cuts that deselect everything (in-range pairs still feed the eta terms, nothing is
+    added), and forests of two pixels (shorter than a warp step)."""
+    from picca_b200 import synth
+    data, num, z_min, _, cosmo = helpers.small_sample(n=60, seed=5, max_pix=2, side_deg=2.)
+    ang_max = synth.compute_ang_max(cosmo, 60., z_min)
+    used = _dmat_vs_oracle(data, num, ang_max, reject=0.)
+    assert used > 10
+    data, num, z_min, cosmo = cases.dmat_forests()
+    from oracle import cf as ocf
+    from picca_b200 import cf
+    cfg = dict(cases.DMAT_CASES["default"], reject=0.5, z_min_pairs=9., z_max_pairs=10.)
+    for mod in (ocf, cf):
+        helpers.configure(mod, data, num, cases.ang_max_for(cosmo, cfg, z_min), **cfg)
+    hps = sorted(data)
+    cf.fill_neighs(hps)
+    np.random.seed(3)
+    got = cf.compute_dmat(hps)
+    assert got[7] > 100 and not got[1].any() and not got[0].any() and not got[5].any()
