@@ -44,6 +44,7 @@ struct DrShared {
     double vP[4][DR_W];            // P0, P2, P1, P12   by compact data bin
     double vE[4][DR_W];            // eta5 .. eta8       by compact model bin
     double vO[5][DR_W];            // weight_eff, r_par_eff, r_trans_eff, z_eff, diagonal term
+    double Ob[5][DR_ROWS][DR_W];   // ... their per-row parts during the row sweep
     double rowc[DR_ROWS][4];       // dll_i, w_i / sw1, w_i dll_i / swsll1, (unused)
     long long e;
     int cnt[2];
@@ -153,49 +154,72 @@ __device__ __forceinline__ void dr_sweep_row(
         }
         const long long prev = __shfl_up_sync(0xffffffffu, key, 1);
         const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key || key < 0);
-        if (key < 0) continue;
-        if (!(lane == 31 || ((heads >> (lane + 1)) & 1u))) continue;   // not the last lane of a run
-        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-        const int s0 = sb + start, s1 = s + 1;   // the run covers swept pixels [s0, s1)
-        const double S0 = pf[0 * pf_stride + s1] - pf[0 * pf_stride + s0];   // sum w
-        const double S1 = pf[1 * pf_stride + s1] - pf[1 * pf_stride + s0];   // sum w dll
-        const double F0 = pf[2 * pf_stride + s1] - pf[2 * pf_stride + s0];   // sum fz w
-        const double F1 = pf[3 * pf_stride + s1] - pf[3 * pf_stride + s0];   // sum fz w dll
-        const int kb = kidx[B] - kc;
-        if (kb >= 0 && kb < Uc) {
-            atomicAdd(&S.Yb[0][r][dr_ypos(kb)], fz_f * F0 * inv_e);                   // eta1 / eta2
-            if (has_e3) atomicAdd(&S.Yb[1][r][dr_ypos(kb)], fz_f * F1 * inv_e3);      // eta3 / eta4
-        }
-        if (!sel) continue;
-        const int ka = aidx[A] - ac;
-        if (ka >= 0 && ka < UAc) {
-            atomicAdd(&S.Xb[0][r][dr_xpos(ka)], w_f * S0);                            // Q1 / Q2
-            atomicAdd(&S.Xb[1][r][dr_xpos(ka)], w_f * S1);                            // Q1d / Q2d
-        }
-        if (ROW && first) {
-            // cf.py:714-718, :873 summed over the run
-            const double R = pf[4 * pf_stride + s1] - pf[4 * pf_stride + s0];   // sum w (rc - rc0)
-            const double Dm = pf[5 * pf_stride + s1] - pf[5 * pf_stride + s0];  // sum w (dm - dm0)
-            const double Z = pf[6 * pf_stride + s1] - pf[6 * pf_stride + s0];   // sum w z
-            double rp = D.ch * ((rc_f - rc0) * S0 - R);
-            if (!P.x_correlation) rp = fabs(rp);
-            const double rt = D.sh * ((dm_f + dm0) * S0 + Dm);
-            const double zz = 0.5 * (z_f * S0 + Z);
-            const double dg = w_f * fz_f * F0;
-            if (!big && kb >= 0) {   // (kb < 0: a model bin outside the truncated np.unique, Q8)
-                atomicAdd(&S.vO[0][kb], w_f * S0);
-                atomicAdd(&S.vO[1][kb], w_f * rp);
-                atomicAdd(&S.vO[2][kb], w_f * rt);
-                atomicAdd(&S.vO[3][kb], w_f * zz);
-                if (F.same) atomicAdd(&S.vO[4][kb], dg);
-                else atomic_add_f64(dmat + (long long)A * nbm + B, dg);
-            } else {
-                atomic_add_f64(weight_eff + B, w_f * S0);
-                atomic_add_f64(r_par_eff + B, w_f * rp);
-                atomic_add_f64(r_trans_eff + B, w_f * rt);
-                atomic_add_f64(z_eff + B, w_f * zz);
-                atomic_add_f64(dmat + (long long)A * nbm + B, dg);
+        // the last lane of every run writes the run's sums into the row's cells
+        const bool tail = key >= 0 && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+        int kb = -1, ka = -1;
+        if (tail) {
+            kb = kidx[B] - kc;       // (< 0: a model bin outside the truncated np.unique, Q8)
+            if (kb >= Uc) kb = -1;
+            if (sel) {
+                ka = aidx[A] - ac;
+                if (ka < 0 || ka >= UAc) ka = -1;
             }
+        }
+        // The row's cells belong to this warp: plain read-add-write, no atomics (shared-memory
+        // fp64 atomics are compare-and-swap loops whose latency would bound the sweep).  Two runs
+        // of ONE step can still meet in a cell (the bins fold back where r_par changes sign; runs
+        // that differ only in `selected`): then the tails take turns.
+        const unsigned same_b = __match_any_sync(0xffffffffu, kb >= 0 ? kb : -1 - lane);
+        const unsigned same_a = __match_any_sync(0xffffffffu, ka >= 0 ? ka : -1 - lane);
+        const bool clash = __any_sync(0xffffffffu, (same_b & (same_b - 1)) || (same_a & (same_a - 1)));
+        unsigned turns = clash ? __ballot_sync(0xffffffffu, tail) : 1u;
+        while (turns) {
+            const bool mine = tail && (!clash || lane == __ffs(turns) - 1);
+            if (mine) {
+                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const int s0 = sb + start, s1 = s + 1;   // the run covers swept pixels [s0, s1)
+                const double S0 = pf[0 * pf_stride + s1] - pf[0 * pf_stride + s0];   // sum w
+                const double F0 = pf[2 * pf_stride + s1] - pf[2 * pf_stride + s0];   // sum fz w
+                if (kb >= 0) {
+                    S.Yb[0][r][dr_ypos(kb)] += fz_f * F0 * inv_e;                    // eta1 / eta2
+                    if (has_e3) {
+                        const double F1 = pf[3 * pf_stride + s1] - pf[3 * pf_stride + s0];  // sum fz w dll
+                        S.Yb[1][r][dr_ypos(kb)] += fz_f * F1 * inv_e3;               // eta3 / eta4
+                    }
+                }
+                if (ka >= 0) {
+                    const double S1 = pf[1 * pf_stride + s1] - pf[1 * pf_stride + s0];   // sum w dll
+                    S.Xb[0][r][dr_xpos(ka)] += w_f * S0;                             // Q1 / Q2
+                    S.Xb[1][r][dr_xpos(ka)] += w_f * S1;                             // Q1d / Q2d
+                }
+                if (ROW && first && sel) {
+                    // cf.py:714-718, :873 summed over the run
+                    const double R = pf[4 * pf_stride + s1] - pf[4 * pf_stride + s0];   // sum w (rc - rc0)
+                    const double Dm = pf[5 * pf_stride + s1] - pf[5 * pf_stride + s0];  // sum w (dm - dm0)
+                    const double Z = pf[6 * pf_stride + s1] - pf[6 * pf_stride + s0];   // sum w z
+                    double rp = D.ch * ((rc_f - rc0) * S0 - R);
+                    if (!P.x_correlation) rp = fabs(rp);
+                    const double rt = D.sh * ((dm_f + dm0) * S0 + Dm);
+                    const double zz = 0.5 * (z_f * S0 + Z);
+                    const double dg = w_f * fz_f * F0;
+                    if (!big && kb >= 0) {
+                        S.Ob[0][r][kb] += w_f * S0;
+                        S.Ob[1][r][kb] += w_f * rp;
+                        S.Ob[2][r][kb] += w_f * rt;
+                        S.Ob[3][r][kb] += w_f * zz;
+                        if (F.same) S.Ob[4][r][kb] += dg;
+                        else atomic_add_f64(dmat + (long long)A * nbm + B, dg);
+                    } else {
+                        atomic_add_f64(weight_eff + B, w_f * S0);
+                        atomic_add_f64(r_par_eff + B, w_f * rp);
+                        atomic_add_f64(r_trans_eff + B, w_f * rt);
+                        atomic_add_f64(z_eff + B, w_f * zz);
+                        atomic_add_f64(dmat + (long long)A * nbm + B, dg);
+                    }
+                }
+            }
+            turns = clash ? (turns & (turns - 1)) : 0u;
+            __syncwarp();
         }
     }
 }
@@ -459,6 +483,9 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                         (&S.Xb[0][0][0])[x] = 0.;
                         (&S.Yb[0][0][0])[x] = 0.;
                     }
+                    if (first && !big)
+                        for (int x = tid; x < 5 * DR_ROWS * DR_W; x += DR_THREADS)
+                            (&S.Ob[0][0][0])[x] = 0.;
                     __syncthreads();
                     const int i = ib + warp;
                     const bool rowok = i < n1 && D.w1[i] != 0.;
@@ -511,6 +538,17 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                             if (D.order2 == 1) S.vE[1][kb] += e6;
                             if (D.order1 == 1) S.vE[2][kb] += e7;
                             if (D.order1 == 1 && D.order2 == 1) S.vE[3][kb] += e8;
+                        }
+                    } else if (tid < 3 * DR_W && first && !big) {
+                        const int kb = tid - 2 * DR_W;
+                        if (kb < Uc) {
+#pragma unroll
+                            for (int o = 0; o < 5; o++) {
+                                double t = 0.;
+#pragma unroll 4
+                                for (int r = 0; r < DR_ROWS; r++) t += S.Ob[o][r][kb];
+                                S.vO[o][kb] += t;
+                            }
                         }
                     }
                     dr_rank_update(S, c, np_, nq_);

@@ -15,7 +15,7 @@ from tests import helpers  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2_100k"
 t0 = time.time()
-data, num, ang_max = bench.make_workload(workload)
+data, num, ang_max = bench.make_workload(workload)[:3]
 print("generated %d forests in %.1fs" % (num, time.time() - t0), flush=True)
 helpers.configure(cf, data, num, ang_max, num_bins_r_par=50, num_bins_r_trans=50, r_par_max=200.,
                   r_trans_max=200., num_model_bins_r_par=50, num_model_bins_r_trans=50, nside=32,

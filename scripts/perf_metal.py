@@ -14,7 +14,7 @@ from picca_b200.engine import get_engine  # noqa: E402
 from tests import helpers  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2_20k"
-data, num, ang_max = bench.make_workload(workload)
+data, num, ang_max = bench.make_workload(workload)[:3]
 from picca_b200 import synth  # noqa: E402
 cosmo = synth.FlatLCDM()
 cfg = dict(num_bins_r_par=50, num_bins_r_trans=50, r_par_max=200., r_trans_max=200.,

@@ -12,7 +12,7 @@ from picca_b200 import _lib, catalog  # noqa: E402
 from picca_b200.engine import get_engine  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2_100k"
-data, num, ang_max = bench.make_workload(workload)
+data, num, ang_max = bench.make_workload(workload)[:3]
 t0 = time.perf_counter()
 host = catalog.pack(data)
 print("host pack(): %.2f s for %d forests, %d pixels, %.2f GB of host arrays"

@@ -165,11 +165,12 @@ def test_dmat_same_half_plate_close_pairs_truncated_unique(dmat_kernel):
     assert used > 100
 
 
-def test_dmat_no_selected_pair_and_two_pixel_forests(dmat_kernel):
+def test_dmat_no_selected_pair_and_three_pixel_forests(dmat_kernel):
     """z-pair cuts that deselect everything (in-range pairs still feed the eta terms, nothing is
-    added), and forests of two pixels (shorter than a warp step)."""
+    added), and forests of three pixels (shorter than a warp step)."""
     from picca_b200 import synth
-    data, num, z_min, _, cosmo = helpers.small_sample(n=60, seed=5, max_pix=2, side_deg=2.)
+    data, num, z_min, _, cosmo = helpers.small_sample(n=60, seed=5, max_pix=3, side_deg=2.,
+                                                      zero_weight_frac=0.)
     ang_max = synth.compute_ang_max(cosmo, 60., z_min)
     used = _dmat_vs_oracle(data, num, ang_max, reject=0.)
     assert used > 10
