@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 21
+#define PB2_ABI_VERSION 22
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -187,6 +187,12 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
 int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
                      const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                      double *d_out, int32_t variant, void *stream);
+
+/* ---- per-pixel products of the packed catalogue, formed in HBM when the host deferred them
+ * (catalog.pack(defer_products=True)): delta_w = Delta.delta * Delta.weights -- the product the
+ * reference forms first, cf.py:367-368 -- set to 0 where the weight is 0, and z_w = z * weights. */
+int32_t pb2_derive_products(int64_t n_pix, const double *d_weights, const double *d_delta,
+                            const double *d_z, double *d_delta_w, double *d_z_w, void *stream);
 
 /* Write the packed record copies of the diagonal-lane xi kernel (cat->dg_rec: dg_total records,
  * cat->il_rec: PB2_DIAG_LANES * il_total records; layout above) from the SoA arrays of the

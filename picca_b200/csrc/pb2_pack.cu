@@ -54,7 +54,35 @@ __global__ void pb2_pack_diag_kernel(pb2_catalog c, double *__restrict__ dg_rec,
     }
 }
 
+// delta_w = delta * weights (0 where the weight is 0: a NaN delta there must not leak, and the
+// reference never visits such pixels, cf.py:318,331) and z_w = z * weights, rounded like NumPy's
+__global__ void pb2_derive_products_kernel(long long n, const double *__restrict__ w,
+                                           const double *__restrict__ delta,
+                                           const double *__restrict__ z, double *__restrict__ delta_w,
+                                           double *__restrict__ z_w)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double wi = w[i];
+    delta_w[i] = wi != 0. ? mul_rn(delta[i], wi) : 0.;
+    z_w[i] = mul_rn(z[i], wi);
+}
+
 extern "C" {
+
+int32_t pb2_derive_products(int64_t n_pix, const double *d_weights, const double *d_delta,
+                            const double *d_z, double *d_delta_w, double *d_z_w, void *stream)
+{
+    if (n_pix < 0 || (n_pix > 0 && (!d_weights || !d_delta || !d_z || !d_delta_w || !d_z_w))) {
+        pb2_set_error("pb2_derive_products: bad argument");
+        return PB2_EINVAL;
+    }
+    if (n_pix == 0) return 0;
+    pb2_derive_products_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n_pix, d_weights, d_delta, d_z, d_delta_w, d_z_w);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_derive_products_kernel");
+}
 
 /* Fill cat->dg_rec (dg_total records) and cat->il_rec (PB2_DIAG_LANES * il_total records) from the
  * SoA arrays of the catalogue, whose dg_offset / dg_count / il_offset / il_total describe the

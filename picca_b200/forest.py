@@ -35,8 +35,31 @@ class QSO:
         self.neighbours = None
 
 
+class SoAToken:
+    """Shared by the forests a producer built as views into one SoA (see ``register_soa``):
+    re-binding a per-pixel or positional attribute of any of them marks the whole catalogue
+    dirty, which sends ``catalog.pack`` back to its generic (object-walking) path."""
+    __slots__ = ("dirty",)
+
+    def __init__(self):
+        self.dirty = False
+
+
+_WATCHED = frozenset(("log_lambda", "delta", "weights", "z", "r_comov", "dist_m", "ra", "dec",
+                      "x_cart", "y_cart", "z_cart", "cos_dec", "z_qso", "thingid", "plate",
+                      "fiberid", "order"))
+
+
 class Delta(QSO):
     """Attributes as reference ``data.Delta`` (``py/picca/data.py:296-373``), hot-path subset."""
+    _soa_token = None
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in _WATCHED:
+            token = self._soa_token
+            if token is not None:
+                token.dirty = True
 
     def __init__(self, los_id, ra, dec, z_qso, plate, mjd, fiberid, log_lambda, weights, delta,
                  order):
@@ -61,18 +84,51 @@ PIXEL_FIELDS = ("log_lambda", "delta", "weights", "z", "r_comov", "dist_m")
 _SOA_OF = {}
 
 
+LOS_FIELDS = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso", "thingid", "plate",
+              "fiberid", "order")
+
+
 def register_soa(data, soa):
     """``soa``: dict with ``offset`` (int64[n_los + 1]) and the PIXEL_FIELDS arrays (float64,
-    C-contiguous, catalogue order).  One or two catalogues live in a run: older entries whose
-    dict has been garbage-collected are dropped."""
+    C-contiguous, catalogue order).  The per-line-of-sight attributes are gathered from the
+    objects here, once; the forests get a shared ``SoAToken`` so that a later re-binding of any
+    watched attribute is noticed without walking 100 000 objects again (in-place edits of the
+    arrays need no notice: the views share the SoA's memory)."""
+    import numpy as np
     if len(_SOA_OF) > 8:
         _SOA_OF.clear()
-    _SOA_OF[id(data)] = (data, soa)
+    objs = [obj for hp in sorted(data) for obj in data[hp]]
+    entry = dict(soa)
+    entry["objs"] = objs
+    watched = all(type(o) is Delta for o in objs)
+    if watched and objs:
+        los = {}
+        for name in LOS_FIELDS:
+            vals = [getattr(o, name) for o in objs]
+            if name == "order":
+                vals = [-1 if v is None else int(v) for v in vals]
+            los[name] = vals
+        entry["los"] = los
+        token = SoAToken()
+        for o in objs:
+            object.__setattr__(o, "_soa_token", token)
+        entry["token"] = token
+        entry["lists"] = tuple((hp, id(v), len(v)) for hp, v in sorted(data.items()))
+    _SOA_OF[id(data)] = (data, entry)
 
 
 def soa_of(data):
     hit = _SOA_OF.get(id(data))
     return hit[1] if hit is not None and hit[0] is data else None
+
+
+def registered_clean(data, soa):
+    """True when ``data`` still is exactly what its producer registered: same per-pixel list
+    objects of the same lengths and no watched attribute re-bound since (``SoAToken``)."""
+    token = soa.get("token")
+    if token is None or token.dirty:
+        return False
+    return soa.get("lists") == tuple((hp, id(v), len(v)) for hp, v in sorted(data.items()))
 
 
 def views_intact(objs, soa, fields):
