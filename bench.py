@@ -470,19 +470,27 @@ def run_cuda(args):
     # and copies the blocks back (D2H).  N > 1: blocks stay on the device for the gather.
     h2d = int(host.nbytes()) + shard.f1_index.nbytes + shard.rows.nbytes
     e2e_detail = {"api": "cf.fill_neighs + cf.compute_xi_batch on the data dict (pack + H2D + "
-                         "neighbours + kernel + D2H per step)", "pack_s_first": pack_s}
+                         "neighbours + kernel + D2H per step)" if world == 1 else
+                         "dist.BandShard + dist.xi_banded on the data dict (per rank: pack and H2D "
+                         "of its band of HEALPix rows + halo, neighbours, kernel, NCCL gather, D2H)",
+                  "pack_s_first": pack_s}
 
     def step_e2e():
         catalog.invalidate(data)
         eng.drop_catalogs()
         t_0 = time.perf_counter()
-        catalog.cached_pack(data)
-        e2e_detail["pack_s"] = time.perf_counter() - t_0
-        cf.fill_neighs(my_hps)
         if world == 1:
+            catalog.cached_pack(data)
+            e2e_detail["pack_s"] = time.perf_counter() - t_0
+            cf.fill_neighs(my_hps)
             return cf.compute_xi_batch(my_hps)
-        block = cf.compute_xi_batch(my_hps, to_host=False)
-        full = pdist.gather_rows(block, shard.mine, len(hps))
+        # N > 1: every rank packs and uploads only its band of HEALPix rows + the halo its
+        # neighbour searches reach into (dist.BandShard), not the whole catalogue
+        band = pdist.BandShard(eng, data, ang_max, world, rank)
+        e2e_detail["pack_s"] = time.perf_counter() - t_0
+        e2e_detail["band_rows"], e2e_detail["halo_rows"] = band.b1 - band.b0, band.h1 - band.h0
+        e2e_detail["h2d_bytes_rank0"] = band.h2d_bytes
+        full = pdist.xi_banded(eng, band, params, MODE_AUTO)
         return full.cpu().numpy() if full is not None else None
     if args.no_e2e:
         e2e_ms = total_ms
@@ -542,8 +550,13 @@ def run_cuda(args):
         dm_host = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in dm_res]
 
         def dmat_e2e():
-            fresh = eng.device_catalog(host, pin=False, cache=False)
-            r_ = dmat_step(fresh)
+            if world == 1:
+                fresh = eng.device_catalog(host, pin=False, cache=False)
+                r_ = dmat_step(fresh)
+            else:   # band shards: pack + upload of the band, counts all-gathered
+                band = pdist.BandShard(eng, data, ang_max, world, rank)
+                r_, _, _ = pdist.dmat_chunk_banded(eng, band, dparams, MODE_AUTO, DMAT_REJECT,
+                                                   hps[0], segments=args.dmat_segments)
             if rank == 0:
                 for h_, t_ in zip(dm_host, r_):
                     h_.copy_(t_, non_blocking=True)

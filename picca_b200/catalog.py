@@ -152,8 +152,12 @@ def diag_records_host(cat):
     return dg_rec.reshape(-1), il_rec.reshape(-1)
 
 
-def pack(data, is_object=False, ang_correlation=False, defer_products=False):
+def pack(data, is_object=False, ang_correlation=False, defer_products=False, rows=None):
     """Pack a ``dict[healpix] -> list`` into a HostCatalog.
+
+    ``rows = (r0, r1)``: only the HEALPix pixels ``sorted(data)[r0:r1]`` (a band of a multi-GPU
+    shard and its halo, ``dist.BandShard``): with a registered SoA the result is made of views
+    into it, at a cost proportional to the band.
 
     ``defer_products``: leave ``delta_w = delta * weights`` and ``z_w = z * weights`` to the device
     (``pb2_derive_products`` when the catalogue is placed in HBM): the host then hands over
@@ -162,31 +166,38 @@ def pack(data, is_object=False, ang_correlation=False, defer_products=False):
     ``ang_correlation``: the reference then feeds ``10**log_lambda`` in place of both distances
     (cf.py:186-208, xcf.py:161-182); the packed r_comov/dist_m hold that instead.
     """
+    from . import forest as _forest
+    all_hps = sorted(data)
+    reg = None if is_object else _forest.soa_of(data)
+    clean = reg is not None and len(reg["objs"]) > 0 and _forest.registered_clean(data, reg)
+    if rows is not None and not clean:   # no registered SoA to slice: pack the band's own dict
+        return pack({hp: data[hp] for hp in all_hps[rows[0]:rows[1]]}, is_object=is_object,
+                    ang_correlation=ang_correlation, defer_products=defer_products)
     cat = HostCatalog()
     cat.is_object = is_object
-    cat.healpixs = sorted(data)
+    cat.healpixs = all_hps if rows is None else all_hps[rows[0]:rows[1]]
     cat.hp_index = {hp: k for k, hp in enumerate(cat.healpixs)}
-    objs = [obj for hp in cat.healpixs for obj in data[hp]]
+    l0 = 0   # first line of sight / first pixel of the band inside the registered SoA
+    if rows is not None:
+        l0 = sum(len(data[hp]) for hp in all_hps[:rows[0]])
+    counts = np.array([len(data[hp]) for hp in cat.healpixs], dtype=np.int64)
+    n = int(counts.sum())
+    if clean:
+        # the producer (B200 loader, synthetic generator) gathered these when it built the forests
+        los = reg["los"]
+        col = lambda name: los[name][l0:l0 + n]
+        objs = reg["objs"][l0:l0 + n]
+    else:
+        objs = [obj for hp in cat.healpixs for obj in data[hp]]
+        col = lambda name: [getattr(o, name) for o in objs]
     cat.objs = objs
-    n = len(objs)
     cat.n_los = n
     A = cat.arrays
-    counts = np.array([len(data[hp]) for hp in cat.healpixs], dtype=np.int64)
     hp_first = np.zeros(len(cat.healpixs) + 1, dtype=np.int32)
     hp_first[1:] = np.cumsum(counts)
     A["hp_first"] = hp_first
     A["row"] = np.repeat(np.arange(len(cat.healpixs), dtype=np.int32), counts)
 
-    from . import forest as _forest
-    reg = None if is_object else _forest.soa_of(data)
-    clean = reg is not None and n and _forest.registered_clean(data, reg)
-    if clean:
-        # the producer (B200 loader, synthetic generator) gathered these when it built the forests
-        los = reg["los"]
-        col = lambda name: los[name]
-        objs = cat.objs = reg["objs"]
-    else:
-        col = lambda name: [getattr(o, name) for o in objs]
     for name in ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso"):
         A[name] = np.array(col(name), dtype=np.float64).reshape(n)
     A["thingid"], ok_t = _as_int64(col("thingid"))
@@ -228,8 +239,10 @@ def pack(data, is_object=False, ang_correlation=False, defer_products=False):
             # the producer built these forests as views into one array per field in catalogue
             # order: pack without touching the objects' arrays
             cat.from_soa = True
-            offset = np.ascontiguousarray(soa["offset"], dtype=np.int64)
-            cat_field = lambda name: soa[name]
+            full_offset = np.asarray(soa["offset"], dtype=np.int64)
+            p0, p1 = int(full_offset[l0]), int(full_offset[l0 + n])
+            offset = np.ascontiguousarray(full_offset[l0:l0 + n + 1] - p0)
+            cat_field = lambda name: soa[name][p0:p1]
         else:
             cat.from_soa = False
             npix = np.array([len(o.weights) for o in objs], dtype=np.int64)

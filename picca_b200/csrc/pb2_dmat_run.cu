@@ -1,4 +1,4 @@
-// Distortion matrix, product kernel for the standard binning (everything but rmu_binning):
+// Distortion matrix, run-list kernel for the standard binning (everything but rmu_binning):
 // cf.compute_dmat_forest_pairs_fast, reference py/picca/cf.py:520-887.
 //
 // Same algebra as pb2_dmat.cu: per forest pair
@@ -6,78 +6,71 @@
 //                  - sum_i ( Q1[A,i] eta1[i,k] + Q1d[A,i] eta3[i,k] )
 //                  - sum_j ( Q2[A,j] eta2[j,k] + Q2d[A,j] eta4[j,k] )
 //                  + P0[A] eta5[k] + P2[A] eta6[k] + P1[A] eta7[k] + P12[A] eta8[k]
-// but nothing of it goes through global memory any more:
-//  * a pixel row i of forest 1 meets the pixels j of forest 2 in RUNS of equal (data bin, model
-//    bin, selected) -- r_par moves ~0.6 Mpc/h per pixel -- and every sum the reference forms over
-//    a run factorises into (row constants) x (sums over the run's columns of w, w dll, fz w,
-//    fz w dll, w r_comov, w dist_m, w z).  Those column sums are differences of per-forest PREFIX
-//    sums (built once per forest pair, 11 short arrays in an L2-resident slab).  One warp per row,
-//    lane = column: the lanes evaluate the exact bins of 32 consecutive columns (sandwich proof or
-//    the reference's IEEE expression, pb2_dmat.cuh), a ballot marks where the key changes, and
-//    only the last lane of a run touches memory: a handful of shared-memory adds.
-//  * rows are processed 16 at a time (one per warp): their Q1 / Q1d / eta1 / eta3 rows live in
-//    shared memory as two [32][<=128] blocks, and a rank-32 update takes them into the
-//    (data bins) x (model bins) tile of the forest pair held in REGISTERS (8 x 4 per thread,
-//    512 threads, compact bin indices); the same for the columns of forest 2 (Q2, Q2d, eta2,
-//    eta4).  P0..P12 / eta5..eta8 are column sums of those blocks; the four rank-1 terms and the
-//    scatter into dmat (one native red.global.add.f64 per touched cell) happen once per forest pair.
-//  * weights_dmat, the effective r_par / r_trans / z / weight and the diagonal term are summed per
-//    forest pair in shared memory and flushed once.
-// Pixel pairs are evaluated three times (pass 0: touched bins and the early exit of cf.py:570-571;
-// row sweep; column sweep), 25 instructions each; the contraction executes
-// 2 (n1 + n2) x UA x U DFMAs on compact indices (U, UA ~ 85 at config 4).
-// Roofline: FP64 issue.  Sums are re-associated w.r.t. the reference (1e-9; prefix differences add
-// ~1e-13), pair counts and the sets of touched bins are exact, including the reference's
-// truncated np.unique when same-half-plate close pairs exist (see pass 0).
+// What the measurements of round 2 say about a forest pair of config 4 (two forests of ~500
+// pixels, 1e5 in-range pixel pairs): it touches U ~ 95 model bins (up to 260), but ONE pixel row
+// only ~34 of them, in runs of ~6 columns; the dense X / Y scratch of pb2_dmat.cu is therefore
+// mostly zeros, its contraction mostly multiplications by zero, and its sweeps spend their time
+// in ~3e5 global reductions per forest pair.  Here:
+//  S  each pixel pair is evaluated twice (once per sweep; pb2_dmat.cu: three times): a thread
+//     walks the row of one pixel of forest 1 (then: one pixel of forest 2), accumulates the sums
+//     of a RUN of equal (data bin, model bin, selected) in registers and appends one record per
+//     run to the row's list in an L2-resident slab -- plain stores, no atomics, no zero fill.
+//     The pair counts, the touched bins (the set of np.unique, cf.py:846-848, including its
+//     truncation when same-half-plate close pairs exist) come out of the same sweep.
+//  V  the per-bin vectors (P0..P12, eta5..eta8, weights_dmat, the effective r_par / r_trans / z /
+//     weight, the diagonal term) are summed from the run records into shared memory.
+//  C  contraction: 16 rows at a time.  The bins those rows touch (~45) get LOCAL indices, their
+//     runs are expanded into two [32][64] blocks in shared memory, a rank-32 update takes them
+//     into a 64 x 64 register tile, and the tile is added into the forest pair's (data bins) x
+//     (model bins) matrix in shared memory (128 x 128 compact bins; larger forest pairs replay the
+//     run lists per 128 x 128 window -- the sweeps are not repeated).
+//  F  rank-1 terms and ONE native red.global.add.f64 per touched cell of dmat.
+// Roofline: FP64 issue / shared-memory bandwidth.  Sums are re-associated w.r.t. the reference
+// (1e-9 tolerance); pair counts and the sets of touched bins are exact.
+// (An earlier form of this kernel -- lane = column, prefix sums, 128 x 128 register tile -- is kept
+// under profiles/experiments/r02_dmat_prefix_run_kernel.cu.txt: 2.4x slower than pb2_dmat.cu.)
 #include "pb2_dmat.cuh"
 
-#define DR_THREADS 512
-#define DR_WARPS 16
-#define DR_ROWS 16   // pixel rows per block = one per warp
-#define DR_W 128     // compact columns (data bins / model bins) per pass
-#define DR_NPF2 7    // prefix arrays of the swept-over forest in the row sweep
-#define DR_NPF1 4    // ... in the column sweep
+#define RL_THREADS 512
+#define RL_WARPS 16
+#define RL_ROWS 16    // rows per contraction group = one per warp
+#define RL_LOC 64     // local bins of a group (data and model)
+#define RL_W 128      // window of compact bins held in shared memory
+#define RL_VEC 384    // compact bins whose per-pair vectors live in shared memory
+#define RL_SEL (1 << 30)
 
-struct DrShared {
-    double Xb[2][DR_ROWS][DR_W];   // Q1, Q1d (row sweep) / Q2, Q2d (column sweep), permuted columns
-    double Yb[2][DR_ROWS][DR_W];   // eta1, eta3 / eta2, eta4
-    double vP[4][DR_W];            // P0, P2, P1, P12   by compact data bin
-    double vE[4][DR_W];            // eta5 .. eta8       by compact model bin
-    double vO[5][DR_W];            // weight_eff, r_par_eff, r_trans_eff, z_eff, diagonal term
-    double Ob[5][DR_ROWS][DR_W];   // ... their per-row parts during the row sweep
-    double rowc[DR_ROWS][4];       // dll_i, w_i / sw1, w_i dll_i / swsll1, (unused)
-    long long e;
-    int cnt[2];
-    int U, UA;
+struct RlRun1 {       // a run of the row sweep (pixel i of forest 1 against forest 2)
+    int A, Bs, n, pad;   // data bin, model bin | RL_SEL when selected, in-range pixel pairs
+    double e1, e3;       // sum zf w2, sum zf w2 dll2        (eta1, eta3 before normalisation)
+    double q1, q1d;      // w1 sum w2, w1 sum w2 dll2        (selected runs; Q1, Q1d)
+    double rp, rt, zz, dg;  // sums of w12 r_par, w12 r_trans, w12 z, w12 zf (selected runs)
+};
+struct RlRun2 {       // a run of the column sweep (pixel j of forest 2 against forest 1)
+    int A, Bs;
+    double e2, e4, q2, q2d;
 };
 
-// position of compact column k inside a block row: thread (ty, tx) owns the data bins ty + 16 p and
-// the model bins tx + 32 q, stored contiguously per thread so that its operands are 128-bit loads
-__device__ __forceinline__ int dr_xpos(int ka) { return ((ka & 15) << 3) | (ka >> 4); }
-__device__ __forceinline__ int dr_ypos(int kb) { return ((kb & 31) << 2) | (kb >> 5); }
+struct RlShared {
+    double C[RL_W][RL_W];              // (compact data bin, compact model bin) window
+    double Xl[2][RL_ROWS][RL_LOC];     // Q1, Q1d / Q2, Q2d of the group, local permuted columns
+    double Yl[2][RL_ROWS][RL_LOC];     // eta1, eta3 / eta2, eta4
+    double vP[4][RL_VEC];              // P0, P2, P1, P12       by compact data bin
+    double vE[4][RL_VEC];              // eta5 .. eta8          by compact model bin
+    double vO[5][RL_VEC];              // weight_eff, r_par_eff, r_trans_eff, z_eff, diagonal
+    short locA[RL_W], locB[RL_W];      // window-relative compact bin -> local index (-1: absent)
+    short lstA[RL_LOC], lstB[RL_LOC];  // local index -> window-relative compact bin
+    unsigned char flgA[RL_W], flgB[RL_W];
+    long long e;
+    int cnt[2];
+    int U, UA, nA, nB;
+};
 
-// inclusive prefix sums of f(x) over x = 0..n-1 into out[1..n] (out[0] = 0), one warp
-template <typename F>
-__device__ __forceinline__ void dr_warp_prefix(double *__restrict__ out, int n, int lane, F f)
-{
-    double carry = 0.;
-    if (lane == 0) out[0] = 0.;
-    for (int b = 0; b < n; b += 32) {
-        const int x = b + lane;
-        double v = x < n ? f(x) : 0.;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += t;
-        }
-        v += carry;
-        if (x < n) out[x + 1] = v;
-        carry = __shfl_sync(0xffffffffu, v, 31);
-    }
-}
+// thread (ty, tx) of the contraction owns the local data bins ty + 16 p (p < 4) and the local
+// model bins tx + 32 q (q < 2); a block row stores them contiguously per thread
+__device__ __forceinline__ int rl_xpos(int la) { return ((la & 15) << 2) | (la >> 4); }
+__device__ __forceinline__ int rl_ypos(int lb) { return ((lb & 31) << 1) | (lb >> 5); }
 
-struct DrPair {
-    // everything a sweep needs about the forest pair
+struct RlPair {
     const double *rc1, *dm1, *z1, *w1, *f1z, *dl1;
     const double *rc2, *dm2, *z2, *w2, *f2z, *dl2;
     int n1, n2, order1, order2;
@@ -85,194 +78,146 @@ struct DrPair {
     bool zerr_on, shp, windows;
 };
 
-// selection of an in-range pixel pair beyond the geometry (cf.py:629-658, :669-671): z-pair cut,
-// zerr cut on either side, same-half-plate close pairs
-__device__ __forceinline__ bool dr_selected(const pb2_params &P, const DrPair &D, const DmatGeom &g,
-                                            double zi, double zj, bool i_sel)
-{
-    if (!i_sel || g.close) return false;
-    if (P.has_z_min_pairs || P.has_z_max_pairs) {
-        const double z = div_rn(add_rn(zi, zj), 2.);
-        if ((P.has_z_min_pairs && z < P.z_min_pairs) || (P.has_z_max_pairs && z > P.z_max_pairs))
-            return false;
-    }
-    if (D.zerr_on && pb2_zerr_close(P, zj, D.zq1)) return false;
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------
-// one row of the row sweep (ROW = true: pixel i of forest 1 against the columns of forest 2) or of
-// the column sweep (ROW = false: pixel j of forest 2 against the pixels of forest 1), whole warp
+// S: one sweep.  ROW: thread = pixel of forest 1 walking forest 2 (records RlRun1, counts, bin
+// marks); !ROW: thread = pixel of forest 2 walking forest 1 (records RlRun2).
 // ------------------------------------------------------------------------------------------
 template <bool ROW>
-__device__ __forceinline__ void dr_sweep_row(
-    const pb2_params &P, const DmatFast &F, const DrPair &D, DrShared &S, int r, int px,
-    const double *__restrict__ pf, int pf_stride, const int *__restrict__ kidx,
-    const int *__restrict__ aidx, int kc, int Uc, int ac, int UAc, bool first, bool big,
-    long long nbm, double *__restrict__ dmat, double *__restrict__ r_par_eff,
-    double *__restrict__ r_trans_eff, double *__restrict__ z_eff, double *__restrict__ weight_eff)
+__device__ __forceinline__ void rl_sweep(const pb2_params &P, const DmatFast &F, const RlPair &D,
+                                         void *__restrict__ runs, int cap, int *__restrict__ nruns,
+                                         int *__restrict__ rowcnt, int *__restrict__ kidx,
+                                         int *__restrict__ aidx, int &cnt_nc, int &cnt_in)
 {
-    const int lane = threadIdx.x & 31;
-    // the fixed pixel and the swept forest
-    const double rc_f = ROW ? D.rc1[px] : D.rc2[px], dm_f = ROW ? D.dm1[px] : D.dm2[px];
-    const double z_f = ROW ? D.z1[px] : D.z2[px], w_f = ROW ? D.w1[px] : D.w2[px];
-    const double fz_f = ROW ? D.f1z[px] : D.f2z[px];
+    const int tid = threadIdx.x;
+    const int nf = ROW ? D.n1 : D.n2, ns = ROW ? D.n2 : D.n1;
+    const double *__restrict__ rcf = ROW ? D.rc1 : D.rc2, *__restrict__ dmf = ROW ? D.dm1 : D.dm2;
+    const double *__restrict__ zf_ = ROW ? D.z1 : D.z2, *__restrict__ wf = ROW ? D.w1 : D.w2;
+    const double *__restrict__ fzf = ROW ? D.f1z : D.f2z;
     const double *__restrict__ rcs = ROW ? D.rc2 : D.rc1, *__restrict__ dms = ROW ? D.dm2 : D.dm1;
     const double *__restrict__ zs = ROW ? D.z2 : D.z1, *__restrict__ ws = ROW ? D.w2 : D.w1;
-    const int ns = ROW ? D.n2 : D.n1;
-    // row sweep: zerr cut of the fixed pixel of forest 1 against quasar 2 (cf.py:629-636)
-    bool f_sel = true;
-    if (ROW && D.zerr_on && pb2_zerr_close(P, z_f, D.zq2)) f_sel = false;
-    int lo, hi;
-    if (ROW) row_window(P, D.windows, rc_f, dm_f, rcs, dms, ns, D.ch, D.sh, P.x_correlation, lo, hi);
-    else col_window(P, D.windows, rc_f, dm_f, rcs, dms, ns, D.ch, D.sh, P.x_correlation, lo, hi);
-    // normalisations of the eta rows (cf.py:767-813): the swept forest's sums
-    const double inv_e = ROW ? 1. / D.sw2 : 1. / D.sw1;
-    const double inv_e3 = ROW ? 1. / D.swsll2 : 1. / D.swsll1;
-    const bool has_e3 = ROW ? (D.order2 == 1) : (D.order1 == 1);
-    const double rc0 = rcs[0], dm0 = dms[0];
-    for (int sb = lo; sb < hi; sb += 32) {
-        const int s = sb + lane;
-        long long key = -1;
-        bool sel = false;
-        int A = 0, B = 0;
-        if (s < hi && ws[s] != 0.) {
-            const DmatGeom g = ROW ? dmat_pair(P, F, rc_f, dm_f, rcs[s], dms[s], D.ch, D.sh, false, D.shp)
-                                   : dmat_pair(P, F, rcs[s], dms[s], rc_f, dm_f, D.ch, D.sh, false, D.shp);
-            if (g.in) {
-                // pixel of forest 1 = the fixed one (row sweep) or the swept one (column sweep)
-                const bool i_sel = ROW ? f_sel
-                                       : !(D.zerr_on && pb2_zerr_close(P, zs[s], D.zq2));
-                sel = dr_selected(P, D, g, ROW ? z_f : zs[s], ROW ? zs[s] : z_f, i_sel);
-                A = g.A;
-                B = g.B;
-                // the sign of r_par before abs() decides the sign of a run's sum of r_par
-                const long long sgn = (!P.x_correlation && (ROW ? rc_f < rcs[s] : rcs[s] < rc_f)) ? 1 : 0;
-                key = (long long)A | ((long long)B << 24) | ((long long)(sel ? 1 : 0) << 48) |
-                      (sgn << 49);
-            }
+    const double *__restrict__ fzs = ROW ? D.f2z : D.f1z, *__restrict__ dls = ROW ? D.dl2 : D.dl1;
+    for (int fb = 0; fb < nf; fb += RL_THREADS) {
+        const int f = min(fb + tid, nf - 1);
+        const bool live = (fb + tid < nf) && (wf[f] != 0.);
+        const double rc_f = rcf[f], dm_f = dmf[f], z_f = zf_[f], w_f = wf[f], fz_f = fzf[f];
+        // zerr cut of the fixed pixel against the OTHER quasar (cf.py:629-636, :650-658)
+        bool f_sel = true;
+        if (D.zerr_on && pb2_zerr_close(P, z_f, ROW ? D.zq2 : D.zq1)) f_sel = false;
+        int lo = 0, hi = -1;
+        if (live) {
+            if (ROW) row_window(P, D.windows, rc_f, dm_f, rcs, dms, ns, D.ch, D.sh, P.x_correlation, lo, hi);
+            else col_window(P, D.windows, rc_f, dm_f, rcs, dms, ns, D.ch, D.sh, P.x_correlation, lo, hi);
         }
-        const long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key || key < 0);
-        // the last lane of every run writes the run's sums into the row's cells
-        const bool tail = key >= 0 && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-        int kb = -1, ka = -1;
-        if (tail) {
-            kb = kidx[B] - kc;       // (< 0: a model bin outside the truncated np.unique, Q8)
-            if (kb >= Uc) kb = -1;
-            if (sel) {
-                ka = aidx[A] - ac;
-                if (ka < 0 || ka >= UAc) ka = -1;
-            }
-        }
-        // The row's cells belong to this warp: plain read-add-write, no atomics (shared-memory
-        // fp64 atomics are compare-and-swap loops whose latency would bound the sweep).  Two runs
-        // of ONE step can still meet in a cell (the bins fold back where r_par changes sign; runs
-        // that differ only in `selected`): then the tails take turns.
-        const unsigned same_b = __match_any_sync(0xffffffffu, kb >= 0 ? kb : -1 - lane);
-        const unsigned same_a = __match_any_sync(0xffffffffu, ka >= 0 ? ka : -1 - lane);
-        const bool clash = __any_sync(0xffffffffu, (same_b & (same_b - 1)) || (same_a & (same_a - 1)));
-        unsigned turns = clash ? __ballot_sync(0xffffffffu, tail) : 1u;
-        while (turns) {
-            const bool mine = tail && (!clash || lane == __ffs(turns) - 1);
-            if (mine) {
-                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-                const int s0 = sb + start, s1 = s + 1;   // the run covers swept pixels [s0, s1)
-                const double S0 = pf[0 * pf_stride + s1] - pf[0 * pf_stride + s0];   // sum w
-                const double F0 = pf[2 * pf_stride + s1] - pf[2 * pf_stride + s0];   // sum fz w
-                if (kb >= 0) {
-                    S.Yb[0][r][dr_ypos(kb)] += fz_f * F0 * inv_e;                    // eta1 / eta2
-                    if (has_e3) {
-                        const double F1 = pf[3 * pf_stride + s1] - pf[3 * pf_stride + s0];  // sum fz w dll
-                        S.Yb[1][r][dr_ypos(kb)] += fz_f * F1 * inv_e3;               // eta3 / eta4
-                    }
-                }
-                if (ka >= 0) {
-                    const double S1 = pf[1 * pf_stride + s1] - pf[1 * pf_stride + s0];   // sum w dll
-                    S.Xb[0][r][dr_xpos(ka)] += w_f * S0;                             // Q1 / Q2
-                    S.Xb[1][r][dr_xpos(ka)] += w_f * S1;                             // Q1d / Q2d
-                }
-                if (ROW && first && sel) {
-                    // cf.py:714-718, :873 summed over the run
-                    const double R = pf[4 * pf_stride + s1] - pf[4 * pf_stride + s0];   // sum w (rc - rc0)
-                    const double Dm = pf[5 * pf_stride + s1] - pf[5 * pf_stride + s0];  // sum w (dm - dm0)
-                    const double Z = pf[6 * pf_stride + s1] - pf[6 * pf_stride + s0];   // sum w z
-                    double rp = D.ch * ((rc_f - rc0) * S0 - R);
-                    if (!P.x_correlation) rp = fabs(rp);
-                    const double rt = D.sh * ((dm_f + dm0) * S0 + Dm);
-                    const double zz = 0.5 * (z_f * S0 + Z);
-                    const double dg = w_f * fz_f * F0;
-                    if (!big && kb >= 0) {
-                        S.Ob[0][r][kb] += w_f * S0;
-                        S.Ob[1][r][kb] += w_f * rp;
-                        S.Ob[2][r][kb] += w_f * rt;
-                        S.Ob[3][r][kb] += w_f * zz;
-                        if (F.same) S.Ob[4][r][kb] += dg;
-                        else atomic_add_f64(dmat + (long long)A * nbm + B, dg);
-                    } else {
-                        atomic_add_f64(weight_eff + B, w_f * S0);
-                        atomic_add_f64(r_par_eff + B, w_f * rp);
-                        atomic_add_f64(r_trans_eff + B, w_f * rt);
-                        atomic_add_f64(z_eff + B, w_f * zz);
-                        atomic_add_f64(dmat + (long long)A * nbm + B, dg);
-                    }
-                }
-            }
-            turns = clash ? (turns & (turns - 1)) : 0u;
+        int cA = -1, cB = -1, cn = 0, nrun = 0, row_in = 0;
+        bool cS = false;
+        double ea = 0., eb = 0., qa = 0., qb = 0., srp = 0., srt = 0., sz = 0., dg = 0.;
+        // (a warp-uniform number of iterations with a __syncwarp() on top: the rows of a warp have
+        // different windows and flush points and would otherwise run the loop a few lanes at a time)
+        const int len = hi - lo + 1, maxlen = warp_max(len);
+        for (int t = 0; t < maxlen; t++) {
             __syncwarp();
-        }
-    }
-}
-
-// rank-(2 DR_ROWS) update of the register tile: c[p][q] -= sum_r Xb[.][r][ty + 16 p] Yb[.][r][tx + 32 q]
-__device__ __forceinline__ void dr_rank_update(const DrShared &S, double (&c)[8][4], int np_, int nq_)
-{
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
-    if (np_ == 0 || nq_ == 0) return;
-#pragma unroll 1
-    for (int r = 0; r < DR_ROWS; r++) {
-#pragma unroll
-        for (int kind = 0; kind < 2; kind++) {
-            const double4 xa = *reinterpret_cast<const double4 *>(&S.Xb[kind][r][ty * 8]);
-            const double4 xb = *reinterpret_cast<const double4 *>(&S.Xb[kind][r][ty * 8 + 4]);
-            const double4 yv = *reinterpret_cast<const double4 *>(&S.Yb[kind][r][tx * 4]);
-            const double x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            const double y[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if (p < np_) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) c[p][q] = fma(-x[p], y[q], c[p][q]);
+            if (t >= len) continue;
+            const int s = lo + t;
+            DmatGeom g;
+            g.in = false;
+            bool sel = false;
+            double z = 0.;
+            if (s < hi && ws[s] != 0.) {
+                g = ROW ? dmat_pair(P, F, rc_f, dm_f, rcs[s], dms[s], D.ch, D.sh, false, D.shp)
+                        : dmat_pair(P, F, rcs[s], dms[s], rc_f, dm_f, D.ch, D.sh, false, D.shp);
+                if (g.in) {
+                    z = div_rn(add_rn(z_f, zs[s]), 2.);
+                    sel = f_sel && !g.close;
+                    if (sel && ((P.has_z_min_pairs && z < P.z_min_pairs) ||
+                                (P.has_z_max_pairs && z > P.z_max_pairs))) sel = false;
+                    if (sel && D.zerr_on && pb2_zerr_close(P, zs[s], ROW ? D.zq1 : D.zq2)) sel = false;
+                    if (ROW) {
+                        row_in++;
+                        if (!g.close) cnt_nc++;
+                    }
+                }
+            }
+            const bool brk = (s == hi) || (g.in && (g.A != cA || g.B != cB || sel != cS));
+            if (brk && cB >= 0) {   // the finished run
+                if (ROW) {
+                    RlRun1 r;
+                    r.A = cA; r.Bs = cB | (cS ? RL_SEL : 0); r.n = cn; r.pad = 0;
+                    r.e1 = ea; r.e3 = eb; r.q1 = w_f * qa; r.q1d = w_f * qb;
+                    r.rp = srp; r.rt = srt; r.zz = sz; r.dg = dg;
+                    reinterpret_cast<RlRun1 *>(runs)[(long long)f * cap + nrun] = r;
+                    kidx[cB] = 0;   // every in-range pair marks its model bin (cf.py:702)
+                } else {
+                    RlRun2 r;
+                    r.A = cA; r.Bs = cB | (cS ? RL_SEL : 0);
+                    r.e2 = ea; r.e4 = eb; r.q2 = w_f * qa; r.q2d = w_f * qb;
+                    reinterpret_cast<RlRun2 *>(runs)[(long long)f * cap + nrun] = r;
+                }
+                if (ROW && cS) aidx[cA] = 0;
+                nrun++;
+                ea = eb = qa = qb = srp = srt = sz = dg = 0.;
+                cn = 0;
+                cB = -1;
+            }
+            if (s == hi || !g.in) continue;
+            cA = g.A;
+            cB = g.B;
+            cS = sel;
+            cn++;
+            const double wj = ws[s], dlj = dls[s];
+            const double zf = mul_rn(fz_f, fzs[s]);
+            ea += zf * wj;            // cf.py:767 / :771
+            eb += zf * wj * dlj;      // cf.py:782-787 / :808-813
+            if (sel) {
+                qa += wj;
+                qb += wj * dlj;
+                if (ROW) {
+                    const double w12 = mul_rn(w_f, wj);
+                    dg += w12 * zf;       // cf.py:873
+                    srp += w12 * g.rp;    // cf.py:714-717
+                    srt += w12 * g.rt;
+                    sz += w12 * z;
                 }
             }
         }
+        if (fb + tid < nf) {
+            nruns[f] = nrun;
+            if (ROW) rowcnt[f] = row_in;
+        }
+        if (ROW) cnt_in += row_in;
     }
 }
 
-__global__ void __launch_bounds__(DR_THREADS, 1)
+// double-precision add into shared memory (compare-and-swap; used where many threads issue
+// independent adds, so the latency of the loop is hidden)
+__device__ __forceinline__ void rl_sadd(double *p, double v) { atomicAdd(p, v); }
+
+__global__ void __launch_bounds__(RL_THREADS, 1)
 pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, DmatWork W,
-                         double *__restrict__ weights_dmat, double *__restrict__ dmat,
-                         double *__restrict__ r_par_eff, double *__restrict__ r_trans_eff,
-                         double *__restrict__ z_eff, double *__restrict__ weight_eff)
+                         int cap1, int cap2, double *__restrict__ weights_dmat,
+                         double *__restrict__ dmat, double *__restrict__ r_par_eff,
+                         double *__restrict__ r_trans_eff, double *__restrict__ z_eff,
+                         double *__restrict__ weight_eff)
 {
-    extern __shared__ __align__(16) unsigned char dr_smem[];
-    DrShared &S = *reinterpret_cast<DrShared *>(dr_smem);
+    extern __shared__ __align__(16) unsigned char rl_smem[];
+    RlShared &S = *reinterpret_cast<RlShared *>(rl_smem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = P.num_bins_r_par * P.num_bins_r_trans;
     const int nbm = P.num_model_bins_r_par * P.num_model_bins_r_trans;
     const double zerr_ang = mul_rn(P.zerr_cut_deg, PB2_PI) / 180.0;
 
-    // per-CTA scratch (global, L2-resident): compact-index tables, per-row counts, prefix sums
+    // per-CTA scratch (global, L2-resident)
     char *base = W.cta_base + (long long)blockIdx.x * W.cta_stride;
     int *kidx = (int *)base;                     // [nbm] compact model index, -1 = untouched
     int *aidx = kidx + nbm;                      // [nb]
     int *klist = aidx + nb;                      // [nbm]
     int *alist = klist + nbm;                    // [nb]
-    int *rowcnt = alist + nb;                    // [max_pix1 + 1] in-range pairs per row (Q8)
-    const int pstride = max(c1.max_pix, c2.max_pix) + 1;
-    double *pf2 = (double *)(((uintptr_t)(rowcnt + c1.max_pix + 2) + 15) & ~(uintptr_t)15);
-    double *pf1 = pf2 + (long long)DR_NPF2 * pstride;
+    int *nrun1 = alist + nb;                     // [max_pix1] runs per row
+    int *nrun2 = nrun1 + c1.max_pix + 1;         // [max_pix2] runs per column
+    int *rowcnt = nrun2 + c2.max_pix + 1;        // [max_pix1] in-range pairs per row
+    RlRun1 *R1 = (RlRun1 *)(((uintptr_t)(rowcnt + c1.max_pix + 1) + 15) & ~(uintptr_t)15);
+    RlRun2 *R2 = (RlRun2 *)(R1 + (long long)c1.max_pix * cap1);
+    double *gvec = (double *)(R2 + (long long)c2.max_pix * cap2);   // vectors of pairs with > RL_VEC bins
 
     for (;;) {
         __syncthreads();
@@ -285,7 +230,7 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
         const long long e = S.e;
         if (e < 0) break;
 
-        DrPair D;
+        RlPair D;
         const int f1 = pr.f1_index[pr.nb_f1[e]], f2 = pr.nb_f2[e];
         const long long a = c1.offset[f1], b = c2.offset[f2];
         D.n1 = (int)(c1.offset[f1 + 1] - a);
@@ -307,40 +252,17 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
         D.sw2 = W.fs2[f2].x; D.swsll2 = W.fs2[f2].y;
         const int n1 = D.n1, n2 = D.n2;
 
-        // ---------------- pass 0: touched bins, pair counts (cf.py:547-571 + the bins of pass 1)
-        for (int x = tid; x < nbm; x += DR_THREADS) kidx[x] = -1;
-        for (int x = tid; x < nb; x += DR_THREADS) aidx[x] = -1;
+        // ---------------- S: row sweep (counts, touched bins, run lists of forest 1)
+        for (int x = tid; x < nbm; x += RL_THREADS) kidx[x] = -1;
+        for (int x = tid; x < nb; x += RL_THREADS) aidx[x] = -1;
         __syncthreads();
         {
             int cnt_nc = 0, cnt_in = 0;
-            for (int i = warp; i < n1; i += DR_WARPS) {
-                int row_in = 0;
-                if (D.w1[i] != 0.) {
-                    bool i_sel = true;
-                    if (D.zerr_on && pb2_zerr_close(P, D.z1[i], D.zq2)) i_sel = false;
-                    int lo, hi;
-                    row_window(P, D.windows, D.rc1[i], D.dm1[i], D.rc2, D.dm2, n2, D.ch, D.sh,
-                               P.x_correlation, lo, hi);
-                    for (int jb = lo; jb < hi; jb += 32) {
-                        const int j = jb + lane;
-                        bool in = false, nc = false;
-                        if (j < hi && D.w2[j] != 0.) {
-                            const DmatGeom g = dmat_pair(P, W.fast, D.rc1[i], D.dm1[i], D.rc2[j],
-                                                         D.dm2[j], D.ch, D.sh, false, D.shp);
-                            if (g.in) {
-                                in = true;
-                                nc = !g.close;
-                                kidx[g.B] = 0;
-                                if (dr_selected(P, D, g, D.z1[i], D.z2[j], i_sel)) aidx[g.A] = 0;
-                            }
-                        }
-                        const int n_in = __popc(__ballot_sync(0xffffffffu, in));
-                        cnt_in += n_in;
-                        row_in += n_in;
-                        cnt_nc += __popc(__ballot_sync(0xffffffffu, nc));
-                    }
-                }
-                if (lane == 0) rowcnt[i] = row_in;
+            rl_sweep<true>(P, W.fast, D, R1, cap1, nrun1, rowcnt, kidx, aidx, cnt_nc, cnt_in);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                cnt_nc += __shfl_xor_sync(0xffffffffu, cnt_nc, m);
+                cnt_in += __shfl_xor_sync(0xffffffffu, cnt_in, m);
             }
             if (lane == 0) {
                 if (cnt_nc) atomicAdd(&S.cnt[0], cnt_nc);
@@ -354,10 +276,9 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
             // reference's pass 0 (cf.py:565-568), so its `all_model_bins` -- sized by that count,
             // filled by EVERY in-range pair in (i, j) order (cf.py:702-703) -- only keeps the model
             // bins of the first `count` in-range pairs inside the array np.unique sees
-            // (cf.py:846-848).  Re-mark the model bins with that rank limit.
+            // (cf.py:846-848).  Re-mark the model bins from the run lists with that rank limit.
             const int limit = S.cnt[0];
-            __syncthreads();
-            for (int x = tid; x < nbm; x += DR_THREADS) kidx[x] = -1;
+            for (int x = tid; x < nbm; x += RL_THREADS) kidx[x] = -1;
             if (warp == 0) {   // exclusive scan of the per-row counts, in place
                 int carry = 0;
                 for (int ib = 0; ib < n1; ib += 32) {
@@ -374,26 +295,12 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                 }
             }
             __syncthreads();
-            for (int i = warp; i < n1; i += DR_WARPS) {
-                if (D.w1[i] == 0.) continue;
+            for (int i = tid; i < n1; i += RL_THREADS) {
                 int rank = rowcnt[i];
-                if (rank >= limit) continue;
-                int lo, hi;
-                row_window(P, D.windows, D.rc1[i], D.dm1[i], D.rc2, D.dm2, n2, D.ch, D.sh,
-                           P.x_correlation, lo, hi);
-                for (int jb = lo; jb < hi && rank < limit; jb += 32) {
-                    const int j = jb + lane;
-                    bool in = false;
-                    DmatGeom g;
-                    g.B = 0;
-                    if (j < hi && D.w2[j] != 0.) {
-                        g = dmat_pair(P, W.fast, D.rc1[i], D.dm1[i], D.rc2[j], D.dm2[j], D.ch, D.sh,
-                                      false, D.shp);
-                        in = g.in;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (in && rank + __popc(m & ((1u << lane) - 1u)) < limit) kidx[g.B] = 0;
-                    rank += __popc(m);
+                const RlRun1 *rr = R1 + (long long)i * cap1;
+                for (int k = 0; k < nrun1[i] && rank < limit; k++) {
+                    kidx[rr[k].Bs & ~RL_SEL] = 0;   // the run's first pair has rank < limit
+                    rank += rr[k].n;
                 }
             }
             __syncthreads();
@@ -428,25 +335,11 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                 if (warp == 0) S.U = u; else S.UA = u;
             }
         }
-        // prefix sums of both forests (11 arrays, one warp each)
-        if (warp >= 2 && warp < 2 + DR_NPF2 + DR_NPF1) {
-            const int k = warp - 2;
-            const double *w2 = D.w2, *dl2 = D.dl2, *f2z = D.f2z, *w1 = D.w1, *dl1 = D.dl1, *f1z = D.f1z;
-            const double *rc2 = D.rc2, *dm2 = D.dm2, *z2 = D.z2;
-            const double rc0 = rc2[0], dm0 = dm2[0];
-            switch (k) {
-            case 0: dr_warp_prefix(pf2 + 0 * pstride, n2, lane, [&](int x) { return w2[x]; }); break;
-            case 1: dr_warp_prefix(pf2 + 1 * pstride, n2, lane, [&](int x) { return w2[x] * dl2[x]; }); break;
-            case 2: dr_warp_prefix(pf2 + 2 * pstride, n2, lane, [&](int x) { return f2z[x] * w2[x]; }); break;
-            case 3: dr_warp_prefix(pf2 + 3 * pstride, n2, lane, [&](int x) { return f2z[x] * w2[x] * dl2[x]; }); break;
-            case 4: dr_warp_prefix(pf2 + 4 * pstride, n2, lane, [&](int x) { return w2[x] * (rc2[x] - rc0); }); break;
-            case 5: dr_warp_prefix(pf2 + 5 * pstride, n2, lane, [&](int x) { return w2[x] * (dm2[x] - dm0); }); break;
-            case 6: dr_warp_prefix(pf2 + 6 * pstride, n2, lane, [&](int x) { return w2[x] * z2[x]; }); break;
-            case 7: dr_warp_prefix(pf1 + 0 * pstride, n1, lane, [&](int x) { return w1[x]; }); break;
-            case 8: dr_warp_prefix(pf1 + 1 * pstride, n1, lane, [&](int x) { return w1[x] * dl1[x]; }); break;
-            case 9: dr_warp_prefix(pf1 + 2 * pstride, n1, lane, [&](int x) { return f1z[x] * w1[x]; }); break;
-            default: dr_warp_prefix(pf1 + 3 * pstride, n1, lane, [&](int x) { return f1z[x] * w1[x] * dl1[x]; }); break;
-            }
+        // ---------------- S: column sweep (run lists of forest 2); warps 0 / 1 join after the
+        // compaction, which only touches kidx / aidx (not read by this sweep)
+        {
+            int d0 = 0, d1 = 0;
+            rl_sweep<false>(P, W.fast, D, R2, cap2, nrun2, nullptr, nullptr, nullptr, d0, d1);
         }
         __syncthreads();
         const int U = S.U, UA = S.UA;
@@ -455,163 +348,249 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
             atomicAdd(W.stats + 1, (double)U);
             atomicAdd(W.stats + 2, (double)S.cnt[1]);
         }
-        const bool big = U > DR_W || UA > DR_W;
 
-        for (int kc = 0; kc < U; kc += DR_W) {
-            const int Uc = min(DR_W, U - kc);
-            for (int ac = 0; ac < max(UA, 1); ac += DR_W) {
-                const int UAc = min(DR_W, UA - ac);   // <= 0: no selected pair (effective sums only)
-                const bool first = (kc == 0 && ac == 0);
-                const int np_ = UAc > 0 ? min(8, (UAc - (tid >> 5) + 15) / 16) : 0;   // ka = ty + 16 p
-                const int nq_ = min(4, (Uc - (tid & 31) + 31) / 32);                   // kb = tx + 32 q
-                double c[8][4];
-#pragma unroll
-                for (int p = 0; p < 8; p++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) c[p][q] = 0.;
+        // ---------------- V: per-bin vectors from the row runs
+        const bool vec_smem = U <= RL_VEC && UA <= RL_VEC;
+        const int vstride = vec_smem ? RL_VEC : max(nb, nbm);
+        double *vP = vec_smem ? &S.vP[0][0] : gvec;
+        double *vE = vP + 4 * (long long)vstride;
+        double *vO = vE + 4 * (long long)vstride;
+        for (int x = tid; x < 13 * vstride; x += RL_THREADS) vP[x] = 0.;
+        __syncthreads();
+        for (int i = warp; i < n1; i += RL_WARPS) {
+            const int nr = nrun1[i];
+            if (nr == 0) continue;
+            const double dli = D.dl1[i], wi = D.w1[i];
+            const double a5 = wi / D.sw1, a7 = wi * dli / D.swsll1;
+            const double fe1 = 1. / D.sw2, fe3 = 1. / D.swsll2;   // eta1 / eta3 normalisations
+            const RlRun1 *rr = R1 + (long long)i * cap1;
+            for (int k = lane; k < nr; k += 32) {
+                const RlRun1 r = rr[k];
+                const int B = r.Bs & ~RL_SEL;
+                const int kb = kidx[B];
+                if (kb >= 0) {   // (< 0: outside the truncated np.unique, Q8)
+                    const double e1 = r.e1 * fe1, e3 = D.order2 == 1 ? r.e3 * fe3 : 0.;
+                    rl_sadd(vE + 0 * vstride + kb, a5 * e1);                          // cf.py:775
+                    if (D.order2 == 1) rl_sadd(vE + 1 * vstride + kb, a5 * e3);       // :793-802
+                    if (D.order1 == 1) rl_sadd(vE + 2 * vstride + kb, a7 * e1);       // :818-827
+                    if (D.order1 == 1 && D.order2 == 1) rl_sadd(vE + 3 * vstride + kb, a7 * e3);
+                }
+                if (r.Bs & RL_SEL) {
+                    const int ka = aidx[r.A];
+                    rl_sadd(vP + 0 * vstride + ka, r.q1);
+                    rl_sadd(vP + 1 * vstride + ka, r.q1d);
+                    rl_sadd(vP + 2 * vstride + ka, dli * r.q1);
+                    rl_sadd(vP + 3 * vstride + ka, dli * r.q1d);
+                    if (kb >= 0) {
+                        rl_sadd(vO + 0 * vstride + kb, r.q1);   // weight_eff: sum of w12 (cf.py:717)
+                        rl_sadd(vO + 1 * vstride + kb, r.rp);
+                        rl_sadd(vO + 2 * vstride + kb, r.rt);
+                        rl_sadd(vO + 3 * vstride + kb, r.zz);
+                        if (W.fast.same) rl_sadd(vO + 4 * vstride + kb, r.dg);
+                        else atomic_add_f64(dmat + (long long)r.A * nbm + B, r.dg);
+                    } else {
+                        atomic_add_f64(weight_eff + B, r.q1);
+                        atomic_add_f64(r_par_eff + B, r.rp);
+                        atomic_add_f64(r_trans_eff + B, r.rt);
+                        atomic_add_f64(z_eff + B, r.zz);
+                        atomic_add_f64(dmat + (long long)r.A * nbm + B, r.dg);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // flush of the per-pair sums that are complete now
+        for (int ka = tid; ka < UA; ka += RL_THREADS)
+            if (vP[ka] != 0.) atomic_add_f64(weights_dmat + alist[ka], vP[ka]);   // cf.py:718
+        for (int kb = tid; kb < U; kb += RL_THREADS) {
+            const double we = vO[kb];
+            if (we != 0.) {
+                const int Bm = klist[kb];
+                atomic_add_f64(weight_eff + Bm, we);
+                atomic_add_f64(r_par_eff + Bm, vO[1 * vstride + kb]);
+                atomic_add_f64(r_trans_eff + Bm, vO[2 * vstride + kb]);
+                atomic_add_f64(z_eff + Bm, vO[3 * vstride + kb]);
+                if (W.fast.same) atomic_add_f64(dmat + (long long)Bm * nbm + Bm, vO[4 * vstride + kb]);
+            }
+        }
+
+        // ---------------- C: contraction, one window of RL_W x RL_W compact bins at a time
+        const int ty = tid >> 5, tx = tid & 31;
+        for (int kc = 0; kc < U; kc += RL_W) {
+            const int Uc = min(RL_W, U - kc);
+            for (int ac = 0; ac < UA; ac += RL_W) {
+                const int UAc = min(RL_W, UA - ac);
                 __syncthreads();
-                for (int x = tid; x < 4 * DR_W; x += DR_THREADS) {
-                    (&S.vP[0][0])[x] = 0.;
-                    (&S.vE[0][0])[x] = 0.;
-                }
-                for (int x = tid; x < 5 * DR_W; x += DR_THREADS) (&S.vO[0][0])[x] = 0.;
-
-                // ---------------- row sweep: pixels of forest 1, 16 at a time
-                for (int ib = 0; ib < n1; ib += DR_ROWS) {
-                    __syncthreads();
-                    for (int x = tid; x < 2 * DR_ROWS * DR_W; x += DR_THREADS) {
-                        (&S.Xb[0][0][0])[x] = 0.;
-                        (&S.Yb[0][0][0])[x] = 0.;
-                    }
-                    if (first && !big)
-                        for (int x = tid; x < 5 * DR_ROWS * DR_W; x += DR_THREADS)
-                            (&S.Ob[0][0][0])[x] = 0.;
-                    __syncthreads();
-                    const int i = ib + warp;
-                    const bool rowok = i < n1 && D.w1[i] != 0.;
-                    if (lane == 0) {
-                        const double wi = rowok ? D.w1[i] : 0., dli = rowok ? D.dl1[i] : 0.;
-                        S.rowc[warp][0] = dli;
-                        S.rowc[warp][1] = wi / D.sw1;
-                        S.rowc[warp][2] = wi * dli / D.swsll1;
-                    }
-                    if (rowok)
-                        dr_sweep_row<true>(P, W.fast, D, S, warp, i, pf2, pstride, kidx, aidx, kc, Uc,
-                                           ac, UAc, first, big, nbm, dmat, r_par_eff, r_trans_eff,
-                                           z_eff, weight_eff);
-                    __syncthreads();
-                    // column sums of the block: P0, P2, P1, P12 and eta5 .. eta8 (cf.py:775-843)
-                    if (tid < DR_W) {
-                        const int ka = tid;
-                        if (ka < UAc) {
-                            double p0 = 0., p2 = 0., p1 = 0., p12 = 0.;
-                            const int xp = dr_xpos(ka);
-#pragma unroll 4
-                            for (int r = 0; r < DR_ROWS; r++) {
-                                const double q1 = S.Xb[0][r][xp], q1d = S.Xb[1][r][xp];
-                                const double dli = S.rowc[r][0];
-                                p0 += q1;
-                                p2 += q1d;
-                                p1 += dli * q1;
-                                p12 += dli * q1d;
-                            }
-                            S.vP[0][ka] += p0;
-                            S.vP[1][ka] += p2;
-                            S.vP[2][ka] += p1;
-                            S.vP[3][ka] += p12;
+                for (int x = tid; x < RL_W * RL_W; x += RL_THREADS) (&S.C[0][0])[x] = 0.;
+                // rows of forest 1 (side 0), then columns of forest 2 (side 1)
+                for (int side = 0; side < 2; side++) {
+                    const int nrows = side == 0 ? n1 : n2;
+                    const int *nrun = side == 0 ? nrun1 : nrun2;
+                    for (int g0 = 0; g0 < nrows; g0 += RL_ROWS) {
+                        __syncthreads();
+                        if (tid < RL_W) {
+                            S.flgA[tid] = 0;
+                            S.flgB[tid] = 0;
                         }
-                    } else if (tid < 2 * DR_W) {
-                        const int kb = tid - DR_W;
-                        if (kb < Uc) {
-                            double e5 = 0., e6 = 0., e7 = 0., e8 = 0.;
-                            const int yp = dr_ypos(kb);
-#pragma unroll 4
-                            for (int r = 0; r < DR_ROWS; r++) {
-                                const double e1 = S.Yb[0][r][yp], e3 = S.Yb[1][r][yp];
-                                const double a5 = S.rowc[r][1], a7 = S.rowc[r][2];
-                                e5 += a5 * e1;
-                                e6 += a5 * e3;
-                                e7 += a7 * e1;
-                                e8 += a7 * e3;
-                            }
-                            S.vE[0][kb] += e5;
-                            if (D.order2 == 1) S.vE[1][kb] += e6;
-                            if (D.order1 == 1) S.vE[2][kb] += e7;
-                            if (D.order1 == 1 && D.order2 == 1) S.vE[3][kb] += e8;
+                        for (int x = tid; x < 2 * RL_ROWS * RL_LOC; x += RL_THREADS) {
+                            (&S.Xl[0][0][0])[x] = 0.;
+                            (&S.Yl[0][0][0])[x] = 0.;
                         }
-                    } else if (tid < 3 * DR_W && first && !big) {
-                        const int kb = tid - 2 * DR_W;
-                        if (kb < Uc) {
-#pragma unroll
-                            for (int o = 0; o < 5; o++) {
-                                double t = 0.;
-#pragma unroll 4
-                                for (int r = 0; r < DR_ROWS; r++) t += S.Ob[o][r][kb];
-                                S.vO[o][kb] += t;
+                        __syncthreads();
+                        // -- the bins of the window this group touches
+                        const int i = g0 + warp;
+                        const int nr = i < nrows ? nrun[i] : 0;
+                        for (int k = lane; k < nr; k += 32) {
+                            int A, Bs;
+                            if (side == 0) {
+                                const RlRun1 *r = R1 + (long long)i * cap1 + k;
+                                A = r->A; Bs = r->Bs;
+                            } else {
+                                const RlRun2 *r = R2 + (long long)i * cap2 + k;
+                                A = r->A; Bs = r->Bs;
+                            }
+                            const int kb = kidx[Bs & ~RL_SEL] - kc;
+                            if (kb >= 0 && kb < Uc) S.flgB[kb] = 1;
+                            if (Bs & RL_SEL) {
+                                const int ka = aidx[A] - ac;
+                                if (ka >= 0 && ka < UAc) S.flgA[ka] = 1;
                             }
                         }
-                    }
-                    dr_rank_update(S, c, np_, nq_);
-                }
-
-                // ---------------- column sweep: pixels of forest 2
-                for (int jb = 0; jb < n2; jb += DR_ROWS) {
-                    __syncthreads();
-                    for (int x = tid; x < 2 * DR_ROWS * DR_W; x += DR_THREADS) {
-                        (&S.Xb[0][0][0])[x] = 0.;
-                        (&S.Yb[0][0][0])[x] = 0.;
-                    }
-                    __syncthreads();
-                    const int j = jb + warp;
-                    if (j < n2 && D.w2[j] != 0.)
-                        dr_sweep_row<false>(P, W.fast, D, S, warp, j, pf1, pstride, kidx, aidx, kc, Uc,
-                                            ac, UAc, false, big, nbm, dmat, r_par_eff, r_trans_eff,
-                                            z_eff, weight_eff);
-                    __syncthreads();
-                    dr_rank_update(S, c, np_, nq_);
-                }
-                __syncthreads();
-
-                // ---------------- rank-1 terms, scatter of the tile, per-forest-pair sums
-                {
-                    const int ty = tid >> 5, tx = tid & 31;
-#pragma unroll
-                    for (int p = 0; p < 8; p++) {
-                        const int ka = ty + 16 * p;
-                        if (p >= np_ || ka >= UAc) continue;
-                        const double p0 = S.vP[0][ka], p2 = S.vP[1][ka], p1 = S.vP[2][ka], p12 = S.vP[3][ka];
-                        const long long rowp = (long long)alist[ac + ka] * nbm;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int kb = tx + 32 * q;
-                            if (q >= nq_ || kb >= Uc) continue;
-                            const double v = c[p][q] + p0 * S.vE[0][kb] + p2 * S.vE[1][kb] +
-                                             p1 * S.vE[2][kb] + p12 * S.vE[3][kb];
-                            if (v != 0.) atomic_add_f64(dmat + rowp + klist[kc + kb], v);
+                        __syncthreads();
+                        if (warp < 2) {   // local indices: warp 0 the data bins, warp 1 the model bins
+                            const unsigned char *flg = warp == 0 ? S.flgA : S.flgB;
+                            short *loc = warp == 0 ? S.locA : S.locB;
+                            short *lst = warp == 0 ? S.lstA : S.lstB;
+                            int u = 0;
+                            for (int xb = 0; xb < RL_W; xb += 32) {
+                                const bool on = flg[xb + lane] != 0;
+                                const unsigned m = __ballot_sync(0xffffffffu, on);
+                                const int k = u + __popc(m & ((1u << lane) - 1u));
+                                loc[xb + lane] = on ? (short)k : (short)-1;
+                                if (on && k < RL_LOC) lst[k] = (short)(xb + lane);
+                                u += __popc(m);
+                            }
+                            if (lane == 0) {
+                                if (warp == 0) S.nA = u; else S.nB = u;
+                            }
                         }
-                    }
-                    if (first) {
-                        // weights_dmat[A] = sum over the selected pairs of the bin = P0[A] (cf.py:718)
-                        for (int ka = tid; ka < UAc; ka += DR_THREADS)
-                            if (S.vP[0][ka] != 0.) atomic_add_f64(weights_dmat + alist[ac + ka], S.vP[0][ka]);
-                        if (!big) {
-                            for (int kb = tid; kb < Uc; kb += DR_THREADS) {
-                                const int Bm = klist[kc + kb];
-                                if (S.vO[0][kb] != 0.) {
-                                    atomic_add_f64(weight_eff + Bm, S.vO[0][kb]);
-                                    atomic_add_f64(r_par_eff + Bm, S.vO[1][kb]);
-                                    atomic_add_f64(r_trans_eff + Bm, S.vO[2][kb]);
-                                    atomic_add_f64(z_eff + Bm, S.vO[3][kb]);
-                                    if (W.fast.same)
-                                        atomic_add_f64(dmat + (long long)Bm * nbm + Bm, S.vO[4][kb]);
+                        __syncthreads();
+                        const int nA = S.nA, nB = S.nB;
+                        if (nA == 0 || nB == 0) continue;
+                        const bool local = nA <= RL_LOC && nB <= RL_LOC;
+                        // -- expand the runs of the group (normalised eta rows, cf.py:767-813)
+                        double fa = 0., fb3 = 0.;
+                        if (i < nrows) {
+                            if (side == 0) {
+                                fa = 1. / D.sw2;
+                                fb3 = D.order2 == 1 ? 1. / D.swsll2 : 0.;
+                            } else {
+                                fa = 1. / D.sw1;
+                                fb3 = D.order1 == 1 ? 1. / D.swsll1 : 0.;
+                            }
+                        }
+                        if (local) {
+                            for (int k = lane; k < nr; k += 32) {
+                                int A, Bs;
+                                double ea, eb, qa, qb;
+                                if (side == 0) {
+                                    const RlRun1 *r = R1 + (long long)i * cap1 + k;
+                                    A = r->A; Bs = r->Bs; ea = r->e1; eb = r->e3; qa = r->q1; qb = r->q1d;
+                                } else {
+                                    const RlRun2 *r = R2 + (long long)i * cap2 + k;
+                                    A = r->A; Bs = r->Bs; ea = r->e2; eb = r->e4; qa = r->q2; qb = r->q2d;
+                                }
+                                const int kb = kidx[Bs & ~RL_SEL] - kc;
+                                if (kb >= 0 && kb < Uc) {
+                                    const int p = rl_ypos(S.locB[kb]);
+                                    rl_sadd(&S.Yl[0][warp][p], ea * fa);
+                                    if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], eb * fb3);
+                                }
+                                if (Bs & RL_SEL) {
+                                    const int ka = aidx[A] - ac;
+                                    if (ka >= 0 && ka < UAc) {
+                                        const int p = rl_xpos(S.locA[ka]);
+                                        rl_sadd(&S.Xl[0][warp][p], qa);
+                                        rl_sadd(&S.Xl[1][warp][p], qb);
+                                    }
+                                }
+                            }
+                            __syncthreads();
+                            // -- rank-32 update of the 64 x 64 register tile, added into the window
+                            double c[4][2];
+#pragma unroll
+                            for (int p = 0; p < 4; p++) c[p][0] = c[p][1] = 0.;
+                            if (ty < nA && tx < nB) {
+#pragma unroll 4
+                                for (int r = 0; r < RL_ROWS; r++) {
+#pragma unroll
+                                    for (int kind = 0; kind < 2; kind++) {
+                                        const double4 xv = *reinterpret_cast<const double4 *>(&S.Xl[kind][r][ty * 4]);
+                                        const double2 yv = *reinterpret_cast<const double2 *>(&S.Yl[kind][r][tx * 2]);
+                                        const double x[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                                        for (int p = 0; p < 4; p++) {
+                                            c[p][0] = fma(x[p], yv.x, c[p][0]);
+                                            c[p][1] = fma(x[p], yv.y, c[p][1]);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int p = 0; p < 4; p++) {
+                                    const int la = ty + 16 * p;
+                                    if (la >= nA) continue;
+                                    const int ka = S.lstA[la];
+#pragma unroll
+                                    for (int q = 0; q < 2; q++) {
+                                        const int lb = tx + 32 * q;
+                                        if (lb < nB && c[p][q] != 0.) S.C[ka][S.lstB[lb]] -= c[p][q];
+                                    }
+                                }
+                            }
+                        } else {
+                            // more than 64 bins in a group of 16 rows (fine model grids): the
+                            // products of a row's runs go to the window one by one
+                            for (int ka_ = 0; ka_ < nr; ka_++) {
+                                int A, Bs;
+                                double qa, qb;
+                                if (side == 0) {
+                                    const RlRun1 *r = R1 + (long long)i * cap1 + ka_;
+                                    A = r->A; Bs = r->Bs; qa = r->q1; qb = r->q1d;
+                                } else {
+                                    const RlRun2 *r = R2 + (long long)i * cap2 + ka_;
+                                    A = r->A; Bs = r->Bs; qa = r->q2; qb = r->q2d;
+                                }
+                                if (!(Bs & RL_SEL)) continue;
+                                const int ka = aidx[A] - ac;
+                                if (ka < 0 || ka >= UAc) continue;
+                                for (int k = lane; k < nr; k += 32) {
+                                    int B2;
+                                    double ea, eb;
+                                    if (side == 0) {
+                                        const RlRun1 *r = R1 + (long long)i * cap1 + k;
+                                        B2 = r->Bs & ~RL_SEL; ea = r->e1; eb = r->e3;
+                                    } else {
+                                        const RlRun2 *r = R2 + (long long)i * cap2 + k;
+                                        B2 = r->Bs & ~RL_SEL; ea = r->e2; eb = r->e4;
+                                    }
+                                    const int kb = kidx[B2] - kc;
+                                    if (kb >= 0 && kb < Uc)
+                                        rl_sadd(&S.C[ka][kb], -(qa * ea * fa + qb * eb * fb3));
                                 }
                             }
                         }
-                    } else if (kc == 0) {
-                        // further data-bin passes of a big forest pair: their weights_dmat
-                        for (int ka = tid; ka < UAc; ka += DR_THREADS)
-                            if (S.vP[0][ka] != 0.) atomic_add_f64(weights_dmat + alist[ac + ka], S.vP[0][ka]);
                     }
+                }
+                __syncthreads();
+                // ---------------- F: rank-1 terms and the scatter of the window
+                for (int x = tid; x < UAc * Uc; x += RL_THREADS) {
+                    const int ka = x / Uc, kb = x - ka * Uc;
+                    const int ga = ac + ka, gb = kc + kb;
+                    const double v = S.C[ka][kb] + vP[0 * vstride + ga] * vE[0 * vstride + gb] +
+                                     vP[1 * vstride + ga] * vE[1 * vstride + gb] +
+                                     vP[2 * vstride + ga] * vE[2 * vstride + gb] +
+                                     vP[3 * vstride + ga] * vE[3 * vstride + gb];
+                    if (v != 0.) atomic_add_f64(dmat + (long long)alist[ga] * nbm + klist[gb], v);
                 }
             }
         }
@@ -619,13 +598,16 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
 }
 
 // ------------------------------------------------------------------------------------------
+static int rl_cap(int n_other) { return n_other + 2; }   // runs of a row <= pixels of the other forest
+
 long long pb2_dmat_run_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
 {
     const long long nb = (long long)par->num_bins_r_par * par->num_bins_r_trans;
     const long long nbm = (long long)par->num_model_bins_r_par * par->num_model_bins_r_trans;
-    const long long pstride = (c1->max_pix > c2->max_pix ? c1->max_pix : c2->max_pix) + 1;
-    long long bytes = (2 * nb + 2 * nbm) * 4 + (c1->max_pix + 2) * 4 + 64;
-    bytes += (DR_NPF2 + DR_NPF1) * pstride * 8;
+    long long bytes = (2 * nb + 2 * nbm) * 4 + (2ll * c1->max_pix + c2->max_pix + 3) * 4 + 64;
+    bytes += (long long)c1->max_pix * rl_cap(c2->max_pix) * (long long)sizeof(RlRun1);
+    bytes += (long long)c2->max_pix * rl_cap(c1->max_pix) * (long long)sizeof(RlRun2);
+    bytes += 13 * (nb > nbm ? nb : nbm) * 8;
     return (bytes + 255) / 256 * 256;
 }
 
@@ -643,11 +625,11 @@ int32_t pb2_launch_dmat_run(const pb2_catalog *cat1, const pb2_catalog *cat2, co
                             double *d_r_trans_eff, double *d_z_eff, double *d_weight_eff,
                             cudaStream_t s)
 {
-    const size_t smem = sizeof(DrShared);
+    const size_t smem = sizeof(RlShared);
     PB2_CUDA(cudaFuncSetAttribute(pb2_dmat_auto_run_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pb2_dmat_auto_run_kernel<<<blocks, DR_THREADS, smem, s>>>(*cat1, *cat2, *par, *pairs, W,
-                                                              d_weights_dmat, d_dmat, d_r_par_eff,
-                                                              d_r_trans_eff, d_z_eff, d_weight_eff);
+    pb2_dmat_auto_run_kernel<<<blocks, RL_THREADS, smem, s>>>(
+        *cat1, *cat2, *par, *pairs, W, rl_cap(cat2->max_pix), rl_cap(cat1->max_pix),
+        d_weights_dmat, d_dmat, d_r_par_eff, d_r_trans_eff, d_z_eff, d_weight_eff);
     return 0;
 }

@@ -159,35 +159,45 @@ def dmat_chunk_sharded(eng, dev1, dev2, params, shard, mode, reject, seed, cross
     The --rej draw is a property of the chunk: one legacy MT19937 stream, ``len(neighbours)``
     numbers per forest in catalogue order (cf.py:444, xcf.py:379), so every rank needs the
     neighbour COUNT of every forest (count-only pass, replicated: milliseconds) but the neighbour
-    LISTS of its own forests only.  The stream is drawn on the host in ``segments`` pieces while
-    the device works on the previous piece: piece k of the mask is uploaded, this rank's forest
-    pairs inside it are selected on the device and the kernels run on them, accumulating into
-    the same matrices; ONE all-reduce(SUM) of a flat buffer (matrix + five vectors) follows.
+    LISTS of its own forests only.  See ``_dmat_stream`` for the rest.
 
     Returns ([weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff] device tensors,
     NPALL, NPUSED)."""
     torch = eng.torch
-    dev = eng.device
-    # ---- 1. neighbour counts of every forest of the chunk -> stream offsets
     count_all = eng.neighbour_counts(dev1, dev2, params, mode, shard.d_all_f1)
-    off_all = torch.zeros(count_all.numel() + 1, dtype=torch.int64, device=dev)
+    off_all = torch.zeros(count_all.numel() + 1, dtype=torch.int64, device=eng.device)
     torch.cumsum(count_all, dim=0, out=off_all[1:])
+    pairs = eng.neighbours(dev1, dev2, params, mode, shard.d_f1)
+    return _dmat_stream(eng, dev1, dev2, params, pairs, shard.f1_index.astype(np.int64), off_all,
+                        reject, seed, cross_obj, segments, shard.world, group)
+
+
+def _dmat_stream(eng, dev1, dev2, params, pairs, my_f1, off_all, reject, seed, cross_obj,
+                 segments, world, group):
+    """``pairs``: the neighbour lists of this rank's forests, whose positions in the CHUNK's
+    catalogue order are ``my_f1`` (ascending); ``off_all``: device int64 [n_los_chunk + 1], the
+    offsets of every forest of the chunk in the --rej stream.  The stream is drawn on the host in
+    ``segments`` pieces while the device works on the previous piece: piece k of the mask is
+    uploaded, this rank's forest pairs inside it are selected on the device and the kernels run
+    on them, accumulating into the same matrices; ONE all-reduce(SUM) of a flat buffer (matrix +
+    five vectors) follows."""
+    torch = eng.torch
+    dev = eng.device
     h_off_all = off_all.cpu().numpy()                     # 0.8 MB per 100k forests
     npall = int(h_off_all[-1])
-    # ---- 2. neighbour lists of this rank's forests
-    pairs = eng.neighbours(dev1, dev2, params, mode, shard.d_f1)
+    n_los = h_off_all.size - 1
     # stream position of each of my pairs: start of its forest's draw + rank inside the forest
-    f1_cat = shard.d_f1.to(torch.int64)[pairs.nb_f1.to(torch.int64)]
+    d_my_f1 = torch.from_numpy(np.ascontiguousarray(my_f1)).to(dev)
+    f1_cat = d_my_f1[pairs.nb_f1.to(torch.int64)]
     pos = off_all[f1_cat] + (torch.arange(pairs.n_pairs, dtype=torch.int64, device=dev) -
                              pairs.nb_offset[pairs.nb_f1.to(torch.int64)])
-    # ---- 3. segments of the stream, cut at forest boundaries
-    n_los = count_all.numel()
+    # segments of the stream, cut at forest boundaries
     cuts = np.unique(np.linspace(0, n_los, max(1, segments) + 1).astype(np.int64))
     state = np.random.RandomState(seed)
     outs = eng.dmat_outputs(params)
     keep_dev = torch.zeros(max(pairs.n_pairs, 1), dtype=torch.uint8, device=dev)
     npused = npall_cross = 0
-    my_f1 = shard.f1_index.astype(np.int64)
+    h_my_off = pairs.host_offset()
     for a, b in zip(cuts[:-1], cuts[1:]):
         s0, s1 = int(h_off_all[a]), int(h_off_all[b])
         if s1 == s0:
@@ -205,8 +215,7 @@ def dmat_chunk_sharded(eng, dev1, dev2, params, shard, mode, reject, seed, cross
         lo, hi = np.searchsorted(my_f1, [a, b])           # my forests inside this segment
         if hi == lo:
             continue
-        p0 = int(pairs.host_offset()[lo])
-        p1 = int(pairs.host_offset()[hi])
+        p0, p1 = int(h_my_off[lo]), int(h_my_off[hi])
         if p1 == p0:
             continue
         d_mask = torch.from_numpy(mask.view(np.uint8)).to(dev, non_blocking=True)
@@ -214,8 +223,8 @@ def dmat_chunk_sharded(eng, dev1, dev2, params, shard, mode, reject, seed, cross
         keep_dev[p0:p1] = d_mask[pos[p0:p1] - s0]
         pairs.nb_keep = keep_dev
         eng.dmat(dev1, dev2, params, pairs, cross_obj=cross_obj, out=outs)
-    # ---- 4. one collective over a flat buffer
-    if shard.world > 1:
+    # one collective over a flat buffer
+    if world > 1:
         import torch.distributed as dist
         flat = torch.cat([t.reshape(-1) for t in outs])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
@@ -224,3 +233,146 @@ def dmat_chunk_sharded(eng, dev1, dev2, params, shard, mode, reject, seed, cross
             t.copy_(flat[k:k + t.numel()].view_as(t))
             k += t.numel()
     return list(outs), (npall_cross if cross_obj else npall), npused
+
+
+# ---------------------------------------------------------------------------------------------
+# Band shards: every rank holds only a contiguous band of HEALPix rows plus the halo its
+# neighbour searches reach into -- the host packs and uploads 1/N of the catalogue (+ halo)
+# instead of all of it, which is what the end-to-end path costs per rank.
+# ---------------------------------------------------------------------------------------------
+class RowIndex:
+    """Per HEALPix row of a ``data`` dict (ascending pixel id): forests, spectral pixels and the
+    bounding cap of the members -- what the partition and the halo need, without packing."""
+
+    def __init__(self, data):
+        from . import forest as _forest
+        self.healpixs = sorted(data)
+        self.counts = np.array([len(data[hp]) for hp in self.healpixs], dtype=np.int64)
+        self.first = np.zeros(len(self.healpixs) + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.first[1:])
+        reg = _forest.soa_of(data)
+        if reg is not None and reg["objs"] and _forest.registered_clean(data, reg):
+            los = reg["los"]
+            xyz = np.stack([np.array(los[k], dtype=np.float64) for k in ("x_cart", "y_cart", "z_cart")],
+                           axis=1)
+            npix = np.diff(np.asarray(reg["offset"], dtype=np.int64)).astype(np.float64)
+        else:
+            objs = [o for hp in self.healpixs for o in data[hp]]
+            xyz = np.array([[o.x_cart, o.y_cart, o.z_cart] for o in objs], dtype=np.float64)
+            npix = np.array([np.size(o.weights) for o in objs], dtype=np.float64)
+        n = len(self.healpixs)
+        self.npix = np.add.reduceat(npix, self.first[:-1]) if npix.size else np.zeros(n)
+        self.cap = np.zeros((n, 3))
+        self.cap_rad = np.zeros(n)
+        for k in range(n):
+            v = xyz[self.first[k]:self.first[k + 1]]
+            c = v.sum(axis=0)
+            norm = np.sqrt((c * c).sum())
+            c = c / norm if norm > 0 else v[0]
+            self.cap[k] = c
+            self.cap_rad[k] = float(np.arccos(np.clip(v @ c, -1., 1.).min())) + 1e-7
+
+    def near(self, other, rows, ang_max):
+        """bool [len(rows), n_other]: can a member of row r be within ang_max of a member of a row
+        of ``other`` (bounding caps: a superset, like the device neighbour search)"""
+        ang = np.arccos(np.clip(self.cap[rows] @ other.cap.T, -1., 1.))
+        return ang <= (ang_max + self.cap_rad[rows, None] + other.cap_rad[None, :])
+
+    def work(self, other, ang_max):
+        out = np.zeros(len(self.healpixs))
+        for a in range(0, len(out), 512):
+            rows = np.arange(a, min(a + 512, len(out)))
+            out[rows] = self.npix[rows] * (self.near(other, rows, ang_max) * other.npix[None, :]).sum(axis=1)
+        return out
+
+
+def band_bounds(work, n_parts):
+    """Contiguous bands [b0, b1) of the rows with balanced cumulative work (every band non-empty
+    when there are at least ``n_parts`` rows)."""
+    work = np.asarray(work, dtype=np.float64)
+    n = work.size
+    c = np.concatenate([[0.], np.cumsum(work)])
+    cuts = [0]
+    for k in range(1, n_parts):
+        b = int(np.searchsorted(c, c[-1] * k / n_parts, side="left"))
+        b = min(max(b, cuts[-1] + 1), n - (n_parts - k)) if n >= n_parts else min(b, n)
+        cuts.append(max(b, cuts[-1]))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(n_parts)]
+
+
+def all_gather_concat(t, group=None):
+    """Concatenation over the ranks, in rank order, of 1-D tensors of different lengths."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    lens = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(lens, torch.tensor([t.numel()], dtype=torch.int64, device=t.device), group=group)
+    lens = [int(x.item()) for x in lens]
+    cap = max(max(lens), 1)
+    pad = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:n] for b, n in zip(bufs, lens)])
+
+
+class BandShard:
+    """Rank ``rank`` of ``world``: the band [b0, b1) of HEALPix rows it owns and, packed and
+    resident in HBM, the rows [h0, h1) >= band that contain every possible neighbour of the
+    band's forests (auto-correlation: ``data`` against itself)."""
+
+    def __init__(self, eng, data, ang_max, world, rank, ang_correlation=False):
+        from . import catalog as _catalog
+        torch = eng.torch
+        self.world, self.rank = world, rank
+        idx = RowIndex(data)
+        self.n_rows_total = len(idx.healpixs)
+        self.healpixs = idx.healpixs
+        self.bounds = band_bounds(idx.work(idx, ang_max), world)
+        self.b0, self.b1 = self.bounds[rank]
+        if self.b1 > self.b0:
+            reach = np.nonzero(idx.near(idx, np.arange(self.b0, self.b1), ang_max).any(axis=0))[0]
+            self.h0, self.h1 = int(min(reach.min(), self.b0)), int(max(reach.max() + 1, self.b1))
+        else:
+            self.h0, self.h1 = self.b0, self.b1
+        self.host = _catalog.pack(data, ang_correlation=ang_correlation, defer_products=True,
+                                  rows=(self.h0, self.h1))
+        self.dev = eng.device_catalog(self.host, cache=False)
+        self.mine = np.arange(self.b0, self.b1, dtype=np.int64)       # global rows of the band
+        first = self.host.arrays["hp_first"]
+        lo, hi = self.b0 - self.h0, self.b1 - self.h0                  # the band inside the halo
+        self.f1_index = np.arange(first[lo], first[hi], dtype=np.int32)
+        self.rows = (np.repeat(np.arange(lo, hi, dtype=np.int32), np.diff(first[lo:hi + 1])) - lo
+                     ).astype(np.int32)
+        self.d_f1 = torch.as_tensor(self.f1_index, device=eng.device)
+        self.d_rows = torch.as_tensor(self.rows, device=eng.device)
+        # positions of the band's forests in the whole catalogue (the --rej stream order)
+        self.global_f1 = int(idx.first[self.b0]) + np.arange(self.f1_index.size, dtype=np.int64)
+        self.n_los_total = int(idx.first[-1])
+        self.h2d_bytes = int(self.host.nbytes())
+
+
+def xi_banded(eng, shard, params, mode, gather=True):
+    """compute_xi of every HEALPix row from band shards: neighbour search + pair kernel + per-row
+    normalisation on the band, rows gathered to rank 0 ([n_rows_total, 6, nb]; None elsewhere)."""
+    pairs = eng.neighbours(shard.dev, shard.dev, params, mode, shard.d_f1)
+    out = eng.xi(shard.dev, shard.dev, params, pairs, shard.d_rows, len(shard.mine), normalise=True)
+    if shard.world > 1 and gather:
+        return gather_rows(out, shard.mine, shard.n_rows_total)
+    return out
+
+
+def dmat_chunk_banded(eng, shard, params, mode, reject, seed, segments=8, group=None):
+    """``dmat_chunk_sharded`` from band shards: a rank can only count the neighbours of ITS
+    forests, so the counts of the whole chunk -- the offsets of the --rej stream -- are
+    all-gathered (bands are contiguous and ordered by rank: a concatenation)."""
+    torch = eng.torch
+    count_mine = eng.neighbour_counts(shard.dev, shard.dev, params, mode, shard.d_f1)
+    count_all = all_gather_concat(count_mine, group) if shard.world > 1 else count_mine
+    assert count_all.numel() == shard.n_los_total
+    off_all = torch.zeros(count_all.numel() + 1, dtype=torch.int64, device=eng.device)
+    torch.cumsum(count_all, dim=0, out=off_all[1:])
+    pairs = eng.neighbours(shard.dev, shard.dev, params, mode, shard.d_f1)
+    return _dmat_stream(eng, shard.dev, shard.dev, params, pairs, shard.global_f1, off_all, reject,
+                        seed, False, segments, shard.world, group)

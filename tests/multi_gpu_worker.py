@@ -38,6 +38,12 @@ def main():
     full = pdist.xi_sharded(eng, dev, dev, params, shard, MODE_AUTO)
     res, npall, npused = pdist.dmat_chunk_sharded(eng, dev, dev, params, shard, MODE_AUTO,
                                                   cf.reject, hps[0], segments=5)
+    # band shards: each rank packs and uploads only its band of rows + halo
+    band = pdist.BandShard(eng, data, ang_max, world, rank)
+    assert band.host.n_los <= host.n_los and band.host.from_soa
+    full_b = pdist.xi_banded(eng, band, params, MODE_AUTO)
+    res_b, npall_b, npused_b = pdist.dmat_chunk_banded(eng, band, params, MODE_AUTO, cf.reject,
+                                                       hps[0], segments=3)
     if rank == 0:
         cf.fill_neighs(hps)
         want = cf.compute_xi_batch(hps)
@@ -49,10 +55,16 @@ def main():
         np.random.seed(hps[0])
         one = cf.compute_dmat(hps)
         assert (npall, npused) == (one[6], one[7]) and npused > 500
-        for k, (a, b) in enumerate(zip(res, one[:6])):
-            a = a.cpu().numpy()
-            scale = np.abs(b).max()
-            assert np.abs(a - b).max() <= 1e-11 * scale, (k, np.abs(a - b).max(), scale)
+        assert (npall_b, npused_b) == (one[6], one[7])
+        for got_res in (res, res_b):
+            for k, (a, b) in enumerate(zip(got_res, one[:6])):
+                a = a.cpu().numpy()
+                scale = np.abs(b).max()
+                assert np.abs(a - b).max() <= 1e-11 * scale, (k, np.abs(a - b).max(), scale)
+        got_b = full_b.cpu().numpy()
+        assert np.array_equal(got_b[:, 5].view(np.int64), want[:, 5].view(np.int64))
+        for k in range(5):
+            np.testing.assert_allclose(got_b[:, k], want[:, k], rtol=1e-12, atol=1e-300)
         print("multi-gpu ok: world %d, %d binned pairs, NPALL %d NPUSED %d" % (
             world, int(want[:, 5].view(np.int64).sum()), npall, npused))
     dist.barrier()

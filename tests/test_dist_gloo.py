@@ -82,3 +82,54 @@ def test_keep_mask_draw_and_shards():
     assert not np.any(shards[0] & shards[1])
     assert np.array_equal(shards[0] | shards[1], got)
     assert np.array_equal(shards[1], got & np.isin(pair_row, [0, 2]))
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = torch.arange(3 * rank, 3 * rank + 2 + 3 * rank, dtype=torch.int32)  # lengths 2 and 5
+    got = pdist.all_gather_concat(mine)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "cat.npy"), got.numpy())
+    dist.destroy_process_group()
+
+
+def test_all_gather_concat_of_ragged_tensors(tmp_path):
+    """the per-band neighbour counts of the distortion matrix (dist.dmat_chunk_banded) have
+    different lengths on every rank"""
+    mp.spawn(_gather_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert np.array_equal(np.load(tmp_path / "cat.npy"), [0, 1, 3, 4, 5, 6, 7])
+
+
+def test_band_bounds_and_halo_cover_every_neighbour():
+    """Band shards: contiguous, balanced, and the packed rows [h0, h1) of a band contain every
+    true neighbour (ang < ang_max, brute force) of the band's forests."""
+    from oracle import _host
+    from picca_b200 import synth
+    data, num, z_min, _, cosmo = synth.make_forests(2500, seed=8, nside=32, ra_deg=(0., 20.),
+                                                    dec_deg=(0., 14.), max_pix=12)
+    ang_max = synth.compute_ang_max(cosmo, 200., z_min)
+    idx = pdist.RowIndex(data)
+    work = idx.work(idx, ang_max)
+    host = catalog.pack(data)
+    np.testing.assert_allclose(work, pdist.estimate_work(host, host, ang_max), rtol=1e-12)
+    cat = _host.catalogue(data)
+    row_of = np.repeat(np.arange(len(idx.healpixs)), idx.counts)
+    for world in (1, 2, 5):
+        bounds = pdist.band_bounds(work, world)
+        assert bounds[0][0] == 0 and bounds[-1][1] == len(work)
+        assert all(a[1] == b[0] and a[1] > a[0] for a, b in zip(bounds[:-1], bounds[1:]))
+        loads = np.array([work[a:b].sum() for a, b in bounds])
+        assert loads.max() <= loads.mean() + work.max()
+        for b0, b1 in bounds:
+            reach = np.nonzero(idx.near(idx, np.arange(b0, b1), ang_max).any(axis=0))[0]
+            h0, h1 = min(reach.min(), b0), max(reach.max() + 1, b1)
+            for f in range(idx.first[b0], idx.first[b1], 23):
+                d = cat.objs[f]
+                ang = _host.angle_between_many(d, cat)
+                nb_ = np.nonzero((ang < ang_max) & (cat.thingid != d.thingid))[0]
+                assert np.all((row_of[nb_] >= h0) & (row_of[nb_] < h1))
+    # more ranks than rows: trailing bands are empty, nothing is lost
+    tiny = pdist.band_bounds(np.ones(3), 5)
+    assert tiny[0][0] == 0 and tiny[-1][1] == 3 and sum(b - a for a, b in tiny) == 3

@@ -68,3 +68,13 @@ def test_one_rank_shard_equals_plugin_call():
     cf.fill_neighs(hps)
     want = cf.compute_xi_batch(hps)
     assert np.array_equal(full[:, 5].view(np.int64), want[:, 5].view(np.int64))
+    # the band-shard entry points with one band (= everything, no halo)
+    band = pdist.BandShard(eng, data, ang_max, 1, 0)
+    assert (band.b0, band.b1, band.h0, band.h1) == (0, len(hps), 0, len(hps))
+    full_b = pdist.xi_banded(eng, band, params, MODE_AUTO).cpu().numpy()
+    assert np.array_equal(full_b[:, 5].view(np.int64), want[:, 5].view(np.int64))
+    res_b, npall_b, npused_b = pdist.dmat_chunk_banded(eng, band, params, MODE_AUTO, cf.reject,
+                                                       hps[0], segments=3)
+    assert (npall_b, npused_b) == (one[6], one[7])
+    for a, b in zip(res_b, one[:6]):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300)
