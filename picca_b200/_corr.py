@@ -43,16 +43,66 @@ class LazyNeighbours:
         return [self._objs2[q] for q in idx]
 
 
+class PendingNeighbours:
+    """``delta.neighbours`` after a DEFERRED fill_neighs (see ``defer_fill``): the neighbour
+    search runs when somebody looks at the list or a compute_* function needs it."""
+
+    def __init__(self, owner, fill_now, healpixs):
+        self._owner, self._fill_now, self._healpixs = owner, fill_now, healpixs
+
+    def _real(self):
+        if self._owner.neighbours is self:
+            self._fill_now(self._healpixs)     # replaces .neighbours of every forest of the list
+        return self._owner.neighbours
+
+    def __len__(self):
+        return len(self._real())
+
+    @property
+    def size(self):
+        return len(self)
+
+    def __iter__(self):
+        return iter(self._real())
+
+    def __getitem__(self, item):
+        return self._real()[item]
+
+
+def defer_fill():
+    """fill_neighs is deferred when it is called in the MAIN process before this process has
+    touched CUDA: picca_xwick.py fills the neighbours in the parent and only then forks its pool
+    (picca_xwick.py:446, :452), and a CUDA context does not survive a fork.  The forked workers
+    (and an in-process caller such as picca_dmat.py --nproc 1) run the search on first use."""
+    import multiprocessing
+    from . import engine
+    if engine._ENGINE is not None and engine._ENGINE._pid == os.getpid():
+        return False
+    if os.environ.get("PICCA_B200_EAGER_FILL", "0") == "1":
+        return False
+    return multiprocessing.current_process().name == "MainProcess"
+
+
 class NeighbourStore:
     """Neighbour lists produced by fill_neighs, kept on the device until compute_* uses them."""
 
     def __init__(self):
         self.by_healpix = {}
+        self.pending = set()      # healpixs whose fill_neighs was deferred
+
+    def defer(self, healpixs, data, fill_now):
+        healpixs = list(healpixs)
+        for hp in healpixs:
+            self.pending.add(hp)
+            self.by_healpix.pop(hp, None)
+            for obj in data[hp]:
+                obj.neighbours = PendingNeighbours(obj, fill_now, healpixs)
 
     def put(self, healpixs, pairs, ranges, cats=()):
         """``cats``: the packed catalogues the list was built from (kept alive with it)."""
         for hp in healpixs:
             self.by_healpix[hp] = (pairs, ranges[hp], tuple(cats))
+            self.pending.discard(hp)
 
     def take(self, healpixs, cats=()):
         """The stored PairList when ``healpixs`` is exactly one stored batch built from the
@@ -60,6 +110,8 @@ class NeighbourStore:
         from a catalogue that has been re-packed since)."""
         missing = [hp for hp in healpixs if hp not in self.by_healpix]
         if missing:
+            if all(hp in self.pending for hp in missing):
+                return None   # deferred fill_neighs: the caller runs it now
             raise RuntimeError("picca_b200: compute called before fill_neighs for healpix %r"
                                % (missing[:5],))
         for hp in healpixs:
@@ -79,6 +131,7 @@ class NeighbourStore:
     def drop(self, healpixs):
         for hp in healpixs:
             self.by_healpix.pop(hp, None)
+            self.pending.discard(hp)
 
 
 def forest_index_of(host_cat, healpixs):

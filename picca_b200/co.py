@@ -67,6 +67,14 @@ def fill_neighs(healpixs):
     below ``ang_max`` (no ordering: an auto-correlation visits every pair from both ends, as the
     reference does); the mean-redshift cut of :70-74 is applied when the pairs are counted."""
     healpixs = list(healpixs)
+    if _corr.defer_fill():   # main process, no CUDA yet: see _corr.defer_fill
+        _STORE.defer(healpixs, objs, _fill_neighs_now)
+        return
+    _fill_neighs_now(healpixs)
+
+
+def _fill_neighs_now(healpixs):
+    healpixs = list(healpixs)
     eng, host1, dev1, host2, dev2 = _catalogs()
     params = params_from_module(_THIS)
     index, ranges = _corr.forest_index_of(host1, healpixs)
@@ -87,7 +95,7 @@ def compute_xi(healpixs):
     params = params_from_module(_THIS)
     pairs = _STORE.take(healpixs, (host1, host2))
     if pairs is None:
-        fill_neighs(healpixs)
+        _fill_neighs_now(healpixs)
         pairs = _STORE.take(healpixs, (host1, host2))
     torch = eng.torch
     nb = params.num_bins_r_par * params.num_bins_r_trans

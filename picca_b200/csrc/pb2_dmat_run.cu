@@ -598,15 +598,28 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
 }
 
 // ------------------------------------------------------------------------------------------
-static int rl_cap(int n_other) { return n_other + 2; }   // runs of a row <= pixels of the other forest
+// Runs of one row: at most one per pixel of the other forest; and, when the forests are sorted,
+// r_par is monotone along the row (V-shaped after abs()) and r_trans increasing, so the key
+// (data bin, model bin, selected) changes at most 2 np + nt + 2 npm + ntm times plus a few flips
+// of `selected` (z-pair cut, zerr cut, half-plate cut: each an interval of the row).
+static int rl_cap(int n_other, const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
+{
+    long long cap = (long long)n_other + 2;
+    if (c1->sorted && c2->sorted) {
+        const long long geo = 2ll * (par->num_bins_r_par + par->num_model_bins_r_par) +
+                              par->num_bins_r_trans + par->num_model_bins_r_trans + 16;
+        if (geo < cap) cap = geo;
+    }
+    return (int)cap;
+}
 
 long long pb2_dmat_run_cta_bytes(const pb2_catalog *c1, const pb2_catalog *c2, const pb2_params *par)
 {
     const long long nb = (long long)par->num_bins_r_par * par->num_bins_r_trans;
     const long long nbm = (long long)par->num_model_bins_r_par * par->num_model_bins_r_trans;
     long long bytes = (2 * nb + 2 * nbm) * 4 + (2ll * c1->max_pix + c2->max_pix + 3) * 4 + 64;
-    bytes += (long long)c1->max_pix * rl_cap(c2->max_pix) * (long long)sizeof(RlRun1);
-    bytes += (long long)c2->max_pix * rl_cap(c1->max_pix) * (long long)sizeof(RlRun2);
+    bytes += (long long)c1->max_pix * rl_cap(c2->max_pix, c1, c2, par) * (long long)sizeof(RlRun1);
+    bytes += (long long)c2->max_pix * rl_cap(c1->max_pix, c1, c2, par) * (long long)sizeof(RlRun2);
     bytes += 13 * (nb > nbm ? nb : nbm) * 8;
     return (bytes + 255) / 256 * 256;
 }
@@ -629,7 +642,8 @@ int32_t pb2_launch_dmat_run(const pb2_catalog *cat1, const pb2_catalog *cat2, co
     PB2_CUDA(cudaFuncSetAttribute(pb2_dmat_auto_run_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pb2_dmat_auto_run_kernel<<<blocks, RL_THREADS, smem, s>>>(
-        *cat1, *cat2, *par, *pairs, W, rl_cap(cat2->max_pix), rl_cap(cat1->max_pix),
+        *cat1, *cat2, *par, *pairs, W, rl_cap(cat2->max_pix, cat1, cat2, par),
+        rl_cap(cat1->max_pix, cat1, cat2, par),
         d_weights_dmat, d_dmat, d_r_par_eff, d_r_trans_eff, d_z_eff, d_weight_eff);
     return 0;
 }

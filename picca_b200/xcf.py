@@ -88,6 +88,14 @@ def fill_neighs(healpixs):
     """Neighbouring objects of every forest of ``healpixs`` (xcf.py:71-123), incl. the optional
     quasar-pair zerr cut (:102-115) and the r_par pre-filter (:117-121), on the device."""
     healpixs = list(healpixs)
+    if _corr.defer_fill():   # main process, no CUDA yet: see _corr.defer_fill
+        _STORE.defer(healpixs, data, _fill_neighs_now)
+        return
+    _fill_neighs_now(healpixs)
+
+
+def _fill_neighs_now(healpixs):
+    healpixs = list(healpixs)
     eng, host1, dev1, host2, dev2 = _catalogs()
     params = params_from_module(_THIS, cross=True)
     index, ranges = _corr.forest_index_of(host1, healpixs)
@@ -103,7 +111,7 @@ def _pairs_for(healpixs):
     _, host1, _, host2, _ = _catalogs()
     pairs = _STORE.take(healpixs, (host1, host2))
     if pairs is None:  # stored in different batches or for a re-packed catalogue: rebuild
-        fill_neighs(healpixs)
+        _fill_neighs_now(healpixs)
         pairs = _STORE.take(healpixs, (host1, host2))
     return pairs
 
