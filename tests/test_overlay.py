@@ -68,8 +68,14 @@ def test_product_fails_loudly_without_cuda(overlay_on):
     from tests import helpers
     data, num, z_min, _, cosmo = helpers.small_sample(n=20, seed=2, max_pix=30)
     helpers.configure(cf, data, num, 0.01)
+    hps = sorted(data)[:1]
+    # in a CUDA-free main process fill_neighs is deferred (picca_xwick.py fills before it forks
+    # its pool); the first use of the neighbours, or compute_*, needs the device: loud failure
+    cf.fill_neighs(hps)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        cf.fill_neighs(sorted(data)[:1])
+        len(data[hps[0]][0].neighbours)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cf.compute_xi(hps)
 
 
 def test_export_script_binds_b200_covariance(overlay_on):
