@@ -364,10 +364,15 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
             const double a5 = wi / D.sw1, a7 = wi * dli / D.swsll1;
             const double fe1 = 1. / D.sw2, fe3 = 1. / D.swsll2;   // eta1 / eta3 normalisations
             const RlRun1 *rr = R1 + (long long)i * cap1;
+            RlRun1 *rr_w = R1 + (long long)i * cap1;
             for (int k = lane; k < nr; k += 32) {
                 const RlRun1 r = rr[k];
                 const int B = r.Bs & ~RL_SEL;
                 const int kb = kidx[B];
+                // from here on the record carries COMPACT indices: data bin (-1 when the run is
+                // not selected) and model bin (-1 when outside the truncated np.unique, Q8)
+                rr_w[k].A = (r.Bs & RL_SEL) ? aidx[r.A] : -1;
+                rr_w[k].Bs = kb;
                 if (kb >= 0) {   // (< 0: outside the truncated np.unique, Q8)
                     const double e1 = r.e1 * fe1, e3 = D.order2 == 1 ? r.e3 * fe3 : 0.;
                     rl_sadd(vE + 0 * vstride + kb, a5 * e1);                          // cf.py:775
@@ -396,6 +401,15 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                         atomic_add_f64(dmat + (long long)r.A * nbm + B, r.dg);
                     }
                 }
+            }
+        }
+        for (int j = warp; j < n2; j += RL_WARPS) {   // the same rewrite for the column runs
+            const int nr = nrun2[j];
+            RlRun2 *rr2 = R2 + (long long)j * cap2;
+            for (int k = lane; k < nr; k += 32) {
+                const int A = rr2[k].A, Bs = rr2[k].Bs;
+                rr2[k].A = (Bs & RL_SEL) ? aidx[A] : -1;
+                rr2[k].Bs = kidx[Bs & ~RL_SEL];
             }
         }
         __syncthreads();
@@ -427,157 +441,136 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                     const int nrows = side == 0 ? n1 : n2;
                     const int *nrun = side == 0 ? nrun1 : nrun2;
                     for (int g0 = 0; g0 < nrows; g0 += RL_ROWS) {
-                        __syncthreads();
-                        if (tid < RL_W) {
-                            S.flgA[tid] = 0;
-                            S.flgB[tid] = 0;
-                        }
-                        for (int x = tid; x < 2 * RL_ROWS * RL_LOC; x += RL_THREADS) {
-                            (&S.Xl[0][0][0])[x] = 0.;
-                            (&S.Yl[0][0][0])[x] = 0.;
-                        }
-                        __syncthreads();
-                        // -- the bins of the window this group touches
-                        const int i = g0 + warp;
-                        const int nr = i < nrows ? nrun[i] : 0;
-                        for (int k = lane; k < nr; k += 32) {
-                            int A, Bs;
-                            if (side == 0) {
-                                const RlRun1 *r = R1 + (long long)i * cap1 + k;
-                                A = r->A; Bs = r->Bs;
-                            } else {
-                                const RlRun2 *r = R2 + (long long)i * cap2 + k;
-                                A = r->A; Bs = r->Bs;
+                        // rows g0 + r0 .. g0 + r0 + rp - 1 (warp = row) form a block; a block whose
+                        // rows touch more than RL_LOC bins of the window is halved
+                        int r0 = 0, rp = RL_ROWS;
+                        while (r0 < RL_ROWS) {
+                            rp = min(rp, RL_ROWS - r0);
+                            __syncthreads();
+                            if (tid < RL_W) {
+                                S.flgA[tid] = 0;
+                                S.flgB[tid] = 0;
                             }
-                            const int kb = kidx[Bs & ~RL_SEL] - kc;
-                            if (kb >= 0 && kb < Uc) S.flgB[kb] = 1;
-                            if (Bs & RL_SEL) {
-                                const int ka = aidx[A] - ac;
-                                if (ka >= 0 && ka < UAc) S.flgA[ka] = 1;
+                            for (int x = tid; x < 2 * RL_ROWS * RL_LOC; x += RL_THREADS) {
+                                (&S.Xl[0][0][0])[x] = 0.;
+                                (&S.Yl[0][0][0])[x] = 0.;
                             }
-                        }
-                        __syncthreads();
-                        if (warp < 2) {   // local indices: warp 0 the data bins, warp 1 the model bins
-                            const unsigned char *flg = warp == 0 ? S.flgA : S.flgB;
-                            short *loc = warp == 0 ? S.locA : S.locB;
-                            short *lst = warp == 0 ? S.lstA : S.lstB;
-                            int u = 0;
-                            for (int xb = 0; xb < RL_W; xb += 32) {
-                                const bool on = flg[xb + lane] != 0;
-                                const unsigned m = __ballot_sync(0xffffffffu, on);
-                                const int k = u + __popc(m & ((1u << lane) - 1u));
-                                loc[xb + lane] = on ? (short)k : (short)-1;
-                                if (on && k < RL_LOC) lst[k] = (short)(xb + lane);
-                                u += __popc(m);
-                            }
-                            if (lane == 0) {
-                                if (warp == 0) S.nA = u; else S.nB = u;
-                            }
-                        }
-                        __syncthreads();
-                        const int nA = S.nA, nB = S.nB;
-                        if (nA == 0 || nB == 0) continue;
-                        const bool local = nA <= RL_LOC && nB <= RL_LOC;
-                        // -- expand the runs of the group (normalised eta rows, cf.py:767-813)
-                        double fa = 0., fb3 = 0.;
-                        if (i < nrows) {
-                            if (side == 0) {
-                                fa = 1. / D.sw2;
-                                fb3 = D.order2 == 1 ? 1. / D.swsll2 : 0.;
-                            } else {
-                                fa = 1. / D.sw1;
-                                fb3 = D.order1 == 1 ? 1. / D.swsll1 : 0.;
-                            }
-                        }
-                        if (local) {
+                            __syncthreads();
+                            // -- the bins of the window this block touches
+                            const int i = g0 + warp;
+                            const bool mine = warp >= r0 && warp < r0 + rp && i < nrows;
+                            const int nr = mine ? nrun[i] : 0;
+                            const char *rbase = side == 0 ? (const char *)(R1 + (long long)i * cap1)
+                                                          : (const char *)(R2 + (long long)i * cap2);
+                            const int rsz = side == 0 ? (int)sizeof(RlRun1) : (int)sizeof(RlRun2);
                             for (int k = lane; k < nr; k += 32) {
-                                int A, Bs;
-                                double ea, eb, qa, qb;
-                                if (side == 0) {
-                                    const RlRun1 *r = R1 + (long long)i * cap1 + k;
-                                    A = r->A; Bs = r->Bs; ea = r->e1; eb = r->e3; qa = r->q1; qb = r->q1d;
-                                } else {
-                                    const RlRun2 *r = R2 + (long long)i * cap2 + k;
-                                    A = r->A; Bs = r->Bs; ea = r->e2; eb = r->e4; qa = r->q2; qb = r->q2d;
+                                const int2 ab = *reinterpret_cast<const int2 *>(rbase + (long long)k * rsz);
+                                const int ka = ab.x - ac, kb = ab.y - kc;
+                                if (ab.y >= 0 && kb >= 0 && kb < Uc) S.flgB[kb] = 1;
+                                if (ab.x >= 0 && ka >= 0 && ka < UAc) S.flgA[ka] = 1;
+                            }
+                            __syncthreads();
+                            if (warp < 2) {   // local indices: warp 0 the data bins, warp 1 the model bins
+                                const unsigned char *flg = warp == 0 ? S.flgA : S.flgB;
+                                short *loc = warp == 0 ? S.locA : S.locB;
+                                short *lst = warp == 0 ? S.lstA : S.lstB;
+                                int u = 0;
+                                for (int xb = 0; xb < RL_W; xb += 32) {
+                                    const bool on = flg[xb + lane] != 0;
+                                    const unsigned m = __ballot_sync(0xffffffffu, on);
+                                    const int k = u + __popc(m & ((1u << lane) - 1u));
+                                    loc[xb + lane] = on ? (short)k : (short)-1;
+                                    if (on && k < RL_LOC) lst[k] = (short)(xb + lane);
+                                    u += __popc(m);
                                 }
-                                const int kb = kidx[Bs & ~RL_SEL] - kc;
-                                if (kb >= 0 && kb < Uc) {
-                                    const int p = rl_ypos(S.locB[kb]);
-                                    rl_sadd(&S.Yl[0][warp][p], ea * fa);
-                                    if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], eb * fb3);
-                                }
-                                if (Bs & RL_SEL) {
-                                    const int ka = aidx[A] - ac;
-                                    if (ka >= 0 && ka < UAc) {
-                                        const int p = rl_xpos(S.locA[ka]);
-                                        rl_sadd(&S.Xl[0][warp][p], qa);
-                                        rl_sadd(&S.Xl[1][warp][p], qb);
-                                    }
+                                if (lane == 0) {
+                                    if (warp == 0) S.nA = u; else S.nB = u;
                                 }
                             }
                             __syncthreads();
-                            // -- rank-32 update of the 64 x 64 register tile, added into the window
-                            double c[4][2];
+                            const int nA = S.nA, nB = S.nB;
+                            if (nA == 0 || nB == 0) {
+                                r0 += rp;
+                                continue;
+                            }
+                            if ((nA > RL_LOC || nB > RL_LOC) && rp > 1) {
+                                rp >>= 1;   // too many bins for the local tile: fewer rows
+                                continue;
+                            }
+                            // normalisations of the eta rows (cf.py:767-813)
+                            const double fa = side == 0 ? 1. / D.sw2 : 1. / D.sw1;
+                            const double fb3 = side == 0 ? (D.order2 == 1 ? 1. / D.swsll2 : 0.)
+                                                         : (D.order1 == 1 ? 1. / D.swsll1 : 0.);
+                            if (nA <= RL_LOC && nB <= RL_LOC) {
+                                // -- expand the runs of the block
+                                for (int k = lane; k < nr; k += 32) {
+                                    const char *rec = rbase + (long long)k * rsz;
+                                    const int2 ab = *reinterpret_cast<const int2 *>(rec);
+                                    const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
+                                    const int ka = ab.x - ac, kb = ab.y - kc;
+                                    if (ab.y >= 0 && kb >= 0 && kb < Uc) {
+                                        const int p = rl_ypos(S.locB[kb]);
+                                        rl_sadd(&S.Yl[0][warp][p], v[0] * fa);
+                                        if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], v[1] * fb3);
+                                    }
+                                    if (ab.x >= 0 && ka >= 0 && ka < UAc) {
+                                        const int p = rl_xpos(S.locA[ka]);
+                                        rl_sadd(&S.Xl[0][warp][p], v[2]);
+                                        rl_sadd(&S.Xl[1][warp][p], v[3]);
+                                    }
+                                }
+                                __syncthreads();
+                                // -- rank-(2 rp) update of the 64 x 64 register tile, added into the window
+                                if (ty < nA && tx < nB) {
+                                    double c[4][2];
 #pragma unroll
-                            for (int p = 0; p < 4; p++) c[p][0] = c[p][1] = 0.;
-                            if (ty < nA && tx < nB) {
-#pragma unroll 4
-                                for (int r = 0; r < RL_ROWS; r++) {
+                                    for (int p = 0; p < 4; p++) c[p][0] = c[p][1] = 0.;
+                                    for (int r = r0; r < r0 + rp; r++) {
 #pragma unroll
-                                    for (int kind = 0; kind < 2; kind++) {
-                                        const double4 xv = *reinterpret_cast<const double4 *>(&S.Xl[kind][r][ty * 4]);
-                                        const double2 yv = *reinterpret_cast<const double2 *>(&S.Yl[kind][r][tx * 2]);
-                                        const double x[4] = {xv.x, xv.y, xv.z, xv.w};
+                                        for (int kind = 0; kind < 2; kind++) {
+                                            const double4 xv = *reinterpret_cast<const double4 *>(&S.Xl[kind][r][ty * 4]);
+                                            const double2 yv = *reinterpret_cast<const double2 *>(&S.Yl[kind][r][tx * 2]);
+                                            const double x[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                                        for (int p = 0; p < 4; p++) {
-                                            c[p][0] = fma(x[p], yv.x, c[p][0]);
-                                            c[p][1] = fma(x[p], yv.y, c[p][1]);
+                                            for (int p = 0; p < 4; p++) {
+                                                c[p][0] = fma(x[p], yv.x, c[p][0]);
+                                                c[p][1] = fma(x[p], yv.y, c[p][1]);
+                                            }
+                                        }
+                                    }
+#pragma unroll
+                                    for (int p = 0; p < 4; p++) {
+                                        const int la = ty + 16 * p;
+                                        if (la >= nA) continue;
+                                        const int ka = S.lstA[la];
+#pragma unroll
+                                        for (int q = 0; q < 2; q++) {
+                                            const int lb = tx + 32 * q;
+                                            if (lb < nB && c[p][q] != 0.) S.C[ka][S.lstB[lb]] -= c[p][q];
                                         }
                                     }
                                 }
-#pragma unroll
-                                for (int p = 0; p < 4; p++) {
-                                    const int la = ty + 16 * p;
-                                    if (la >= nA) continue;
-                                    const int ka = S.lstA[la];
-#pragma unroll
-                                    for (int q = 0; q < 2; q++) {
-                                        const int lb = tx + 32 * q;
-                                        if (lb < nB && c[p][q] != 0.) S.C[ka][S.lstB[lb]] -= c[p][q];
+                            } else {
+                                // one row with more than RL_LOC bins of the window (fine model
+                                // grids): the products of its runs go to the window one by one
+                                for (int ka_ = 0; ka_ < nr; ka_++) {
+                                    const char *reca = rbase + (long long)ka_ * rsz;
+                                    const int2 ab = *reinterpret_cast<const int2 *>(reca);
+                                    const double *va = reinterpret_cast<const double *>(reca + (side == 0 ? 16 : 8));
+                                    const int ka = ab.x - ac;
+                                    if (ab.x < 0 || ka < 0 || ka >= UAc) continue;
+                                    const double qa = va[2], qb = va[3];
+                                    for (int k = lane; k < nr; k += 32) {
+                                        const char *rec = rbase + (long long)k * rsz;
+                                        const int2 ab2 = *reinterpret_cast<const int2 *>(rec);
+                                        const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
+                                        const int kb = ab2.y - kc;
+                                        if (ab2.y >= 0 && kb >= 0 && kb < Uc)
+                                            rl_sadd(&S.C[ka][kb], -(qa * v[0] * fa + qb * v[1] * fb3));
                                     }
                                 }
                             }
-                        } else {
-                            // more than 64 bins in a group of 16 rows (fine model grids): the
-                            // products of a row's runs go to the window one by one
-                            for (int ka_ = 0; ka_ < nr; ka_++) {
-                                int A, Bs;
-                                double qa, qb;
-                                if (side == 0) {
-                                    const RlRun1 *r = R1 + (long long)i * cap1 + ka_;
-                                    A = r->A; Bs = r->Bs; qa = r->q1; qb = r->q1d;
-                                } else {
-                                    const RlRun2 *r = R2 + (long long)i * cap2 + ka_;
-                                    A = r->A; Bs = r->Bs; qa = r->q2; qb = r->q2d;
-                                }
-                                if (!(Bs & RL_SEL)) continue;
-                                const int ka = aidx[A] - ac;
-                                if (ka < 0 || ka >= UAc) continue;
-                                for (int k = lane; k < nr; k += 32) {
-                                    int B2;
-                                    double ea, eb;
-                                    if (side == 0) {
-                                        const RlRun1 *r = R1 + (long long)i * cap1 + k;
-                                        B2 = r->Bs & ~RL_SEL; ea = r->e1; eb = r->e3;
-                                    } else {
-                                        const RlRun2 *r = R2 + (long long)i * cap2 + k;
-                                        B2 = r->Bs & ~RL_SEL; ea = r->e2; eb = r->e4;
-                                    }
-                                    const int kb = kidx[B2] - kc;
-                                    if (kb >= 0 && kb < Uc)
-                                        rl_sadd(&S.C[ka][kb], -(qa * ea * fa + qb * eb * fb3));
-                                }
-                            }
+                            r0 += rp;
                         }
                     }
                 }
