@@ -34,9 +34,9 @@
 #define RL_THREADS 512
 #define RL_WARPS 16
 #define RL_ROWS 16    // rows per contraction group = one per warp
-#define RL_LOC 64     // local bins of a group (data and model)
+#define RL_LOC 128    // local bins of a group (data and model): up to the whole window
 #define RL_W 128      // window of compact bins held in shared memory
-#define RL_VEC 384    // compact bins whose per-pair vectors live in shared memory
+#define RL_VEC 256    // compact bins whose per-pair vectors live in shared memory
 #define RL_SEL (1 << 30)
 
 struct RlRun1 {       // a run of the row sweep (pixel i of forest 1 against forest 2)
@@ -65,10 +65,11 @@ struct RlShared {
     int U, UA, nA, nB;
 };
 
-// thread (ty, tx) of the contraction owns the local data bins ty + 16 p (p < 4) and the local
-// model bins tx + 32 q (q < 2); a block row stores them contiguously per thread
-__device__ __forceinline__ int rl_xpos(int la) { return ((la & 15) << 2) | (la >> 4); }
-__device__ __forceinline__ int rl_ypos(int lb) { return ((lb & 31) << 1) | (lb >> 5); }
+// thread (ty, tx) of the contraction owns the local data bins ty + 16 p (p < 8) and the local
+// model bins tx + 32 q (q < 4); a block row stores them contiguously per thread.  A group of 16
+// rows touches ~43 bins (p90: 71, max ~105 at config 4), so p < 3, q < 2 is the common case.
+__device__ __forceinline__ int rl_xpos(int la) { return ((la & 15) << 3) | (la >> 4); }
+__device__ __forceinline__ int rl_ypos(int lb) { return ((lb & 31) << 2) | (lb >> 5); }
 
 struct RlPair {
     const double *rc1, *dm1, *z1, *w1, *f1z, *dl1;
@@ -441,136 +442,107 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                     const int nrows = side == 0 ? n1 : n2;
                     const int *nrun = side == 0 ? nrun1 : nrun2;
                     for (int g0 = 0; g0 < nrows; g0 += RL_ROWS) {
-                        // rows g0 + r0 .. g0 + r0 + rp - 1 (warp = row) form a block; a block whose
-                        // rows touch more than RL_LOC bins of the window is halved
-                        int r0 = 0, rp = RL_ROWS;
-                        while (r0 < RL_ROWS) {
-                            rp = min(rp, RL_ROWS - r0);
-                            __syncthreads();
-                            if (tid < RL_W) {
-                                S.flgA[tid] = 0;
-                                S.flgB[tid] = 0;
+                        __syncthreads();
+                        if (tid < RL_W) {
+                            S.flgA[tid] = 0;
+                            S.flgB[tid] = 0;
+                        }
+                        for (int x = tid; x < 2 * RL_ROWS * RL_LOC; x += RL_THREADS) {
+                            (&S.Xl[0][0][0])[x] = 0.;
+                            (&S.Yl[0][0][0])[x] = 0.;
+                        }
+                        __syncthreads();
+                        // -- the bins of the window this group touches (warp = row)
+                        const int i = g0 + warp;
+                        const int nr = i < nrows ? nrun[i] : 0;
+                        const char *rbase = side == 0 ? (const char *)(R1 + (long long)i * cap1)
+                                                      : (const char *)(R2 + (long long)i * cap2);
+                        const int rsz = side == 0 ? (int)sizeof(RlRun1) : (int)sizeof(RlRun2);
+                        for (int k = lane; k < nr; k += 32) {
+                            const int2 ab = *reinterpret_cast<const int2 *>(rbase + (long long)k * rsz);
+                            const int ka = ab.x - ac, kb = ab.y - kc;
+                            if (ab.y >= 0 && kb >= 0 && kb < Uc) S.flgB[kb] = 1;
+                            if (ab.x >= 0 && ka >= 0 && ka < UAc) S.flgA[ka] = 1;
+                        }
+                        __syncthreads();
+                        if (warp < 2) {   // local indices: warp 0 the data bins, warp 1 the model bins
+                            const unsigned char *flg = warp == 0 ? S.flgA : S.flgB;
+                            short *loc = warp == 0 ? S.locA : S.locB;
+                            short *lst = warp == 0 ? S.lstA : S.lstB;
+                            int u = 0;
+                            for (int xb = 0; xb < RL_W; xb += 32) {
+                                const bool on = flg[xb + lane] != 0;
+                                const unsigned m = __ballot_sync(0xffffffffu, on);
+                                const int k = u + __popc(m & ((1u << lane) - 1u));
+                                loc[xb + lane] = on ? (short)k : (short)-1;
+                                if (on) lst[k] = (short)(xb + lane);
+                                u += __popc(m);
                             }
-                            for (int x = tid; x < 2 * RL_ROWS * RL_LOC; x += RL_THREADS) {
-                                (&S.Xl[0][0][0])[x] = 0.;
-                                (&S.Yl[0][0][0])[x] = 0.;
+                            if (lane == 0) {
+                                if (warp == 0) S.nA = u; else S.nB = u;
                             }
-                            __syncthreads();
-                            // -- the bins of the window this block touches
-                            const int i = g0 + warp;
-                            const bool mine = warp >= r0 && warp < r0 + rp && i < nrows;
-                            const int nr = mine ? nrun[i] : 0;
-                            const char *rbase = side == 0 ? (const char *)(R1 + (long long)i * cap1)
-                                                          : (const char *)(R2 + (long long)i * cap2);
-                            const int rsz = side == 0 ? (int)sizeof(RlRun1) : (int)sizeof(RlRun2);
-                            for (int k = lane; k < nr; k += 32) {
-                                const int2 ab = *reinterpret_cast<const int2 *>(rbase + (long long)k * rsz);
-                                const int ka = ab.x - ac, kb = ab.y - kc;
-                                if (ab.y >= 0 && kb >= 0 && kb < Uc) S.flgB[kb] = 1;
-                                if (ab.x >= 0 && ka >= 0 && ka < UAc) S.flgA[ka] = 1;
+                        }
+                        __syncthreads();
+                        const int nA = S.nA, nB = S.nB;
+                        if (nA == 0 || nB == 0) continue;
+                        // normalisations of the eta rows (cf.py:767-813)
+                        const double fa = side == 0 ? 1. / D.sw2 : 1. / D.sw1;
+                        const double fb3 = side == 0 ? (D.order2 == 1 ? 1. / D.swsll2 : 0.)
+                                                     : (D.order1 == 1 ? 1. / D.swsll1 : 0.);
+                        // -- expand the runs of the group
+                        for (int k = lane; k < nr; k += 32) {
+                            const char *rec = rbase + (long long)k * rsz;
+                            const int2 ab = *reinterpret_cast<const int2 *>(rec);
+                            const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
+                            const int ka = ab.x - ac, kb = ab.y - kc;
+                            if (ab.y >= 0 && kb >= 0 && kb < Uc) {
+                                const int p = rl_ypos(S.locB[kb]);
+                                rl_sadd(&S.Yl[0][warp][p], v[0] * fa);
+                                if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], v[1] * fb3);
                             }
-                            __syncthreads();
-                            if (warp < 2) {   // local indices: warp 0 the data bins, warp 1 the model bins
-                                const unsigned char *flg = warp == 0 ? S.flgA : S.flgB;
-                                short *loc = warp == 0 ? S.locA : S.locB;
-                                short *lst = warp == 0 ? S.lstA : S.lstB;
-                                int u = 0;
-                                for (int xb = 0; xb < RL_W; xb += 32) {
-                                    const bool on = flg[xb + lane] != 0;
-                                    const unsigned m = __ballot_sync(0xffffffffu, on);
-                                    const int k = u + __popc(m & ((1u << lane) - 1u));
-                                    loc[xb + lane] = on ? (short)k : (short)-1;
-                                    if (on && k < RL_LOC) lst[k] = (short)(xb + lane);
-                                    u += __popc(m);
-                                }
-                                if (lane == 0) {
-                                    if (warp == 0) S.nA = u; else S.nB = u;
-                                }
+                            if (ab.x >= 0 && ka >= 0 && ka < UAc) {
+                                const int p = rl_xpos(S.locA[ka]);
+                                rl_sadd(&S.Xl[0][warp][p], v[2]);
+                                rl_sadd(&S.Xl[1][warp][p], v[3]);
                             }
-                            __syncthreads();
-                            const int nA = S.nA, nB = S.nB;
-                            if (nA == 0 || nB == 0) {
-                                r0 += rp;
-                                continue;
-                            }
-                            if ((nA > RL_LOC || nB > RL_LOC) && rp > 1) {
-                                rp >>= 1;   // too many bins for the local tile: fewer rows
-                                continue;
-                            }
-                            // normalisations of the eta rows (cf.py:767-813)
-                            const double fa = side == 0 ? 1. / D.sw2 : 1. / D.sw1;
-                            const double fb3 = side == 0 ? (D.order2 == 1 ? 1. / D.swsll2 : 0.)
-                                                         : (D.order1 == 1 ? 1. / D.swsll1 : 0.);
-                            if (nA <= RL_LOC && nB <= RL_LOC) {
-                                // -- expand the runs of the block
-                                for (int k = lane; k < nr; k += 32) {
-                                    const char *rec = rbase + (long long)k * rsz;
-                                    const int2 ab = *reinterpret_cast<const int2 *>(rec);
-                                    const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
-                                    const int ka = ab.x - ac, kb = ab.y - kc;
-                                    if (ab.y >= 0 && kb >= 0 && kb < Uc) {
-                                        const int p = rl_ypos(S.locB[kb]);
-                                        rl_sadd(&S.Yl[0][warp][p], v[0] * fa);
-                                        if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], v[1] * fb3);
-                                    }
-                                    if (ab.x >= 0 && ka >= 0 && ka < UAc) {
-                                        const int p = rl_xpos(S.locA[ka]);
-                                        rl_sadd(&S.Xl[0][warp][p], v[2]);
-                                        rl_sadd(&S.Xl[1][warp][p], v[3]);
-                                    }
-                                }
-                                __syncthreads();
-                                // -- rank-(2 rp) update of the 64 x 64 register tile, added into the window
-                                if (ty < nA && tx < nB) {
-                                    double c[4][2];
+                        }
+                        __syncthreads();
+                        // -- rank-32 update of the local tile in registers, added into the window
+                        const int np_ = ty < nA ? (nA - ty + 15) >> 4 : 0;   // local data bins ty + 16 p
+                        const int nq_ = tx < nB ? (nB - tx + 31) >> 5 : 0;   // local model bins tx + 32 q
+                        if (np_ > 0 && nq_ > 0) {
+                            double c[8][4];
 #pragma unroll
-                                    for (int p = 0; p < 4; p++) c[p][0] = c[p][1] = 0.;
-                                    for (int r = r0; r < r0 + rp; r++) {
+                            for (int p = 0; p < 8; p++)
 #pragma unroll
-                                        for (int kind = 0; kind < 2; kind++) {
-                                            const double4 xv = *reinterpret_cast<const double4 *>(&S.Xl[kind][r][ty * 4]);
-                                            const double2 yv = *reinterpret_cast<const double2 *>(&S.Yl[kind][r][tx * 2]);
-                                            const double x[4] = {xv.x, xv.y, xv.z, xv.w};
+                                for (int q = 0; q < 4; q++) c[p][q] = 0.;
+                            const int nqw = (nB + 31) >> 5;   // warp-uniform bound of q
+#pragma unroll 2
+                            for (int r = 0; r < RL_ROWS; r++) {
 #pragma unroll
-                                            for (int p = 0; p < 4; p++) {
-                                                c[p][0] = fma(x[p], yv.x, c[p][0]);
-                                                c[p][1] = fma(x[p], yv.y, c[p][1]);
-                                            }
-                                        }
-                                    }
+                                for (int kind = 0; kind < 2; kind++) {
+                                    const double4 ya = *reinterpret_cast<const double4 *>(&S.Yl[kind][r][tx * 4]);
+                                    const double y[4] = {ya.x, ya.y, ya.z, ya.w};
+                                    const double *xr = &S.Xl[kind][r][ty * 8];
 #pragma unroll
-                                    for (int p = 0; p < 4; p++) {
-                                        const int la = ty + 16 * p;
-                                        if (la >= nA) continue;
-                                        const int ka = S.lstA[la];
+                                    for (int p = 0; p < 8; p++) {
+                                        if (p < np_) {
+                                            const double x = xr[p];
 #pragma unroll
-                                        for (int q = 0; q < 2; q++) {
-                                            const int lb = tx + 32 * q;
-                                            if (lb < nB && c[p][q] != 0.) S.C[ka][S.lstB[lb]] -= c[p][q];
+                                            for (int q = 0; q < 4; q++)
+                                                if (q < nqw) c[p][q] = fma(x, y[q], c[p][q]);
                                         }
                                     }
                                 }
-                            } else {
-                                // one row with more than RL_LOC bins of the window (fine model
-                                // grids): the products of its runs go to the window one by one
-                                for (int ka_ = 0; ka_ < nr; ka_++) {
-                                    const char *reca = rbase + (long long)ka_ * rsz;
-                                    const int2 ab = *reinterpret_cast<const int2 *>(reca);
-                                    const double *va = reinterpret_cast<const double *>(reca + (side == 0 ? 16 : 8));
-                                    const int ka = ab.x - ac;
-                                    if (ab.x < 0 || ka < 0 || ka >= UAc) continue;
-                                    const double qa = va[2], qb = va[3];
-                                    for (int k = lane; k < nr; k += 32) {
-                                        const char *rec = rbase + (long long)k * rsz;
-                                        const int2 ab2 = *reinterpret_cast<const int2 *>(rec);
-                                        const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
-                                        const int kb = ab2.y - kc;
-                                        if (ab2.y >= 0 && kb >= 0 && kb < Uc)
-                                            rl_sadd(&S.C[ka][kb], -(qa * v[0] * fa + qb * v[1] * fb3));
-                                    }
-                                }
                             }
-                            r0 += rp;
+#pragma unroll
+                            for (int p = 0; p < 8; p++) {
+                                if (p >= np_) continue;
+                                const int ka = S.lstA[ty + 16 * p];
+#pragma unroll
+                                for (int q = 0; q < 4; q++)
+                                    if (q < nq_ && c[p][q] != 0.) S.C[ka][S.lstB[tx + 32 * q]] -= c[p][q];
+                            }
                         }
                     }
                 }
