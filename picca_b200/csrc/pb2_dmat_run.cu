@@ -188,6 +188,57 @@ __device__ __forceinline__ void rl_sweep(const pb2_params &P, const DmatFast &F,
     }
 }
 
+// rank-(2 RL_ROWS) update of the local tile: thread (ty, tx) accumulates the local data bins
+// ty + 16 p (p < np_w) x the local model bins tx + 32 q (q < NQ) over the rows of the group and
+// subtracts the result from the window.  NQ is a template parameter and np_w warp-uniform: real
+// branches, no predicated multiplications by zero.
+template <int NQ>
+__device__ __forceinline__ void rl_rank_update(RlShared &S, int np_w, int nA, int nB)
+{
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    double c[8][NQ];
+#pragma unroll
+    for (int p = 0; p < 8; p++)
+#pragma unroll
+        for (int q = 0; q < NQ; q++) c[p][q] = 0.;
+#pragma unroll 2
+    for (int r = 0; r < RL_ROWS; r++) {
+#pragma unroll
+        for (int kind = 0; kind < 2; kind++) {
+            double y[NQ];
+            if (NQ >= 3) {
+                const double4 ya = *reinterpret_cast<const double4 *>(&S.Yl[kind][r][tx * 4]);
+                y[0] = ya.x; y[1] = ya.y; y[2] = ya.z;
+                if (NQ == 4) y[NQ - 1] = ya.w;
+            } else {
+                const double2 ya = *reinterpret_cast<const double2 *>(&S.Yl[kind][r][tx * 4]);
+                y[0] = ya.x;
+                if (NQ == 2) y[NQ - 1] = ya.y;
+            }
+            const double *xr = &S.Xl[kind][r][ty * 8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                if (p >= np_w) break;
+                const double x = xr[p];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) c[p][q] = fma(x, y[q], c[p][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        if (p >= np_w) break;
+        const int la = ty + 16 * p;
+        if (la >= nA) continue;
+        const int ka = S.lstA[la];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int lb = tx + 32 * q;
+            if (lb < nB && c[p][q] != 0.) S.C[ka][S.lstB[lb]] -= c[p][q];
+        }
+    }
+}
+
 // double-precision add into shared memory (compare-and-swap; used where many threads issue
 // independent adds, so the latency of the loop is hidden)
 __device__ __forceinline__ void rl_sadd(double *p, double v) { atomicAdd(p, v); }
@@ -458,7 +509,24 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                         const char *rbase = side == 0 ? (const char *)(R1 + (long long)i * cap1)
                                                       : (const char *)(R2 + (long long)i * cap2);
                         const int rsz = side == 0 ? (int)sizeof(RlRun1) : (int)sizeof(RlRun2);
-                        for (int k = lane; k < nr; k += 32) {
+                        // (the first 64 runs of the row stay in registers for the expansion below)
+                        int2 cab[2];
+                        double cv[2][4];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int k = lane + 32 * h;
+                            cab[h] = make_int2(-1, -1);
+                            if (k < nr) {
+                                const char *rec = rbase + (long long)k * rsz;
+                                cab[h] = *reinterpret_cast<const int2 *>(rec);
+                                const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
+                                cv[h][0] = v[0]; cv[h][1] = v[1]; cv[h][2] = v[2]; cv[h][3] = v[3];
+                                const int ka = cab[h].x - ac, kb = cab[h].y - kc;
+                                if (cab[h].y >= 0 && kb >= 0 && kb < Uc) S.flgB[kb] = 1;
+                                if (cab[h].x >= 0 && ka >= 0 && ka < UAc) S.flgA[ka] = 1;
+                            }
+                        }
+                        for (int k = lane + 64; k < nr; k += 32) {
                             const int2 ab = *reinterpret_cast<const int2 *>(rbase + (long long)k * rsz);
                             const int ka = ab.x - ac, kb = ab.y - kc;
                             if (ab.y >= 0 && kb >= 0 && kb < Uc) S.flgB[kb] = 1;
@@ -490,7 +558,22 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                         const double fb3 = side == 0 ? (D.order2 == 1 ? 1. / D.swsll2 : 0.)
                                                      : (D.order1 == 1 ? 1. / D.swsll1 : 0.);
                         // -- expand the runs of the group
-                        for (int k = lane; k < nr; k += 32) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int2 ab = cab[h];
+                            const int ka = ab.x - ac, kb = ab.y - kc;
+                            if (ab.y >= 0 && kb >= 0 && kb < Uc) {
+                                const int p = rl_ypos(S.locB[kb]);
+                                rl_sadd(&S.Yl[0][warp][p], cv[h][0] * fa);
+                                if (fb3 != 0.) rl_sadd(&S.Yl[1][warp][p], cv[h][1] * fb3);
+                            }
+                            if (ab.x >= 0 && ka >= 0 && ka < UAc) {
+                                const int p = rl_xpos(S.locA[ka]);
+                                rl_sadd(&S.Xl[0][warp][p], cv[h][2]);
+                                rl_sadd(&S.Xl[1][warp][p], cv[h][3]);
+                            }
+                        }
+                        for (int k = lane + 64; k < nr; k += 32) {
                             const char *rec = rbase + (long long)k * rsz;
                             const int2 ab = *reinterpret_cast<const int2 *>(rec);
                             const double *v = reinterpret_cast<const double *>(rec + (side == 0 ? 16 : 8));
@@ -508,40 +591,13 @@ pb2_dmat_auto_run_kernel(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs
                         }
                         __syncthreads();
                         // -- rank-32 update of the local tile in registers, added into the window
-                        const int np_ = ty < nA ? (nA - ty + 15) >> 4 : 0;   // local data bins ty + 16 p
-                        const int nq_ = tx < nB ? (nB - tx + 31) >> 5 : 0;   // local model bins tx + 32 q
-                        if (np_ > 0 && nq_ > 0) {
-                            double c[8][4];
-#pragma unroll
-                            for (int p = 0; p < 8; p++)
-#pragma unroll
-                                for (int q = 0; q < 4; q++) c[p][q] = 0.;
-                            const int nqw = (nB + 31) >> 5;   // warp-uniform bound of q
-#pragma unroll 2
-                            for (int r = 0; r < RL_ROWS; r++) {
-#pragma unroll
-                                for (int kind = 0; kind < 2; kind++) {
-                                    const double4 ya = *reinterpret_cast<const double4 *>(&S.Yl[kind][r][tx * 4]);
-                                    const double y[4] = {ya.x, ya.y, ya.z, ya.w};
-                                    const double *xr = &S.Xl[kind][r][ty * 8];
-#pragma unroll
-                                    for (int p = 0; p < 8; p++) {
-                                        if (p < np_) {
-                                            const double x = xr[p];
-#pragma unroll
-                                            for (int q = 0; q < 4; q++)
-                                                if (q < nqw) c[p][q] = fma(x, y[q], c[p][q]);
-                                        }
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int p = 0; p < 8; p++) {
-                                if (p >= np_) continue;
-                                const int ka = S.lstA[ty + 16 * p];
-#pragma unroll
-                                for (int q = 0; q < 4; q++)
-                                    if (q < nq_ && c[p][q] != 0.) S.C[ka][S.lstB[tx + 32 * q]] -= c[p][q];
+                        {
+                            const int np_w = (nA + 15) >> 4, nq_w = (nB + 31) >> 5;
+                            if (ty < nA) {
+                                if (nq_w == 1) rl_rank_update<1>(S, np_w, nA, nB);
+                                else if (nq_w == 2) rl_rank_update<2>(S, np_w, nA, nB);
+                                else if (nq_w == 3) rl_rank_update<3>(S, np_w, nA, nB);
+                                else rl_rank_update<4>(S, np_w, nA, nB);
                             }
                         }
                     }
