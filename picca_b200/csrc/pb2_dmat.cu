@@ -706,22 +706,19 @@ int32_t pb2_launch_dmat_run(const pb2_catalog *cat1, const pb2_catalog *cat2, co
 
 // Two kernels compute the auto / delta x delta distortion matrix (same results to 1e-9; the GPU
 // tests run both):
-//   dense  pb2_dmat_auto_kernel (this file): per-CTA X / Y scratch in global memory + 64x64
-//          register-tiled contraction with tile skipping.  The faster one at config 4 (8.7e4 used
-//          forest pairs/s against 3.6e4, profiles/r02_dmat_run_v1_*): default.
-//   run    pb2_dmat_auto_run_kernel (pb2_dmat_run.cu): run lengths + prefix sums, row blocks in
-//          shared memory, register tile; no global scratch traffic (0.25 GB of DRAM traffic per
-//          launch instead of 76 GB) and the ONLY one that reproduces the reference's truncated
-//          np.unique, so it is the one used whenever
-//          remove_same_half_plate_close_pairs is set.  r-mu binning: dense only (the sums of a
-//          run do not factorise).
+//   run    pb2_dmat_auto_run_kernel (pb2_dmat_run.cu): run lists + local register tiles; every
+//          pixel pair evaluated twice, no dense scratch, and the reference's truncated np.unique
+//           reproduced.  Default.
+//   dense  pb2_dmat_auto_kernel (this file): per-CTA dense X / Y scratch in global memory + 64x64
+//          register-tiled contraction with tile skipping (the round-1 kernel).  Kept for r-mu
+//          binning (a run's sums are still exact there, but it is the validated path) and as the
+//          cross-check of the run kernel.
 // PB2_DMAT_KERNEL=run|dense forces one of them (A/B measurements, cross-checks).
 static bool use_run_kernel(const pb2_params *par)
 {
     if (par->rmu_binning) return false;
     const char *force = getenv("PB2_DMAT_KERNEL");
     if (force && force[0] == 'd') return false;
-    if (!(force && force[0] == 'r') && !par->remove_same_half_plate_close_pairs) return false;
     const long long nb = (long long)par->num_bins_r_par * par->num_bins_r_trans;
     const long long nbm = (long long)par->num_model_bins_r_par * par->num_model_bins_r_trans;
     return nb < (1 << 24) && nbm < (1 << 24);   // run keys pack both bins in 24 bits each

@@ -115,17 +115,28 @@ __device__ __forceinline__ void rl_sweep(const pb2_params &P, const DmatFast &F,
         // (a warp-uniform number of iterations with a __syncwarp() on top: the rows of a warp have
         // different windows and flush points and would otherwise run the loop a few lanes at a time)
         const int len = hi - lo + 1, maxlen = warp_max(len);
+        // the swept pixel of the NEXT step is loaded one step ahead (the loop is latency-bound at
+        // 16 warps per SM: without it every step waits for its own loads)
+        const int last = ns - 1;
+        double n_rc = rcs[min(lo, last)], n_dm = dms[min(lo, last)], n_w = ws[min(lo, last)];
         for (int t = 0; t < maxlen; t++) {
             __syncwarp();
             if (t >= len) continue;
             const int s = lo + t;
+            const double s_rc = n_rc, s_dm = n_dm, s_w = n_w;
+            {
+                const int sn = min(s + 1, last);
+                n_rc = rcs[sn];
+                n_dm = dms[sn];
+                n_w = ws[sn];
+            }
             DmatGeom g;
             g.in = false;
             bool sel = false;
             double z = 0.;
-            if (s < hi && ws[s] != 0.) {
-                g = ROW ? dmat_pair(P, F, rc_f, dm_f, rcs[s], dms[s], D.ch, D.sh, false, D.shp)
-                        : dmat_pair(P, F, rcs[s], dms[s], rc_f, dm_f, D.ch, D.sh, false, D.shp);
+            if (s < hi && s_w != 0.) {
+                g = ROW ? dmat_pair(P, F, rc_f, dm_f, s_rc, s_dm, D.ch, D.sh, false, D.shp)
+                        : dmat_pair(P, F, s_rc, s_dm, rc_f, dm_f, D.ch, D.sh, false, D.shp);
                 if (g.in) {
                     z = div_rn(add_rn(z_f, zs[s]), 2.);
                     sel = f_sel && !g.close;
@@ -164,7 +175,7 @@ __device__ __forceinline__ void rl_sweep(const pb2_params &P, const DmatFast &F,
             cB = g.B;
             cS = sel;
             cn++;
-            const double wj = ws[s], dlj = dls[s];
+            const double wj = s_w, dlj = dls[s];
             const double zf = mul_rn(fz_f, fzs[s]);
             ea += zf * wj;            // cf.py:767 / :771
             eb += zf * wj * dlj;      // cf.py:782-787 / :808-813
