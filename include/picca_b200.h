@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 22
+#define PB2_ABI_VERSION 23
 
 /* layout constants of the packed copies read by the diagonal-lane xi kernel */
 #ifndef PB2_DIAG_LANES
@@ -191,6 +191,15 @@ int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2
 /* ---- per-pixel products of the packed catalogue, formed in HBM when the host deferred them
  * (catalog.pack(defer_products=True)): delta_w = Delta.delta * Delta.weights -- the product the
  * reference forms first, cf.py:367-368 -- set to 0 where the weight is 0, and z_w = z * weights. */
+/* ---- one pass over the packed SoA in HBM for what catalog.pack otherwise computes with ~12 NumPy
+ * passes on the host: d_count[f] = pixels of line of sight f with a non-zero weight (the reference
+ * never visits the others, cf.py:318,331); d_flags[0] != 0: a kept pixel is not finite;
+ * d_flags[1] != 0: r_comov or dist_m decreases inside a line of sight (or is not finite);
+ * d_flags[2]: bit pattern of max(|r_comov|, |dist_m|) over the kept pixels.  d_flags zeroed by the
+ * caller. */
+int32_t pb2_catalog_stats(int64_t n_los, const int64_t *d_offset, const double *d_weights,
+                          const double *d_r_comov, const double *d_dist_m, const double *d_z,
+                          const double *d_delta_w, int32_t *d_count, int64_t *d_flags, void *stream);
 int32_t pb2_derive_products(int64_t n_pix, const double *d_weights, const double *d_delta,
                             const double *d_z, double *d_delta_w, double *d_z_w, void *stream);
 

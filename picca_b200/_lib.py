@@ -112,7 +112,7 @@ class Pairs(ctypes.Structure):
 EXPORTS = [
     "pb2_abi_version", "pb2_last_error", "pb2_sizeof_params", "pb2_sizeof_catalog",
     "pb2_sizeof_pairs", "pb2_diag_lanes", "pb2_neigh_count", "pb2_neigh_fill", "pb2_xi_auto", "pb2_xi_cross",
-    "pb2_pack_diag", "pb2_derive_products", "pb2_build_prefix", "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross", "pb2_dmat_stats",
+    "pb2_pack_diag", "pb2_catalog_stats", "pb2_derive_products", "pb2_build_prefix", "pb2_xi_normalise", "pb2_dmat_scratch_bytes", "pb2_dmat_auto", "pb2_dmat_cross", "pb2_dmat_stats",
     "pb2_metal_dmat_auto", "pb2_metal_dmat_cross", "pb2_wick_scratch_bytes", "pb2_wick_auto",
     "pb2_wick_cross", "pb2_co_pairs", "pb2_cov_scratch_bytes", "pb2_cov_subsample", "pb2_cov_smooth",
     "pb2_cov_boot_scratch_bytes", "pb2_cov_boot",
@@ -122,7 +122,7 @@ EXPORTS = [
     "pb2_fp64_peak", "pb2_launch_count", "pb2_set_timing", "pb2_last_kernel_ms",
 ]
 
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 
 def lib():

@@ -34,6 +34,7 @@ class HostCatalog:
         self.max_pix = 0
         self.ids_are_int = True
         self.thingid_remapped = False
+        self.meta_deferred = False   # diag metadata / sorted flag still to come from the device
         self.from_soa = False     # packed straight from a registered SoA (forest.register_soa)
         self.is_object = False
         self.il_total = 0         # diagonal-lane copies (see _diag_metadata)
@@ -76,9 +77,10 @@ def _diag_metadata(cat, offset):
     """Geometry of the packed copies the diagonal-lane xi kernel reads (layout:
     include/picca_b200.h, pb2_catalog): per-forest counts of non-zero-weight pixels, record
     offsets of the natural-order and of the interleaved copy, totals, and the flags the launcher
-    checks.  The records themselves are written on the device (``pb2_pack_diag``)."""
+    checks.  The records themselves are written on the device (``pb2_pack_diag``).  Host version
+    (``pack`` without ``defer_products``); the product path takes the counts and flags from one
+    pass over the SoA in HBM instead (``pb2_catalog_stats``, DeviceCatalog._finish)."""
     A = cat.arrays
-    lanes, pad, row_pad, chunk = diag_layout()
     n = cat.n_los
     keep = A["weights"] != 0
     if n and keep.size:
@@ -88,6 +90,27 @@ def _diag_metadata(cat, offset):
         count[np.diff(offset) == 0] = 0
     else:
         count = np.zeros(n, np.int64)
+    _diag_layout(cat, count)
+    fields = ("r_comov", "dist_m", "weights", "delta_w" if "delta_w" in A else "delta", "z")
+    # a sum is finite iff every term is (no overflow at these magnitudes): one pass per field,
+    # the masked test only when a zero-weight pixel carries the non-finite value
+    # (a deferred delta * weights is finite when both factors are, far from overflow)
+    finite = all(bool(np.isfinite(A[name].sum())) or bool(np.all(np.isfinite(A[name][keep])))
+                 for name in fields)
+    cat.dg_ok = int(finite)
+    if keep.any() and finite:
+        cat.dg_reach = float(max(np.abs(A["r_comov"][keep]).max(),
+                                 np.abs(A["dist_m"][keep]).max()))
+    else:
+        cat.dg_reach = 0.0
+
+
+def _diag_layout(cat, count):
+    """Record offsets and totals of the two packed copies from the per-forest counts."""
+    A = cat.arrays
+    lanes, pad, row_pad, chunk = diag_layout()
+    n = cat.n_los
+    count = np.asarray(count, dtype=np.int64)
     first = np.zeros(n + 1, dtype=np.int64)
     first[1:] = np.cumsum(count)
     A["dg_offset"] = np.ascontiguousarray(first[:-1] + row_pad * np.arange(n, dtype=np.int64))
@@ -100,24 +123,6 @@ def _diag_metadata(cat, offset):
     cat.il_total = int(il_offset[-1]) + chunk + 64
     cat.dg_lanes = lanes
     cat.dg_max_pix = int(count.max()) if n else 0
-    fields = ("r_comov", "dist_m", "weights", "delta_w" if "delta_w" in A else "delta", "z")
-    # a sum is finite iff every term is (no overflow at these magnitudes): one pass per field,
-    # the masked test only when a zero-weight pixel carries the non-finite value
-    # (a deferred delta * weights is finite when both factors are, far from overflow)
-    finite = all(bool(np.isfinite(A[name].sum())) or bool(np.all(np.isfinite(A[name][keep])))
-                 for name in fields)
-    cat.dg_ok = int(finite)
-    if keep.any() and finite:
-        if np.isfinite(A["r_comov"].sum()) and np.isfinite(A["dist_m"].sum()):
-            # over all pixels: an upper bound of the reach of the kept ones (conservative: the
-            # launcher only uses it to rule the low-word bin arithmetic out)
-            cat.dg_reach = float(max(-A["r_comov"].min(), A["r_comov"].max(),
-                                     -A["dist_m"].min(), A["dist_m"].max()))
-        else:
-            cat.dg_reach = float(max(np.abs(A["r_comov"][keep]).max(),
-                                     np.abs(A["dist_m"][keep]).max()))
-    else:
-        cat.dg_reach = 0.0
 
 
 def diag_records_host(cat):
@@ -283,12 +288,16 @@ def pack(data, is_object=False, ang_correlation=False, defer_products=False, row
     lengths = np.diff(offset)
     cat.max_pix = int(lengths.max()) if n else 0
 
-    if not is_object:
+    # deferred: the counts of non-zero weights, the finiteness / sortedness flags and the reach
+    # come from ONE pass over the SoA once it is in HBM (pb2_catalog_stats) instead of ~12 NumPy
+    # passes here
+    cat.meta_deferred = bool(defer_products and not is_object and n > 0)
+    if not is_object and not cat.meta_deferred:
         _diag_metadata(cat, offset)
 
     # sortedness inside each forest (enables the column windows of the pair kernel)
     cat.sorted = 1
-    if not is_object and cat.n_pix > 1:
+    if not is_object and cat.n_pix > 1 and not cat.meta_deferred:
         inner = np.ones(cat.n_pix - 1, dtype=bool)
         inner[offset[1:-1][(offset[1:-1] > 0) & (offset[1:-1] < cat.n_pix)] - 1] = False
         for name in ("r_comov", "dist_m"):
@@ -391,6 +400,28 @@ class DeviceCatalog:
                     ctypes.c_int64(host.n_pix), ptr(tensors["weights"]), ptr(delta),
                     ptr(tensors["z"]), ptr(tensors["delta_w"]), ptr(tensors["z_w"]), stream),
                     "pb2_derive_products")
+        if getattr(host, "meta_deferred", False):
+            # one pass over the SoA in HBM: non-zero-weight pixels per forest, finiteness,
+            # sortedness, reach; the host turns the counts into the record offsets
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+            d_count = torch.zeros(host.n_los, dtype=torch.int32, device=device)
+            d_flags = torch.zeros(4, dtype=torch.int64, device=device)
+            _lib.check(_lib.lib().pb2_catalog_stats(
+                ctypes.c_int64(host.n_los), ptr(tensors["offset"]), ptr(tensors["weights"]),
+                ptr(tensors["r_comov"]), ptr(tensors["dist_m"]), ptr(tensors["z"]),
+                ptr(tensors["delta_w"]), ptr(d_count), ptr(d_flags), stream), "pb2_catalog_stats")
+            flags = d_flags.cpu().numpy()
+            _diag_layout(host, d_count.cpu().numpy())
+            host.dg_ok = int(flags[0] == 0)
+            host.sorted = int(flags[1] == 0)
+            host.dg_reach = float(flags[2:3].view(np.float64)[0]) if host.dg_ok else 0.0
+            host.meta_deferred = False
+            for name in ("dg_offset", "dg_count", "il_offset"):
+                tensors[name] = torch.from_numpy(host.arrays[name]).to(device)
+        else:
+            for name in ("dg_offset", "dg_count", "il_offset"):
+                if name in host.arrays and name not in tensors:
+                    tensors[name] = torch.from_numpy(host.arrays[name]).to(device)
         if not host.is_object and host.n_los:
             tensors["dg_rec"] = torch.empty(6 * host.dg_total, dtype=torch.float64, device=device)
             tensors["il_rec"] = torch.empty(6 * host.dg_lanes * host.il_total, dtype=torch.float64,

@@ -68,7 +68,68 @@ __global__ void pb2_derive_products_kernel(long long n, const double *__restrict
     z_w[i] = mul_rn(z[i], wi);
 }
 
+// One warp per forest: count of non-zero-weight pixels; flags[0] != 0 when a kept pixel carries a
+// non-finite r_comov / dist_m / weight / delta*weight / z, flags[1] != 0 when r_comov or dist_m
+// decreases inside a forest or is not finite anywhere; flags[2] = bit pattern of
+// max(|r_comov|, |dist_m|) over the kept pixels (non-negative doubles order like integers).
+__global__ void pb2_catalog_stats_kernel(long long n_los, const long long *__restrict__ offset,
+                                         const double *__restrict__ w, const double *__restrict__ rc,
+                                         const double *__restrict__ dm, const double *__restrict__ z,
+                                         const double *__restrict__ dw, int *__restrict__ count,
+                                         unsigned long long *__restrict__ flags)
+{
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= n_los) return;
+    const int lane = threadIdx.x & 31;
+    const long long a = offset[f];
+    const int n = (int)(offset[f + 1] - a);
+    int cnt = 0;
+    bool bad = false, unsorted = false;
+    double reach = 0.;
+    for (int p = lane; p < n; p += 32) {
+        const double wi = w[a + p], r = rc[a + p], d = dm[a + p];
+        if (!isfinite(r) || !isfinite(d)) unsorted = true;
+        if (p + 1 < n && (rc[a + p + 1] < r || dm[a + p + 1] < d)) unsorted = true;
+        if (wi != 0.) {
+            cnt++;
+            if (!isfinite(r) || !isfinite(d) || !isfinite(wi) || !isfinite(dw[a + p]) ||
+                !isfinite(z[a + p])) bad = true;
+            reach = fmax(reach, fmax(fabs(r), fabs(d)));
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+        reach = fmax(reach, __shfl_xor_sync(0xffffffffu, reach, m));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    unsorted = __any_sync(0xffffffffu, unsorted);
+    if (lane == 0) {
+        count[f] = cnt;
+        if (bad) atomicOr(flags, 1ull);
+        if (unsorted) atomicOr(flags + 1, 1ull);
+        if (isfinite(reach)) atomicMax(flags + 2, (unsigned long long)__double_as_longlong(reach));
+    }
+}
+
 extern "C" {
+
+int32_t pb2_catalog_stats(int64_t n_los, const int64_t *d_offset, const double *d_weights,
+                          const double *d_r_comov, const double *d_dist_m, const double *d_z,
+                          const double *d_delta_w, int32_t *d_count, int64_t *d_flags, void *stream)
+{
+    if (n_los < 0 || (n_los > 0 && (!d_offset || !d_weights || !d_r_comov || !d_dist_m || !d_z ||
+                                    !d_delta_w || !d_count || !d_flags))) {
+        pb2_set_error("pb2_catalog_stats: bad argument");
+        return PB2_EINVAL;
+    }
+    if (n_los == 0) return 0;
+    pb2_catalog_stats_kernel<<<(unsigned)((n_los + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        n_los, (const long long *)d_offset, d_weights, d_r_comov, d_dist_m, d_z, d_delta_w, d_count,
+        (unsigned long long *)d_flags);
+    pb2_count_launch(1);
+    return pb2_check_launch("pb2_catalog_stats_kernel");
+}
 
 int32_t pb2_derive_products(int64_t n_pix, const double *d_weights, const double *d_delta,
                             const double *d_z, double *d_delta_w, double *d_z_w, void *stream)

@@ -205,3 +205,39 @@ def test_string_ids_across_two_catalogues(base):
         total += int(want[5].sum())
     assert total > 0
     cf.data2 = ocf.data2 = None
+
+
+@pytest.mark.parametrize("spoil", ["none", "unsorted", "nan_kept", "nan_zero_weight"])
+def test_deferred_pack_equals_host_pack(base, spoil):
+    """The product path leaves delta*weights, z*weights, the counts of non-zero weights and the
+    finiteness / sortedness / reach flags to the device (pb2_derive_products, pb2_catalog_stats):
+    same arrays, same layout, same flags as the NumPy packing."""
+    from picca_b200 import catalog
+    from picca_b200.engine import get_engine
+    data, num, ang_max = base
+    hp = sorted(data)[1]
+    d = data[hp][0]
+    if spoil == "unsorted":
+        d.r_comov = d.r_comov[::-1].copy()
+    elif spoil == "nan_kept":
+        d.delta = d.delta.copy()
+        d.delta[np.nonzero(d.weights)[0][0]] = np.nan
+    elif spoil == "nan_zero_weight":
+        d.weights = d.weights.copy()
+        d.delta = d.delta.copy()
+        d.weights[3] = 0.
+        d.delta[3] = np.nan
+    want = catalog.pack(data)
+    got = catalog.pack(data, defer_products=True)
+    assert got.meta_deferred and "delta_w" not in got.arrays
+    dev = get_engine().device_catalog(got, cache=False)
+    assert not got.meta_deferred
+    for name in ("dg_offset", "dg_count", "il_offset"):
+        assert np.array_equal(got.arrays[name], want.arrays[name]), name
+    for attr in ("dg_total", "il_total", "dg_max_pix", "dg_ok", "sorted", "dg_lanes"):
+        assert getattr(got, attr) == getattr(want, attr), attr
+    assert got.dg_reach == want.dg_reach
+    for name in ("delta_w", "z_w"):
+        assert np.array_equal(dev.tensors[name].cpu().numpy(), want.arrays[name]), name
+    assert (want.sorted, want.dg_ok) == {"none": (1, 1), "unsorted": (0, 1), "nan_kept": (1, 0),
+                                         "nan_zero_weight": (1, 1)}[spoil]
