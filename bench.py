@@ -725,7 +725,8 @@ def run_cuda(args):
                        "l2_policy": "inputs (%.2f GB in HBM) larger than L2"
                                     % (eng.device_catalog(host).device_bytes() / 1e9),
                        "parallelism": "healpix LPT shards x%d, gather to rank 0" % world},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": e2e_value, "unit": "pairs/s",
+                    "h2d_bytes_per_step": e2e_detail.get("h2d_bytes_rank0", h2d),
                     "d2h_bytes_per_step": int(n_rows * 6 * nb * 8), "steps": args.e2e_steps,
                     **e2e_detail},
             "gpu_launches": int(launches),

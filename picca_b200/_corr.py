@@ -43,6 +43,16 @@ class LazyNeighbours:
         return [self._objs2[q] for q in idx]
 
 
+def set_neighbours(obj, value):
+    """``obj.neighbours = value`` without going through a Python-level ``__setattr__`` (the
+    forests of a registered catalogue watch their attributes, forest.Delta.__setattr__): this runs
+    once per forest and per call."""
+    try:
+        obj.__dict__["neighbours"] = value
+    except (AttributeError, TypeError):
+        obj.neighbours = value
+
+
 class PendingNeighbours:
     """``delta.neighbours`` after a DEFERRED fill_neighs (see ``defer_fill``): the neighbour
     search runs when somebody looks at the list or a compute_* function needs it."""
@@ -96,7 +106,7 @@ class NeighbourStore:
             self.pending.add(hp)
             self.by_healpix.pop(hp, None)
             for obj in data[hp]:
-                obj.neighbours = PendingNeighbours(obj, fill_now, healpixs)
+                set_neighbours(obj, PendingNeighbours(obj, fill_now, healpixs))
 
     def put(self, healpixs, pairs, ranges, cats=()):
         """``cats``: the packed catalogues the list was built from (kept alive with it)."""

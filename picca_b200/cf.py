@@ -132,7 +132,7 @@ def _fill_neighs_now(healpixs):
         _corr.apply_host_angles(pairs, host1, host2)
     _STORE.put(healpixs, pairs, ranges, (host1, host2))
     for k, f1 in enumerate(index):
-        host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
+        _corr.set_neighbours(host1.objs[f1], _corr.LazyNeighbours(pairs, k, host2.objs))
 
 
 def _pairs_for(healpixs):
@@ -159,7 +159,7 @@ def compute_xi(healpixs):
     host = out.cpu().numpy()[0]
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
     for f1 in pairs.f1_index.cpu().numpy():
-        setattr(host1.objs[f1], "neighbours", None)  # cf.py:240
+        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:240
     _STORE.drop(healpixs)
     weights, xi, r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in range(5))
     num_pairs = np.ascontiguousarray(host[5]).view(np.int64)
@@ -182,7 +182,7 @@ def compute_xi_batch(healpixs, normalise=True, to_host=True):
     host = out.cpu().numpy() if to_host else out  # to_host=False: device tensor (multi-GPU gather)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
     for f1 in pairs.f1_index.cpu().numpy():
-        setattr(host1.objs[f1], "neighbours", None)
+        _corr.set_neighbours(host1.objs[f1], None)
     _STORE.drop(healpixs)
     return host
 
@@ -303,7 +303,7 @@ def compute_dmat(healpixs):
     weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = (t.cpu().numpy() for t in res)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
     for f1 in f1_index:
-        setattr(host1.objs[f1], "neighbours", None)  # cf.py:502
+        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:502
     _STORE.drop(healpixs)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
@@ -442,6 +442,6 @@ def compute_metal_dmat(healpixs, abs_igm1="LYA", abs_igm2="SiIII(1207)"):
                                           weight_eff))
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
     for f1 in f1_index:
-        setattr(host1.objs[f1], "neighbours", None)  # cf.py:1219
+        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:1219
     _STORE.drop(healpixs)
     return res + (num_pairs, num_pairs_used)

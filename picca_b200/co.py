@@ -83,7 +83,7 @@ def _fill_neighs_now(healpixs):
         _corr.apply_host_angles(pairs, host1, host2)
     _STORE.put(healpixs, pairs, ranges, (host1, host2))
     for k, f1 in enumerate(index):
-        host1.objs[f1].neighbours = _corr.LazyNeighbours(pairs, k, host2.objs)
+        _corr.set_neighbours(host1.objs[f1], _corr.LazyNeighbours(pairs, k, host2.objs))
 
 
 def compute_xi(healpixs):
@@ -125,7 +125,7 @@ def compute_xi(healpixs):
         has = np.where(has, np.add.reduceat(np.append(ok, 0), offset[:-1]) > 0, False)
     for k, f1 in enumerate(f1_index):
         if has[k]:
-            setattr(host1.objs[f1], "neighbours", None)
+            _corr.set_neighbours(host1.objs[f1], None)
     _STORE.drop(healpixs)
     weights = np.ascontiguousarray(host[0])
     r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in (1, 2, 3))
