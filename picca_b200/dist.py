@@ -261,16 +261,19 @@ class RowIndex:
             xyz = np.array([[o.x_cart, o.y_cart, o.z_cart] for o in objs], dtype=np.float64)
             npix = np.array([np.size(o.weights) for o in objs], dtype=np.float64)
         n = len(self.healpixs)
-        self.npix = np.add.reduceat(npix, self.first[:-1]) if npix.size else np.zeros(n)
-        self.cap = np.zeros((n, 3))
-        self.cap_rad = np.zeros(n)
-        for k in range(n):
-            v = xyz[self.first[k]:self.first[k + 1]]
-            c = v.sum(axis=0)
-            norm = np.sqrt((c * c).sum())
-            c = c / norm if norm > 0 else v[0]
-            self.cap[k] = c
-            self.cap_rad[k] = float(np.arccos(np.clip(v @ c, -1., 1.).min())) + 1e-7
+        if not npix.size:
+            self.npix, self.cap, self.cap_rad = np.zeros(n), np.zeros((n, 3)), np.zeros(n)
+            return
+        # (rows are never empty: a HEALPix pixel is a key of `data` because a forest fell in it)
+        start = self.first[:-1]
+        self.npix = np.add.reduceat(npix, start)
+        c = np.add.reduceat(xyz, start, axis=0)
+        norm = np.sqrt((c * c).sum(axis=1))
+        c = np.where(norm[:, None] > 0, c / np.where(norm > 0, norm, 1.)[:, None], xyz[start])
+        row = np.repeat(np.arange(n), self.counts)
+        dots = np.clip((xyz * c[row]).sum(axis=1), -1., 1.)
+        self.cap = c
+        self.cap_rad = np.arccos(np.minimum.reduceat(dots, start)) + 1e-7
 
     def near(self, other, rows, ang_max):
         """bool [len(rows), n_other]: can a member of row r be within ang_max of a member of a row
