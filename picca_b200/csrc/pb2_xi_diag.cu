@@ -151,6 +151,25 @@ __device__ __forceinline__ void dg_emit(double *__restrict__ dst, int cnt, doubl
     atomic_add_i64(dst + 5, (long long)cnt);
 }
 
+#ifdef DG_OPAQUE_SROW
+__device__ __forceinline__ void dg_emit(unsigned long long dst, int cnt, double a0, double a1,
+                                        double a2, double a3, double a4)
+{
+    asm volatile(
+        "red.global.add.f64 [%0], %1;\n\t"
+        "red.global.add.f64 [%0+8], %2;\n\t"
+        "red.global.add.f64 [%0+16], %3;\n\t"
+        "red.global.add.f64 [%0+24], %4;\n\t"
+        "red.global.add.f64 [%0+32], %5;\n\t"
+        "red.global.add.u64 [%0+40], %6;" ::"l"(dst), "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(a4),
+        "l"((unsigned long long)(unsigned)cnt)
+        : "memory");
+}
+#define DG_BIN_ADDR(srow, bin) ((srow) + ((unsigned long long)(unsigned)(bin) << 6))
+#else
+#define DG_BIN_ADDR(srow, bin) ((srow) + (size_t)(bin) * 8)
+#endif
+
 // ABS: auto-correlation (r_par = |r_par|, cf.py:361-362).  FOLD: r_par_min == 0, so the r_par bin
 // is floor(|d| * (cos * K)) and cos folds into the constant; otherwise x = fl(fl(d cos) - min) is
 // formed exactly as the reference does (cf.py:356,372).
@@ -283,7 +302,15 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         request(stage);
         request(stage ^ 1u);
 
+#ifdef DG_OPAQUE_SROW
+        // the full scratch address of the row in ONE register pair (ptxas otherwise re-adds the
+        // kernel parameter at every run change); reductions through red.global on that address
+        unsigned long long srow = (unsigned long long)__cvta_generic_to_global(
+            scr + (size_t)out_row[k1] * nb * 8);
+        asm volatile("" : "+l"(srow));
+#else
         double *__restrict__ const srow = scr + (size_t)out_row[k1] * nb * 8;
+#endif
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
         const unsigned np16 = (unsigned)np_i << 16, nt16 = (unsigned)nt_i << 16;
@@ -364,7 +391,7 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                                 const int sl = (uu + k) % DG_C;
                                 // ---- diagonal k left its run: add the run to its bin
                                 if (cb[k] >= 0)
-                                    dg_emit(srow + (size_t)cb[k] * 8, sidx - start[k], a0[k], a1[k],
+                                    dg_emit(DG_BIN_ADDR(srow, cb[k]), sidx - start[k], a0[k], a1[k],
                                             a2[k] * ch, a3[k] * sh, a4[k]);
                                 // ---- the new run.  The low words hold floor(65536 x K): bin in
                                 // the upper, a 16-bit fraction in the lower half.  (Recomputed
@@ -436,7 +463,7 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
 #pragma unroll
         for (int k = 0; k < DG_C; k++) {
             if (cb[k] >= 0)
-                dg_emit(srow + (size_t)cb[k] * 8, s - start[k], a0[k], a1[k], a2[k] * ch, a3[k] * sh,
+                dg_emit(DG_BIN_ADDR(srow, cb[k]), s - start[k], a0[k], a1[k], a2[k] * ch, a3[k] * sh,
                         a4[k]);
         }
         }  // blocks of the forest pair
