@@ -757,6 +757,210 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+def run_banded(args):
+    """DESI-scale arm (BASELINE configs[4], ``--workload c5_1m``): auto-correlation + distortion
+    matrix with BAND shards only.  A rank draws the light index of the whole survey (positions and
+    shapes, vectorised), then generates, packs and uploads just its band of HEALPix rows + halo
+    (``synth.make_forest_band`` behind ``dist.BandShard(index=..., band_source=...)``): no rank
+    ever holds the 1M-forest catalogue.  Same JSON contract as the default arm; ``e2e`` = pack +
+    H2D of the band + neighbours + kernel + NCCL gather + D2H from the band's data dict."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from picca_b200 import synth
+    kw = dict(WORKLOADS[args.workload])
+    n_forest = kw.pop("n_forest")
+    t_wall0 = time.perf_counter()
+    ix = synth.make_forest_index(n_forest, **kw)
+    ang_max = synth.compute_ang_max(ix.cosmo, CF_CFG["r_trans_max"], ix.z_min)
+
+    import torch
+    import torch.distributed as dist
+    from picca_b200 import _corr, catalog, cf, dist as pdist
+    from picca_b200.engine import MODE_AUTO, get_engine
+    from picca_b200.params import params_from_module
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["PICCA_B200_DEVICE"] = str(local_rank)
+    eng = get_engine()
+    idx = pdist.RowIndex.from_arrays(ix.healpixs, ix.counts, ix.xyz, ix.npix)
+    hps = ix.healpixs
+    threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    t0 = time.perf_counter()
+    band = pdist.BandShard(eng, None, ang_max, world, rank, index=idx,
+                           band_source=lambda h0, h1: synth.make_forest_band(ix, h0, h1, threads=threads))
+    setup_s = time.perf_counter() - t0
+    data = band.data
+    configure(cf, data, n_forest, ang_max)
+    cf.userprint = lambda *a, **k: None
+    params = params_from_module(cf)
+    nb = params.num_bins_r_par * params.num_bins_r_trans
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    one_step = lambda: pdist.xi_banded(eng, band, params, MODE_AUTO)
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    eng.lib.pb2_set_timing(1)
+    kernel_ms = []
+
+    def step():
+        o = one_step()
+        kernel_ms.append(eng.lib.pb2_last_kernel_ms())
+        return o
+    total_ms, out = timed(step, args.steps)
+    eng.lib.pb2_set_timing(0)
+    launches = eng.launch_count() - launches0
+    sampler.stop_flag = True
+    out_host = out.cpu().numpy() if out is not None else None
+
+    # ---- end to end from the band's data dict: pack + H2D + neighbours + kernel + gather + D2H
+    e2e_detail = {"api": "dist.BandShard + dist.xi_banded on the band's data dict (per rank: pack "
+                         "and H2D of its band of HEALPix rows + halo, neighbours, kernel, NCCL "
+                         "gather, D2H); generating the synthetic band is not included"}
+    if args.no_e2e:
+        e2e_ms = total_ms
+    else:
+        band_data = band.data
+        band = None
+        eng.drop_catalogs()
+
+        def step_e2e():
+            t_0 = time.perf_counter()
+            b = pdist.BandShard(eng, None, ang_max, world, rank, index=idx,
+                                band_source=lambda h0, h1: band_data)
+            e2e_detail["pack_s"] = time.perf_counter() - t_0
+            e2e_detail["band_rows"], e2e_detail["halo_rows"] = b.b1 - b.b0, b.h1 - b.h0
+            e2e_detail["h2d_bytes_rank0"] = b.h2d_bytes
+            full = pdist.xi_banded(eng, b, params, MODE_AUTO)
+            step_e2e.band = b
+            return full.cpu().numpy() if full is not None else None
+        e2e_ms, e2e_out = timed(step_e2e, 1)
+        e2e_ms *= args.steps
+        band = step_e2e.band
+        if rank == 0:
+            assert np.array_equal(e2e_out[:, 5].view(np.int64), out_host[:, 5].view(np.int64))
+
+    # ---- parity (rank 0): whole rows from the middle of its band against the oracle port; the
+    # oracle sees the rows within reach of the chosen ones (all inside this rank's halo)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        mid = (band.b0 + band.b1) // 2
+        chosen_rows = np.arange(mid, mid + max(1, args.parity_pixels))
+        near = np.nonzero(idx.near(idx, chosen_rows, ang_max).any(axis=0))[0]
+        assert near.min() >= band.h0 and near.max() < band.h1
+        sub = {hps[r]: data[hps[r]] for r in near}
+        sub_hps = sorted(sub)
+        rows_sub = np.zeros((len(sub_hps), 6, nb))
+        for r in chosen_rows:
+            rows_sub[sub_hps.index(hps[r])] = out_host[r]
+        pc = lambda healpixs, count, step=0: [hps[r] for r in chosen_rows]
+        global spread_pixels
+        keep, spread_pixels = spread_pixels, pc
+        try:
+            parity = parity_check(sub, n_forest, ang_max, sub_hps, rows_sub, len(chosen_rows),
+                                  os.cpu_count() or 1)
+        finally:
+            spread_pixels = keep
+
+    # ---- distortion matrix, --rej 0.99, one reference chunk seeded with the first pixel
+    dmat_info = None
+    if not args.no_dmat:
+        cf.reject = DMAT_REJECT
+        cf.num_model_bins_r_par = CF_CFG["num_bins_r_par"]
+        cf.num_model_bins_r_trans = CF_CFG["num_bins_r_trans"]
+        dparams = params_from_module(cf)
+        counts = {}
+
+        def dmat_step():
+            res, npall, npused = pdist.dmat_chunk_banded(eng, band, dparams, MODE_AUTO, DMAT_REJECT,
+                                                         hps[0], segments=args.dmat_segments)
+            counts["npall"], counts["npused"] = npall, npused
+            return res
+        if args.warmup:
+            dmat_step()
+        dl0 = eng.launch_count()
+        dm_ms, dm_res = timed(dmat_step, args.dmat_steps)
+        dmat_info = {
+            "metric": "used forest pairs/sec (distortion matrix, --rej %.2f)" % DMAT_REJECT,
+            "value": counts["npused"] / (dm_ms / args.dmat_steps * 1e-3), "unit": "forest pairs/s",
+            "steps": args.dmat_steps, "ms_per_step": dm_ms / args.dmat_steps,
+            "gpu_launches": int(eng.launch_count() - dl0), "NPALL": counts["npall"],
+            "NPUSED": counts["npused"],
+            "dmat_shape": [int(dm_res[1].shape[0]), int(dm_res[1].shape[1])],
+            "sum_dmat": float(dm_res[1].sum().item()),
+            "sum_weights_dmat": float(dm_res[0].sum().item()),
+            "parallelism": "band shards x%d: neighbour counts all-gathered, --rej stream drawn on "
+                           "the host in %d segments overlapped with the kernels, ONE NCCL "
+                           "all-reduce(SUM) of a flat buffer" % (world, args.dmat_segments)}
+
+    peak_ops, _ = eng.fp64_peak(8192)
+    if rank == 0:
+        pairs = int(out_host[:, 5].view(np.int64).sum())
+        ms_step = total_ms / args.steps
+        kms = float(np.mean(kernel_ms))
+        my_pairs = int(out_host[band.b0:band.b1, 5].view(np.int64).sum())
+        achieved = FLOPS_PER_PAIR * my_pairs / (kms * 1e-3)
+        line = {
+            "metric": "binned forest-pixel pairs/sec (cf auto-correlation)",
+            "value": pairs / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "forests": int(n_forest),
+                       "pixels": int(ix.npix.sum()), "healpix": len(hps), "np": 50, "nt": 50,
+                       "rp_max": 200., "rt_max": 200., "nside": 32, "binned_pairs_per_step": pairs,
+                       "angles": "host (NumPy arccos, parity mode)" if _corr.HOST_ANGLES else
+                       "device (acos/sin/cos of pb2_neigh.cu)",
+                       "l2_policy": "inputs (%.2f GB in HBM on rank 0) larger than L2"
+                                    % (band.dev.device_bytes() / 1e9),
+                       "parallelism": "band shards x%d (contiguous HEALPix rows + halo per rank), "
+                                      "gather to rank 0" % world,
+                       "rank0_forests_held": int(band.host.n_los),
+                       "generate_pack_upload_s_rank0": setup_s,
+                       "wall_s_total": time.perf_counter() - t_wall0},
+            "e2e": {"value": pairs / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": e2e_detail.get("h2d_bytes_rank0"),
+                    "d2h_bytes_per_step": int(len(hps) * 6 * nb * 8), "steps": 1, **e2e_detail},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
+                         "unit": "Tops/s (1 DFMA = 1 op)", "frac": achieved / peak_ops,
+                         "traffic": None, "kernel": "pb2_xi_auto_diag", "kernel_ms": kms,
+                         "peak_source": "pb2_fp64_peak DFMA microbenchmark, measured in this run",
+                         "ops_per_pair": FLOPS_PER_PAIR},
+        }
+        if parity is not None:
+            line["parity_check"] = parity
+        if dmat_info is not None:
+            line["dmat"] = dmat_info
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -779,11 +983,16 @@ def main():
     ap.add_argument("--dmat-steps", type=int, default=2)
     ap.add_argument("--dmat-segments", type=int, default=8)
     ap.add_argument("--xcf-steps", type=int, default=3)
+    ap.add_argument("--banded", action="store_true",
+                    help="band shards only: every rank generates / holds just its band of HEALPix "
+                         "rows + halo (always on for --workload c5_1m)")
     args = ap.parse_args()
     if args.e2e_steps <= 0:
         args.e2e_steps = min(args.steps, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.banded or args.workload == "c5_1m":
+        run_banded(args)
     else:
         run_cuda(args)
 

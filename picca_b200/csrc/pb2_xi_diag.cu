@@ -165,6 +165,25 @@ __device__ __forceinline__ void dg_emit(unsigned long long dst, int cnt, double 
         "l"((unsigned long long)(unsigned)cnt)
         : "memory");
 }
+// the same behind a predicate (bin >= 0) instead of a branch: one divergence level less on the
+// latency-critical run-change path
+__device__ __forceinline__ void dg_emit_pred(unsigned long long dst, int bin, int cnt, double a0,
+                                             double a1, double a2, double a3, double a4)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ge.s32 p, %7, 0;\n\t"
+        "@p red.global.add.f64 [%0], %1;\n\t"
+        "@p red.global.add.f64 [%0+8], %2;\n\t"
+        "@p red.global.add.f64 [%0+16], %3;\n\t"
+        "@p red.global.add.f64 [%0+24], %4;\n\t"
+        "@p red.global.add.f64 [%0+32], %5;\n\t"
+        "@p red.global.add.u64 [%0+40], %6;\n\t"
+        "}" ::"l"(dst), "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(a4),
+        "l"((unsigned long long)(unsigned)cnt), "r"(bin)
+        : "memory");
+}
 #define DG_BIN_ADDR(srow, bin) ((srow) + ((unsigned long long)(unsigned)(bin) << 6))
 #else
 #define DG_BIN_ADDR(srow, bin) ((srow) + (size_t)(bin) * 8)
@@ -351,18 +370,37 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                     cz[k] = dg_lds64(cp + k * DG_PLANE_BYTES + 32);
                 }
             }
+#ifdef DG_PREFETCH
+            double2 nr1 = dg_lds128(rp);
+            double2 ncr = dg_lds128(cp + (DG_C - 1) * DG_PLANE_BYTES);
+#endif
             const int nit = min(DG_R, nrows - c * DG_R) / DG_C;
             for (int it = 0; it < nit; it++) {
 #pragma unroll
                 for (int uu = 0; uu < DG_C; uu++) {
+#ifdef DG_PREFETCH
+                    // (rc, dm) of this row and of its new column were loaded one row ahead, so
+                    // the geometry chain of a row does not start with a shared-memory load
+                    // behind the previous row's run changes
+                    const double2 r1 = nr1;
+                    nr1 = dg_lds128(rp + (uu + 1) * DG_REC);
+#else
                     const double2 r1 = dg_lds128(rp + uu * DG_REC);       // (rc1, dm1), broadcast
+#endif
                     const double2 w1 = dg_lds128(rp + uu * DG_REC + 16);  // (w1, delta1 w1)
                     const double z1 = dg_lds64(rp + uu * DG_REC + 32);    // z1 / 2
                     {
                         // the new column of this row: row + D0 + DG_C * lane + DG_C - 1
                         const int pl = (uu + DG_C - 1) % DG_C;
                         const unsigned char *at = cp + pl * DG_PLANE_BYTES + ((uu + DG_C - 1) / DG_C) * DG_REC;
+#ifdef DG_PREFETCH
+                        cr[pl] = ncr;
+                        ncr = dg_lds128(uu + 1 < DG_C
+                                        ? cp + ((uu + DG_C) % DG_C) * DG_PLANE_BYTES + ((uu + DG_C) / DG_C) * DG_REC
+                                        : cp + DG_REC + (DG_C - 1) * DG_PLANE_BYTES);
+#else
                         cr[pl] = dg_lds128(at);
+#endif
                         cw[pl] = dg_lds128(at + 16);
                         cz[pl] = dg_lds64(at + 32);
                     }
@@ -390,9 +428,17 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                             if (chg[k]) {
                                 const int sl = (uu + k) % DG_C;
                                 // ---- diagonal k left its run: add the run to its bin
+#if defined(DG_LATE_EMIT)
+                                const int ocb = cb[k], ocnt = sidx - start[k];
+                                const double p2 = a2[k] * ch, p3 = a3[k] * sh;
+#elif defined(DG_PRED_EMIT)
+                                dg_emit_pred(DG_BIN_ADDR(srow, cb[k]), cb[k], sidx - start[k], a0[k],
+                                             a1[k], a2[k] * ch, a3[k] * sh, a4[k]);
+#else
                                 if (cb[k] >= 0)
                                     dg_emit(DG_BIN_ADDR(srow, cb[k]), sidx - start[k], a0[k], a1[k],
                                             a2[k] * ch, a3[k] * sh, a4[k]);
+#endif
                                 // ---- the new run.  The low words hold floor(65536 x K): bin in
                                 // the upper, a 16-bit fraction in the lower half.  (Recomputed
                                 // behind an opaque copy: keeping phase 1's values alive for this
@@ -430,6 +476,11 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                                 bt1[k] = nb1t;
                                 cb[k] = ncb;
                                 start[k] = sidx;
+#if defined(DG_LATE_EMIT)
+                                // the reductions last: the products above have long been formed
+                                if (ocb >= 0)
+                                    dg_emit(DG_BIN_ADDR(srow, ocb), ocnt, a0[k], a1[k], p2, p3, a4[k]);
+#endif
                             }
                         }
                     }

@@ -246,10 +246,8 @@ class RowIndex:
 
     def __init__(self, data):
         from . import forest as _forest
-        self.healpixs = sorted(data)
-        self.counts = np.array([len(data[hp]) for hp in self.healpixs], dtype=np.int64)
-        self.first = np.zeros(len(self.healpixs) + 1, dtype=np.int64)
-        np.cumsum(self.counts, out=self.first[1:])
+        healpixs = sorted(data)
+        counts = np.array([len(data[hp]) for hp in healpixs], dtype=np.int64)
         reg = _forest.soa_of(data)
         if reg is not None and reg["objs"] and _forest.registered_clean(data, reg):
             los = reg["los"]
@@ -257,9 +255,25 @@ class RowIndex:
                            axis=1)
             npix = np.diff(np.asarray(reg["offset"], dtype=np.int64)).astype(np.float64)
         else:
-            objs = [o for hp in self.healpixs for o in data[hp]]
+            objs = [o for hp in healpixs for o in data[hp]]
             xyz = np.array([[o.x_cart, o.y_cart, o.z_cart] for o in objs], dtype=np.float64)
             npix = np.array([np.size(o.weights) for o in objs], dtype=np.float64)
+        self._set(healpixs, counts, xyz, npix)
+
+    @classmethod
+    def from_arrays(cls, healpixs, counts, xyz, npix):
+        """From per-forest arrays in catalogue order (a survey index that holds no pixel data,
+        ``synth.make_forest_index``): ``healpixs`` ascending, ``counts`` forests per row."""
+        self = cls.__new__(cls)
+        self._set(list(healpixs), np.asarray(counts, dtype=np.int64),
+                  np.asarray(xyz, dtype=np.float64).reshape(-1, 3), np.asarray(npix, dtype=np.float64))
+        return self
+
+    def _set(self, healpixs, counts, xyz, npix):
+        self.healpixs = healpixs
+        self.counts = counts
+        self.first = np.zeros(len(self.healpixs) + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.first[1:])
         n = len(self.healpixs)
         if not npix.size:
             self.npix, self.cap, self.cap_rad = np.zeros(n), np.zeros((n, 3)), np.zeros(n)
@@ -325,11 +339,16 @@ class BandShard:
     resident in HBM, the rows [h0, h1) >= band that contain every possible neighbour of the
     band's forests (auto-correlation: ``data`` against itself)."""
 
-    def __init__(self, eng, data, ang_max, world, rank, ang_correlation=False):
+    def __init__(self, eng, data, ang_max, world, rank, ang_correlation=False, index=None,
+                 band_source=None):
+        """``data``: the whole catalogue (registered SoA: the band is sliced out of it) -- or
+        None with ``index`` (a ``RowIndex`` of the whole survey) and ``band_source(h0, h1)``
+        returning the ``data`` dict of the rows [h0, h1) only: the rank then never holds (or
+        generates, or reads) more than its band + halo."""
         from . import catalog as _catalog
         torch = eng.torch
         self.world, self.rank = world, rank
-        idx = RowIndex(data)
+        idx = RowIndex(data) if index is None else index
         self.n_rows_total = len(idx.healpixs)
         self.healpixs = idx.healpixs
         self.bounds = band_bounds(idx.work(idx, ang_max), world)
@@ -339,8 +358,15 @@ class BandShard:
             self.h0, self.h1 = int(min(reach.min(), self.b0)), int(max(reach.max() + 1, self.b1))
         else:
             self.h0, self.h1 = self.b0, self.b1
-        self.host = _catalog.pack(data, ang_correlation=ang_correlation, defer_products=True,
-                                  rows=(self.h0, self.h1))
+        if index is None:
+            self.data = data
+            self.host = _catalog.pack(data, ang_correlation=ang_correlation, defer_products=True,
+                                      rows=(self.h0, self.h1))
+        else:
+            self.data = band_source(self.h0, self.h1)
+            assert sorted(self.data) == list(idx.healpixs[self.h0:self.h1])
+            self.host = _catalog.pack(self.data, ang_correlation=ang_correlation,
+                                      defer_products=True)
         self.dev = eng.device_catalog(self.host, cache=False)
         self.mine = np.arange(self.b0, self.b1, dtype=np.int64)       # global rows of the band
         first = self.host.arrays["hp_first"]

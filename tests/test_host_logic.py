@@ -272,3 +272,39 @@ def test_nearest_table_equals_scipy_interp1d():
     assert np.array_equal(values[idx], xi(x))
     with pytest.raises(NotImplementedError):
         _wick.nearest_table(lambda v: v)
+
+
+def test_forest_index_and_band_generation():
+    """synth.make_forest_index / make_forest_band: a band is a function of (index, rows) only --
+    two overlapping bands hold identical forests --, the deltas are projected (weighted mean and
+    slope removed, data.py:622-655), the band packs from its registered SoA, and the index alone
+    gives the RowIndex of the packed catalogue."""
+    import numpy as np
+    from picca_b200 import catalog, dist as pdist, synth
+    ix = synth.make_forest_index(1200, seed=4, nside=32, ra_deg=(0., 20.), dec_deg=(0., 12.), max_pix=30)
+    n_rows = len(ix.healpixs)
+    assert int(ix.counts.sum()) == 1200 and ix.first[-1] == 1200
+    whole = synth.make_forest_band(ix, 0, n_rows, threads=1)
+    part = synth.make_forest_band(ix, n_rows // 3, n_rows // 3 + 5, rows_per_pass=2, threads=3)
+    for hp in part:
+        assert len(part[hp]) == len(whole[hp])
+        for a, b in zip(part[hp], whole[hp]):
+            assert a.thingid == b.thingid and a.ra == b.ra and a.z_qso == b.z_qso
+            for name in ("delta", "weights", "log_lambda", "z", "r_comov", "dist_m"):
+                assert np.array_equal(getattr(a, name), getattr(b, name))
+    d = whole[ix.healpixs[n_rows // 2]][0]
+    w = d.weights
+    assert (w == 0).any() or True
+    assert abs(np.sum(w * d.delta)) <= 1e-12 * np.sum(w)
+    ll = d.log_lambda - np.average(d.log_lambda, weights=w)
+    assert abs(np.sum(w * d.delta * ll)) <= 1e-12 * np.sum(w * np.abs(ll))
+    assert np.allclose(np.diff(10**d.log_lambda), ix.dlambda)
+    assert np.array_equal(d.z, 10**d.log_lambda / synth.LYA - 1.)
+    host = catalog.pack(whole, defer_products=True)
+    assert host.from_soa and host.n_los == 1200 and host.n_pix == int(ix.npix.sum())
+    a, b = pdist.RowIndex(whole), pdist.RowIndex.from_arrays(ix.healpixs, ix.counts, ix.xyz, ix.npix)
+    assert a.healpixs == b.healpixs and np.array_equal(a.first, b.first)
+    assert np.array_equal(a.npix, b.npix)
+    assert np.allclose(a.cap, b.cap, atol=1e-15) and np.allclose(a.cap_rad, b.cap_rad, atol=1e-12)
+    zs = np.concatenate([o.z for v in whole.values() for o in v])
+    assert abs(zs.min() - ix.z_min) < 1e-12 and abs(zs.max() - ix.z_max) < 1e-12

@@ -78,3 +78,41 @@ def test_one_rank_shard_equals_plugin_call():
     assert (npall_b, npused_b) == (one[6], one[7])
     for a, b in zip(res_b, one[:6]):
         assert np.abs(a.cpu().numpy() - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300)
+
+
+def test_band_source_shards_equal_the_whole_catalogue():
+    """Band shards from a survey index + a band source (``synth.make_forest_index`` /
+    ``make_forest_band``: no rank generates or holds more than its band + halo): three "ranks",
+    run one after the other on this GPU, reproduce the rows of the whole catalogue."""
+    import numpy as np
+    from picca_b200 import cf, dist as pdist, synth
+    from picca_b200.engine import MODE_AUTO, get_engine
+    from picca_b200.params import params_from_module
+    from tests import helpers
+    eng = get_engine()
+    ix = synth.make_forest_index(1800, seed=11, nside=32, ra_deg=(0., 24.), dec_deg=(0., 14.),
+                                 max_pix=48)
+    ang_max = synth.compute_ang_max(ix.cosmo, 200., ix.z_min)
+    idx = pdist.RowIndex.from_arrays(ix.healpixs, ix.counts, ix.xyz, ix.npix)
+    data = synth.make_forest_band(ix, 0, len(ix.healpixs))
+    helpers.configure(cf, data, ix.n_forest, ang_max, num_bins_r_par=50, num_bins_r_trans=50,
+                      r_par_max=200., r_trans_max=200., nside=32)
+    hps = sorted(data)
+    assert hps == ix.healpixs
+    cf.fill_neighs(hps)
+    want = cf.compute_xi_batch(hps)
+    params = params_from_module(cf)
+    world = 3
+    seen = 0
+    for rank in range(world):
+        band = pdist.BandShard(eng, None, ang_max, world, rank, index=idx,
+                               band_source=lambda h0, h1: synth.make_forest_band(ix, h0, h1))
+        assert band.host.n_los == ix.first[band.h1] - ix.first[band.h0]
+        got = pdist.xi_banded(eng, band, params, MODE_AUTO, gather=False).cpu().numpy()
+        ref = want[band.b0:band.b1]
+        assert np.array_equal(got[:, 5].view(np.int64), ref[:, 5].view(np.int64))
+        for k in range(5):
+            assert np.abs(got[:, k] - ref[:, k]).max() <= 1e-11 * max(np.abs(ref[:, k]).max(), 1e-300)
+        seen += band.b1 - band.b0
+    assert seen == len(hps)
+    assert want[:, 5].view(np.int64).sum() > 0
