@@ -941,9 +941,13 @@ def run_banded(args):
                        "rank0_forests_held": int(band.host.n_los),
                        "generate_pack_upload_s_rank0": setup_s,
                        "wall_s_total": time.perf_counter() - t_wall0},
-            "e2e": {"value": pairs / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": e2e_detail.get("h2d_bytes_rank0"),
-                    "d2h_bytes_per_step": int(len(hps) * 6 * nb * 8), "steps": 1, **e2e_detail},
+            "e2e": ({"value": None, "unit": "pairs/s", "note": "--no-e2e: not measured in this run; "
+                     "config.generate_pack_upload_s_rank0 and config.wall_s_total bound it",
+                     "h2d_bytes_per_step": int(band.h2d_bytes),
+                     "d2h_bytes_per_step": int(len(hps) * 6 * nb * 8)} if args.no_e2e else
+                    {"value": pairs / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
+                     "h2d_bytes_per_step": e2e_detail.get("h2d_bytes_rank0"),
+                     "d2h_bytes_per_step": int(len(hps) * 6 * nb * 8), "steps": 1, **e2e_detail}),
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tops/s (1 DFMA = 1 op)", "frac": achieved / peak_ops,

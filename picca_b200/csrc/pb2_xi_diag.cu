@@ -139,19 +139,11 @@ __device__ __noinline__ int dg_exact_bin(const pb2_params &P, double rc1, double
     return pb2_pair_exact(P, rc1, dm1, rc2, dm2, ang, ch, sh, false, false).bin;
 }
 
-// one finished run -> the six sums of its bin (one 64-byte line of the scratch histogram)
-__device__ __forceinline__ void dg_emit(double *__restrict__ dst, int cnt, double a0, double a1,
-                                        double a2, double a3, double a4)
-{
-    atomic_add_f64(dst, a0);
-    atomic_add_f64(dst + 1, a1);
-    atomic_add_f64(dst + 2, a2);
-    atomic_add_f64(dst + 3, a3);
-    atomic_add_f64(dst + 4, a4);
-    atomic_add_i64(dst + 5, (long long)cnt);
-}
-
-#ifdef DG_OPAQUE_SROW
+// one finished run -> the six sums of its bin (one 64-byte line of the scratch histogram), through
+// red.global on a 64-bit address + immediates: the row's scratch address lives in ONE register pair
+// for the whole forest pair.  (With a C++ pointer ptxas re-adds the kernel parameter at every run
+// change -- a constant-bank load and two adds on the latency-critical path of the warp's divergent
+// lanes; without them the kernel is 7 % faster.)
 __device__ __forceinline__ void dg_emit(unsigned long long dst, int cnt, double a0, double a1,
                                         double a2, double a3, double a4)
 {
@@ -165,29 +157,7 @@ __device__ __forceinline__ void dg_emit(unsigned long long dst, int cnt, double 
         "l"((unsigned long long)(unsigned)cnt)
         : "memory");
 }
-// the same behind a predicate (bin >= 0) instead of a branch: one divergence level less on the
-// latency-critical run-change path
-__device__ __forceinline__ void dg_emit_pred(unsigned long long dst, int bin, int cnt, double a0,
-                                             double a1, double a2, double a3, double a4)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ge.s32 p, %7, 0;\n\t"
-        "@p red.global.add.f64 [%0], %1;\n\t"
-        "@p red.global.add.f64 [%0+8], %2;\n\t"
-        "@p red.global.add.f64 [%0+16], %3;\n\t"
-        "@p red.global.add.f64 [%0+24], %4;\n\t"
-        "@p red.global.add.f64 [%0+32], %5;\n\t"
-        "@p red.global.add.u64 [%0+40], %6;\n\t"
-        "}" ::"l"(dst), "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(a4),
-        "l"((unsigned long long)(unsigned)cnt), "r"(bin)
-        : "memory");
-}
 #define DG_BIN_ADDR(srow, bin) ((srow) + ((unsigned long long)(unsigned)(bin) << 6))
-#else
-#define DG_BIN_ADDR(srow, bin) ((srow) + (size_t)(bin) * 8)
-#endif
 
 // ABS: auto-correlation (r_par = |r_par|, cf.py:361-362).  FOLD: r_par_min == 0, so the r_par bin
 // is floor(|d| * (cos * K)) and cos folds into the constant; otherwise x = fl(fl(d cos) - min) is
@@ -321,18 +291,19 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         request(stage);
         request(stage ^ 1u);
 
-#ifdef DG_OPAQUE_SROW
-        // the full scratch address of the row in ONE register pair (ptxas otherwise re-adds the
-        // kernel parameter at every run change); reductions through red.global on that address
+        // the full scratch address of the row in one register pair (see dg_emit)
         unsigned long long srow = (unsigned long long)__cvta_generic_to_global(
             scr + (size_t)out_row[k1] * nb * 8);
         asm volatile("" : "+l"(srow));
-#else
-        double *__restrict__ const srow = scr + (size_t)out_row[k1] * nb * 8;
-#endif
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
         const unsigned np16 = (unsigned)np_i << 16, nt16 = (unsigned)nt_i << 16;
+#ifdef DG_NT_REG
+        unsigned nt_r = (unsigned)nt_i;
+        asm volatile("" : "+r"(nt_r));
+#else
+        const unsigned nt_r = (unsigned)nt_i;
+#endif
         const double kpf = FOLD ? mul_rn(ch, C.kp16) : C.kp16;
         const double ktf = mul_rn(sh, C.kt16);
 
@@ -370,37 +341,18 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                     cz[k] = dg_lds64(cp + k * DG_PLANE_BYTES + 32);
                 }
             }
-#ifdef DG_PREFETCH
-            double2 nr1 = dg_lds128(rp);
-            double2 ncr = dg_lds128(cp + (DG_C - 1) * DG_PLANE_BYTES);
-#endif
             const int nit = min(DG_R, nrows - c * DG_R) / DG_C;
             for (int it = 0; it < nit; it++) {
 #pragma unroll
                 for (int uu = 0; uu < DG_C; uu++) {
-#ifdef DG_PREFETCH
-                    // (rc, dm) of this row and of its new column were loaded one row ahead, so
-                    // the geometry chain of a row does not start with a shared-memory load
-                    // behind the previous row's run changes
-                    const double2 r1 = nr1;
-                    nr1 = dg_lds128(rp + (uu + 1) * DG_REC);
-#else
                     const double2 r1 = dg_lds128(rp + uu * DG_REC);       // (rc1, dm1), broadcast
-#endif
                     const double2 w1 = dg_lds128(rp + uu * DG_REC + 16);  // (w1, delta1 w1)
                     const double z1 = dg_lds64(rp + uu * DG_REC + 32);    // z1 / 2
                     {
                         // the new column of this row: row + D0 + DG_C * lane + DG_C - 1
                         const int pl = (uu + DG_C - 1) % DG_C;
                         const unsigned char *at = cp + pl * DG_PLANE_BYTES + ((uu + DG_C - 1) / DG_C) * DG_REC;
-#ifdef DG_PREFETCH
-                        cr[pl] = ncr;
-                        ncr = dg_lds128(uu + 1 < DG_C
-                                        ? cp + ((uu + DG_C) % DG_C) * DG_PLANE_BYTES + ((uu + DG_C) / DG_C) * DG_REC
-                                        : cp + DG_REC + (DG_C - 1) * DG_PLANE_BYTES);
-#else
                         cr[pl] = dg_lds128(at);
-#endif
                         cw[pl] = dg_lds128(at + 16);
                         cz[pl] = dg_lds64(at + 32);
                     }
@@ -428,17 +380,9 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                             if (chg[k]) {
                                 const int sl = (uu + k) % DG_C;
                                 // ---- diagonal k left its run: add the run to its bin
-#if defined(DG_LATE_EMIT)
-                                const int ocb = cb[k], ocnt = sidx - start[k];
-                                const double p2 = a2[k] * ch, p3 = a3[k] * sh;
-#elif defined(DG_PRED_EMIT)
-                                dg_emit_pred(DG_BIN_ADDR(srow, cb[k]), cb[k], sidx - start[k], a0[k],
-                                             a1[k], a2[k] * ch, a3[k] * sh, a4[k]);
-#else
                                 if (cb[k] >= 0)
                                     dg_emit(DG_BIN_ADDR(srow, cb[k]), sidx - start[k], a0[k], a1[k],
                                             a2[k] * ch, a3[k] * sh, a4[k]);
-#endif
                                 // ---- the new run.  The low words hold floor(65536 x K): bin in
                                 // the upper, a 16-bit fraction in the lower half.  (Recomputed
                                 // behind an opaque copy: keeping phase 1's values alive for this
@@ -457,7 +401,7 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                                 const int hp = lp & (int)0xffff0000, ht = lt & (int)0xffff0000;
                                 int nb1p = hp + (hp != 0), nb1t = ht + (ht != 0);
                                 const unsigned bp = (unsigned)lp >> 16, bt = (unsigned)lt >> 16;
-                                int ncb = (int)(bp * (unsigned)nt_i + bt);
+                                int ncb = (int)(bp * nt_r + bt);
                                 if ((unsigned)lp >= np16 || (unsigned)lt >= nt16) ncb = -1;
                                 if (!fmt) {  // dummy pixel: no bin, and quiet while it lasts
                                     nb1p = lp - 1;
@@ -476,11 +420,6 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
                                 bt1[k] = nb1t;
                                 cb[k] = ncb;
                                 start[k] = sidx;
-#if defined(DG_LATE_EMIT)
-                                // the reductions last: the products above have long been formed
-                                if (ocb >= 0)
-                                    dg_emit(DG_BIN_ADDR(srow, ocb), ocnt, a0[k], a1[k], p2, p3, a4[k]);
-#endif
                             }
                         }
                     }

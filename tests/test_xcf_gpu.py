@@ -20,7 +20,7 @@ def neighbour_ids(data, hps):
     return np.array(counts, dtype=np.int64), np.array(ids, dtype=np.int64)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])  # prefix-sum kernel, validation, lane = object kernel
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])  # prefix-sum kernel (transposed reductions), validation, lane = object kernel, prefix-sum kernel with per-lane reductions
 @pytest.mark.parametrize("name", sorted(cases.XCF_CASES))
 def test_xcf_matches_reference_golden(name, variant):
     from picca_b200 import xcf
