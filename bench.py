@@ -683,7 +683,7 @@ def run_cuda(args):
                         "api": "xcf.fill_neighs + xcf.compute_xi_batch on the data / objs dicts"},
                 "roofline": {"bound": "fp64", "achieved": x_ach / 1e12, "peak": x_peak / 1e12,
                              "unit": "Tops/s (1 DFMA = 1 op)", "frac": x_ach / x_peak,
-                             "ops_per_pair": FLOPS_PER_PAIR_XCF, "kernel": "pb2_xi_cross_chunk",
+                             "ops_per_pair": FLOPS_PER_PAIR_XCF, "kernel": "pb2_xi_cross_chunk_t",
                              "kernel_ms": xk,
                              "traffic": xprof.get("dram_bytes_per_launch")
                              if xprof.get("workload") == args.workload and world == 1 else None},
