@@ -393,10 +393,10 @@ __device__ __forceinline__ void xcf_red(double *p, double v)
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-#ifndef XCF_T_CTAS
-#define XCF_T_CTAS 3
-#endif
-__global__ void __launch_bounds__(256, XCF_T_CTAS)
+// (a minimum-blocks launch bound makes ptxas produce 20 % slower code here, at 3, 4 and 5 CTAs per SM
+// alike: profiles/r02_xcf_variants.log; three CTAs are resident at 77 registers)
+#define XCF_T_GRID 4
+__global__ void __launch_bounds__(256)
 pb2_xi_cross_chunk_t(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, XcfFast F,
                      const int32_t *__restrict__ out_row, double *__restrict__ scr,
                      unsigned long long *__restrict__ counter)
@@ -636,7 +636,7 @@ int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2
             reinterpret_cast<unsigned char *>(d_scr) + scr_bytes);
         PB2_CUDA(cudaFuncSetAttribute(pb2_xi_cross_chunk_t, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)chunk_smem));
-        long long ctas = pairs->n_f1 < 148 * XCF_T_CTAS ? pairs->n_f1 : 148 * XCF_T_CTAS;
+        long long ctas = pairs->n_f1 < 148 * XCF_T_GRID ? pairs->n_f1 : 148 * XCF_T_GRID;
         pb2_xi_cross_chunk_t<<<(unsigned)ctas, 256, chunk_smem, s>>>(*cat1, *objs, *par, *pairs, F,
                                                                      d_out_row, d_scr, d_ctr);
         pb2_count_launch(1);
