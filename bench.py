@@ -917,6 +917,10 @@ def run_banded(args):
                            "all-reduce(SUM) of a flat buffer" % (world, args.dmat_segments)}
 
     peak_ops, _ = eng.fp64_peak(8192)
+    kms_all = torch.zeros(world, dtype=torch.float64, device=eng.device)
+    kms_all[rank] = float(np.mean(kernel_ms))
+    if world > 1:
+        dist.all_reduce(kms_all)
     if rank == 0:
         pairs = int(out_host[:, 5].view(np.int64).sum())
         ms_step = total_ms / args.steps
@@ -939,6 +943,7 @@ def run_banded(args):
                        "parallelism": "band shards x%d (contiguous HEALPix rows + halo per rank), "
                                       "gather to rank 0" % world,
                        "rank0_forests_held": int(band.host.n_los),
+                       "kernel_ms_per_rank": [round(float(x), 1) for x in kms_all.tolist()],
                        "generate_pack_upload_s_rank0": setup_s,
                        "wall_s_total": time.perf_counter() - t_wall0},
             "e2e": ({"value": None, "unit": "pairs/s", "note": "--no-e2e: not measured in this run; "

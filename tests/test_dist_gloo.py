@@ -133,3 +133,21 @@ def test_band_bounds_and_halo_cover_every_neighbour():
     # more ranks than rows: trailing bands are empty, nothing is lost
     tiny = pdist.band_bounds(np.ones(3), 5)
     assert tiny[0][0] == 0 and tiny[-1][1] == 3 and sum(b - a for a, b in tiny) == 3
+
+
+def test_exact_row_work_equals_brute_force_and_balances_bands():
+    """RowIndex.work_exact: sum of npix1 * npix2 over the forest pairs a row owns (ang < ang_max,
+    ra1 > ra2), block by block == brute force; bands cut by it carry even exact loads."""
+    from picca_b200 import synth
+    ix = synth.make_forest_index(6000, seed=3, nside=32, ra_deg=(0., 40.), dec_deg=(0., 20.), max_pix=20)
+    ang_max = synth.compute_ang_max(ix.cosmo, 200., ix.z_min)
+    idx = pdist.RowIndex.from_arrays(ix.healpixs, ix.counts, ix.xyz, ix.npix)
+    w = idx.work_exact(ang_max, max_elems=1 << 18)     # several blocks
+    ok = (ix.xyz @ ix.xyz.T > np.cos(ang_max)) & (ix.ra[:, None] > ix.ra[None, :])
+    per_f = (ok * ix.npix[None, :]).sum(axis=1) * ix.npix
+    row_of = np.repeat(np.arange(len(ix.healpixs)), ix.counts)
+    np.testing.assert_allclose(w, np.bincount(row_of, weights=per_f), rtol=1e-12)
+    import torch
+    np.testing.assert_allclose(idx.work_exact(ang_max, torch, torch.device("cpu")), w, rtol=1e-12)
+    loads = np.array([w[a:b].sum() for a, b in pdist.band_bounds(w, 4)])
+    assert loads.max() <= loads.mean() + w.max()
