@@ -138,7 +138,7 @@ __device__ __forceinline__ void rl_sweep(const pb2_params &P, const DmatFast &F,
                 g = ROW ? dmat_pair(P, F, rc_f, dm_f, s_rc, s_dm, D.ch, D.sh, false, D.shp)
                         : dmat_pair(P, F, s_rc, s_dm, rc_f, dm_f, D.ch, D.sh, false, D.shp);
                 if (g.in) {
-                    z = div_rn(add_rn(z_f, zs[s]), 2.);
+                    z = mul_rn(add_rn(z_f, zs[s]), 0.5);   // == (z1 + z2) / 2 exactly (cf.py:690)
                     sel = f_sel && !g.close;
                     if (sel && ((P.has_z_min_pairs && z < P.z_min_pairs) ||
                                 (P.has_z_max_pairs && z > P.z_max_pairs))) sel = false;
