@@ -9,6 +9,8 @@ sight: CSR offset, unit vector, ra, dec, cos_dec, z_qso, thingid, plate, fiberid
 row.  Per HEALPix pixel: member range and the bounding cap of its members (used by the device
 neighbour search instead of healpy.query_disc).
 """
+import operator
+
 import numpy as np
 
 from . import _lib
@@ -194,7 +196,25 @@ def pack(data, is_object=False, ang_correlation=False, defer_products=False, row
         objs = reg["objs"][l0:l0 + n]
     else:
         objs = [obj for hp in cat.healpixs for obj in data[hp]]
-        col = lambda name: [getattr(o, name) for o in objs]
+        # one attrgetter call per object for all positional attributes (a tenth of the getattr
+        # calls of a column-by-column walk: 0.5 s -> 0.15 s per 170k quasars)
+        fast_cols = {}
+        names_f = ("x_cart", "y_cart", "z_cart", "ra", "dec", "cos_dec", "z_qso") + \
+            (("r_comov", "dist_m", "weights") if is_object and not ang_correlation else ())
+        if n:
+            try:
+                get = operator.attrgetter(*names_f)
+                table = np.array([get(o) for o in objs], dtype=np.float64)
+                if table.shape == (n, len(names_f)):
+                    fast_cols = {nm: np.ascontiguousarray(table[:, k]) for k, nm in enumerate(names_f)}
+            except (TypeError, ValueError, AttributeError):
+                fast_cols = {}
+            try:
+                ids = list(zip(*map(operator.attrgetter("thingid", "plate", "fiberid"), objs)))
+                fast_cols.update(thingid=list(ids[0]), plate=list(ids[1]), fiberid=list(ids[2]))
+            except AttributeError:
+                pass
+        col = lambda name: fast_cols[name] if name in fast_cols else [getattr(o, name) for o in objs]
     cat.objs = objs
     cat.n_los = n
     A = cat.arrays
@@ -225,10 +245,10 @@ def pack(data, is_object=False, ang_correlation=False, defer_products=False, row
             A["r_comov"] = lam
             A["dist_m"] = lam.copy()
         else:
-            A["r_comov"] = np.array([o.r_comov for o in objs], dtype=np.float64).reshape(n)
-            A["dist_m"] = np.array([o.dist_m for o in objs], dtype=np.float64).reshape(n)
+            A["r_comov"] = np.array(col("r_comov"), dtype=np.float64).reshape(n)
+            A["dist_m"] = np.array(col("dist_m"), dtype=np.float64).reshape(n)
         A["z"] = zq.copy()
-        A["weights"] = np.array([o.weights for o in objs], dtype=np.float64).reshape(n)
+        A["weights"] = np.array(col("weights"), dtype=np.float64).reshape(n)
         A["delta_w"] = np.zeros(n, dtype=np.float64)
         A["z_w"] = A["z"] * A["weights"]
         A["log_lambda"] = np.zeros(n, dtype=np.float64)

@@ -23,7 +23,9 @@
 //               num_pairs of a run is its length, and columns outside forest 2 read dummies
 //               (distance 1e300, weight 0) that add zeros and land in no bin.
 //   run change  the lane adds its five sums and the run length to the finished run's bin with six
-//               native red.global.add.f64 / .u64 (~40 instructions, divergent).  The sums restart
+//               native red.global.add.f64 / .u64 (~45 instructions, divergent; the LATENCY of this
+//               path -- the rest of the warp waits at the reconvergence point -- bounds the kernel,
+//               see dg_emit).  The sums restart
 //               through five selects in the MAIN path (high word := 0 when the bin changed, which
 //               leaves at most a 1e-314 denormal behind): the accumulators are then written only
 //               by the accumulate instructions and ptxas keeps them in place -- clearing them
@@ -298,12 +300,7 @@ pb2_xi_auto_diag(pb2_catalog c1, pb2_catalog c2, pb2_params P, pb2_pairs pr, Dia
         const double ang = pr.nb_ang[e];
         // bin constants of this forest pair
         const unsigned np16 = (unsigned)np_i << 16, nt16 = (unsigned)nt_i << 16;
-#ifdef DG_NT_REG
-        unsigned nt_r = (unsigned)nt_i;
-        asm volatile("" : "+r"(nt_r));
-#else
         const unsigned nt_r = (unsigned)nt_i;
-#endif
         const double kpf = FOLD ? mul_rn(ch, C.kp16) : C.kp16;
         const double ktf = mul_rn(sh, C.kt16);
 

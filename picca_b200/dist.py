@@ -321,9 +321,9 @@ class RowIndex:
         while r0 < n:
             # rows [r0, r1) against the forests of every row near one of them
             r1 = r0 + 1
-            near = self.near(self, np.arange(r0, min(n, r0 + 64)), ang_max)
+            near = self.near(self, np.arange(r0, min(n, r0 + 256)), ang_max)
             reach = near[0]
-            while r1 < n and r1 - r0 < 64:
+            while r1 < n and r1 - r0 < 256:
                 grown = reach | near[r1 - r0]
                 n_c = int(self.counts[grown].sum())
                 if (self.first[r1 + 1] - self.first[r0]) * n_c > max_elems:
