@@ -18,6 +18,8 @@ class LazyNeighbours:
     device neighbour list of one line of sight (reference stores a list/array of objects,
     cf.py:125-135, xcf.py:123).  Materialised only if somebody iterates it."""
 
+    __slots__ = ("_pairs", "_k", "_objs2")
+
     def __init__(self, pairs, k, objs2):
         self._pairs, self._k, self._objs2 = pairs, k, objs2
 
@@ -51,6 +53,30 @@ def set_neighbours(obj, value):
         obj.__dict__["neighbours"] = value
     except (AttributeError, TypeError):
         obj.neighbours = value
+
+
+def set_lazy_neighbours(objs1, index, pairs, objs2):
+    """``objs1[f1].neighbours = LazyNeighbours(pairs, k, objs2)`` for f1 = index[k]: once per
+    forest and fill_neighs call (100 000 times on config 2), so without a function call per
+    forest where the objects have an instance dict."""
+    new = LazyNeighbours
+    try:
+        for k, f1 in enumerate(index):
+            objs1[f1].__dict__["neighbours"] = new(pairs, k, objs2)
+    except (AttributeError, TypeError):   # slotted / foreign classes: plain attribute assignment
+        for k, f1 in enumerate(index):
+            objs1[f1].neighbours = new(pairs, k, objs2)
+
+
+def clear_neighbours(objs1, index):
+    """``objs1[f1].neighbours = None`` for every f1 of ``index`` (what the reference does once a
+    forest has been used, cf.py:240, xcf.py:213)."""
+    try:
+        for f1 in index:
+            objs1[f1].__dict__["neighbours"] = None
+    except (AttributeError, TypeError):
+        for f1 in index:
+            objs1[f1].neighbours = None
 
 
 class PendingNeighbours:

@@ -131,8 +131,7 @@ def _fill_neighs_now(healpixs):
     if _corr.HOST_ANGLES:
         _corr.apply_host_angles(pairs, host1, host2)
     _STORE.put(healpixs, pairs, ranges, (host1, host2))
-    for k, f1 in enumerate(index):
-        _corr.set_neighbours(host1.objs[f1], _corr.LazyNeighbours(pairs, k, host2.objs))
+    _corr.set_lazy_neighbours(host1.objs, index, pairs, host2.objs)
 
 
 def _pairs_for(healpixs):
@@ -158,8 +157,7 @@ def compute_xi(healpixs):
     out = eng.xi(dev1, dev2, params, pairs, out_row, 1, variant=_XI_VARIANT, normalise=True)
     host = out.cpu().numpy()[0]
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in pairs.f1_index.cpu().numpy():
-        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:240
+    _corr.clear_neighbours(host1.objs, pairs.f1_index.cpu().numpy())  # cf.py:240
     _STORE.drop(healpixs)
     weights, xi, r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in range(5))
     num_pairs = np.ascontiguousarray(host[5]).view(np.int64)
@@ -181,8 +179,7 @@ def compute_xi_batch(healpixs, normalise=True, to_host=True):
                  normalise=normalise)
     host = out.cpu().numpy() if to_host else out  # to_host=False: device tensor (multi-GPU gather)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in pairs.f1_index.cpu().numpy():
-        _corr.set_neighbours(host1.objs[f1], None)
+    _corr.clear_neighbours(host1.objs, pairs.f1_index.cpu().numpy())
     _STORE.drop(healpixs)
     return host
 
@@ -302,8 +299,7 @@ def compute_dmat(healpixs):
     res = eng.dmat(dev1, dev2, params, pairs)
     weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff = (t.cpu().numpy() for t in res)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in f1_index:
-        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:502
+    _corr.clear_neighbours(host1.objs, f1_index)  # cf.py:502
     _STORE.drop(healpixs)
     return (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff, weight_eff, num_pairs,
             num_pairs_used)
@@ -441,7 +437,6 @@ def compute_metal_dmat(healpixs, abs_igm1="LYA", abs_igm2="SiIII(1207)"):
     res = tuple(t.cpu().numpy() for t in (weights_dmat, dmat, r_par_eff, r_trans_eff, z_eff,
                                           weight_eff))
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in f1_index:
-        _corr.set_neighbours(host1.objs[f1], None)  # cf.py:1219
+    _corr.clear_neighbours(host1.objs, f1_index)  # cf.py:1219
     _STORE.drop(healpixs)
     return res + (num_pairs, num_pairs_used)

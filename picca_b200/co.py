@@ -82,8 +82,7 @@ def _fill_neighs_now(healpixs):
     if _corr.HOST_ANGLES:
         _corr.apply_host_angles(pairs, host1, host2)
     _STORE.put(healpixs, pairs, ranges, (host1, host2))
-    for k, f1 in enumerate(index):
-        _corr.set_neighbours(host1.objs[f1], _corr.LazyNeighbours(pairs, k, host2.objs))
+    _corr.set_lazy_neighbours(host1.objs, index, pairs, host2.objs)
 
 
 def compute_xi(healpixs):

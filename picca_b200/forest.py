@@ -107,6 +107,15 @@ def register_soa(data, soa):
             vals = [getattr(o, name) for o in objs]
             if name == "order":
                 vals = [-1 if v is None else int(v) for v in vals]
+            # numeric columns are kept as arrays (catalog.pack slices them on every re-pack;
+            # converting 100 000-element lists again costs 5 ms per column and call); ids that
+            # are not numbers (combined re-observations) stay lists
+            try:
+                arr = np.array(vals)
+                if arr.dtype.kind in "iuf" and arr.shape == (len(vals),):
+                    vals = arr
+            except (TypeError, ValueError):
+                pass
             los[name] = vals
         entry["los"] = los
         token = SoAToken()

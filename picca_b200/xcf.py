@@ -103,8 +103,7 @@ def _fill_neighs_now(healpixs):
     if _corr.HOST_ANGLES:
         _corr.apply_host_angles(pairs, host1, host2)
     _STORE.put(healpixs, pairs, ranges, (host1, host2))
-    for k, f1 in enumerate(index):
-        _corr.set_neighbours(host1.objs[f1], _corr.LazyNeighbours(pairs, k, host2.objs))
+    _corr.set_lazy_neighbours(host1.objs, index, pairs, host2.objs)
 
 
 def _pairs_for(healpixs):
@@ -128,8 +127,7 @@ def compute_xi(healpixs):
                  normalise=True)
     host = out.cpu().numpy()[0]
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in pairs.f1_index.cpu().numpy():
-        _corr.set_neighbours(host1.objs[f1], None)  # xcf.py:213
+    _corr.clear_neighbours(host1.objs, pairs.f1_index.cpu().numpy())  # xcf.py:213
     _STORE.drop(healpixs)
     weights, xi, r_par, r_trans, z = (np.ascontiguousarray(host[k]) for k in range(5))
     num_pairs = np.ascontiguousarray(host[5]).view(np.int64)
@@ -148,8 +146,7 @@ def compute_xi_batch(healpixs, normalise=True, to_host=True):
                  variant=_XI_VARIANT, normalise=normalise)
     host = out.cpu().numpy() if to_host else out  # to_host=False: device tensor (multi-GPU gather)
     _corr.bump_progress(_THIS, pairs.n_f1, userprint)
-    for f1 in pairs.f1_index.cpu().numpy():
-        _corr.set_neighbours(host1.objs[f1], None)
+    _corr.clear_neighbours(host1.objs, pairs.f1_index.cpu().numpy())
     _STORE.drop(healpixs)
     return host
 
