@@ -349,13 +349,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def parity_check(data, num, ang_max, healpixs, gpu_rows, n_pixels, threads):
+def parity_check(data, num, ang_max, healpixs, gpu_rows, n_pixels, threads, chosen=None):
     """Whole HEALPix rows of the timed GPU result against the oracle port on the same pixels:
-    num_pairs bit for bit, the five fp64 sums to 1e-9 (north_star)."""
+    num_pairs bit for bit, the five fp64 sums to 1e-9 (north_star).  ``chosen``: the pixels to
+    check (default: ``n_pixels`` spread over the footprint)."""
     soa = OracleSoA(data)
     cfg = Cfg()
     configure(cfg, data, num, ang_max)
-    chosen = spread_pixels(healpixs, n_pixels, step=7)
+    if chosen is None:
+        chosen = spread_pixels(healpixs, n_pixels, step=7)
     tasks = [(hp, list(range(len(data[hp])))) for hp in chosen]
     want, _ = port_run_tasks(soa, cfg, ang_max, tasks, threads)
     w = want[:, 0] > 0
@@ -883,14 +885,8 @@ def run_banded(args):
         rows_sub = np.zeros((len(sub_hps), 6, nb))
         for r in chosen_rows:
             rows_sub[sub_hps.index(hps[r])] = out_host[r]
-        pc = lambda healpixs, count, step=0: [hps[r] for r in chosen_rows]
-        global spread_pixels
-        keep, spread_pixels = spread_pixels, pc
-        try:
-            parity = parity_check(sub, n_forest, ang_max, sub_hps, rows_sub, len(chosen_rows),
-                                  os.cpu_count() or 1)
-        finally:
-            spread_pixels = keep
+        parity = parity_check(sub, n_forest, ang_max, sub_hps, rows_sub, len(chosen_rows),
+                              os.cpu_count() or 1, chosen=[hps[r] for r in chosen_rows])
 
     # ---- distortion matrix, --rej 0.99, one reference chunk seeded with the first pixel
     dmat_info = None
