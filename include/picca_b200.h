@@ -183,7 +183,12 @@ int32_t pb2_xi_auto(const pb2_catalog *cat1, const pb2_catalog *cat2, const pb2_
                     double *d_out, int32_t variant, void *stream);
 
 /* ---- forest x object correlation: replaces xcf.compute_xi's loop and
- * xcf.compute_xi_forest_pairs_fast (xcf.py:149-213, 223-322).  Same output layout. */
+ * xcf.compute_xi_forest_pairs_fast (xcf.py:149-213, 223-322).  Same output layout; `n_rows` =
+ * rows of d_out (sizes the bin-major scratch histogram of the product kernel).  `variant`: 0 =
+ * product (prefix-sum kernel with transposed reductions when the catalogue carries prefix records,
+ * the forests are sorted and no per-pair z cut is set; the general lane = object kernel otherwise),
+ * 1 = validation (every pair through the reference expression), 2 = force the general kernel,
+ * 4 = prefix-sum kernel with per-lane reductions (same results; used by the tests). */
 int32_t pb2_xi_cross(const pb2_catalog *cat1, const pb2_catalog *objs, const pb2_params *par,
                      const pb2_pairs *pairs, const int32_t *d_out_row, int64_t n_rows,
                      double *d_out, int32_t variant, void *stream);
